@@ -1,0 +1,649 @@
+// capi.cu — the C ABI declared in include/gar.h on top of gar::Engine.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/gar.h"
+#include "engine.hpp"
+
+using namespace gar;
+
+struct gar_handle {
+    gar_config cfg{};
+    Engine eng;
+    double ratio = 1.0;
+    int rows = 1;
+    int compute_dtype = DT_F64;
+    std::string err;
+    std::string gpu_name;
+    // batch pipelining
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    void* slot_in[2] = {nullptr, nullptr};
+    void* slot_out[2] = {nullptr, nullptr};
+    size_t slot_in_cap = 0, slot_out_cap = 0;
+    void* slot_cin = nullptr;   // cast scratch (compute dtype) for I/O dtype != compute dtype
+    void* slot_cout = nullptr;
+    size_t slot_cin_cap = 0, slot_cout_cap = 0;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(gar_handle* h, int status, const std::string& msg) {
+    if (h) h->err = msg;
+    return status;
+}
+
+static inline size_t dsize(int dt) { return dt == GAR_F32 ? 4 : 8; }
+
+extern "C" {
+
+const char* gar_version(void) { return "gar-b200 0.1.0 (sm_100a)"; }
+
+const char* gar_status_string(int32_t s) {
+    switch (s) {
+        case GAR_OK: return "ok";
+        case GAR_INVALID_CONFIG: return "invalid resampler configuration";
+        case GAR_BUFFER_TOO_SMALL: return "output buffer too small";
+        case GAR_NOT_SUPPORTED: return "operation not supported";
+        case GAR_CUDA_ERROR: return "CUDA error";
+        default: return "internal error";
+    }
+}
+
+const char* gar_last_error(const gar_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int32_t gar_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int32_t gar_create(const gar_config* cfg, gar_handle** out) {
+    if (out) *out = nullptr;
+    if (!cfg || !out) {
+        g_create_err = "config is nil";
+        return GAR_INVALID_CONFIG;
+    }
+    auto bad = [&](const char* m) {
+        g_create_err = m;
+        return (int32_t)GAR_INVALID_CONFIG;
+    };
+    // Config.Validate (resample.go:168-214) / NewResampler (resampler.go:51-70)
+    if (!(cfg->input_rate > 0) || !(cfg->output_rate > 0)) return bad("sample rates must be positive");
+    const int path = cfg->path;
+    if (path != GAR_PATH_PIPELINE && path != GAR_PATH_ENGINE) return bad("unknown path");
+    int channels = cfg->channels;
+    if (path == GAR_PATH_ENGINE && channels == 0) channels = 1;
+    if (channels < 1) return bad("channels must be at least 1");
+    if (channels > 256) return bad("too many channels (max 256)");
+    const double ratio = cfg->output_rate / cfg->input_rate;
+    if (ratio < 1.0 / 256.0 || ratio > 256.0) return bad("resampling ratio out of range");
+    if (cfg->preset == GAR_QUALITY_CUSTOM && path == GAR_PATH_PIPELINE) {  // QualitySpec.Validate
+        if (cfg->custom_precision < 8 || cfg->custom_precision > 33) return bad("precision must be 8-33 bits");
+        if (cfg->custom_phase_response < 0 || cfg->custom_phase_response > 100) return bad("phase response must be 0-100");
+        if (!(cfg->custom_passband_end > 0) || !(cfg->custom_passband_end < 1)) return bad("passband end must be in (0, 1)");
+        if (!(cfg->custom_stopband_begin > cfg->custom_passband_end) || cfg->custom_stopband_begin > 1)
+            return bad("stopband begin must be in (passband_end, 1]");
+    }
+    if (cfg->dtype != GAR_F64 && cfg->dtype != GAR_F32) return bad("unknown dtype");
+    if (cfg->n_streams < 0) return bad("n_streams must be >= 0");
+
+    Chain chain;
+    std::string err;
+    int compute = DT_F64;
+    if (path == GAR_PATH_PIPELINE) {
+        // the pipeline always computes in float64 (constant.go:161-199); dtype only selects the I/O type
+        const int precision = cfg->preset == GAR_QUALITY_CUSTOM ? cfg->custom_precision : preset_precision(cfg->preset);
+        if (!design_pipeline(cfg->input_rate, cfg->output_rate, precision, chain, err)) {
+            g_create_err = err;
+            return GAR_INVALID_CONFIG;
+        }
+    } else {
+        const int q = cfg->engine_quality >= 0 ? cfg->engine_quality : preset_to_engine_quality(cfg->preset);
+        if (q > EQ_32BIT) return bad("unknown engine quality");
+        chain.ratio = ratio;
+        if (!design_engine(cfg->input_rate, cfg->output_rate, q, chain, err)) {
+            g_create_err = err;
+            return GAR_INVALID_CONFIG;
+        }
+        compute = cfg->dtype == GAR_F32 ? DT_F32 : DT_F64;
+    }
+    chain.ratio = ratio;
+
+    std::unique_ptr<gar_handle> h(new gar_handle());
+    h->cfg = *cfg;
+    h->cfg.channels = channels;
+    h->ratio = ratio;
+    h->rows = channels * (cfg->n_streams > 1 ? cfg->n_streams : 1);
+    h->compute_dtype = compute;
+    int rc = h->eng.init(chain, h->rows, compute, cfg->device, err);
+    if (rc) {
+        g_create_err = err;
+        return rc;
+    }
+    cudaDeviceProp prop{};
+    if (cfg->device >= 0 && cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) h->gpu_name = prop.name;
+    *out = h.release();
+    return GAR_OK;
+}
+
+void gar_destroy(gar_handle* h) {
+    if (!h) return;
+    if (h->eng.device() < 0) {
+        delete h;
+        return;
+    }
+    cudaSetDevice(h->eng.device());
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+        if (h->slot_in[i]) cudaFree(h->slot_in[i]);
+        if (h->slot_out[i]) cudaFree(h->slot_out[i]);
+    }
+    if (h->slot_cin) cudaFree(h->slot_cin);
+    if (h->slot_cout) cudaFree(h->slot_cout);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    delete h;
+}
+
+// ---- geometry / info -------------------------------------------------------------------------
+int64_t gar_estimate_output(const gar_handle* h, int64_t n_in) {
+    return (int64_t)((double)n_in * h->ratio) + 64;  // constants.go:58
+}
+
+int64_t gar_next_output_count(const gar_handle* h, int32_t stream, int64_t n_in) {
+    if (!h || stream < 0 || stream >= h->rows || n_in < 0) return -1;
+    StreamState st = h->eng.state(stream);
+    Plan p;
+    h->eng.plan(st, n_in, false, p);
+    return p.n_out;
+}
+
+int64_t gar_next_flush_count(const gar_handle* h, int32_t stream) {
+    if (!h || stream < 0 || stream >= h->rows) return -1;
+    StreamState st = h->eng.state(stream);
+    Plan p;
+    h->eng.plan(st, 0, true, p);
+    return p.n_out;
+}
+
+double gar_get_ratio(const gar_handle* h) { return h->ratio; }
+
+static int engine_latency(const Chain& c, const EngineDesign& e) {  // stage_adapter.go:43-57
+    if (e.has_cubic) return 2;                                      // cubic.go:98 (cubicLatencySamples)
+    int l = 0;
+    if (e.has_pre) {
+        const StageDesign& s = c.stages[(size_t)e.first_stage];
+        if (s.factor > 1) l += (s.taps * s.factor) / 2;
+    }
+    if (e.has_poly) l += c.stages[(size_t)e.first_stage + 1].taps / 2;
+    return l;
+}
+
+int32_t gar_get_latency(const gar_handle* h) {  // constant.go:407-423
+    const Chain& c = h->eng.chain();
+    int tot = 0;
+    for (const EngineDesign& e : c.engines) tot += (int)((double)engine_latency(c, e) * e.ratio);
+    return tot;
+}
+
+int32_t gar_get_info(const gar_handle* h, gar_info* out) {  // constant.go:452-485
+    if (!h || !out) return GAR_INVALID_CONFIG;
+    std::memset(out, 0, sizeof(*out));
+    std::snprintf(out->algorithm, sizeof(out->algorithm), "%s", "multi-stage");
+    out->latency = gar_get_latency(h);
+    out->memory_usage = h->eng.device_bytes();
+    const Chain& c = h->eng.chain();
+    if (!c.engines.empty()) {
+        const EngineDesign& e = c.engines[0];
+        if (e.has_cubic) {
+            out->filter_length = 4;  // cubic.go:110
+        } else {
+            if (e.has_pre) {
+                const StageDesign& s = c.stages[(size_t)e.first_stage];
+                if (s.factor > 1) out->filter_length += s.taps * s.factor;  // stage_adapter.go:98-110
+            }
+            if (e.has_poly) {
+                const StageDesign& s = c.stages[(size_t)e.first_stage + 1];
+                out->filter_length += s.taps * s.factor;
+                out->phases = s.factor;
+            }
+            out->simd_enabled = 1;
+        }
+    }
+    std::snprintf(out->simd_type, sizeof(out->simd_type), "CUDA sm_100a (%s)", h->gpu_name.c_str());
+    return GAR_OK;
+}
+
+int32_t gar_get_stats(const gar_handle* h, int32_t stream, int32_t e, int64_t* in, int64_t* outp) {
+    if (!h || stream < 0 || stream >= h->rows) return GAR_INVALID_CONFIG;
+    const StreamState& st = h->eng.state(stream);
+    if (e < 0 || e >= (int)st.samples_in.size()) return GAR_INVALID_CONFIG;
+    if (in) *in = st.samples_in[(size_t)e];
+    if (outp) *outp = st.samples_out[(size_t)e];
+    return GAR_OK;
+}
+
+int32_t gar_num_stages(const gar_handle* h) { return (int32_t)h->eng.chain().stages.size(); }
+int32_t gar_num_engines(const gar_handle* h) { return (int32_t)h->eng.chain().engines.size(); }
+
+int32_t gar_describe_stage(const gar_handle* h, int32_t stream, int32_t stage, gar_stage_desc* out) {
+    if (!h || !out || stream < 0 || stream >= h->rows) return GAR_INVALID_CONFIG;
+    const Chain& c = h->eng.chain();
+    if (stage < 0 || stage >= (int)c.stages.size()) return GAR_INVALID_CONFIG;
+    const StageDesign& s = c.stages[(size_t)stage];
+    const StageState& st = h->eng.state(stream).st[(size_t)stage];
+    out->kind = s.kind;
+    out->engine_index = s.engine_index;
+    out->factor = s.factor;
+    out->taps = s.taps;
+    out->proto_taps = s.proto_taps;
+    out->engine_quality = s.quality;
+    out->step = s.step;
+    out->at = st.at;
+    out->hist_len = s.kind == STAGE_CUBIC ? 0 : st.hist_len;
+    out->decim_phase = st.decim_phase;
+    out->ratio = s.ratio;
+    return GAR_OK;
+}
+
+int32_t gar_plan_stage_type(const gar_handle* h, int32_t e) {
+    const Chain& c = h->eng.chain();
+    if (e < 0 || e >= (int)c.engines.size()) return -1;
+    return c.engines[(size_t)e].plan_type;
+}
+
+int64_t gar_get_bank(const gar_handle* h, int32_t stage, int32_t which, double* out, int64_t cap) {
+    const Chain& c = h->eng.chain();
+    if (stage < 0 || stage >= (int)c.stages.size() || which < 0 || which > 3) return -1;
+    const std::vector<double>& b = c.stages[(size_t)stage].bank[which];
+    if ((int64_t)b.size() > cap) return -(int64_t)b.size();
+    const bool f32 = h->compute_dtype == DT_F32;
+    for (size_t i = 0; i < b.size(); ++i) out[i] = f32 ? (double)(float)b[i] : b[i];
+    return (int64_t)b.size();
+}
+
+int32_t gar_upload_bank(gar_handle* h, int32_t stage, int32_t which, const double* coef, int64_t n) {
+    if (!h || !coef) return GAR_INVALID_CONFIG;
+    return h->eng.set_bank(stage, which, coef, n, h->err);
+}
+
+int64_t gar_kernel_launches(const gar_handle* h, int32_t reset) {
+    (void)h;  // process-wide counter: every <<<>>> of this library
+    return (int64_t)launch_count(reset != 0);
+}
+
+const char* gar_stage_kernel_name(const gar_handle* h, int32_t stage) {
+    if (!h || stage < 0 || stage >= (int)h->eng.chain().stages.size()) return "";
+    return h->eng.stage_dev(stage).kernel;
+}
+
+// ---- processing --------------------------------------------------------------------------------
+
+// rows [row0,row0+count) with per-row host pointers; io dtype may differ from the compute dtype
+static int process_rows_host(gar_handle* h, int row0, int count, int io_dtype, const void* const* in,
+                             const int64_t* n_in, void* const* out, int64_t out_cap, int64_t* n_out, bool flush,
+                             bool check_estimate) {
+    Engine& E = h->eng;
+    if (row0 < 0 || count < 1 || row0 + count > h->rows) return fail(h, GAR_INVALID_CONFIG, "channel out of range");
+    if (E.device() < 0) return fail(h, GAR_CUDA_ERROR, "geometry-only handle (device = -1) cannot process samples");
+    int64_t max_in = 0;
+    for (int r = 0; r < count; ++r) {
+        const int64_t n = flush ? 0 : n_in[r];
+        if (n < 0) return fail(h, GAR_INVALID_CONFIG, "negative input length");
+        if (!flush && check_estimate && out_cap < gar_estimate_output(h, n))
+            return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer smaller than EstimateOutput(len(input))");
+        max_in = n > max_in ? n : max_in;
+    }
+    // exact output counts first (pure integer), so nothing is advanced when a buffer is too small
+    std::vector<int64_t> cnt((size_t)count, 0);
+    int64_t max_out = 0;
+    for (int r = 0; r < count; ++r) {
+        cnt[(size_t)r] = flush ? gar_next_flush_count(h, row0 + r) : gar_next_output_count(h, row0 + r, n_in[r]);
+        if (cnt[(size_t)r] > out_cap) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
+        max_out = cnt[(size_t)r] > max_out ? cnt[(size_t)r] : max_out;
+    }
+    cudaSetDevice(E.device());
+    cudaStream_t s = E.stream();
+    const size_t iosz = dsize(io_dtype), csz = dsize(h->compute_dtype);
+    const int64_t in_stride = (max_in + 3) & ~int64_t(3), out_stride = (max_out + 3) & ~int64_t(3);
+    const bool cast = io_dtype != h->compute_dtype;
+    char* d_in_io = nullptr;
+    char* d_in_c = nullptr;
+    if (max_in > 0) {
+        d_in_io = (char*)E.scratch(0, (size_t)count * (size_t)in_stride * iosz, h->err);
+        if (!d_in_io) return GAR_CUDA_ERROR;
+        d_in_c = d_in_io;
+        if (cast) {
+            d_in_c = (char*)E.scratch(1, (size_t)count * (size_t)in_stride * csz, h->err);
+            if (!d_in_c) return GAR_CUDA_ERROR;
+        }
+    }
+    char* d_out_c = nullptr;
+    char* d_out_io = nullptr;
+    if (max_out > 0) {
+        d_out_c = (char*)E.scratch(2, (size_t)count * (size_t)out_stride * csz, h->err);
+        if (!d_out_c) return GAR_CUDA_ERROR;
+        d_out_io = d_out_c;
+        if (cast) {
+            d_out_io = (char*)E.scratch(3, (size_t)count * (size_t)out_stride * iosz, h->err);
+            if (!d_out_io) return GAR_CUDA_ERROR;
+        }
+    }
+    if (!flush)
+        for (int r = 0; r < count; ++r)
+            if (n_in[r] > 0)
+                cudaMemcpyAsync(d_in_io + (size_t)r * (size_t)in_stride * iosz, in[r], (size_t)n_in[r] * iosz,
+                                cudaMemcpyHostToDevice, s);
+    if (cast && max_in > 0) {
+        launch_cast(d_in_io, in_stride, io_dtype, d_in_c, in_stride, h->compute_dtype, (int32_t)max_in, count, s);
+    }
+    // lock-step groups: consecutive rows with identical state and identical chunk length share launches
+    int r = 0;
+    while (r < count) {
+        int run = E.lockstep_run(row0 + r, row0 + count);
+        if (!flush) {
+            int k = 1;
+            while (k < run && n_in[r + k] == n_in[r]) ++k;
+            run = k;
+        }
+        int64_t got = 0;
+        int rc = E.run(row0 + r, run, d_in_c ? d_in_c + (size_t)r * (size_t)in_stride * csz : nullptr, in_stride,
+                       flush ? 0 : n_in[r], d_out_c ? d_out_c + (size_t)r * (size_t)out_stride * csz : nullptr,
+                       out_stride, out_stride, flush, s, &got, h->err);
+        if (rc) return rc;
+        for (int k = 0; k < run; ++k) n_out[r + k] = got;
+        r += run;
+    }
+    if (cast && max_out > 0)
+        launch_cast(d_out_c, out_stride, h->compute_dtype, d_out_io, out_stride, io_dtype, (int32_t)max_out, count, s);
+    for (int q = 0; q < count; ++q)
+        if (n_out[q] > 0)
+            cudaMemcpyAsync(out[q], d_out_io + (size_t)q * (size_t)out_stride * iosz, (size_t)n_out[q] * iosz,
+                            cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fail(h, GAR_CUDA_ERROR, std::string("stream sync: ") + cudaGetErrorString(e));
+    return GAR_OK;
+}
+
+int32_t gar_process_f64(gar_handle* h, int32_t ch, const double* in, int64_t n_in, double* out, int64_t out_cap,
+                        int64_t* n_out) {
+    if (!h || !n_out) return GAR_INVALID_CONFIG;
+    *n_out = 0;
+    if (h->compute_dtype != DT_F64) return fail(h, GAR_NOT_SUPPORTED, "float32 engine: use gar_process_f32");
+    if (n_in < 0) return fail(h, GAR_INVALID_CONFIG, "negative input length");
+    if (out_cap < gar_estimate_output(h, n_in)) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
+    if (n_in == 0) return GAR_OK;
+    const void* ip = in;
+    void* op = out;
+    return process_rows_host(h, ch, 1, GAR_F64, &ip, &n_in, &op, out_cap, n_out, false, true);
+}
+
+int32_t gar_process_f32(gar_handle* h, int32_t ch, const float* in, int64_t n_in, float* out, int64_t out_cap,
+                        int64_t* n_out) {
+    if (!h || !n_out) return GAR_INVALID_CONFIG;
+    *n_out = 0;
+    if (h->cfg.path == GAR_PATH_ENGINE && h->compute_dtype != DT_F32)
+        return fail(h, GAR_NOT_SUPPORTED, "float64 engine: use gar_process_f64");
+    if (n_in < 0) return fail(h, GAR_INVALID_CONFIG, "negative input length");
+    if (out_cap < gar_estimate_output(h, n_in)) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
+    if (n_in == 0) return GAR_OK;
+    const void* ip = in;
+    void* op = out;
+    return process_rows_host(h, ch, 1, GAR_F32, &ip, &n_in, &op, out_cap, n_out, false, true);
+}
+
+int32_t gar_process_multi_f64(gar_handle* h, const double* const* in, const int64_t* n_in, double* const* out,
+                              int64_t out_cap, int64_t* n_out) {
+    if (!h || !in || !n_in || !out || !n_out) return GAR_INVALID_CONFIG;
+    if (h->compute_dtype != DT_F64) return fail(h, GAR_NOT_SUPPORTED, "float32 engine has no ProcessMulti");
+    const int C = h->cfg.channels;
+    for (int c = 0; c < C; ++c) n_out[c] = 0;
+    return process_rows_host(h, 0, C, GAR_F64, (const void* const*)in, n_in, (void* const*)out, out_cap, n_out, false,
+                             false);
+}
+
+int32_t gar_flush_f64(gar_handle* h, int32_t ch, double* out, int64_t out_cap, int64_t* n_out) {
+    if (!h || !n_out) return GAR_INVALID_CONFIG;
+    *n_out = 0;
+    if (h->compute_dtype != DT_F64) return fail(h, GAR_NOT_SUPPORTED, "float32 engine: use gar_flush_f32");
+    void* op = out;
+    return process_rows_host(h, ch, 1, GAR_F64, nullptr, nullptr, &op, out_cap, n_out, true, false);
+}
+
+int32_t gar_flush_f32(gar_handle* h, int32_t ch, float* out, int64_t out_cap, int64_t* n_out) {
+    if (!h || !n_out) return GAR_INVALID_CONFIG;
+    *n_out = 0;
+    if (h->cfg.path == GAR_PATH_ENGINE && h->compute_dtype != DT_F32)
+        return fail(h, GAR_NOT_SUPPORTED, "float64 engine: use gar_flush_f64");
+    void* op = out;
+    return process_rows_host(h, ch, 1, GAR_F32, nullptr, nullptr, &op, out_cap, n_out, true, false);
+}
+
+int32_t gar_flush_multi_f64(gar_handle* h, double* const* out, int64_t out_cap, int64_t* n_out) {
+    if (!h || !out || !n_out) return GAR_INVALID_CONFIG;
+    if (h->compute_dtype != DT_F64) return fail(h, GAR_NOT_SUPPORTED, "float32 engine has no FlushMulti");
+    const int C = h->cfg.channels;
+    for (int c = 0; c < C; ++c) n_out[c] = 0;
+    return process_rows_host(h, 0, C, GAR_F64, nullptr, nullptr, (void* const*)out, out_cap, n_out, true, false);
+}
+
+int32_t gar_advance_geometry(gar_handle* h, int32_t stream, int64_t n_in, int32_t flush, int64_t* n_out) {
+    if (!h || stream < 0 || stream >= h->rows || n_in < 0) return GAR_INVALID_CONFIG;
+    const int64_t n = h->eng.advance(stream, flush ? 0 : n_in, flush != 0);
+    if (n_out) *n_out = n;
+    return GAR_OK;
+}
+
+int32_t gar_reset(gar_handle* h) {
+    if (!h) return GAR_INVALID_CONFIG;
+    h->eng.reset_state();
+    return GAR_OK;
+}
+
+// ---- batched streams --------------------------------------------------------------------------
+
+static int batch_dev(gar_handle* h, int io_dtype, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out,
+                     int64_t out_stride, int64_t out_cap, int64_t* n_out, bool flush, cudaStream_t s, int row0,
+                     int count) {
+    Engine& E = h->eng;
+    const size_t iosz = dsize(io_dtype), csz = dsize(h->compute_dtype);
+    const bool cast = io_dtype != h->compute_dtype;
+    cudaSetDevice(E.device());
+    int r = 0;
+    int64_t got_all = -1;
+    while (r < count) {
+        const int run = E.lockstep_run(row0 + r, row0 + count);
+        const char* ip = d_in ? (const char*)d_in + (size_t)r * (size_t)in_stride * iosz : nullptr;
+        char* op = d_out ? (char*)d_out + (size_t)r * (size_t)out_stride * iosz : nullptr;
+        int64_t got = 0;
+        int rc;
+        if (!cast) {
+            rc = E.run(row0 + r, run, ip, in_stride, flush ? 0 : n_in, op, out_stride, out_cap, flush, s, &got, h->err);
+        } else {
+            // I/O dtype differs from the compute dtype (path A with float32 I/O): cast through scratch
+            const int64_t want = flush ? gar_next_flush_count(h, row0 + r) : gar_next_output_count(h, row0 + r, n_in);
+            if (want > out_cap) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
+            const int64_t cis = (n_in + 3) & ~int64_t(3), cos = (want + 3) & ~int64_t(3);
+            char* cin = nullptr;
+            if (!flush && n_in > 0) {
+                cin = (char*)E.scratch(1, (size_t)run * (size_t)cis * csz, h->err);
+                if (!cin) return GAR_CUDA_ERROR;
+                launch_cast(ip, in_stride, io_dtype, cin, cis, h->compute_dtype, (int32_t)n_in, run, s);
+            }
+            char* cout = nullptr;
+            if (want > 0) {
+                cout = (char*)E.scratch(2, (size_t)run * (size_t)cos * csz, h->err);
+                if (!cout) return GAR_CUDA_ERROR;
+            }
+            rc = E.run(row0 + r, run, cin, cis, flush ? 0 : n_in, cout, cos, cos, flush, s, &got, h->err);
+            if (!rc && got > 0) launch_cast(cout, cos, h->compute_dtype, op, out_stride, io_dtype, (int32_t)got, run, s);
+        }
+        if (rc) return rc;
+        if (got_all < 0) got_all = got;
+        else if (got != got_all)
+            return fail(h, GAR_NOT_SUPPORTED, "batch rows are not in lock step (mixed per-channel calls before a batch call)");
+        r += run;
+    }
+    if (n_out) *n_out = got_all < 0 ? 0 : got_all;
+    return GAR_OK;
+}
+
+int32_t gar_process_batch_dev(gar_handle* h, int32_t io_dtype, const void* d_in, int64_t in_stride, int64_t n_in,
+                              void* d_out, int64_t out_stride, int64_t out_cap, int64_t* n_out, void* cuda_stream) {
+    if (!h) return GAR_INVALID_CONFIG;
+    if (n_in < 0) return fail(h, GAR_INVALID_CONFIG, "negative input length");
+    if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->compute_dtype)
+        return fail(h, GAR_NOT_SUPPORTED, "engine handles take their own dtype");
+    if (n_in == 0) {
+        if (n_out) *n_out = 0;
+        return GAR_OK;
+    }
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->eng.stream();
+    return batch_dev(h, io_dtype, d_in, in_stride, n_in, d_out, out_stride, out_cap, n_out, false, s, 0, h->rows);
+}
+
+int32_t gar_flush_batch_dev(gar_handle* h, int32_t io_dtype, void* d_out, int64_t out_stride, int64_t out_cap,
+                            int64_t* n_out, void* cuda_stream) {
+    if (!h) return GAR_INVALID_CONFIG;
+    if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->compute_dtype)
+        return fail(h, GAR_NOT_SUPPORTED, "engine handles take their own dtype");
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->eng.stream();
+    return batch_dev(h, io_dtype, nullptr, 0, 0, d_out, out_stride, out_cap, n_out, true, s, 0, h->rows);
+}
+
+// Host-buffer batch: rows are cut into slices; slice k's H2D copy, kernels and D2H copy run on three
+// streams chained by events, with two staging slots, so PCIe traffic in both directions overlaps the SMs.
+static int batch_host(gar_handle* h, int io_dtype, const void* in, int64_t in_stride, int64_t n_in, void* out,
+                      int64_t out_stride, int64_t out_cap, int64_t* n_out, bool flush) {
+    Engine& E = h->eng;
+    if (E.device() < 0) return fail(h, GAR_CUDA_ERROR, "geometry-only handle (device = -1) cannot process samples");
+    cudaSetDevice(E.device());
+    const size_t iosz = dsize(io_dtype);
+    const int rows = h->rows;
+    // exact per-row output count; all rows must agree (lock step)
+    const int64_t want = flush ? gar_next_flush_count(h, 0) : gar_next_output_count(h, 0, n_in);
+    if (E.lockstep_run(0, rows) != rows)
+        return fail(h, GAR_NOT_SUPPORTED, "batch rows are not in lock step (mixed per-channel calls before a batch call)");
+    if (want > out_cap) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
+    if (n_out) *n_out = want;
+    if (!flush && n_in == 0) return GAR_OK;
+    if (!h->s_in) {
+        cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+        for (int i = 0; i < 2; ++i) {
+            cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming);
+        }
+    }
+    const int64_t is = (n_in + 3) & ~int64_t(3), os = (want + 3) & ~int64_t(3);
+    // slice size: ~64 MiB of input per slice, at least 1 row, at most all rows
+    const int64_t row_bytes = (int64_t)((flush ? 0 : n_in) + want) * (int64_t)iosz;
+    int slice = (int)std::max<int64_t>(1, std::min<int64_t>(rows, (64ll << 20) / std::max<int64_t>(row_bytes, 1)));
+    if (rows <= 2) slice = rows;
+    const size_t need_in = (size_t)slice * (size_t)is * iosz, need_out = (size_t)slice * (size_t)os * iosz;
+    if (need_in > h->slot_in_cap) {
+        cudaDeviceSynchronize();
+        for (int i = 0; i < 2; ++i) {
+            if (h->slot_in[i]) cudaFree(h->slot_in[i]);
+            if (cudaMalloc(&h->slot_in[i], need_in) != cudaSuccess) return fail(h, GAR_CUDA_ERROR, "cudaMalloc(staging in)");
+        }
+        h->slot_in_cap = need_in;
+    }
+    if (need_out > h->slot_out_cap) {
+        cudaDeviceSynchronize();
+        for (int i = 0; i < 2; ++i) {
+            if (h->slot_out[i]) cudaFree(h->slot_out[i]);
+            if (cudaMalloc(&h->slot_out[i], need_out) != cudaSuccess) return fail(h, GAR_CUDA_ERROR, "cudaMalloc(staging out)");
+        }
+        h->slot_out_cap = need_out;
+    }
+    cudaStream_t sc = E.stream();
+    int k = 0;
+    for (int r0 = 0; r0 < rows; r0 += slice, ++k) {
+        const int cnt = std::min(slice, rows - r0);
+        const int slot = k & 1;
+        if (!flush) {
+            if (k >= 2) cudaStreamWaitEvent(h->s_in, h->ev_comp[slot], 0);  // slot's previous kernels done reading
+            cudaMemcpy2DAsync(h->slot_in[slot], (size_t)is * iosz, (const char*)in + (size_t)r0 * (size_t)in_stride * iosz,
+                              (size_t)in_stride * iosz, (size_t)n_in * iosz, (size_t)cnt, cudaMemcpyHostToDevice, h->s_in);
+            cudaEventRecord(h->ev_in[slot], h->s_in);
+            cudaStreamWaitEvent(sc, h->ev_in[slot], 0);
+        }
+        if (k >= 2) cudaStreamWaitEvent(sc, h->ev_out[slot], 0);  // slot's previous D2H done
+        int64_t got = 0;
+        int rc = batch_dev(h, io_dtype, h->slot_in[slot], is, n_in, h->slot_out[slot], os, os, &got, flush, sc, r0, cnt);
+        if (rc) {
+            cudaDeviceSynchronize();
+            return rc;
+        }
+        cudaEventRecord(h->ev_comp[slot], sc);
+        if (got > 0) {
+            cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0);
+            cudaMemcpy2DAsync((char*)out + (size_t)r0 * (size_t)out_stride * iosz, (size_t)out_stride * iosz,
+                              h->slot_out[slot], (size_t)os * iosz, (size_t)got * iosz, (size_t)cnt,
+                              cudaMemcpyDeviceToHost, h->s_out);
+        }
+        cudaEventRecord(h->ev_out[slot], h->s_out);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(h->s_in);
+    cudaError_t e2 = cudaStreamSynchronize(sc);
+    cudaError_t e3 = cudaStreamSynchronize(h->s_out);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+        return fail(h, GAR_CUDA_ERROR, std::string("batch sync: ") + cudaGetErrorString(e));
+    }
+    return GAR_OK;
+}
+
+int32_t gar_process_batch(gar_handle* h, int32_t io_dtype, const void* in, int64_t in_stride, int64_t n_in, void* out,
+                          int64_t out_stride, int64_t out_cap, int64_t* n_out) {
+    if (!h) return GAR_INVALID_CONFIG;
+    if (n_in < 0) return fail(h, GAR_INVALID_CONFIG, "negative input length");
+    if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->compute_dtype)
+        return fail(h, GAR_NOT_SUPPORTED, "engine handles take their own dtype");
+    if (out_cap < gar_estimate_output(h, n_in)) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
+    return batch_host(h, io_dtype, in, in_stride, n_in, out, out_stride, out_cap, n_out, false);
+}
+
+int32_t gar_flush_batch(gar_handle* h, int32_t io_dtype, void* out, int64_t out_stride, int64_t out_cap,
+                        int64_t* n_out) {
+    if (!h) return GAR_INVALID_CONFIG;
+    if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->compute_dtype)
+        return fail(h, GAR_NOT_SUPPORTED, "engine handles take their own dtype");
+    return batch_host(h, io_dtype, nullptr, 0, 0, out, out_stride, out_cap, n_out, true);
+}
+
+// ---- utilities ---------------------------------------------------------------------------------
+void* gar_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void gar_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int32_t gar_measure_fma_peak(int32_t device, int32_t dtype, double* tflops) {
+    if (!tflops) return GAR_INVALID_CONFIG;
+    if (cudaSetDevice(device) != cudaSuccess) return GAR_CUDA_ERROR;
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        double flops = 0;
+        const float ms = run_fma_probe(dtype == GAR_F32 ? DT_F32 : DT_F64, dtype == GAR_F32 ? 4096 : 2048, &flops, 0);
+        if (ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    if (cudaGetLastError() != cudaSuccess || best <= 0) return GAR_CUDA_ERROR;
+    *tflops = best;
+    return GAR_OK;
+}
+
+}  // extern "C"

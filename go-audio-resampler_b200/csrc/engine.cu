@@ -1,0 +1,576 @@
+// engine.cu — host runtime (no device code here; built by nvcc for the CUDA runtime API).
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace gar {
+
+namespace {
+inline bool cuda_ok(cudaError_t e, std::string& err, const char* what) {
+    if (e == cudaSuccess) return true;
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+}  // namespace
+
+Engine::~Engine() {
+    if (device_ >= 0 && (stream_ || !dev_.empty())) cudaSetDevice(device_);
+    for (auto& d : dev_) {
+        for (auto& b : d.bank) if (b) cudaFree(b);
+        for (auto& h : d.hist) if (h) cudaFree(h);
+    }
+    for (void* b : ibuf_) if (b) cudaFree(b);
+    if (zeros_) cudaFree(zeros_);
+    for (void* p : scratch_) if (p) cudaFree(p);
+    if (d_cubic_idx_) cudaFree(d_cubic_idx_);
+    if (d_cubic_phase_) cudaFree(d_cubic_phase_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+int Engine::upload_bank(int stage, int which, const std::vector<double>& v, std::string& err) {
+    StageDev& d = dev_[(size_t)stage];
+    if (d.bank[which]) {
+        cudaFree(d.bank[which]);
+        d.bank[which] = nullptr;
+    }
+    if (v.empty()) return 0;
+    const size_t bytes = v.size() * esz_;
+    if (!cuda_ok(cudaMalloc(&d.bank[which], bytes), err, "cudaMalloc(bank)")) return 4;
+    device_bytes_ += (int64_t)bytes;
+    if (dtype_ == DT_F32) {  // coefficients are designed in f64 and cast (polyphase_stage.go:149-152, dft_stage.go:98,464)
+        std::vector<float> f(v.size());
+        for (size_t i = 0; i < v.size(); ++i) f[i] = (float)v[i];
+        if (!cuda_ok(cudaMemcpy(d.bank[which], f.data(), bytes, cudaMemcpyHostToDevice), err, "bank upload")) return 4;
+    } else {
+        if (!cuda_ok(cudaMemcpy(d.bank[which], v.data(), bytes, cudaMemcpyHostToDevice), err, "bank upload")) return 4;
+    }
+    return 0;
+}
+
+int Engine::init(const Chain& chain, int rows, int compute_dtype, int device, std::string& err) {
+    chain_ = chain;
+    rows_ = rows;
+    dtype_ = compute_dtype;
+    esz_ = compute_dtype == DT_F32 ? 4 : 8;
+    device_ = device;
+    if (device == -1) {  // geometry-only handle: integer state machine and banks on the host, nothing on a device
+        dev_.assign(chain_.stages.size(), StageDev{});
+        name_kernels();
+        streams_.assign((size_t)rows, StreamState{});
+        reset_state();
+        return 0;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        err = "no CUDA device available (this engine has no CPU fallback)";
+        device_ = -1;
+        return 4;
+    }
+    if (device < 0 || device >= ndev) {
+        err = "CUDA device ordinal out of range";
+        device_ = -1;
+        return 1;
+    }
+    if (!cuda_ok(cudaSetDevice(device), err, "cudaSetDevice")) return 4;
+    if (!cuda_ok(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), err, "cudaStreamCreate")) return 4;
+
+    const size_t S = chain_.stages.size();
+    dev_.assign(S, StageDev{});
+    for (size_t s = 0; s < S; ++s) {
+        StageDesign& sd = chain_.stages[s];
+        for (int w = 0; w < 4; ++w) {
+            if (sd.kind == STAGE_POLY || w == 0) {
+                int rc = upload_bank((int)s, w, sd.bank[w], err);
+                if (rc) return rc;
+            }
+        }
+        int64_t cap = 8;
+        switch (sd.kind) {
+            case STAGE_UP: cap = sd.taps + 8; break;
+            case STAGE_DECIM: cap = sd.taps + sd.factor + 8; break;
+            case STAGE_POLY: cap = sd.taps + 600; break;
+            case STAGE_CUBIC: cap = 4; break;
+        }
+        dev_[s].hist_cap = 0;
+        int rc = ensure_hist((int)s, cap, err);
+        if (rc) return rc;
+    }
+    name_kernels();
+    ibuf_.assign(chain_.engines.size() * 2, nullptr);
+    ibuf_cap_.assign(chain_.engines.size() * 2, 0);
+    streams_.assign((size_t)rows, StreamState{});
+    reset_state();
+    return 0;
+}
+
+void Engine::name_kernels() {
+    for (size_t s = 0; s < chain_.stages.size(); ++s) {
+        const StageDesign& sd = chain_.stages[s];
+        switch (sd.kind) {
+            case STAGE_UP: dev_[s].kernel = fir_variant_name(dtype_, 1, sd.factor, sd.taps, 0, rows_); break;
+            case STAGE_DECIM: dev_[s].kernel = fir_variant_name(dtype_, sd.factor, 1, sd.taps, 0, rows_); break;
+            case STAGE_POLY: dev_[s].kernel = dtype_ == DT_F32 ? (sd.interp ? "poly_f32_interp" : "poly_f32")
+                                                               : (sd.interp ? "poly_f64_interp" : "poly_f64"); break;
+            default: dev_[s].kernel = dtype_ == DT_F32 ? "cubic_f32" : "cubic_f64"; break;
+        }
+    }
+}
+
+void Engine::reset_state() {
+    const size_t S = chain_.stages.size(), E = chain_.engines.size();
+    for (auto& st : streams_) {
+        st.st.assign(S, StageState{});
+        st.samples_in.assign(E, 0);
+        st.samples_out.assign(E, 0);
+        for (size_t s = 0; s < S; ++s)
+            if (chain_.stages[s].kind == STAGE_CUBIC) st.st[s].hist_len = 3;  // cubic.go:18: zero-initialised 4-point window
+    }
+    if (device_ < 0) return;
+    cudaSetDevice(device_);
+    for (size_t s = 0; s < S; ++s)
+        if (chain_.stages[s].kind == STAGE_CUBIC)
+            for (auto& h : dev_[s].hist)
+                if (h) cudaMemsetAsync(h, 0, (size_t)rows_ * (size_t)dev_[s].hist_cap * esz_, stream_);
+    if (stream_) cudaStreamSynchronize(stream_);
+}
+
+int Engine::set_bank(int stage, int which, const double* coef, int64_t n, std::string& err) {
+    if (stage < 0 || stage >= (int)chain_.stages.size() || which < 0 || which > 3) {
+        err = "stage/bank index out of range";
+        return 1;
+    }
+    StageDesign& sd = chain_.stages[(size_t)stage];
+    if ((int64_t)sd.bank[which].size() != n) {
+        err = "bank size mismatch";
+        return 1;
+    }
+    sd.bank[which].assign(coef, coef + n);
+    if (device_ < 0) return 0;
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    return upload_bank(stage, which, sd.bank[which], err);
+}
+
+int Engine::ensure_hist(int stage, int64_t need, std::string& err) {
+    StageDev& d = dev_[(size_t)stage];
+    if (need <= d.hist_cap) return 0;
+    const int64_t ncap = std::max<int64_t>(need + need / 2, 16);
+    for (int p = 0; p < 2; ++p) {
+        void* nb = nullptr;
+        const size_t bytes = (size_t)rows_ * (size_t)ncap * esz_;
+        if (!cuda_ok(cudaMalloc(&nb, bytes), err, "cudaMalloc(hist)")) return 4;
+        cudaMemset(nb, 0, bytes);
+        device_bytes_ += (int64_t)bytes;
+        if (d.hist[p]) {
+            cudaDeviceSynchronize();
+            cudaMemcpy2D(nb, (size_t)ncap * esz_, d.hist[p], (size_t)d.hist_cap * esz_, (size_t)d.hist_cap * esz_,
+                         (size_t)rows_, cudaMemcpyDeviceToDevice);
+            cudaFree(d.hist[p]);
+            device_bytes_ -= (int64_t)((size_t)rows_ * (size_t)d.hist_cap * esz_);
+        }
+        d.hist[p] = nb;
+    }
+    d.hist_cap = ncap;
+    return 0;
+}
+
+void* Engine::scratch(int slot, size_t bytes, std::string& err) {
+    if (bytes <= scratch_cap_[slot] && scratch_[slot]) return scratch_[slot];
+    cudaSetDevice(device_);
+    if (scratch_[slot]) {
+        cudaDeviceSynchronize();
+        cudaFree(scratch_[slot]);
+        device_bytes_ -= (int64_t)scratch_cap_[slot];
+        scratch_[slot] = nullptr;
+        scratch_cap_[slot] = 0;
+    }
+    const size_t nb = std::max<size_t>(bytes + bytes / 4, 1 << 16);
+    if (!cuda_ok(cudaMalloc(&scratch_[slot], nb), err, "cudaMalloc(scratch)")) return nullptr;
+    scratch_cap_[slot] = nb;
+    device_bytes_ += (int64_t)nb;
+    return scratch_[slot];
+}
+
+int Engine::ensure_internal(const Plan& p, std::string& err) {
+    for (size_t b = 0; b < p.buf_need.size(); ++b) {
+        if (p.buf_need[b] <= ibuf_cap_[b]) continue;
+        if (ibuf_[b]) {
+            cudaDeviceSynchronize();
+            cudaFree(ibuf_[b]);
+            device_bytes_ -= (int64_t)((size_t)rows_ * (size_t)ibuf_cap_[b] * esz_);
+            ibuf_[b] = nullptr;
+        }
+        // rows padded to 16 bytes so that row starts stay TMA/vector aligned
+        int64_t cap = p.buf_need[b] + p.buf_need[b] / 8 + 64;
+        cap = (cap + 3) & ~int64_t(3);
+        const size_t bytes = (size_t)rows_ * (size_t)cap * esz_;
+        if (!cuda_ok(cudaMalloc(&ibuf_[b], bytes), err, "cudaMalloc(inter-stage buffer)")) return 4;
+        ibuf_cap_[b] = cap;
+        device_bytes_ += (int64_t)bytes;
+    }
+    int64_t zneed = 0;
+    for (const Op& o : p.ops)
+        if (o.src_buf == BUF_ZERO) zneed = std::max(zneed, o.n_in);
+    if (zneed > zeros_cap_) {
+        if (zeros_) {
+            cudaDeviceSynchronize();
+            cudaFree(zeros_);
+        }
+        zeros_cap_ = zneed + 64;
+        if (!cuda_ok(cudaMalloc(&zeros_, (size_t)zeros_cap_ * 8), err, "cudaMalloc(zeros)")) return 4;
+        cudaMemset(zeros_, 0, (size_t)zeros_cap_ * 8);
+    }
+    if ((int64_t)p.cubic_idx.size() > cubic_cap_) {
+        if (d_cubic_idx_) {
+            cudaDeviceSynchronize();
+            cudaFree(d_cubic_idx_);
+            cudaFree(d_cubic_phase_);
+        }
+        cubic_cap_ = (int64_t)p.cubic_idx.size() * 2;
+        if (!cuda_ok(cudaMalloc(&d_cubic_idx_, (size_t)cubic_cap_ * 4), err, "cudaMalloc(cubic idx)")) return 4;
+        if (!cuda_ok(cudaMalloc(&d_cubic_phase_, (size_t)cubic_cap_ * 8), err, "cudaMalloc(cubic phase)")) return 4;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Planning: the reference's streaming state machines, integers only.
+// ------------------------------------------------------------------------------------------------
+void Engine::plan(StreamState& st, int64_t n_in, bool flush, Plan& P) const {
+    const size_t E = chain_.engines.size();
+    P.ops.clear();
+    P.n_out = 0;
+    P.buf_need.assign(E * 2, 0);
+    P.cubic_idx.clear();
+    P.cubic_phase.clear();
+
+    auto note_dst = [&](int buf, int64_t end) {
+        if (buf >= 0) P.buf_need[(size_t)buf] = std::max(P.buf_need[(size_t)buf], end);
+    };
+
+    // One primitive stage call: Process(n samples from src) appended at dst_off. Returns samples produced.
+    auto stage_op = [&](int s, int src_buf, int64_t n, int dst_buf, int64_t dst_off) -> int64_t {
+        if (n <= 0) return 0;  // every stage returns early on empty input without touching state
+        const StageDesign& sd = chain_.stages[(size_t)s];
+        StageState& ss = st.st[(size_t)s];
+        Op op;
+        op.stage = s;
+        op.src_buf = src_buf;
+        op.n_in = n;
+        op.dst_buf = dst_buf;
+        op.dst_off = dst_off;
+        op.hist_len = ss.hist_len;
+        op.parity_in = ss.parity;
+        const int64_t total = ss.hist_len + n;
+        op.drop = 0;
+        op.new_hist_len = total;
+        op.n_out = 0;
+        switch (sd.kind) {
+            case STAGE_UP: {  // dft_stage.go:169-204
+                if (total >= sd.taps) {
+                    const int64_t np = total - sd.taps + 1;
+                    op.n_out = np * sd.factor;
+                    op.drop = np;
+                    op.new_hist_len = total - np;
+                }
+                break;
+            }
+            case STAGE_DECIM: {  // dft_stage.go:499-551
+                if (total >= sd.taps) {
+                    const int64_t nf = total - sd.taps + 1;
+                    const int64_t M = sd.factor;
+                    const int64_t cnt = nf > ss.decim_phase ? (nf - ss.decim_phase + M - 1) / M : 0;
+                    if (cnt > 0) {  // cnt == 0: early return, nothing consumed (dft_stage.go:516-518)
+                        op.n_out = cnt;
+                        op.first = ss.decim_phase;
+                        ss.decim_phase = (((ss.decim_phase - nf) % M) + M) % M;
+                        op.drop = nf;
+                        op.new_hist_len = total - nf;
+                    }
+                }
+                break;
+            }
+            case STAGE_POLY: {  // polyphase_stage.go:186-312
+                const int64_t num_in = total - sd.taps + 1;
+                if (num_in > 0) {
+                    const int64_t L = sd.factor;
+                    const int64_t limit = (num_in * L) << 16;
+                    const int64_t num_out = (limit - ss.at + sd.step - 1) / sd.step;
+                    if (num_out > 0) {
+                        op.n_out = num_out;
+                        op.first = ss.at;
+                        op.interp = ((sd.step | ss.at) & 0xFFFF) != 0;
+                        const int64_t at_end = ss.at + num_out * sd.step;
+                        const int64_t consumed = (at_end >> 16) / L;
+                        if (consumed > 0 && consumed <= total) {  // :300-304
+                            op.drop = consumed;
+                            op.new_hist_len = total - consumed;
+                        }
+                        ss.at = at_end - ((consumed * L) << 16);  // unconditional (:307)
+                    }
+                }
+                break;
+            }
+            case STAGE_CUBIC: {  // cubic.go:33-63 — exact float64 recurrence, host side
+                op.table_off = (int64_t)P.cubic_idx.size();
+                double ph = ss.cubic_phase;
+                const double inc = 1.0 / sd.ratio;
+                for (int64_t i = 0; i < n; ++i) {
+                    while (ph < 1.0) {
+                        P.cubic_idx.push_back((int32_t)i);
+                        P.cubic_phase.push_back(ph);
+                        ph += inc;
+                    }
+                    ph -= 1.0;
+                }
+                ss.cubic_phase = ph;
+                op.n_out = (int64_t)P.cubic_idx.size() - op.table_off;
+                op.hist_len = 3;
+                op.drop = n;
+                op.new_hist_len = 3;
+                break;
+            }
+        }
+        ss.hist_len = op.new_hist_len;
+        ss.parity ^= 1;
+        note_dst(dst_buf, dst_off + op.n_out);
+        P.ops.push_back(op);
+        return op.n_out;
+    };
+
+    auto copy_op = [&](int src_buf, int64_t n, int dst_buf, int64_t dst_off) {
+        Op op;
+        op.stage = -1;
+        op.src_buf = src_buf;
+        op.n_in = n;
+        op.dst_buf = dst_buf;
+        op.dst_off = dst_off;
+        op.n_out = n;
+        note_dst(dst_buf, dst_off + n);
+        P.ops.push_back(op);
+    };
+
+    // engine.Resampler.Process (resampler.go:182-227)
+    auto engine_process = [&](size_t e, int src_buf, int64_t n, int dst_buf, int64_t& fill) {
+        const EngineDesign& ed = chain_.engines[e];
+        st.samples_in[e] += n;
+        int64_t produced = 0;
+        if (ed.n_stages == 0) {
+            copy_op(src_buf, n, dst_buf, fill);
+            produced = n;
+        } else if (ed.n_stages == 1) {
+            produced = stage_op(ed.first_stage, src_buf, n, dst_buf, fill);
+        } else {
+            const int mid = (int)(2 * e);
+            const int64_t t = stage_op(ed.first_stage, src_buf, n, mid, 0);
+            produced = stage_op(ed.first_stage + 1, mid, t, dst_buf, fill);
+        }
+        fill += produced;
+        st.samples_out[e] += produced;
+    };
+
+    // engine.Resampler.Flush (resampler.go:275-322); each stage Flush = Process(zeros[taps]) if it holds history
+    auto engine_flush = [&](size_t e, int dst_buf, int64_t& fill) {
+        const EngineDesign& ed = chain_.engines[e];
+        if (ed.has_cubic) return;
+        int64_t produced = 0;
+        if (ed.has_pre) {
+            const int pre = ed.first_stage;
+            if (st.st[(size_t)pre].hist_len > 0) {
+                const int64_t z = chain_.stages[(size_t)pre].taps;
+                if (ed.has_poly) {
+                    const int mid = (int)(2 * e);
+                    const int64_t t = stage_op(pre, BUF_ZERO, z, mid, 0);
+                    produced += stage_op(pre + 1, mid, t, dst_buf, fill + produced);
+                } else {
+                    produced += stage_op(pre, BUF_ZERO, z, dst_buf, fill + produced);
+                }
+            }
+        }
+        if (ed.has_decim) {
+            const int d = ed.first_stage;
+            if (st.st[(size_t)d].hist_len > 0)
+                produced += stage_op(d, BUF_ZERO, chain_.stages[(size_t)d].taps, dst_buf, fill + produced);
+        }
+        if (ed.has_poly) {
+            const int p = ed.first_stage + 1;
+            if (st.st[(size_t)p].hist_len > 0)
+                produced += stage_op(p, BUF_ZERO, chain_.stages[(size_t)p].taps, dst_buf, fill + produced);
+        }
+        fill += produced;
+        st.samples_out[e] += produced;
+    };
+
+    if (E == 0) {  // ratio within 0.001 of 1: empty pipeline, buffers[0] is also the final buffer (constant.go:255-294)
+        if (!flush && n_in > 0) copy_op(BUF_EXT_IN, n_in, BUF_OUT, 0);
+        P.n_out = flush ? 0 : n_in;
+        return;
+    }
+    // constant.go:255-345 (process) and :360-386 (flush), front to back
+    int cur_buf = BUF_EXT_IN;
+    int64_t cur_n = flush ? 0 : n_in;
+    for (size_t e = 0; e < E; ++e) {
+        const int dst = (e + 1 == E) ? BUF_OUT : (int)(2 * e + 1);
+        int64_t fill = 0;
+        if (cur_n > 0) engine_process(e, cur_buf, cur_n, dst, fill);
+        if (flush) engine_flush(e, dst, fill);
+        cur_buf = dst;
+        cur_n = fill;
+        if (!flush && cur_n == 0) break;
+    }
+    P.n_out = cur_buf == BUF_OUT ? cur_n : 0;
+}
+
+int64_t Engine::advance(int row, int64_t n_in, bool flush) {
+    Plan P;
+    plan(streams_[(size_t)row], n_in, flush, P);
+    return P.n_out;
+}
+
+int Engine::lockstep_run(int row0, int row_end) const {
+    int n = 1;
+    while (row0 + n < row_end && streams_[(size_t)(row0 + n)].same_as(streams_[(size_t)row0])) ++n;
+    return n;
+}
+
+int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
+                int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err) {
+    if (count <= 0) return 0;
+    if (device_ < 0) {
+        err = "geometry-only handle (device = -1) cannot process samples; there is no CPU fallback";
+        return 4;
+    }
+    if (n_in > 0x7ffffff0LL) {
+        err = "chunk too long (row length must fit in 31 bits)";
+        return 1;
+    }
+    cudaSetDevice(device_);
+    StreamState st = streams_[(size_t)row0];
+    const StreamState before = st;
+    Plan P;
+    plan(st, n_in, flush, P);
+    if (n_out) *n_out = P.n_out;
+    if (P.n_out > out_cap) {
+        err = "output buffer too small";
+        return 2;
+    }
+    if (P.n_out > 0x7ffffff0LL) {
+        err = "output too long";
+        return 1;
+    }
+    int rc = ensure_internal(P, err);
+    if (rc) return rc;
+    for (const Op& op : P.ops)
+        if (op.stage >= 0) {
+            rc = ensure_hist(op.stage, op.new_hist_len, err);
+            if (rc) return rc;
+        }
+    if (!P.cubic_idx.empty()) {
+        cudaMemcpyAsync(d_cubic_idx_, P.cubic_idx.data(), P.cubic_idx.size() * 4, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d_cubic_phase_, P.cubic_phase.data(), P.cubic_phase.size() * 8, cudaMemcpyHostToDevice, s);
+        cudaStreamSynchronize(s);  // tables live in pageable vectors
+    }
+
+    auto src_ptr = [&](const Op& op, int64_t& stride) -> const void* {
+        if (op.src_buf == BUF_EXT_IN) {
+            stride = in_stride;
+            return d_in;
+        }
+        if (op.src_buf == BUF_ZERO) {
+            stride = 0;
+            return zeros_;
+        }
+        stride = ibuf_cap_[(size_t)op.src_buf];
+        return (const char*)ibuf_[(size_t)op.src_buf] + ((size_t)row0 * (size_t)stride + (size_t)op.src_off) * esz_;
+    };
+    auto dst_ptr = [&](const Op& op, int64_t& stride) -> void* {
+        if (op.dst_buf == BUF_OUT) {
+            stride = out_stride;
+            return (char*)d_out + (size_t)op.dst_off * esz_;
+        }
+        stride = ibuf_cap_[(size_t)op.dst_buf];
+        return (char*)ibuf_[(size_t)op.dst_buf] + ((size_t)row0 * (size_t)stride + (size_t)op.dst_off) * esz_;
+    };
+
+    for (const Op& op : P.ops) {
+        int64_t sstride = 0, dstride = 0;
+        const void* sp = src_ptr(op, sstride);
+        void* dp = dst_ptr(op, dstride);
+        if (op.stage < 0) {
+            launch_cast(sp, sstride, dtype_, dp, dstride, dtype_, (int32_t)op.n_in, count, s);
+            ++launches_;
+            continue;
+        }
+        const StageDesign& sd = chain_.stages[(size_t)op.stage];
+        const StageDev& dv = dev_[(size_t)op.stage];
+        const void* hin = (const char*)dv.hist[op.parity_in] + (size_t)row0 * (size_t)dv.hist_cap * esz_;
+        void* hout = (char*)dv.hist[op.parity_in ^ 1] + (size_t)row0 * (size_t)dv.hist_cap * esz_;
+        switch (sd.kind) {
+            case STAGE_UP:
+            case STAGE_DECIM: {
+                FirCall c{};
+                c.hist = hin; c.hist_stride = dv.hist_cap; c.hist_len = (int32_t)op.hist_len;
+                c.in = sp; c.in_stride = sstride; c.n_in = (int32_t)op.n_in;
+                c.out = dp; c.out_stride = dstride;
+                c.hist_out = hout; c.hist_out_stride = dv.hist_cap;
+                c.drop = (int32_t)op.drop; c.new_hist_len = (int32_t)op.new_hist_len;
+                c.bank = dv.bank[0];
+                c.taps = sd.taps;
+                if (sd.kind == STAGE_UP) {
+                    c.stride = 1; c.nf = sd.factor; c.first = 0; c.n_pos = (int32_t)(op.n_out / sd.factor);
+                } else {
+                    c.stride = sd.factor; c.nf = 1; c.first = (int32_t)op.first; c.n_pos = (int32_t)op.n_out;
+                }
+                c.n_streams = count;
+                launch_fir(c, dtype_, s);
+                break;
+            }
+            case STAGE_POLY: {
+                PolyCall c{};
+                c.hist = hin; c.hist_stride = dv.hist_cap; c.hist_len = (int32_t)op.hist_len;
+                c.in = sp; c.in_stride = sstride; c.n_in = (int32_t)op.n_in;
+                c.out = dp; c.out_stride = dstride;
+                c.hist_out = hout; c.hist_out_stride = dv.hist_cap;
+                c.drop = (int32_t)op.drop; c.new_hist_len = (int32_t)op.new_hist_len;
+                c.bank_a = dv.bank[0]; c.bank_b = dv.bank[1]; c.bank_c = dv.bank[2]; c.bank_d = dv.bank[3];
+                c.taps = sd.taps; c.L = sd.factor; c.at0 = op.first; c.step = sd.step;
+                c.n_out = (int32_t)op.n_out; c.interp = op.interp ? 1 : 0;
+                c.n_streams = count;
+                launch_poly(c, dtype_, s);
+                break;
+            }
+            case STAGE_CUBIC: {
+                CubicCall c{};
+                c.hist = hin; c.hist_stride = dv.hist_cap;
+                c.in = sp; c.in_stride = sstride; c.n_in = (int32_t)op.n_in;
+                c.out = dp; c.out_stride = dstride;
+                c.hist_out = hout; c.hist_out_stride = dv.hist_cap;
+                c.idx = d_cubic_idx_ + op.table_off; c.phase = d_cubic_phase_ + op.table_off;
+                c.n_out = (int32_t)op.n_out; c.n_streams = count;
+                launch_cubic(c, dtype_, s);
+                break;
+            }
+        }
+        ++launches_;
+    }
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+        err = std::string("kernel launch failed: ") + cudaGetErrorString(le);
+        return 4;
+    }
+    // commit: identical stage state for the whole run, per-row statistics advance by the same delta
+    const size_t E = chain_.engines.size();
+    for (int r = 0; r < count; ++r) {
+        StreamState& dst = streams_[(size_t)(row0 + r)];
+        dst.st = st.st;
+        for (size_t e = 0; e < E; ++e) {
+            dst.samples_in[e] += st.samples_in[e] - before.samples_in[e];
+            dst.samples_out[e] += st.samples_out[e] - before.samples_out[e];
+        }
+    }
+    return 0;
+}
+
+}  // namespace gar

@@ -1,0 +1,141 @@
+// engine.hpp — host runtime of the B200 resampling engine.
+//
+// Split of responsibilities:
+//   * integers on the host: the streaming state machine of every stage (history
+//     length, fixed-point phase accumulator, decimation phase) is advanced on the
+//     CPU with the reference's exact integer logic, because sample counts, phase
+//     positions and flush lengths must be bit-exact and never depend on sample
+//     values;
+//   * samples on the device: carried tails, inter-stage buffers and all arithmetic.
+// A call is first *planned* (a short list of primitive stage launches with their
+// geometry), then executed asynchronously on a CUDA stream.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "design.hpp"
+#include "kernels.cuh"
+
+namespace gar {
+
+struct StageState {      // per stream, per primitive stage
+    int64_t hist_len = 0;
+    int64_t at = 0;           // POLY (polyphase_stage.go:39-41)
+    int64_t decim_phase = 0;  // DECIM (dft_stage.go:381)
+    double cubic_phase = 0;   // CUBIC (cubic.go:17)
+    int parity = 0;           // which ping-pong tail buffer is current
+    bool operator==(const StageState& o) const {
+        return hist_len == o.hist_len && at == o.at && decim_phase == o.decim_phase && cubic_phase == o.cubic_phase &&
+               parity == o.parity;
+    }
+};
+
+struct StreamState {
+    std::vector<StageState> st;
+    std::vector<int64_t> samples_in, samples_out;  // per engine (resampler.go:348-353)
+    bool same_as(const StreamState& o) const { return st == o.st; }
+};
+
+// buffer ids used by ops
+enum : int { BUF_EXT_IN = -1, BUF_ZERO = -2, BUF_OUT = -3 };
+
+struct Op {
+    int stage = -1;          // -1: plain copy src -> dst
+    int src_buf = BUF_EXT_IN;
+    int64_t src_off = 0, n_in = 0;
+    int dst_buf = BUF_OUT;
+    int64_t dst_off = 0, n_out = 0;
+    // geometry of the stage call
+    int64_t hist_len = 0, first = 0, drop = 0, new_hist_len = 0;
+    int parity_in = 0;
+    bool interp = false;
+    // cubic: tables (host) for this op
+    int64_t table_off = 0;
+};
+
+struct Plan {
+    std::vector<Op> ops;
+    int64_t n_out = 0;                  // samples delivered to BUF_OUT
+    std::vector<int64_t> buf_need;      // elements needed per internal buffer
+    std::vector<int32_t> cubic_idx;     // cubic tables, concatenated
+    std::vector<double> cubic_phase;
+};
+
+struct StageDev {
+    void* bank[4] = {nullptr, nullptr, nullptr, nullptr};
+    void* hist[2] = {nullptr, nullptr};
+    int64_t hist_cap = 0;
+    const char* kernel = "";
+};
+
+class Engine {
+  public:
+    Engine() = default;
+    ~Engine();
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+
+    // returns gar_status
+    int init(const Chain& chain, int rows, int compute_dtype, int device, std::string& err);
+
+    const Chain& chain() const { return chain_; }
+    int rows() const { return rows_; }
+    int compute_dtype() const { return dtype_; }
+    int device() const { return device_; }
+    cudaStream_t stream() const { return stream_; }
+    const StreamState& state(int row) const { return streams_[(size_t)row]; }
+    const StageDev& stage_dev(int s) const { return dev_[(size_t)s]; }
+    int64_t launches() const { return launches_; }
+    void reset_launches() { launches_ = 0; }
+    int64_t device_bytes() const { return device_bytes_; }
+
+    // Planning (pure integer; mutates `st`). flush=false: Process(n_in). flush=true: Flush().
+    // pipeline_mode: path A semantics (constant.go) vs single engine (resampler.go).
+    void plan(StreamState& st, int64_t n_in, bool flush, Plan& out) const;
+
+    // Execute on rows [row0,row0+count) which must share identical state. d_in/d_out point at row row0,
+    // compute dtype. Enqueues on `s`; commits the state. Returns status; *n_out per row.
+    int run(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
+            int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err);
+
+    // Advance only the integer state of one row (geometry-only use; no samples move).
+    int64_t advance(int row, int64_t n_in, bool flush);
+
+    // Find the maximal run of rows starting at row0 (within [row0,row_end)) sharing row0's state.
+    int lockstep_run(int row0, int row_end) const;
+
+    void reset_state();
+    int set_bank(int stage, int which, const double* coef, int64_t n, std::string& err);
+
+    // staging helpers (grow-only device scratch in bytes), slot 0..3
+    void* scratch(int slot, size_t bytes, std::string& err);
+
+  private:
+    void name_kernels();
+    int ensure_internal(const Plan& p, std::string& err);
+    int ensure_hist(int stage, int64_t need, std::string& err);
+    int upload_bank(int stage, int which, const std::vector<double>& v, std::string& err);
+
+    Chain chain_;
+    int rows_ = 0, dtype_ = DT_F64, device_ = 0;
+    size_t esz_ = 8;
+    cudaStream_t stream_ = nullptr;
+    std::vector<StreamState> streams_;
+    std::vector<StageDev> dev_;
+    std::vector<void*> ibuf_;         // internal buffers [rows][cap]
+    std::vector<int64_t> ibuf_cap_;   // elements per row
+    void* zeros_ = nullptr;
+    int64_t zeros_cap_ = 0;
+    void* scratch_[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_cap_[4] = {0, 0, 0, 0};
+    int32_t* d_cubic_idx_ = nullptr;
+    double* d_cubic_phase_ = nullptr;
+    int64_t cubic_cap_ = 0;
+    int64_t launches_ = 0;
+    int64_t device_bytes_ = 0;
+};
+
+}  // namespace gar

@@ -1,0 +1,560 @@
+// kernels.cu — hand-written sm_100a kernels for the resampling hot path.
+//
+//  fir_tiled_kernel   K1/K2: integer xL up-sampler and /M decimator as ONE strided
+//                     multi-filter FIR.  Replaces simdops.ConvolveValidMulti + Interleave2
+//                     (dft_stage.go:259-263,322-327) and DotProductUnsafe (dft_stage.go:531).
+//                     The input window of a tile is staged in shared memory with a TMA
+//                     bulk copy (cp.async.bulk + mbarrier) when the tile is regular, the
+//                     filter bank sits beside it, and every thread slides a register
+//                     window over R adjacent outputs so each 16-byte shared-memory read
+//                     feeds VEC*R*NF FMAs (shared-memory bandwidth, not FMA issue, is the
+//                     practical bound otherwise — SURVEY.md H3).
+//  fir_generic_kernel fallback for unusual factors (any stride / phase count).
+//  poly_kernel        K3: arbitrary-ratio polyphase stage with cubic coefficient
+//                     interpolation; replaces simdops.CubicInterpDot (polyphase_stage.go:288).
+//  carry / cast       streaming tail hand-over and f32<->f64 I/O casts.
+//  fma_probe_kernel   dependent-FMA micro-benchmark for the roofline denominator.
+#include "kernels.cuh"
+
+#include <atomic>
+#include <cstdio>
+
+namespace gar {
+namespace {
+
+std::atomic<long long> g_launches{0};
+inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { using type = float4; static constexpr int N = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
+
+__device__ __forceinline__ void vec_unpack(const float4& v, float* d) { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+__device__ __forceinline__ void vec_unpack(const double2& v, double* d) { d[0] = v.x; d[1] = v.y; }
+__device__ __forceinline__ float4 vec_pack(const float* d) { return make_float4(d[0], d[1], d[2], d[3]); }
+__device__ __forceinline__ double2 vec_pack(const double* d) { return make_double2(d[0], d[1]); }
+
+// v[g] of the virtual input  hist ++ in  (zero outside)
+template <typename T>
+__device__ __forceinline__ T vload(const T* __restrict__ hist, int hist_len, const T* __restrict__ in, int n_in, int g) {
+    if (g < 0) return T(0);
+    if (g < hist_len) return hist[g];
+    g -= hist_len;
+    return g < n_in ? in[g] : T(0);
+}
+
+template <typename T>
+__device__ __forceinline__ void carry_row(const T* hist, int hist_len, const T* in, int n_in, T* hist_out, int drop,
+                                          int new_len) {
+    for (int i = threadIdx.x; i < new_len; i += blockDim.x) hist_out[i] = vload(hist, hist_len, in, n_in, drop + i);
+}
+
+// ---- mbarrier / TMA bulk-copy helpers (PTX; SASS: SYNCS.*, UBLKCP) ------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// =============================================================================================
+// Tiled strided multi-filter FIR.
+//   M  = window stride between adjacent outputs (1 for the up-sampler, the decimation factor else)
+//   NF = filters applied to the same window (up-sampling factor; 1 for the decimator)
+//   R  = adjacent output positions per thread; M*R*sizeof(T)/16 is odd for the shipped variants so
+//        the eight threads of a quarter-warp hit eight different 16-byte bank groups (conflict-free
+//        LDS.128)
+//   NT = threads per block; a block produces NT*R positions of one stream row.
+// grid.x = rows * (n_tiles + 1): the extra block of every row writes the carried tail.
+// =============================================================================================
+template <typename T, int M, int NF, int R, int NT>
+__global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const int n_tiles, const int cp /*padded taps*/,
+                                                       const int xlen) {
+    using V = typename VecOf<T>::type;
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int NCH = (M * (R - 1) + VEC - 1) / VEC + 1;  // 16-byte chunks spanned by one step's window
+    constexpr int WREG = NCH * VEC;
+    constexpr int TJ = NT * R;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    T* cs = reinterpret_cast<T*>(smem_raw + 16);  // [NF][cp]
+    T* xs = cs + NF * cp;                         // [xlen]
+
+    const int tile = blockIdx.x % (n_tiles + 1);
+    const int64_t row = blockIdx.x / (n_tiles + 1);
+    const int tid = threadIdx.x;
+
+    const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+
+    if (tile == n_tiles) {  // carry block
+        carry_row(hist, c.hist_len, in, c.n_in, static_cast<T*>(c.hist_out) + row * c.hist_out_stride, c.drop,
+                  c.new_hist_len);
+        return;
+    }
+
+    const int j0 = tile * TJ;
+    const int tj = min(TJ, c.n_pos - j0);
+    const int g0 = c.first + j0 * M;        // virtual index of the tile's first window sample
+    const int need = (tj - 1) * M + c.taps;  // samples the tile reads
+
+    // ---- stage the window: TMA bulk copy when the tile is regular, guarded loads otherwise ----
+    int a = 0;  // leading pad so that the bulk source address is 16-byte aligned
+    bool bulk = false;
+    {
+        const int gi = g0 - c.hist_len;  // index into `in`
+        if (gi >= 0) {
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(in + gi);
+            const int mis = (int)((addr & 15u) / sizeof(T));
+            const int words = ((need + mis + VEC - 1) / VEC) * VEC;
+            if (gi - mis >= 0 && gi - mis + words <= c.n_in && words <= xlen) {
+                bulk = true;
+                a = mis;
+            }
+        }
+    }
+    if (bulk) {
+        const int gi = g0 - c.hist_len - a;
+        const int words = ((need + a + VEC - 1) / VEC) * VEC;
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)(words * sizeof(T)));
+            bulk_g2s(xs, in + gi, (uint32_t)(words * sizeof(T)), bar);
+        }
+        for (int i = words + tid; i < xlen; i += NT) xs[i] = T(0);
+    } else {
+        for (int i = tid; i < xlen; i += NT) xs[i] = i < need ? vload(hist, c.hist_len, in, c.n_in, g0 + i) : T(0);
+    }
+    {  // filter bank, shifted by the pad, zero elsewhere
+        const T* __restrict__ bank = static_cast<const T*>(c.bank);
+        for (int i = tid; i < NF * cp; i += NT) {
+            const int p = i / cp, k = i % cp - a;
+            cs[i] = (k >= 0 && k < c.taps) ? bank[p * c.taps + k] : T(0);
+        }
+    }
+    __syncthreads();
+    if (bulk) {
+        while (!mbar_try_wait(bar, 0)) {
+        }
+    }
+
+    // ---- register-tiled sliding-window FIR ----
+    const int n_iter = (c.taps + a + VEC - 1) / VEC;
+    const T* xt = xs + M * R * tid;
+    T xr[WREG];
+    T acc[R][NF];
+    T tot[R][NF];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < NF; ++p) acc[r][p] = tot[r][p] = T(0);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) vec_unpack(*reinterpret_cast<const V*>(xt + ch * VEC), xr + ch * VEC);
+
+    auto step = [&](const int u, const int it) {
+        T cv[NF][VEC];
+#pragma unroll
+        for (int p = 0; p < NF; ++p) vec_unpack(*reinterpret_cast<const V*>(cs + p * cp + it * VEC), cv[p]);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const T xv = xr[(u * VEC + i + M * r) % WREG];
+#pragma unroll
+                for (int p = 0; p < NF; ++p) acc[r][p] = fma(xv, cv[p][i], acc[r][p]);
+            }
+        // the oldest chunk is dead now: refill its slot with chunk it+NCH (needed from the next step on)
+        vec_unpack(*reinterpret_cast<const V*>(xt + (it + NCH) * VEC), xr + (u % NCH) * VEC);
+    };
+    auto fold = [&]() {
+        if (sizeof(T) == 4) {  // bounded-length f32 partial sums keep |err| well below 1e-6
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int p = 0; p < NF; ++p) {
+                    tot[r][p] += acc[r][p];
+                    acc[r][p] = T(0);
+                }
+        }
+    };
+
+    int it0 = 0;
+    for (; it0 + NCH <= n_iter; it0 += NCH) {
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) step(u, it0 + u);
+        fold();
+    }
+#pragma unroll
+    for (int u = 0; u < NCH; ++u)
+        if (it0 + u < n_iter) step(u, it0 + u);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < NF; ++p) tot[r][p] += acc[r][p];
+
+    // ---- interleaved, vectorised store: out[(j*NF + p)] ----
+    T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+    const int jb = j0 + R * tid;
+    T* op = out + (int64_t)jb * NF;
+    if (jb + R <= c.n_pos && (R * NF) % VEC == 0 && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {
+        const T* flat = &tot[0][0];
+#pragma unroll
+        for (int q = 0; q < R * NF / VEC; ++q) reinterpret_cast<V*>(op)[q] = vec_pack(flat + q * VEC);
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (jb + r < c.n_pos) {
+#pragma unroll
+                for (int p = 0; p < NF; ++p) op[r * NF + p] = tot[r][p];
+            }
+    }
+}
+
+// Fallback: one thread per output element, operands straight from global/L1.
+template <typename T>
+__global__ void __launch_bounds__(256) fir_generic_kernel(const FirCall c, const int n_tiles) {
+    const int tile = blockIdx.x % (n_tiles + 1);
+    const int64_t row = blockIdx.x / (n_tiles + 1);
+    const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    if (tile == n_tiles) {
+        carry_row(hist, c.hist_len, in, c.n_in, static_cast<T*>(c.hist_out) + row * c.hist_out_stride, c.drop,
+                  c.new_hist_len);
+        return;
+    }
+    const int64_t o = (int64_t)tile * 256 + threadIdx.x;
+    if (o >= (int64_t)c.n_pos * c.nf) return;
+    const int j = (int)(o / c.nf), p = (int)(o % c.nf);
+    const int g = c.first + j * c.stride;
+    const T* __restrict__ bank = static_cast<const T*>(c.bank) + (int64_t)p * c.taps;
+    T tot = 0, acc = 0;
+    for (int k = 0; k < c.taps; ++k) {
+        acc = fma(vload(hist, c.hist_len, in, c.n_in, g + k), bank[k], acc);
+        if (sizeof(T) == 4 && (k & 63) == 63) {
+            tot += acc;
+            acc = 0;
+        }
+    }
+    (static_cast<T*>(c.out) + row * c.out_stride)[o] = tot + acc;
+}
+
+// =============================================================================================
+// Polyphase stage. One thread per output; the block's input span sits in shared memory.
+// =============================================================================================
+template <typename T, bool INTERP, int TO>
+__global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_tiles, const int xcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* xs = reinterpret_cast<T*>(smem_raw);
+    const int tile = blockIdx.x % (n_tiles + 1);
+    const int64_t row = blockIdx.x / (n_tiles + 1);
+    const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    if (tile == n_tiles) {
+        carry_row(hist, c.hist_len, in, c.n_in, static_cast<T*>(c.hist_out) + row * c.hist_out_stride, c.drop,
+                  c.new_hist_len);
+        return;
+    }
+    const int n0 = tile * TO;
+    const int n1 = min(n0 + TO, c.n_out) - 1;
+    const int64_t L = c.L;
+    const int div0 = (int)(((c.at0 + (int64_t)n0 * c.step) >> 16) / L);
+    const int div1 = (int)(((c.at0 + (int64_t)n1 * c.step) >> 16) / L);
+    const int span = div1 - div0 + c.taps;
+    const bool staged = span <= xcap;
+    if (staged) {
+        for (int i = threadIdx.x; i < span; i += TO) xs[i] = vload(hist, c.hist_len, in, c.n_in, div0 + i);
+        __syncthreads();
+    }
+    const int n = n0 + threadIdx.x;
+    if (n >= c.n_out) return;
+    const int64_t at = c.at0 + (int64_t)n * c.step;
+    const int64_t full = at >> 16;
+    const int div = (int)(full / L);
+    const int phase = (int)(full - (int64_t)div * L);
+    const T x = (T)(int)(at & 0xFFFF) * (T)(1.0 / 65536.0);
+    const int64_t co = (int64_t)phase * c.taps;
+    const T* __restrict__ ca = static_cast<const T*>(c.bank_a) + co;
+    const T* __restrict__ cb = static_cast<const T*>(c.bank_b) + co;
+    const T* __restrict__ cc = static_cast<const T*>(c.bank_c) + co;
+    const T* __restrict__ cd = static_cast<const T*>(c.bank_d) + co;
+    T acc0 = 0, acc1 = 0;
+    const int base = div - div0;
+    for (int k = 0; k < c.taps; ++k) {
+        T coef = ca[k];
+        if (INTERP) coef = fma(x, fma(x, fma(x, cd[k], cc[k]), cb[k]), coef);
+        const T h = staged ? xs[base + k] : vload(hist, c.hist_len, in, c.n_in, div + k);
+        if (k & 1) acc1 = fma(h, coef, acc1);
+        else acc0 = fma(h, coef, acc0);
+    }
+    (static_cast<T*>(c.out) + row * c.out_stride)[n] = acc0 + acc1;
+}
+
+// =============================================================================================
+// Cubic (QualityQuick) stage: out[n] = poly(x_n) over in[idx_n-3 .. idx_n], evaluated in float64
+// without contraction, exactly as cubic.go:73-85.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) cubic_kernel(const CubicCall c, const int n_tiles) {
+    const int tile = blockIdx.x % (n_tiles + 1);
+    const int64_t row = blockIdx.x / (n_tiles + 1);
+    const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    if (tile == n_tiles) {  // new tail = last 3 samples of hist(3) ++ in
+        carry_row(hist, 3, in, c.n_in, static_cast<T*>(c.hist_out) + row * c.hist_out_stride, c.n_in, 3);
+        return;
+    }
+    const int n = tile * 256 + threadIdx.x;
+    if (n >= c.n_out) return;
+    const int i = c.idx[n];  // newest sample = in[i]; virtual index i+3 in hist(3) ++ in
+    const double s2 = (double)vload(hist, 3, in, c.n_in, i + 3);
+    const double s1 = (double)vload(hist, 3, in, c.n_in, i + 2);
+    const double s0 = (double)vload(hist, 3, in, c.n_in, i + 1);
+    const double sm1 = (double)vload(hist, 3, in, c.n_in, i);
+    const double x = c.phase[n];
+    const double b = __dsub_rn(__dmul_rn(0.5, __dadd_rn(s1, sm1)), s0);
+    const double t = __dsub_rn(__dsub_rn(__dadd_rn(__dsub_rn(s2, s1), sm1), s0), __dmul_rn(4.0, b));
+    const double a = __dmul_rn(1.0 / 6.0, t);
+    const double cc = __dsub_rn(__dsub_rn(__dsub_rn(s1, s0), a), b);
+    const double y = __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(a, x), b), x), cc), x), s0);
+    (static_cast<T*>(c.out) + row * c.out_stride)[n] = (T)y;
+}
+
+template <typename T>
+__global__ void carry_kernel(const T* hist, int64_t hist_stride, int hist_len, const T* in, int64_t in_stride, int n_in,
+                             T* hist_out, int64_t hist_out_stride, int drop, int new_len) {
+    const int64_t row = blockIdx.x;
+    carry_row(hist + row * hist_stride, hist_len, in + row * in_stride, n_in, hist_out + row * hist_out_stride, drop,
+              new_len);
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* src, int64_t src_stride, D* dst, int64_t dst_stride, int n) {
+    const int64_t row = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dst[row * dst_stride + i] = (D)src[row * src_stride + i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) fma_probe_kernel(T* out, int iters, T b, T cadd) {
+    T a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = (T)(threadIdx.x + k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b, cadd);
+    }
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---- variant table for the tiled FIR -----------------------------------------------------------
+struct FirVariant {
+    int dtype, stride, nf, r;
+    const char* name;
+};
+
+template <typename T, int M, int NF, int R>
+void launch_fir_tiled(const FirCall& c, cudaStream_t s) {
+    constexpr int NT = 128;
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int NCH = (M * (R - 1) + VEC - 1) / VEC + 1;
+    constexpr int TJ = NT * R;
+    const int cp = ((c.taps + VEC - 1 + VEC - 1) / VEC) * VEC;  // room for any alignment pad
+    const int xlen = M * R * (NT - 1) + (cp / VEC + NCH + 1) * VEC;
+    const size_t smem = 16 + (size_t)(NF * cp + xlen) * sizeof(T);
+    const int n_tiles = (c.n_pos + TJ - 1) / TJ;
+    auto k = fir_tiled_kernel<T, M, NF, R, NT>;
+    static size_t configured[64] = {0};  // per instantiation, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
+    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, cp, xlen);
+    count_launch();
+}
+
+}  // namespace
+
+#define GAR_FIR_VARIANTS(X)                 \
+    X(float, DT_F32, 3, 1, 12, "fir_f32_s3_r12")  \
+    X(float, DT_F32, 2, 1, 10, "fir_f32_s2_r10")  \
+    X(float, DT_F32, 4, 1, 7, "fir_f32_s4_r7")    \
+    X(float, DT_F32, 1, 2, 12, "fir_f32_up2_r12") \
+    X(float, DT_F32, 1, 3, 4, "fir_f32_up3_r4")   \
+    X(float, DT_F32, 1, 4, 4, "fir_f32_up4_r4")   \
+    X(double, DT_F64, 2, 1, 7, "fir_f64_s2_r7")   \
+    X(double, DT_F64, 3, 1, 6, "fir_f64_s3_r6")   \
+    X(double, DT_F64, 4, 1, 5, "fir_f64_s4_r5")   \
+    X(double, DT_F64, 1, 2, 6, "fir_f64_up2_r6")  \
+    X(double, DT_F64, 1, 3, 2, "fir_f64_up3_r2")  \
+    X(double, DT_F64, 1, 4, 2, "fir_f64_up4_r2")
+
+const char* fir_variant_name(int dtype, int stride, int nf, int taps, int64_t n_pos, int n_streams) {
+    (void)taps; (void)n_pos; (void)n_streams;
+#define X(T, DT, M, NF, R, NAME) \
+    if (dtype == DT && stride == M && nf == NF) return NAME;
+    GAR_FIR_VARIANTS(X)
+#undef X
+    return dtype == DT_F32 ? "fir_f32_generic" : "fir_f64_generic";
+}
+
+const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s) {
+    if (c.n_streams <= 0) return "none";
+    if (c.n_pos <= 0) {
+        launch_carry(c.hist, c.hist_stride, c.hist_len, c.in, c.in_stride, c.n_in, c.hist_out, c.hist_out_stride, c.drop,
+                     c.new_hist_len, c.n_streams, dtype, s);
+        return "carry";
+    }
+#define X(T, DT, M, NF, R, NAME)                           \
+    if (dtype == DT && c.stride == M && c.nf == NF) {      \
+        launch_fir_tiled<T, M, NF, R>(c, s);               \
+        return NAME;                                       \
+    }
+    GAR_FIR_VARIANTS(X)
+#undef X
+    const int64_t n_el = (int64_t)c.n_pos * c.nf;
+    const int n_tiles = (int)((n_el + 255) / 256);
+    const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
+    count_launch();
+    if (dtype == DT_F32) {
+        fir_generic_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(c, n_tiles);
+        return "fir_f32_generic";
+    }
+    fir_generic_kernel<double><<<(unsigned)blocks, 256, 0, s>>>(c, n_tiles);
+    return "fir_f64_generic";
+}
+
+const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s) {
+    if (c.n_streams <= 0) return "none";
+    if (c.n_out <= 0) {
+        launch_carry(c.hist, c.hist_stride, c.hist_len, c.in, c.in_stride, c.n_in, c.hist_out, c.hist_out_stride, c.drop,
+                     c.new_hist_len, c.n_streams, dtype, s);
+        return "carry";
+    }
+    constexpr int TO = 128;
+    const int n_tiles = (c.n_out + TO - 1) / TO;
+    const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
+    const size_t esz = dtype == DT_F32 ? 4 : 8;
+    // span of one tile: ((TO-1)*step >> 16)/L + 2 + taps, capped at 96 KB of shared memory
+    int64_t span = (((int64_t)(TO - 1) * c.step) >> 16) / c.L + 2 + c.taps;
+    const int64_t cap_words = (96 * 1024) / (int64_t)esz;
+    int xcap = (int)(span < cap_words ? span : 0);  // 0 => read straight from global
+    size_t smem = (size_t)xcap * esz;
+#define LAUNCH(T, I)                                                                                          \
+    {                                                                                                         \
+        auto k = poly_kernel<T, I, TO>;                                                                       \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
+        k<<<(unsigned)blocks, TO, smem, s>>>(c, n_tiles, xcap);                                               \
+        count_launch();                                                                                       \
+    }
+    if (dtype == DT_F32) {
+        if (c.interp) { LAUNCH(float, true); return "poly_f32_interp"; }
+        LAUNCH(float, false);
+        return "poly_f32";
+    }
+    if (c.interp) { LAUNCH(double, true); return "poly_f64_interp"; }
+    LAUNCH(double, false);
+    return "poly_f64";
+#undef LAUNCH
+}
+
+const char* launch_cubic(const CubicCall& c, int dtype, cudaStream_t s) {
+    if (c.n_streams <= 0) return "none";
+    const int n_tiles = (c.n_out + 255) / 256;
+    const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
+    count_launch();
+    if (dtype == DT_F32) cubic_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(c, n_tiles);
+    else cubic_kernel<double><<<(unsigned)blocks, 256, 0, s>>>(c, n_tiles);
+    return dtype == DT_F32 ? "cubic_f32" : "cubic_f64";
+}
+
+void launch_carry(const void* hist, int64_t hist_stride, int32_t hist_len, const void* in, int64_t in_stride,
+                  int32_t n_in, void* hist_out, int64_t hist_out_stride, int32_t drop, int32_t new_len,
+                  int32_t n_streams, int dtype, cudaStream_t s) {
+    if (n_streams <= 0 || new_len <= 0) return;
+    count_launch();
+    if (dtype == DT_F32)
+        carry_kernel<float><<<n_streams, 128, 0, s>>>((const float*)hist, hist_stride, hist_len, (const float*)in,
+                                                      in_stride, n_in, (float*)hist_out, hist_out_stride, drop, new_len);
+    else
+        carry_kernel<double><<<n_streams, 128, 0, s>>>((const double*)hist, hist_stride, hist_len, (const double*)in,
+                                                       in_stride, n_in, (double*)hist_out, hist_out_stride, drop,
+                                                       new_len);
+}
+
+void launch_cast(const void* src, int64_t src_stride, int src_dtype, void* dst, int64_t dst_stride, int dst_dtype,
+                 int32_t n, int32_t n_rows, cudaStream_t s) {
+    if (n <= 0 || n_rows <= 0) return;
+    dim3 grid((unsigned)((n + 1023) / 1024 < 4096 ? (n + 1023) / 1024 : 4096), (unsigned)n_rows);
+    count_launch();
+    if (src_dtype == DT_F32 && dst_dtype == DT_F64)
+        cast_kernel<float, double><<<grid, 256, 0, s>>>((const float*)src, src_stride, (double*)dst, dst_stride, n);
+    else if (src_dtype == DT_F64 && dst_dtype == DT_F32)
+        cast_kernel<double, float><<<grid, 256, 0, s>>>((const double*)src, src_stride, (float*)dst, dst_stride, n);
+    else if (src_dtype == DT_F32)
+        cast_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src, src_stride, (float*)dst, dst_stride, n);
+    else
+        cast_kernel<double, double><<<grid, 256, 0, s>>>((const double*)src, src_stride, (double*)dst, dst_stride, n);
+}
+
+long long launch_count(bool reset) {
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+float run_fma_probe(int dtype, int iters, double* flops, cudaStream_t s) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256;
+    void* buf = nullptr;
+    cudaMalloc(&buf, (size_t)blocks * threads * 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    auto run = [&](int n) {
+        if (dtype == DT_F32) fma_probe_kernel<float><<<blocks, threads, 0, s>>>((float*)buf, n, 0.999999f, 1e-7f);
+        else fma_probe_kernel<double><<<blocks, threads, 0, s>>>((double*)buf, n, 0.999999, 1e-7);
+    };
+    run(iters / 8 + 1);  // warm-up
+    cudaEventRecord(e0, s);
+    run(iters);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    *flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    return ms;
+}
+
+}  // namespace gar

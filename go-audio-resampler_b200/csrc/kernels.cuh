@@ -1,0 +1,76 @@
+// kernels.cuh — launch descriptors shared by the host engine and the device kernels.
+//
+// Data model (B200-first): every primitive stage call sees a
+// *virtual input*  v = hist ++ in  per stream row, where `hist` is the stage's
+// carried tail (device resident, ping-pong buffered) and `in` is either the
+// caller's chunk, the previous stage's output, or a shared zero row (flush).
+// All integer geometry (how many outputs, where they start, what is carried) is
+// computed on the host by the exact state machine of the reference and passed
+// in these descriptors, so kernels are pure functions of (v, bank, descriptor).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace gar {
+
+// out[(j*nf + p)] = sum_k v[first + j*stride + k] * bank[p*taps + k],  j < n_pos, p < nf
+//   integer up-sampler  (dft_stage.go:156-338):  stride = 1, nf = factor
+//   integer decimator   (dft_stage.go:488-554):  stride = M, nf = 1, first = decimPhase
+struct FirCall {
+    const void* hist;     int64_t hist_stride;  int32_t hist_len;
+    const void* in;       int64_t in_stride;    int32_t n_in;        // in_stride == 0: shared (zero) row
+    void* out;            int64_t out_stride;                          // already offset to the write position
+    void* hist_out;       int64_t hist_out_stride;                     // new tail = v[drop .. hist_len+n_in)
+    int32_t drop;         int32_t new_hist_len;
+    const void* bank;     // device, [nf][taps]
+    int32_t taps;         int32_t stride;       int32_t nf;
+    int32_t first;        int32_t n_pos;
+    int32_t n_streams;    // rows processed by this launch (row r of every pointer = base + r*stride)
+};
+
+// out[n] = sum_k v[div_n + k] * (a + x(b + x(c + x d)))[phase_n][k]   (polyphase_stage.go:186-312)
+//   at_n = at0 + n*step; full = at_n >> 16; div = full / L; phase = full % L; x = (at_n & 0xFFFF) / 65536
+struct PolyCall {
+    const void* hist;     int64_t hist_stride;  int32_t hist_len;
+    const void* in;       int64_t in_stride;    int32_t n_in;
+    void* out;            int64_t out_stride;
+    void* hist_out;       int64_t hist_out_stride;
+    int32_t drop;         int32_t new_hist_len;
+    const void* bank_a;   const void* bank_b;   const void* bank_c;   const void* bank_d;  // [L][taps]
+    int32_t taps;         int32_t L;
+    int64_t at0;          int64_t step;
+    int32_t n_out;        int32_t interp;       // interp: (step & 0xFFFF) != 0 || (at0 & 0xFFFF) != 0
+    int32_t n_streams;
+};
+
+// cubic.go:33-90 — indices/phases precomputed on the host by the exact float64 recurrence
+struct CubicCall {
+    const void* hist;     int64_t hist_stride;                         // 3 previous samples (zeros at start)
+    const void* in;       int64_t in_stride;    int32_t n_in;
+    void* out;            int64_t out_stride;
+    void* hist_out;       int64_t hist_out_stride;
+    const int32_t* idx;   const double* phase;                         // per output: input index, phase x
+    int32_t n_out;        int32_t n_streams;
+};
+
+enum Dtype : int { DT_F64 = 0, DT_F32 = 1 };
+
+// launchers (kernels.cu). Return the name of the kernel variant used.
+const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s);
+const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s);
+const char* launch_cubic(const CubicCall& c, int dtype, cudaStream_t s);
+// carry only (a call that produced no output but appended to the tail)
+void launch_carry(const void* hist, int64_t hist_stride, int32_t hist_len, const void* in, int64_t in_stride,
+                  int32_t n_in, void* hist_out, int64_t hist_out_stride, int32_t drop, int32_t new_len,
+                  int32_t n_streams, int dtype, cudaStream_t s);
+// row-wise dtype casts between I/O and compute precision (constant.go:171-178,195-197)
+void launch_cast(const void* src, int64_t src_stride, int src_dtype, void* dst, int64_t dst_stride, int dst_dtype,
+                 int32_t n, int32_t n_rows, cudaStream_t s);
+// dependent-FMA probe; returns elapsed ms for `iters` iterations, flops in *flops
+float run_fma_probe(int dtype, int iters, double* flops, cudaStream_t s);
+// kernels launched by this library in this process (optionally resetting the counter)
+long long launch_count(bool reset);
+// name the tiled FIR variant that launch_fir would pick (no launch)
+const char* fir_variant_name(int dtype, int stride, int nf, int taps, int64_t n_pos, int n_streams);
+
+}  // namespace gar

@@ -1,0 +1,189 @@
+"""API-level invariants the reference tests assert, re-run on the GPU engine, plus the
+edge cases of its engine tests (empty / tiny inputs, flush of an unfed stage, reset, unusual factors)."""
+import numpy as np
+import pytest
+
+from helpers import G, O, sig_c3
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(ir, orr, ch=1, preset=G.QualityHigh, precision=0):
+    return G.Config(InputRate=ir, OutputRate=orr, Channels=ch,
+                    Quality=G.QualitySpec(Preset=preset, Precision=precision, PhaseResponse=50, PassbandEnd=0.9,
+                                          StopbandBegin=0.99))
+
+
+def _noise(n, seed=0, dt=np.float64):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    return (0.6 * np.sin(2 * np.pi * 0.01 * t) + 0.3 * (rng.random(n) - 0.5)).astype(dt)
+
+
+RATES = [(44100, 48000), (48000, 44100), (96000, 48000), (48000, 32000), (22050, 44100), (48000, 16000),
+         (8000, 192000), (48000, 48000)]
+
+
+@pytest.mark.parametrize("ir,orr", RATES)
+def test_process_into_equals_process_and_oracle(ir, orr):  # processinto_test.go:36-105,562-618
+    x = _noise(30000, 1)
+    a, b = G.New(_cfg(ir, orr)), G.New(_cfg(ir, orr))
+    p = O.Pipeline(ir, orr, 1, O.PRESET_HIGH)
+    out = np.empty(a.EstimateOutput(5000))
+    for i in range(0, len(x), 5000):
+        n = a.ProcessInto(x[i:i + 5000], out)
+        y = b.Process(x[i:i + 5000])
+        w = p.process(x[i:i + 5000])
+        np.testing.assert_array_equal(out[:n], y)
+        assert len(y) == len(w)
+        if len(w):
+            assert np.max(np.abs(y - w)) <= 1e-12
+    fa, fb, fw = a.Flush(), b.Flush(), p.flush()
+    np.testing.assert_array_equal(fa, fb)
+    assert len(fa) == len(fw) and (len(fw) == 0 or np.max(np.abs(fa - fw)) <= 1e-12)
+
+
+@pytest.mark.parametrize("ir,orr,dt", [(44100, 48000, np.float64), (48000, 44100, np.float32),
+                                       (48000, 16000, np.float32), (44100, 47999, np.float64),
+                                       (48000, 8000, np.float64), (8000, 192000, np.float64),
+                                       (48000, 11025, np.float64), (16000, 48000, np.float32),
+                                       (12000, 48000, np.float64)])
+def test_engine_random_chunking_matches_oracle(ir, orr, dt):  # processinto_test.go:258-449
+    tol = 1e-12 if dt == np.float64 else 1e-6
+    x = _noise(50000, 2, dt)
+    r = G.SimpleResampler(ir, orr, G.QualityHigh, dt)
+    e = O.Engine(ir, orr, O.Q_HIGH, dt)
+    rng = np.random.default_rng(3)
+    i = 0
+    while i < len(x):
+        n = int(rng.integers(1, 7000))
+        y, w = r.Process(x[i:i + n]), e.process(x[i:i + n])
+        assert len(y) == len(w) <= r.EstimateOutput(len(x[i:i + n]))
+        if len(w):
+            assert np.max(np.abs(y.astype(np.float64) - w.astype(np.float64))) <= tol
+        i += n
+    fy, fw = r.Flush(), e.flush()
+    assert len(fy) == len(fw)
+    if len(fw):
+        assert np.max(np.abs(fy.astype(np.float64) - fw.astype(np.float64))) <= tol
+    assert r.GetStatistics() == dict(zip(("samplesIn", "samplesOut"), e.stats()))
+
+
+def test_buffer_too_small_does_not_advance_state():  # processinto_test.go:176-224
+    x = _noise(8192, 4)
+    a, b = G.New(_cfg(44100, 48000)), G.New(_cfg(44100, 48000))
+    a.Process(x[:4096])
+    b.Process(x[:4096])
+    with pytest.raises(G.ErrBufferTooSmall):
+        a.ProcessInto(x[4096:], np.empty(100))
+    np.testing.assert_array_equal(a.Process(x[4096:]), b.Process(x[4096:]))
+
+
+def test_parallel_equals_sequential_and_channels_independent():  # parallel_test.go:12-89
+    xs = [c[:60000] for c in sig_c3(60000, 4)]
+    m = G.New(_cfg(96000, 48000, 4, G.QualityVeryHigh))
+    ys = m.ProcessMulti(xs)
+    fs = m.FlushMulti()
+    for c in range(4):
+        s = G.New(_cfg(96000, 48000, 1, G.QualityVeryHigh))
+        np.testing.assert_array_equal(ys[c], s.Process(xs[c]))
+        np.testing.assert_array_equal(fs[c], s.Flush())
+
+
+def test_process_multi_unequal_channel_lengths_and_flush_is_channel0_only():
+    xs = [_noise(20000, 5), _noise(12345, 6), _noise(20000, 7)]
+    m = G.New(_cfg(44100, 48000, 3))
+    p = O.Pipeline(44100, 48000, 3, O.PRESET_HIGH)
+    ys, ws = m.ProcessMulti(xs), p.process_multi(xs)
+    for y, w in zip(ys, ws):
+        assert len(y) == len(w) and np.max(np.abs(y - w)) <= 1e-12
+    f0, w0 = m.Flush(), p.flush(0)  # Flush drains channel 0 only (constant.go:349-354)
+    assert len(f0) == len(w0) and np.max(np.abs(f0 - w0)) <= 1e-12
+    fs, wf = m.FlushMulti(), p.flush_multi()
+    for y, w in zip(fs, wf):
+        assert len(y) == len(w)
+        if len(w):
+            assert np.max(np.abs(y - w)) <= 1e-12
+
+
+def test_stereo_equals_two_mono():  # convenience_stereo_test.go:40-71
+    l, r = _noise(20000, 8), _noise(20000, 9)
+    lo, ro = G.ResampleStereo(l, r, 44100, 48000, G.QualityHigh)
+    np.testing.assert_array_equal(lo, G.ResampleMono(l, 44100, 48000, G.QualityHigh))
+    np.testing.assert_array_equal(ro, G.ResampleMono(r, 44100, 48000, G.QualityHigh))
+    l32, r32 = l.astype(np.float32), r.astype(np.float32)
+    lo, ro = G.ResampleStereoFloat32(l32, r32, 48000, 44100, G.QualityMedium)
+    np.testing.assert_array_equal(ro, G.ResampleMonoFloat32(r32, 48000, 44100, G.QualityMedium))
+    assert lo.dtype == np.float32
+
+
+def test_float32_vs_float64_within_1e5():  # convenience_float32_test.go:222-266
+    x = _noise(30000, 10)
+    a = G.ResampleMono(x, 44100, 48000, G.QualityHigh)
+    b = G.ResampleMonoFloat32(x.astype(np.float32), 44100, 48000, G.QualityHigh)
+    assert len(a) == len(b) and np.max(np.abs(a - b)) <= 1e-5
+
+
+def test_empty_tiny_inputs_and_flush_of_unfed_stage():  # edge_cases_test.go, polyphase_flush_test.go:94-109
+    for ir, orr in RATES:
+        r = G.New(_cfg(ir, orr))
+        p = O.Pipeline(ir, orr, 1, O.PRESET_HIGH)
+        assert len(r.Flush()) == len(p.flush())  # nothing fed: nothing (or passthrough nothing) to drain
+        assert len(r.Process(np.zeros(0))) == 0
+        for n in (1, 1, 2, 7):
+            y, w = r.Process(np.full(n, 0.25)), p.process(np.full(n, 0.25))
+            assert len(y) == len(w)
+        fy, fw = r.Flush(), p.flush()
+        assert len(fy) == len(fw)
+        if len(fw):
+            assert np.max(np.abs(fy - fw)) <= 1e-12
+
+
+def test_reset_reproduces_first_run():  # reset_state_test.go
+    x = _noise(20000, 11)
+    r = G.NewEngine(48000, 44100, G.QualityHigh)
+    a = np.concatenate([r.Process(x), r.Flush()])
+    r.Reset()
+    assert r.GetStatistics() == {"samplesIn": 0, "samplesOut": 0}
+    b = np.concatenate([r.Process(x), r.Flush()])
+    np.testing.assert_array_equal(a, b)
+
+
+def test_zero_input_gives_zero_output_and_dc_gain():  # regression_test.go:160-185, quality_regression_test.go:26-55
+    r = G.NewEngine(44100, 48000, G.QualityHigh)
+    assert np.max(np.abs(r.Process(np.zeros(20000)))) <= 1e-10
+    r.Reset()
+    y = r.Process(np.ones(40000))
+    assert abs(float(np.mean(y[5000:-5000])) - 1.0) <= 1e-3
+
+
+@pytest.mark.parametrize("preset,prec", [(G.QualityQuick, 0), (G.QualityLow, 0), (G.QualityMedium, 0),
+                                         (G.QualityVeryHigh, 0), (G.QualityCustom, 20), (G.QualityCustom, 28)])
+def test_quality_presets_path_a(preset, prec):  # includes the QualityQuick cubic stage (cubic.go)
+    x = _noise(25000, 12)
+    for ir, orr in ((44100, 48000), (48000, 22050)):
+        r = G.New(_cfg(ir, orr, 1, preset, prec))
+        p = O.Pipeline(ir, orr, 1, preset, prec)
+        outs = 0
+        for i in range(0, len(x), 6000):
+            y, w = r.Process(x[i:i + 6000]), p.process(x[i:i + 6000])
+            assert len(y) == len(w)
+            tol = 0.0 if preset == G.QualityQuick else 1e-12  # the cubic path is evaluated op for op
+            if len(w):
+                assert np.max(np.abs(y - w)) <= tol
+            outs += len(y)
+        fy, fw = r.Flush(), p.flush()
+        assert len(fy) == len(fw)
+        assert outs > 0
+
+
+def test_uploaded_bank_replaces_host_design():
+    """gar_upload_bank: coefficients designed elsewhere (e.g. by the Go internal/filter) drive the kernels."""
+    x = _noise(10000, 13)
+    r = G.NewEngine(48000, 24000, G.QualityLow)
+    base = r.Process(x)
+    r.Reset()
+    bank = r.bank(0, 0)
+    r.upload_bank(0, 0, bank * 0.5)
+    half = r.Process(x)
+    assert np.max(np.abs(half - 0.5 * base)) <= 1e-15
