@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 resampling engine (contract: see README / DESIGN.md §6).
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): 4096 independent mono
+streams, 48 kHz -> 16 kHz, float32 end to end, NewEngineFloat32(48000,16000,QualityMedium) semantics
+(877-tap /3 decimating FIR), 480 000 samples (10 s) per stream, one batched Process + Flush per step.
+The 4096 streams are sharded across the N ranks (strong scaling, no data-path collective).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N>1 is launched by torchrun (one rank per GPU); rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "go-audio-resampler_b200" / "python"))
+sys.path.insert(0, str(ROOT))
+
+IN_RATE, OUT_RATE = 48000, 16000
+PRESETS = {"low": 1, "medium": 2, "high": 3}
+TAPS = {"low": 245, "medium": 877, "high": 1125}  # dft_stage.go:401-475 via the oracle / product design
+METRIC = "output_msamples_per_s"
+UNIT = "Msamples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=4096, help="total streams over all ranks")
+    ap.add_argument("--seconds", type=float, default=10.0, help="audio seconds per stream")
+    ap.add_argument("--preset", default="medium", choices=list(PRESETS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=8.0, help="target wall time of the CPU baseline sample")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"{a.streams} mono streams x {int(a.seconds * IN_RATE)} samples, 48k->16k float32, "
+            f"NewEngineFloat32 Quality{a.preset.capitalize()} ({TAPS[a.preset]}-tap /3 FIR), Process+Flush")
+
+
+def synth_rows_host(first, count, n, dtype=np.float32):
+    t = np.arange(n, dtype=np.float64) / IN_RATE
+    x = np.empty((count, n), dtype=dtype)
+    for i in range(count):
+        s = first + i
+        rng = np.random.default_rng(s)
+        x[i] = (np.sin(2 * np.pi * (200 + 1.7 * s) * t) + 0.05 * (2 * rng.random(n) - 1)).astype(dtype)
+    return x
+
+
+class ClockSampler:
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [q.strip() for q in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                smax = max(smax, float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # under load = upper half of the samples (idle samples before/after the region are dropped)
+        sm_load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(sm_load) if sm_load else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(a, x_host, n_threads, target_s):
+    """The oracle (C++ restatement of the Go path, AVX2+FMA) on the host cores, bounded sample."""
+    from oracle import oracle as O
+    q = O.preset_to_engine_quality(PRESETS[a.preset])
+    n = x_host.shape[1]
+    probe = min(x_host.shape[0], max(n_threads, 4))
+    t0 = time.perf_counter()
+    _, counts = O.batch_resample(x_host[:probe], IN_RATE, OUT_RATE, q, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    ns = int(min(x_host.shape[0], max(probe, probe * target_s / max(dt, 1e-3))))
+    ns = max(n_threads, (ns // n_threads) * n_threads)
+    ns = min(ns, x_host.shape[0])
+    t0 = time.perf_counter()
+    _, counts = O.batch_resample(x_host[:ns], IN_RATE, OUT_RATE, q, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    v_all = float(counts.sum()) / dt / 1e6
+    # single thread on a smaller sample
+    n1 = max(1, min(ns, int(max(1, ns / n_threads / 2))))
+    t0 = time.perf_counter()
+    _, c1 = O.batch_resample(x_host[:n1], IN_RATE, OUT_RATE, q, n_threads=1)
+    d1 = time.perf_counter() - t0
+    return {"value": round(v_all, 3), "unit": UNIT, "cores": n_threads, "kind": "port",
+            "sample": f"{ns} of the streams x {n} samples (Process+Flush), {dt:.2f} s wall; "
+                      "C++ restatement of the Go path (AVX2+FMA), not the Go binary: no Go toolchain in the image",
+            "value_1thread": round(float(c1.sum()) / d1 / 1e6, 3), "avx2": bool(O.lib().orc_has_avx2())}
+
+
+def run_reference(a, rank):
+    """--impl reference: the reference's CPU path (oracle port; Go cannot be built here) on all host cores."""
+    if rank != 0:
+        return
+    n = int(a.seconds * IN_RATE)
+    cores = os.cpu_count() or 1
+    ns = min(a.streams, cores * 4)
+    x = synth_rows_host(0, ns, n)
+    from oracle import oracle as O
+    q = O.preset_to_engine_quality(PRESETS[a.preset])
+    times, outs = [], 0
+    for i in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        _, counts = O.batch_resample(x, IN_RATE, OUT_RATE, q, n_threads=cores)
+        dt = time.perf_counter() - t0
+        if i >= a.warmup:
+            times.append(dt)
+            outs = int(counts.sum())
+    ms = 1e3 * sum(times) / len(times)
+    val = outs / (ms * 1e-3) / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "step": f"bounded sample: {ns} streams per step on {cores} host threads"},
+            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{ns} streams x {n} samples per step; C++ restatement of the Go path "
+                                       "(oracle/, AVX2+FMA) — the Go reference cannot be built in this image"},
+            "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gar_b200 as G
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    n_in = int(a.seconds * IN_RATE)
+    rows = a.streams // world
+    first = rank * rows
+    taps = TAPS[a.preset]
+    flops_per_out = 2.0 * taps  # 2 x MACs per output sample
+
+    b = G.NewBatch(IN_RATE, OUT_RATE, PRESETS[a.preset], rows, np.float32, device=local)
+    assert b.describe()[0]["taps"] == taps
+    kname = b.kernel_names()[0]
+    est = b.EstimateOutput(n_in)
+    ostride = (est + 3) & ~3
+
+    # synthetic input resident in HBM: per-stream sine (200 + 1.7 s) Hz + 0.05 uniform noise
+    x = torch.empty((rows, n_in), dtype=torch.float32, device=dev)
+    t = torch.arange(n_in, device=dev, dtype=torch.float64) / IN_RATE
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    blk = 128
+    for r0 in range(0, rows, blk):
+        r1 = min(rows, r0 + blk)
+        f = 200.0 + 1.7 * torch.arange(first + r0, first + r1, device=dev, dtype=torch.float64)
+        sig = torch.sin(2 * np.pi * f[:, None] * t[None, :]).to(torch.float32)
+        sig += 0.05 * (2 * torch.rand((r1 - r0, n_in), device=dev, generator=g) - 1)
+        x[r0:r1] = sig
+    del sig, t
+    y = torch.zeros((rows, ostride), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device(ev=None):
+        b.Reset()
+        if ev:
+            ev[0].record()
+        n1 = b.process_batch_dev(x.data_ptr(), n_in, n_in, y.data_ptr(), ostride, ostride, stream)
+        if ev:
+            ev[1].record()
+        n2 = b.flush_batch_dev(y.data_ptr() + n1 * 4, ostride, ostride - n1, stream)
+        if ev:
+            ev[2].record()
+        return n1, n2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak32 = G.measure_fma_peak(np.float32, local)
+
+    for _ in range(max(a.warmup, 3)):
+        n1, n2 = step_device()
+    barrier()
+    G.kernel_launches(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e_begin.record()
+    for k in range(a.steps):
+        n1, n2 = step_device(evs[k])
+    e_end.record()
+    barrier()
+    launches = G.kernel_launches()
+    total_ms = e_begin.elapsed_time(e_end)
+    time.sleep(0.15)
+    clocks = sampler.stop()
+    ms_step = total_ms / a.steps
+    k_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)  # the batched FIR kernel (Process)
+    f_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+
+    tmax = torch.tensor([ms_step], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step_max = float(tmax.item())
+    out_per_rank = rows * (n1 + n2)
+    value = out_per_rank * world / (ms_step_max * 1e-3) / 1e6
+
+    achieved_tf = rows * n1 * flops_per_out / (k_ms * 1e-3) / 1e12
+    bytes_alg = rows * (n_in + n1) * 4.0
+    roofline = {"bound": "fma", "kernel": kname, "achieved": round(achieved_tf, 3), "peak": round(peak32, 3),
+                "unit": "TFLOP/s", "frac": round(achieved_tf / peak32, 4),
+                "peak_source": "dependent-FMA fp32 probe (gar_measure_fma_peak) run in this job; MEASURED_PEAKS.json "
+                               "holds only HBM and bf16-tensor peaks, neither bounds this fp32-FMA kernel",
+                "flops_per_output": flops_per_out, "kernel_ms": round(k_ms, 4), "flush_ms": round(f_ms, 4),
+                "traffic": None,
+                "hbm": {"achieved": round(bytes_alg / (k_ms * 1e-3) / 1e9, 1), "peak": 6446.9, "unit": "GB/s",
+                        "frac": round(bytes_alg / (k_ms * 1e-3) / 1e9 / 6446.9, 4),
+                        "algorithmic_bytes_per_output": 16}}
+
+    # ---- e2e: the host-facing C-ABI call (gar_process_batch + gar_flush_batch) on pinned host buffers ----
+    e2e = None
+    xh = None
+    if not a.no_e2e:
+        xh, px = G.host_alloc((rows, n_in), np.float32)
+        yh, py = G.host_alloc((rows, ostride), np.float32)
+        for r0 in range(0, rows, 256):
+            xh[r0:r0 + 256] = x[r0:r0 + 256].cpu().numpy()
+
+        def step_host():
+            b.Reset()
+            _, m1 = b.ProcessBatch(xh, yh)
+            _, m2 = b.FlushBatch(yh[:, m1:])
+            return m1, m2
+
+        for _ in range(2):
+            m1, m2 = step_host()
+        assert (m1, m2) == (n1, n2)
+        ne = max(3, min(a.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ne):
+            step_host()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / ne
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(out_per_rank * world / float(tt.item()) / 1e6, 3), "unit": UNIT,
+               "h2d_bytes_per_step": rows * n_in * 4 * world, "d2h_bytes_per_step": rows * (n1 + n2) * 4 * world,
+               "ms_per_step": round(float(tt.item()) * 1e3, 3),
+               "api": "gar_process_batch + gar_flush_batch (pinned host buffers, sliced H2D/compute/D2H overlap)",
+               "timer": "host wall clock around the synchronous calls, max over ranks"}
+        # spot-check the host path against the device path
+        chk = torch.from_numpy(yh[:2, :n1 + n2].copy()).to(dev)
+        assert torch.equal(chk, y[:2, :n1 + n2]), "host and device paths disagree"
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        xc = xh if xh is not None else x[:min(rows, 512)].cpu().numpy()
+        cpu = cpu_baseline(a, xc, os.cpu_count() or 1, a.cpu_seconds)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": round(ms_step_max, 4), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(a), "streams_per_gpu": rows,
+                           "l2": "inputs larger than L2 (%.1f GB per GPU per step)" % (rows * n_in * 4 / 1e9),
+                           "timer": "CUDA events on the launching stream, max over ranks"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

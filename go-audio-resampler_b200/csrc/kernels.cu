@@ -164,11 +164,14 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
     const T* xt = xs + M * R * tid;
     T xr[WREG];
     T acc[R][NF];
-    T tot[R][NF];
+    double tot[R][NF];  // f32: short f32 partial sums are folded into f64 totals (|err| ~ 1e-7)
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int p = 0; p < NF; ++p) acc[r][p] = tot[r][p] = T(0);
+        for (int p = 0; p < NF; ++p) {
+            acc[r][p] = T(0);
+            tot[r][p] = 0.0;
+        }
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) vec_unpack(*reinterpret_cast<const V*>(xt + ch * VEC), xr + ch * VEC);
 
@@ -188,12 +191,12 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
         vec_unpack(*reinterpret_cast<const V*>(xt + (it + NCH) * VEC), xr + (u % NCH) * VEC);
     };
     auto fold = [&]() {
-        if (sizeof(T) == 4) {  // bounded-length f32 partial sums keep |err| well below 1e-6
+        if (sizeof(T) == 4) {
 #pragma unroll
             for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int p = 0; p < NF; ++p) {
-                    tot[r][p] += acc[r][p];
+                    tot[r][p] += (double)acc[r][p];
                     acc[r][p] = T(0);
                 }
         }
@@ -208,17 +211,18 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
 #pragma unroll
     for (int u = 0; u < NCH; ++u)
         if (it0 + u < n_iter) step(u, it0 + u);
+    T res[R][NF];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int p = 0; p < NF; ++p) tot[r][p] += acc[r][p];
+        for (int p = 0; p < NF; ++p) res[r][p] = (T)(tot[r][p] + (double)acc[r][p]);
 
     // ---- interleaved, vectorised store: out[(j*NF + p)] ----
     T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
     const int jb = j0 + R * tid;
     T* op = out + (int64_t)jb * NF;
     if (jb + R <= c.n_pos && (R * NF) % VEC == 0 && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {
-        const T* flat = &tot[0][0];
+        const T* flat = &res[0][0];
 #pragma unroll
         for (int q = 0; q < R * NF / VEC; ++q) reinterpret_cast<V*>(op)[q] = vec_pack(flat + q * VEC);
     } else {
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
         for (int r = 0; r < R; ++r)
             if (jb + r < c.n_pos) {
 #pragma unroll
-                for (int p = 0; p < NF; ++p) op[r * NF + p] = tot[r][p];
+                for (int p = 0; p < NF; ++p) op[r * NF + p] = res[r][p];
             }
     }
 }
@@ -248,15 +252,16 @@ __global__ void __launch_bounds__(256) fir_generic_kernel(const FirCall c, const
     const int j = (int)(o / c.nf), p = (int)(o % c.nf);
     const int g = c.first + j * c.stride;
     const T* __restrict__ bank = static_cast<const T*>(c.bank) + (int64_t)p * c.taps;
-    T tot = 0, acc = 0;
+    double tot = 0;
+    T acc = 0;
     for (int k = 0; k < c.taps; ++k) {
         acc = fma(vload(hist, c.hist_len, in, c.n_in, g + k), bank[k], acc);
-        if (sizeof(T) == 4 && (k & 63) == 63) {
-            tot += acc;
+        if (sizeof(T) == 4 && (k & 31) == 31) {
+            tot += (double)acc;
             acc = 0;
         }
     }
-    (static_cast<T*>(c.out) + row * c.out_stride)[o] = tot + acc;
+    (static_cast<T*>(c.out) + row * c.out_stride)[o] = (T)(tot + (double)acc);
 }
 
 // =============================================================================================
