@@ -81,6 +81,15 @@ def test_c4_batched_mono_streams_48k_to_16k_f32(preset, taps):
     got = np.concatenate([y, f], axis=1)
     err = float(np.max(np.abs(got.astype(np.float64) - want[:, :ny + nf].astype(np.float64))))
     assert err <= TOL32, err
+    # referee: float64 arithmetic on the same float32 operands (bank as stored on the device, reversed taps)
+    bank = b.bank(0, 0)
+    for r in (0, ns - 1):
+        v = np.concatenate([x[r].astype(np.float64), np.zeros(taps)])
+        exact = np.correlate(v, bank, mode="valid")[::3][:ny + nf]
+        e_gpu = float(np.max(np.abs(got[r].astype(np.float64) - exact)))
+        e_orc = float(np.max(np.abs(want[r, :ny + nf].astype(np.float64) - exact)))
+        assert e_gpu <= 2.5e-7, (e_gpu, e_orc)  # f32 output rounding (6e-8) + short f32 partial sums
+        assert e_orc <= TOL32, e_orc
 
 
 def test_c4_full_length_rows_chunked_equals_one_shot_and_oracle():
