@@ -36,7 +36,7 @@ UNIT = "Msamples/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=4096, help="total streams over all ranks")
@@ -75,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -217,18 +217,23 @@ def main():
         x[r0:r1] = sig
     del sig, t
     y = torch.zeros((rows, ostride), dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-NULL) stream: the kernels are enqueued on it through the C ABI and the CUDA events
+    # that time them are recorded on the same stream
+    tstream = torch.cuda.Stream(device=dev)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    torch.cuda.synchronize()
 
     def step_device(ev=None):
         b.Reset()
         if ev:
-            ev[0].record()
+            ev[0].record(tstream)
         n1 = b.process_batch_dev(x.data_ptr(), n_in, n_in, y.data_ptr(), ostride, ostride, stream)
         if ev:
-            ev[1].record()
+            ev[1].record(tstream)
         n2 = b.flush_batch_dev(y.data_ptr() + n1 * 4, ostride, ostride - n1, stream)
         if ev:
-            ev[2].record()
+            ev[2].record(tstream)
         return n1, n2
 
     def barrier():
@@ -249,10 +254,10 @@ def main():
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e_begin.record()
+    e_begin.record(tstream)
     for k in range(a.steps):
         n1, n2 = step_device(evs[k])
-    e_end.record()
+    e_end.record(tstream)
     barrier()
     launches = G.kernel_launches()
     total_ms = e_begin.elapsed_time(e_end)

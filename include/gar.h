@@ -186,8 +186,9 @@ int32_t gar_reset(gar_handle* h);
  * alternating CUDA streams so PCIe and the SMs overlap. *n_out = samples per row. */
 int32_t gar_process_batch(gar_handle* h, int32_t io_dtype, const void* in, int64_t in_stride, int64_t n_in, void* out, int64_t out_stride, int64_t out_cap, int64_t* n_out);
 int32_t gar_flush_batch(gar_handle* h, int32_t io_dtype, void* out, int64_t out_stride, int64_t out_cap, int64_t* n_out);
-/* Same with DEVICE pointers, enqueued on `cuda_stream` (a cudaStream_t, 0 = the handle's own);
- * returns after enqueue. Use when inputs are already resident in HBM. */
+/* Same with DEVICE pointers, enqueued on `cuda_stream` (a cudaStream_t; NULL = the handle's own stream,
+ * pass cudaStreamLegacy / cudaStreamPerThread to name the default streams); returns after enqueue.
+ * Use when inputs are already resident in HBM. */
 int32_t gar_process_batch_dev(gar_handle* h, int32_t io_dtype, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride, int64_t out_cap, int64_t* n_out, void* cuda_stream);
 int32_t gar_flush_batch_dev(gar_handle* h, int32_t io_dtype, void* d_out, int64_t out_stride, int64_t out_cap, int64_t* n_out, void* cuda_stream);
 

@@ -79,17 +79,19 @@ def test_c4_batched_mono_streams_48k_to_16k_f32(preset, taps):
     want, counts = O.batch_resample(x, 48000, 16000, O.preset_to_engine_quality(preset), n_threads=8)
     assert np.all(counts == ny + nf)
     got = np.concatenate([y, f], axis=1)
-    err = float(np.max(np.abs(got.astype(np.float64) - want[:, :ny + nf].astype(np.float64))))
-    assert err <= TOL32, err
     # referee: float64 arithmetic on the same float32 operands (bank as stored on the device, reversed taps)
     bank = b.bank(0, 0)
-    for r in (0, ns - 1):
+    e_gpu = e_orc = 0.0
+    for r in range(0, ns, 8):
         v = np.concatenate([x[r].astype(np.float64), np.zeros(taps)])
         exact = np.correlate(v, bank, mode="valid")[::3][:ny + nf]
-        e_gpu = float(np.max(np.abs(got[r].astype(np.float64) - exact)))
-        e_orc = float(np.max(np.abs(want[r, :ny + nf].astype(np.float64) - exact)))
-        assert e_gpu <= 2.5e-7, (e_gpu, e_orc)  # f32 output rounding (6e-8) + short f32 partial sums
-        assert e_orc <= TOL32, e_orc
+        e_gpu = max(e_gpu, float(np.max(np.abs(got[r].astype(np.float64) - exact))))
+        e_orc = max(e_orc, float(np.max(np.abs(want[r, :ny + nf].astype(np.float64) - exact))))
+    err = float(np.max(np.abs(got.astype(np.float64) - want[:, :ny + nf].astype(np.float64))))
+    print(f"taps={taps}: |gpu-exact|={e_gpu:.3e} |oracle-exact|={e_orc:.3e} |gpu-oracle|={err:.3e}")
+    assert e_gpu <= 2.5e-7, (e_gpu, e_orc)  # f32 output rounding (6e-8 at |y|~1) + short f32 partial sums
+    assert e_orc <= TOL32, e_orc
+    assert err <= TOL32, (err, e_gpu, e_orc)
 
 
 def test_c4_full_length_rows_chunked_equals_one_shot_and_oracle():
