@@ -202,15 +202,33 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
         }
     };
 
-    int it0 = 0;
+    // f32 only: the three iterations that hold the centre of the main lobe are folded one by one, so the
+    // many small terms that follow are never added to an O(1) float32 partial sum (keeps |err| ~ 1.5e-7).
+    const int itf0 = ((c.taps - 1) / 2 + a) / VEC, itf1 = itf0 + 2;
+    constexpr int FOLD_BODIES = 8;  // periodic fold every 8*NCH*VEC taps (F2F.F64.F32 is ~10x an FFMA slot)
+    int it0 = 0, since_fold = 0;
     for (; it0 + NCH <= n_iter; it0 += NCH) {
+        if (sizeof(T) == 4 && it0 <= itf1 && it0 + NCH > itf0) {
 #pragma unroll
-        for (int u = 0; u < NCH; ++u) step(u, it0 + u);
-        fold();
+            for (int u = 0; u < NCH; ++u) {
+                step(u, it0 + u);
+                if (it0 + u >= itf0 && it0 + u <= itf1) fold();
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) step(u, it0 + u);
+        }
+        if (++since_fold == FOLD_BODIES) {
+            fold();
+            since_fold = 0;
+        }
     }
 #pragma unroll
     for (int u = 0; u < NCH; ++u)
-        if (it0 + u < n_iter) step(u, it0 + u);
+        if (it0 + u < n_iter) {
+            step(u, it0 + u);
+            if (sizeof(T) == 4 && it0 + u >= itf0 && it0 + u <= itf1) fold();
+        }
     T res[R][NF];
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -254,9 +272,10 @@ __global__ void __launch_bounds__(256) fir_generic_kernel(const FirCall c, const
     const T* __restrict__ bank = static_cast<const T*>(c.bank) + (int64_t)p * c.taps;
     double tot = 0;
     T acc = 0;
+    const int kc = (c.taps - 1) / 2;
     for (int k = 0; k < c.taps; ++k) {
         acc = fma(vload(hist, c.hist_len, in, c.n_in, g + k), bank[k], acc);
-        if (sizeof(T) == 4 && (k & 31) == 31) {
+        if (sizeof(T) == 4 && ((k & 255) == 255 || (k >= kc && k < kc + 12 && ((k - kc) & 3) == 3))) {
             tot += (double)acc;
             acc = 0;
         }
@@ -303,16 +322,17 @@ __global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_
     const T* __restrict__ cb = static_cast<const T*>(c.bank_b) + co;
     const T* __restrict__ cc = static_cast<const T*>(c.bank_c) + co;
     const T* __restrict__ cd = static_cast<const T*>(c.bank_d) + co;
-    T acc0 = 0, acc1 = 0;
+    // products of two float32 are exact in float64, so the float32 path only rounds once, at the store
+    double acc0 = 0, acc1 = 0;
     const int base = div - div0;
     for (int k = 0; k < c.taps; ++k) {
         T coef = ca[k];
         if (INTERP) coef = fma(x, fma(x, fma(x, cd[k], cc[k]), cb[k]), coef);
         const T h = staged ? xs[base + k] : vload(hist, c.hist_len, in, c.n_in, div + k);
-        if (k & 1) acc1 = fma(h, coef, acc1);
-        else acc0 = fma(h, coef, acc0);
+        if (k & 1) acc1 = fma((double)h, (double)coef, acc1);
+        else acc0 = fma((double)h, (double)coef, acc0);
     }
-    (static_cast<T*>(c.out) + row * c.out_stride)[n] = acc0 + acc1;
+    (static_cast<T*>(c.out) + row * c.out_stride)[n] = (T)(acc0 + acc1);
 }
 
 // =============================================================================================
