@@ -191,9 +191,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
+    from gar_b200.shard import partition
     n_in = int(a.seconds * IN_RATE)
-    rows = a.streams // world
-    first = rank * rows
+    first, rows = partition(a.streams, world, rank)  # independent streams: shard by rows, no collective
     taps = TAPS[a.preset]
     flops_per_out = 2.0 * taps  # 2 x MACs per output sample
 

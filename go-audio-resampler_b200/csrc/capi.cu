@@ -638,7 +638,8 @@ int32_t gar_measure_fma_peak(int32_t device, int32_t dtype, double* tflops) {
     double best = 0;
     for (int rep = 0; rep < 3; ++rep) {
         double flops = 0;
-        const float ms = run_fma_probe(dtype == GAR_F32 ? DT_F32 : DT_F64, dtype == GAR_F32 ? 4096 : 2048, &flops, 0);
+        // dtype 2 = packed fp32x2 (FFMA2) probe
+        const float ms = run_fma_probe(dtype == 2 ? 2 : (dtype == GAR_F32 ? DT_F32 : DT_F64), dtype == GAR_F64 ? 2048 : 4096, &flops, 0);
         if (ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
     if (cudaGetLastError() != cudaSuccess || best <= 0) return GAR_CUDA_ERROR;

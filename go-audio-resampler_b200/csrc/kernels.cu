@@ -397,6 +397,35 @@ __global__ void __launch_bounds__(256) fma_probe_kernel(T* out, int iters, T b, 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// packed 2 x fp32 FMA (PTX fma.rn.f32x2, SASS FFMA2 — new on sm_100): operands are even/odd register pairs
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+    unsigned long long ra = *reinterpret_cast<const unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<const unsigned long long*>(&b);
+    unsigned long long rc = *reinterpret_cast<const unsigned long long*>(&c);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
+__global__ void __launch_bounds__(256) ffma2_probe_kernel(float2* out, int iters, float2 b, float2 cadd) {
+    float2 a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = make_float2((float)(threadIdx.x + k), (float)(threadIdx.x - k));
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = ffma2(a[k], b, cadd);
+    }
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        s.x += a[k].x;
+        s.y += a[k].y;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ---- variant table for the tiled FIR -----------------------------------------------------------
 struct FirVariant {
     int dtype, stride, nf, r;
@@ -565,7 +594,10 @@ float run_fma_probe(int dtype, int iters, double* flops, cudaStream_t s) {
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     auto run = [&](int n) {
-        if (dtype == DT_F32) fma_probe_kernel<float><<<blocks, threads, 0, s>>>((float*)buf, n, 0.999999f, 1e-7f);
+        if (dtype == 2)  // packed f32x2: 4 reps x 8 chains x 2 lanes = 64 FMA per iteration, same as the others
+            ffma2_probe_kernel<<<blocks, threads, 0, s>>>((float2*)buf, n, make_float2(0.999999f, 0.999998f),
+                                                          make_float2(1e-7f, 2e-7f));
+        else if (dtype == DT_F32) fma_probe_kernel<float><<<blocks, threads, 0, s>>>((float*)buf, n, 0.999999f, 1e-7f);
         else fma_probe_kernel<double><<<blocks, threads, 0, s>>>((double*)buf, n, 0.999999, 1e-7);
     };
     run(iters / 8 + 1);  // warm-up

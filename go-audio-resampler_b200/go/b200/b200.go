@@ -1,0 +1,378 @@
+// Package b200 binds the B200 resampling engine (libgar_b200.so, include/gar.h) with cgo and exposes
+// the reference's own Go API on top of it:
+//
+//	New(*Config) (Resampler, error)             resample.go:272
+//	NewEngine / NewEngineFloat32                convenience.go:125, 329
+//	ResampleMono / ResampleMonoFloat32          convenience.go:204, 407
+//
+// so `resampler.New` can be pointed at the GPU engine without touching callers.
+// NOTE: this file cannot be compiled in the build image (no Go toolchain); it is the shim a
+// maintainer adds, see INTEGRATION.md. Build: CGO_CFLAGS=-I<repo>/include
+// CGO_LDFLAGS="-L<repo>/go-audio-resampler_b200/_build -lgar_b200" go build ./...
+package b200
+
+/*
+#cgo LDFLAGS: -lgar_b200
+#include <stdlib.h>
+#include "gar.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"runtime"
+	"unsafe"
+)
+
+// Error sentinels of the reference (resample.go:156-165).
+var (
+	ErrInvalidConfig  = errors.New("invalid resampler configuration")
+	ErrBufferTooSmall = errors.New("output buffer too small")
+	ErrNotSupported   = errors.New("operation not supported")
+)
+
+// QualityPreset mirrors resample.go:108-131.
+type QualityPreset int
+
+const (
+	QualityQuick QualityPreset = iota
+	QualityLow
+	QualityMedium
+	QualityHigh
+	QualityVeryHigh
+	QualityCustom
+)
+
+// QualitySpec and Config mirror resample.go:46-102.
+type QualitySpec struct {
+	Preset        QualityPreset
+	Precision     int
+	PhaseResponse float64
+	PassbandEnd   float64
+	StopbandBegin float64
+	Flags         uint32
+}
+
+type Config struct {
+	InputRate, OutputRate float64
+	Channels              int
+	Quality               QualitySpec
+	MaxInputSize          int
+	EnableSIMD            bool
+	EnableParallel        bool
+	Device                int // extension: CUDA ordinal
+}
+
+func statusErr(st C.int32_t, h *C.gar_handle) error {
+	if st == C.GAR_OK {
+		return nil
+	}
+	msg := C.GoString(C.gar_last_error(h))
+	switch st {
+	case C.GAR_INVALID_CONFIG:
+		return fmt.Errorf("%w: %s", ErrInvalidConfig, msg)
+	case C.GAR_BUFFER_TOO_SMALL:
+		return ErrBufferTooSmall
+	case C.GAR_NOT_SUPPORTED:
+		return fmt.Errorf("%w: %s", ErrNotSupported, msg)
+	default:
+		return fmt.Errorf("b200: %s (status %d)", msg, int(st))
+	}
+}
+
+type handle struct{ h *C.gar_handle }
+
+func newHandle(cfg *C.gar_config) (*handle, error) {
+	var h *C.gar_handle
+	if st := C.gar_create(cfg, &h); st != C.GAR_OK {
+		return nil, statusErr(st, nil)
+	}
+	r := &handle{h: h}
+	runtime.SetFinalizer(r, func(r *handle) { C.gar_destroy(r.h) })
+	return r, nil
+}
+
+// Resampler implements the reference's Resampler interface (resample.go:14-43) plus the optional
+// ProcessInto / ProcessFloat32Into / EstimateOutput / FlushMulti methods (constant.go:103-199,390-404).
+type Resampler struct {
+	*handle
+	channels int
+}
+
+// New mirrors resample.go:272-292. Validation (Config.Validate) happens inside gar_create.
+func New(config *Config) (*Resampler, error) {
+	if config == nil {
+		return nil, fmt.Errorf("%w: config is nil", ErrInvalidConfig)
+	}
+	flags := C.uint32_t(config.Quality.Flags)
+	if config.EnableParallel {
+		flags |= 1 << 16
+	}
+	cfg := C.gar_config{
+		input_rate: C.double(config.InputRate), output_rate: C.double(config.OutputRate),
+		channels: C.int32_t(config.Channels), path: C.GAR_PATH_PIPELINE,
+		preset: C.int32_t(config.Quality.Preset), custom_precision: C.int32_t(config.Quality.Precision),
+		custom_phase_response: C.double(config.Quality.PhaseResponse),
+		custom_passband_end:   C.double(config.Quality.PassbandEnd),
+		custom_stopband_begin: C.double(config.Quality.StopbandBegin),
+		dtype:                 C.GAR_F64, engine_quality: -1, device: C.int32_t(config.Device),
+		max_input_size: C.int32_t(config.MaxInputSize), flags: flags,
+	}
+	h, err := newHandle(&cfg)
+	if err != nil {
+		return nil, err
+	}
+	return &Resampler{handle: h, channels: config.Channels}, nil
+}
+
+// EstimateOutput: constant.go:117-119.
+func (r *handle) EstimateOutput(n int) int { return int(C.gar_estimate_output(r.h, C.int64_t(n))) }
+func (r *handle) GetRatio() float64        { return float64(C.gar_get_ratio(r.h)) }
+func (r *handle) GetLatency() int          { return int(C.gar_get_latency(r.h)) }
+func (r *handle) Reset()                   { C.gar_reset(r.h) }
+
+// Process returns an owned, exactly-sized slice (constant.go:88-96). The C side never retains `input`.
+func (r *Resampler) Process(input []float64) ([]float64, error) {
+	if len(input) == 0 {
+		return []float64{}, nil
+	}
+	want := int(C.gar_next_output_count(r.h, 0, C.int64_t(len(input))))
+	capN := max(want, r.EstimateOutput(len(input)))
+	out := make([]float64, capN)
+	n, err := r.ProcessInto(input, out)
+	if err != nil {
+		return nil, err
+	}
+	return out[:n:n], nil
+}
+
+// ProcessInto: constant.go:103-112 — ErrBufferTooSmall before any state is advanced.
+func (r *Resampler) ProcessInto(input, output []float64) (int, error) {
+	var n C.int64_t
+	var ip, op *C.double
+	if len(input) > 0 {
+		ip = (*C.double)(unsafe.Pointer(&input[0]))
+	}
+	if len(output) > 0 {
+		op = (*C.double)(unsafe.Pointer(&output[0]))
+	}
+	st := C.gar_process_f64(r.h, 0, ip, C.int64_t(len(input)), op, C.int64_t(len(output)), &n)
+	runtime.KeepAlive(input)
+	runtime.KeepAlive(output)
+	return int(n), statusErr(st, r.h)
+}
+
+// ProcessFloat32Into: constant.go:161-199 (float64 pipeline between the casts, done on the device).
+func (r *Resampler) ProcessFloat32Into(input, output []float32) (int, error) {
+	var n C.int64_t
+	var ip, op *C.float
+	if len(input) > 0 {
+		ip = (*C.float)(unsafe.Pointer(&input[0]))
+	}
+	if len(output) > 0 {
+		op = (*C.float)(unsafe.Pointer(&output[0]))
+	}
+	st := C.gar_process_f32(r.h, 0, ip, C.int64_t(len(input)), op, C.int64_t(len(output)), &n)
+	runtime.KeepAlive(input)
+	runtime.KeepAlive(output)
+	return int(n), statusErr(st, r.h)
+}
+
+// ProcessFloat32: constant.go:128-147.
+func (r *Resampler) ProcessFloat32(input []float32) ([]float32, error) {
+	out := make([]float32, r.EstimateOutput(len(input)))
+	n, err := r.ProcessFloat32Into(input, out)
+	if err != nil {
+		return nil, err
+	}
+	return out[:n:n], nil
+}
+
+// ProcessMulti: constant.go:204-252 — all channels in one device pass (EnableParallel has no meaning here).
+func (r *Resampler) ProcessMulti(input [][]float64) ([][]float64, error) {
+	if len(input) != r.channels {
+		return nil, fmt.Errorf("expected %d channels, got %d", r.channels, len(input))
+	}
+	c := r.channels
+	// pointer arrays live in C memory so no Go pointer to Go pointers crosses the boundary
+	ins := (*[1 << 20]*C.double)(C.malloc(C.size_t(c) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	outs := (*[1 << 20]*C.double)(C.malloc(C.size_t(c) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	defer C.free(unsafe.Pointer(ins))
+	defer C.free(unsafe.Pointer(outs))
+	nin := make([]C.int64_t, c)
+	nout := make([]C.int64_t, c)
+	capN := 1
+	for ch := range input {
+		nin[ch] = C.int64_t(len(input[ch]))
+		capN = max(capN, int(C.gar_next_output_count(r.h, C.int32_t(ch), nin[ch])))
+	}
+	output := make([][]float64, c)
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	for ch := range input {
+		output[ch] = make([]float64, capN)
+		pin.Pin(&output[ch][0])
+		outs[ch] = (*C.double)(unsafe.Pointer(&output[ch][0]))
+		if len(input[ch]) > 0 {
+			pin.Pin(&input[ch][0])
+			ins[ch] = (*C.double)(unsafe.Pointer(&input[ch][0]))
+		}
+	}
+	st := C.gar_process_multi_f64(r.h, (**C.double)(unsafe.Pointer(ins)), &nin[0],
+		(**C.double)(unsafe.Pointer(outs)), C.int64_t(capN), &nout[0])
+	if err := statusErr(st, r.h); err != nil {
+		return nil, err
+	}
+	for ch := range output {
+		output[ch] = output[ch][:nout[ch]:nout[ch]]
+	}
+	return output, nil
+}
+
+// Flush drains channel 0 only (constant.go:349-354); FlushMulti drains every channel (:390-404).
+func (r *Resampler) Flush() ([]float64, error) {
+	n := int(C.gar_next_flush_count(r.h, 0))
+	out := make([]float64, max(n, 1))
+	var got C.int64_t
+	st := C.gar_flush_f64(r.h, 0, (*C.double)(unsafe.Pointer(&out[0])), C.int64_t(len(out)), &got)
+	return out[:got:got], statusErr(st, r.h)
+}
+
+func (r *Resampler) FlushMulti() ([][]float64, error) {
+	out := make([][]float64, r.channels)
+	for ch := range out {
+		// per-channel calls keep the shim simple; gar_flush_multi_f64 does all channels in one pass
+		n := int(C.gar_next_flush_count(r.h, C.int32_t(ch)))
+		buf := make([]float64, max(n, 1))
+		var got C.int64_t
+		st := C.gar_flush_f64(r.h, C.int32_t(ch), (*C.double)(unsafe.Pointer(&buf[0])), C.int64_t(len(buf)), &got)
+		if err := statusErr(st, r.h); err != nil {
+			return nil, err
+		}
+		out[ch] = buf[:got:got]
+	}
+	return out, nil
+}
+
+// SimpleResampler / SimpleResamplerFloat32: convenience.go:118-186, 315-395.
+type SimpleResampler struct{ *handle }
+type SimpleResamplerFloat32 struct{ *handle }
+
+func newEngine(in, out float64, q QualityPreset, dtype C.int32_t) (*handle, error) {
+	cfg := C.gar_config{input_rate: C.double(in), output_rate: C.double(out), channels: 1,
+		path: C.GAR_PATH_ENGINE, preset: C.int32_t(q), dtype: dtype, engine_quality: -1}
+	return newHandle(&cfg)
+}
+
+func NewEngine(in, out float64, q QualityPreset) (*SimpleResampler, error) {
+	h, err := newEngine(in, out, q, C.GAR_F64)
+	if err != nil {
+		return nil, err
+	}
+	return &SimpleResampler{h}, nil
+}
+
+func NewEngineFloat32(in, out float64, q QualityPreset) (*SimpleResamplerFloat32, error) {
+	h, err := newEngine(in, out, q, C.GAR_F32)
+	if err != nil {
+		return nil, err
+	}
+	return &SimpleResamplerFloat32{h}, nil
+}
+
+func (r *SimpleResampler) ProcessInto(input, output []float64) (int, error) {
+	return (&Resampler{handle: r.handle, channels: 1}).ProcessInto(input, output)
+}
+
+func (r *SimpleResampler) Process(input []float64) ([]float64, error) {
+	return (&Resampler{handle: r.handle, channels: 1}).Process(input)
+}
+
+func (r *SimpleResampler) Flush() ([]float64, error) {
+	return (&Resampler{handle: r.handle, channels: 1}).Flush()
+}
+
+func (r *SimpleResamplerFloat32) ProcessInto(input, output []float32) (int, error) {
+	return (&Resampler{handle: r.handle, channels: 1}).ProcessFloat32Into(input, output)
+}
+
+func (r *SimpleResamplerFloat32) Process(input []float32) ([]float32, error) {
+	return (&Resampler{handle: r.handle, channels: 1}).ProcessFloat32(input)
+}
+
+func (r *SimpleResamplerFloat32) Flush() ([]float32, error) {
+	n := int(C.gar_next_flush_count(r.h, 0))
+	out := make([]float32, max(n, 1))
+	var got C.int64_t
+	st := C.gar_flush_f32(r.h, 0, (*C.float)(unsafe.Pointer(&out[0])), C.int64_t(len(out)), &got)
+	return out[:got:got], statusErr(st, r.h)
+}
+
+// GetStatistics: resampler.go:348-353.
+func (r *handle) GetStatistics() map[string]int64 {
+	var in, out C.int64_t
+	C.gar_get_stats(r.h, 0, 0, &in, &out)
+	return map[string]int64{"samplesIn": int64(in), "samplesOut": int64(out)}
+}
+
+// ResampleMono: convenience.go:204-229.
+func ResampleMono(input []float64, inRate, outRate float64, q QualityPreset) ([]float64, error) {
+	r, err := NewEngine(inRate, outRate, q)
+	if err != nil {
+		return nil, err
+	}
+	out, err := r.Process(input)
+	if err != nil {
+		return nil, err
+	}
+	fl, err := r.Flush()
+	if err != nil {
+		return nil, err
+	}
+	return append(out, fl...), nil
+}
+
+// ResampleMonoFloat32: convenience.go:407-429.
+func ResampleMonoFloat32(input []float32, inRate, outRate float64, q QualityPreset) ([]float32, error) {
+	r, err := NewEngineFloat32(inRate, outRate, q)
+	if err != nil {
+		return nil, err
+	}
+	out, err := r.Process(input)
+	if err != nil {
+		return nil, err
+	}
+	fl, err := r.Flush()
+	if err != nil {
+		return nil, err
+	}
+	return append(out, fl...), nil
+}
+
+// Batch is the extension used for BASELINE config 4: n independent mono float32 streams in lock step.
+type Batch struct {
+	*handle
+	Streams int
+}
+
+func NewBatchFloat32(in, out float64, q QualityPreset, streams, device int) (*Batch, error) {
+	cfg := C.gar_config{input_rate: C.double(in), output_rate: C.double(out), channels: 1,
+		path: C.GAR_PATH_ENGINE, preset: C.int32_t(q), dtype: C.GAR_F32, engine_quality: -1,
+		n_streams: C.int32_t(streams), device: C.int32_t(device)}
+	h, err := newHandle(&cfg)
+	if err != nil {
+		return nil, err
+	}
+	return &Batch{h, streams}, nil
+}
+
+// Process resamples planar [Streams][nIn] float32 (row stride nIn) into planar [Streams][outStride].
+func (b *Batch) Process(in []float32, nIn int, out []float32, outStride int) (int, error) {
+	var n C.int64_t
+	st := C.gar_process_batch(b.h, C.GAR_F32, unsafe.Pointer(&in[0]), C.int64_t(nIn), C.int64_t(nIn),
+		unsafe.Pointer(&out[0]), C.int64_t(outStride), C.int64_t(outStride), &n)
+	runtime.KeepAlive(in)
+	runtime.KeepAlive(out)
+	return int(n), statusErr(st, b.h)
+}

@@ -511,9 +511,11 @@ def kernel_launches(reset=False):
     return int(lib().gar_kernel_launches(None, 1 if reset else 0))
 
 
-def measure_fma_peak(dtype=np.float32, device=0):
+def measure_fma_peak(dtype=np.float32, device=0, packed=False):
+    """Dependent-FMA probe (TFLOP/s). packed=True uses fma.rn.f32x2 (FFMA2)."""
     v = C.c_double(0)
-    st = lib().gar_measure_fma_peak(device, F32 if np.dtype(dtype) == np.float32 else F64, C.byref(v))
+    code = 2 if packed else (F32 if np.dtype(dtype) == np.float32 else F64)
+    st = lib().gar_measure_fma_peak(device, code, C.byref(v))
     if st != OK:
         _raise(st, None)
     return v.value
