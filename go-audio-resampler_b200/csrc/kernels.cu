@@ -253,6 +253,196 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
     }
 }
 
+
+// =============================================================================================
+// float32 decimator with packed FMAs (PTX fma.rn.f32x2 -> SASS FFMA2, new on sm_100).
+// Same tiling as fir_tiled_kernel, but adjacent taps are paired: (x[k],x[k+1]) * (c[k],c[k+1]) is ONE
+// instruction on even/odd register pairs. Pairs always span both register banks, so the bank conflicts that
+// cap the scalar-FFMA version at ~78 % issue utilisation cannot occur, and the FMA work needs half the issue
+// slots. A position whose window offset M*r is odd reads its samples from the even address below and uses a
+// copy of the filter shifted by one tap (c'[k] = c[k-1]); lane .x sums even taps, lane .y odd taps.
+// =============================================================================================
+template <int M, int NF, int R, int NT>
+__global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const int n_tiles, const int cp, const int xlen) {
+    typedef unsigned long long u64;
+    constexpr int MAXE = M * (R - 1) - ((M * (R - 1)) & 1);
+    constexpr int NCH = (MAXE + 4 + 3) / 4;
+    constexpr int NS = ((M & 1) && R > 1) ? 2 : 1;  // filter copies: shift 0 (even offsets), shift 1 (odd offsets)
+    constexpr int TJ = NT * R;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    float* cs = reinterpret_cast<float*>(smem_raw + 16);  // [NF][NS][cp]
+    float* xs = cs + NF * NS * cp;                        // [xlen]
+
+    const int tile = blockIdx.x % (n_tiles + 1);
+    const int64_t row = blockIdx.x / (n_tiles + 1);
+    const int tid = threadIdx.x;
+    const float* __restrict__ hist = static_cast<const float*>(c.hist) + row * c.hist_stride;
+    const float* __restrict__ in = static_cast<const float*>(c.in) + row * c.in_stride;
+    if (tile == n_tiles) {
+        carry_row(hist, c.hist_len, in, c.n_in, static_cast<float*>(c.hist_out) + row * c.hist_out_stride, c.drop,
+                  c.new_hist_len);
+        return;
+    }
+    const int j0 = tile * TJ;
+    const int tj = min(TJ, c.n_pos - j0);
+    const int g0 = c.first + j0 * M;
+    const int need = (tj - 1) * M + c.taps;
+
+    int a = 0;
+    bool bulk = false;
+    {
+        const int gi = g0 - c.hist_len;
+        if (gi >= 0) {
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(in + gi);
+            const int mis = (int)((addr & 15u) / sizeof(float));
+            const int words = ((need + mis + 3) / 4) * 4;
+            if (gi - mis >= 0 && gi - mis + words <= c.n_in && words <= xlen) {
+                bulk = true;
+                a = mis;
+            }
+        }
+    }
+    if (bulk) {
+        const int gi = g0 - c.hist_len - a;
+        const int words = ((need + a + 3) / 4) * 4;
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)(words * sizeof(float)));
+            bulk_g2s(xs, in + gi, (uint32_t)(words * sizeof(float)), bar);
+        }
+        for (int i = words + tid; i < xlen; i += NT) xs[i] = 0.f;
+    } else {
+        for (int i = tid; i < xlen; i += NT) xs[i] = i < need ? vload(hist, c.hist_len, in, c.n_in, g0 + i) : 0.f;
+    }
+    {
+        const float* __restrict__ bank = static_cast<const float*>(c.bank);
+#pragma unroll
+        for (int p = 0; p < NF; ++p)
+#pragma unroll
+            for (int sh = 0; sh < NS; ++sh)
+                for (int kk = tid; kk < cp; kk += NT) {
+                    const int k = kk - a - sh;
+                    cs[(p * NS + sh) * cp + kk] = (k >= 0 && k < c.taps) ? bank[p * c.taps + k] : 0.f;
+                }
+    }
+    __syncthreads();
+    if (bulk) {
+        while (!mbar_try_wait(bar, 0)) {
+        }
+    }
+
+    const int n_iter = (c.taps + a + (NS - 1) + 3) / 4;
+    const float* xt = xs + M * R * tid;
+    u64 xw[NCH * 2];
+    u64 acc[R][NF];
+    double tot[R][NF];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < NF; ++p) {
+            acc[r][p] = 0ull;
+            tot[r][p] = 0.0;
+        }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xt + ch * 4);
+        xw[ch * 2] = v.x;
+        xw[ch * 2 + 1] = v.y;
+    }
+    auto step = [&](const int u, const int it) {
+        u64 cv[NF][NS][2];
+#pragma unroll
+        for (int p = 0; p < NF; ++p)
+#pragma unroll
+            for (int sh = 0; sh < NS; ++sh) {
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(cs + (p * NS + sh) * cp + it * 4);
+                cv[p][sh][0] = v.x;
+                cv[p][sh][1] = v.y;
+            }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int sh = (M * r) & 1;
+                const int eh = (M * r - sh) / 2;
+                const u64 xv = xw[(u * 2 + q + eh) % (NCH * 2)];
+#pragma unroll
+                for (int p = 0; p < NF; ++p) {
+                    u64 d;
+                    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(xv), "l"(cv[p][NS == 2 ? sh : 0][q]), "l"(acc[r][p]));
+                    acc[r][p] = d;
+                }
+            }
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xt + (it + NCH) * 4);
+        xw[(u % NCH) * 2] = v.x;
+        xw[(u % NCH) * 2 + 1] = v.y;
+    };
+    auto fold = [&]() {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int p = 0; p < NF; ++p) {
+                const float lo = __uint_as_float((unsigned)(acc[r][p] & 0xffffffffull));
+                const float hi = __uint_as_float((unsigned)(acc[r][p] >> 32));
+                tot[r][p] += (double)lo + (double)hi;
+                acc[r][p] = 0ull;
+            }
+    };
+    // centre-of-main-lobe folds + sparse periodic folds: see fir_tiled_kernel
+    const int itf0 = ((c.taps - 1) / 2 + a) / 4, itf1 = itf0 + 2;
+    constexpr int FOLD_BODIES = 8;
+    int it0 = 0, since_fold = 0;
+    for (; it0 + NCH <= n_iter; it0 += NCH) {
+        if (it0 <= itf1 && it0 + NCH > itf0) {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) {
+                step(u, it0 + u);
+                if (it0 + u >= itf0 && it0 + u <= itf1) fold();
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) step(u, it0 + u);
+        }
+        if (++since_fold == FOLD_BODIES) {
+            fold();
+            since_fold = 0;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NCH; ++u)
+        if (it0 + u < n_iter) {
+            step(u, it0 + u);
+            if (it0 + u >= itf0 && it0 + u <= itf1) fold();
+        }
+    fold();
+    float res[R][NF];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < NF; ++p) res[r][p] = (float)tot[r][p];
+
+    float* __restrict__ out = static_cast<float*>(c.out) + row * c.out_stride;
+    const int jb = j0 + R * tid;
+    float* op = out + (int64_t)jb * NF;
+    if (jb + R <= c.n_pos && (R * NF) % 4 == 0 && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {
+        const float* flat = &res[0][0];
+#pragma unroll
+        for (int q = 0; q < R * NF / 4; ++q) reinterpret_cast<float4*>(op)[q] = vec_pack(flat + q * 4);
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (jb + r < c.n_pos) {
+#pragma unroll
+                for (int p = 0; p < NF; ++p) op[r * NF + p] = res[r][p];
+            }
+    }
+}
+
 // Fallback: one thread per output element, operands straight from global/L1.
 template <typename T>
 __global__ void __launch_bounds__(256) fir_generic_kernel(const FirCall c, const int n_tiles) {
@@ -455,7 +645,37 @@ void launch_fir_tiled(const FirCall& c, cudaStream_t s) {
     count_launch();
 }
 
+template <int M, int NF, int R>
+void launch_fir_f32x2(const FirCall& c, cudaStream_t s) {
+    constexpr int NT = 128;
+    constexpr int MAXE = M * (R - 1) - ((M * (R - 1)) & 1);
+    constexpr int NCH = (MAXE + 4 + 3) / 4;
+    constexpr int NS = ((M & 1) && R > 1) ? 2 : 1;
+    constexpr int TJ = NT * R;
+    const int cp = ((c.taps + 3 + (NS - 1) + 3) / 4) * 4;
+    const int xlen = M * R * (NT - 1) + (cp / 4 + NCH + 1) * 4;
+    const size_t smem = 16 + (size_t)(NF * NS * cp + xlen) * sizeof(float);
+    const int n_tiles = (c.n_pos + TJ - 1) / TJ;
+    auto k = fir_f32x2_kernel<M, NF, R, NT>;
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
+    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, cp, xlen);
+    count_launch();
+}
+
 }  // namespace
+
+// float32 decimators on packed FMAs
+#define GAR_FIR_X2_VARIANTS(X)          \
+    X(3, 1, 12, "fir_f32x2_s3_r12")     \
+    X(2, 1, 10, "fir_f32x2_s2_r10")     \
+    X(4, 1, 7, "fir_f32x2_s4_r7")
 
 #define GAR_FIR_VARIANTS(X)                 \
     X(float, DT_F32, 3, 1, 12, "fir_f32_s3_r12")  \
@@ -473,6 +693,10 @@ void launch_fir_tiled(const FirCall& c, cudaStream_t s) {
 
 const char* fir_variant_name(int dtype, int stride, int nf, int taps, int64_t n_pos, int n_streams) {
     (void)taps; (void)n_pos; (void)n_streams;
+#define X(M, NF, R, NAME) \
+    if (dtype == DT_F32 && stride == M && nf == NF) return NAME;
+    GAR_FIR_X2_VARIANTS(X)
+#undef X
 #define X(T, DT, M, NF, R, NAME) \
     if (dtype == DT && stride == M && nf == NF) return NAME;
     GAR_FIR_VARIANTS(X)
@@ -487,6 +711,13 @@ const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s) {
                      c.new_hist_len, c.n_streams, dtype, s);
         return "carry";
     }
+#define X(M, NF, R, NAME)                                       \
+    if (dtype == DT_F32 && c.stride == M && c.nf == NF) {       \
+        launch_fir_f32x2<M, NF, R>(c, s);                       \
+        return NAME;                                            \
+    }
+    GAR_FIR_X2_VARIANTS(X)
+#undef X
 #define X(T, DT, M, NF, R, NAME)                           \
     if (dtype == DT && c.stride == M && c.nf == NF) {      \
         launch_fir_tiled<T, M, NF, R>(c, s);               \
