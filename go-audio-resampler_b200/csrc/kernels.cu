@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
 // copy of the filter shifted by one tap (c'[k] = c[k-1]); lane .x sums even taps, lane .y odd taps.
 // =============================================================================================
 template <int M, int NF, int R, int NT>
-__global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const int n_tiles, const int cp, const int xlen) {
+__global__ void __launch_bounds__(NT, 5) fir_f32x2_kernel(const FirCall c, const int n_tiles, const int cp, const int xlen) {
     typedef unsigned long long u64;
     constexpr int MAXE = M * (R - 1) - ((M * (R - 1)) & 1);
     constexpr int NCH = (MAXE + 4 + 3) / 4;
@@ -272,8 +272,11 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    float* cs = reinterpret_cast<float*>(smem_raw + 16);  // [NF][NS][cp]
-    float* xs = cs + NF * NS * cp;                        // [xlen]
+    // float64 totals live in shared memory ([R*NF][NT], conflict-free): they are touched ~7 times per tile,
+    // and keeping them out of the register file lifts occupancy from 4 to 5 blocks per SM
+    double* tots = reinterpret_cast<double*>(smem_raw + 16) + threadIdx.x;
+    float* cs = reinterpret_cast<float*>(smem_raw + 16 + sizeof(double) * R * NF * NT);  // [NF][NS][cp]
+    float* xs = cs + NF * NS * cp;                                                        // [xlen]
 
     const int tile = blockIdx.x % (n_tiles + 1);
     const int64_t row = blockIdx.x / (n_tiles + 1);
@@ -338,14 +341,11 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
     const float* xt = xs + M * R * tid;
     u64 xw[NCH * 2];
     u64 acc[R][NF];
-    double tot[R][NF];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int p = 0; p < NF; ++p) {
-            acc[r][p] = 0ull;
-            tot[r][p] = 0.0;
-        }
+        for (int p = 0; p < NF; ++p) acc[r][p] = 0ull;
+    bool first_fold = true;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
         const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xt + ch * 4);
@@ -389,9 +389,12 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
             for (int p = 0; p < NF; ++p) {
                 const float lo = __uint_as_float((unsigned)(acc[r][p] & 0xffffffffull));
                 const float hi = __uint_as_float((unsigned)(acc[r][p] >> 32));
-                tot[r][p] += (double)lo + (double)hi;
+                const double s = (double)lo + (double)hi;
+                double* t = tots + (r * NF + p) * NT;
+                *t = first_fold ? s : *t + s;
                 acc[r][p] = 0ull;
             }
+        first_fold = false;
     };
     // centre-of-main-lobe folds + sparse periodic folds: see fir_tiled_kernel
     const int itf0 = ((c.taps - 1) / 2 + a) / 4, itf1 = itf0 + 2;
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int p = 0; p < NF; ++p) res[r][p] = (float)tot[r][p];
+        for (int p = 0; p < NF; ++p) res[r][p] = (float)tots[(r * NF + p) * NT];
 
     float* __restrict__ out = static_cast<float*>(c.out) + row * c.out_stride;
     const int jb = j0 + R * tid;
@@ -654,7 +657,7 @@ void launch_fir_f32x2(const FirCall& c, cudaStream_t s) {
     constexpr int TJ = NT * R;
     const int cp = ((c.taps + 3 + (NS - 1) + 3) / 4) * 4;
     const int xlen = M * R * (NT - 1) + (cp / 4 + NCH + 1) * 4;
-    const size_t smem = 16 + (size_t)(NF * NS * cp + xlen) * sizeof(float);
+    const size_t smem = 16 + sizeof(double) * R * NF * NT + (size_t)(NF * NS * cp + xlen) * sizeof(float);
     const int n_tiles = (c.n_pos + TJ - 1) / TJ;
     auto k = fir_f32x2_kernel<M, NF, R, NT>;
     static size_t configured[64] = {0};
