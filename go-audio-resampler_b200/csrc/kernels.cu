@@ -263,63 +263,65 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
 // copy of the filter shifted by one tap (c'[k] = c[k-1]); lane .x sums even taps, lane .y odd taps.
 // =============================================================================================
 template <int M, int NF, int R, int NT>
-__global__ void __launch_bounds__(NT, 5) fir_f32x2_kernel(const FirCall c, const int n_tiles, const int cp, const int xlen) {
+__global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const int n_tiles, const int tiles_per_block,
+                                                       const int n_groups, const int cp, const int xlen) {
     typedef unsigned long long u64;
     constexpr int MAXE = M * (R - 1) - ((M * (R - 1)) & 1);
     constexpr int NCH = (MAXE + 4 + 3) / 4;
     constexpr int NS = ((M & 1) && R > 1) ? 2 : 1;  // filter copies: shift 0 (even offsets), shift 1 (odd offsets)
     constexpr int TJ = NT * R;
+    static_assert((TJ * M) % 4 == 0, "tile stride must keep the 16-byte alignment of the window");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    // float64 totals live in shared memory ([R*NF][NT], conflict-free): they are touched ~7 times per tile,
-    // and keeping them out of the register file lifts occupancy from 4 to 5 blocks per SM
-    double* tots = reinterpret_cast<double*>(smem_raw + 16) + threadIdx.x;
-    float* cs = reinterpret_cast<float*>(smem_raw + 16 + sizeof(double) * R * NF * NT);  // [NF][NS][cp]
-    float* xs = cs + NF * NS * cp;                                                        // [xlen]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // two mbarriers, one per window buffer
+    float* cs = reinterpret_cast<float*>(smem_raw + 16);    // [NF][NS][cp]
+    float* xs0 = cs + NF * NS * cp;                         // [2][xlen] double-buffered sample window
 
-    const int tile = blockIdx.x % (n_tiles + 1);
-    const int64_t row = blockIdx.x / (n_tiles + 1);
+    // grid.x = rows * (n_groups + 1): a block owns `tiles_per_block` consecutive tiles of one row; the extra
+    // block of every row writes the carried tail.
+    const int group = blockIdx.x % (n_groups + 1);
+    const int64_t row = blockIdx.x / (n_groups + 1);
     const int tid = threadIdx.x;
     const float* __restrict__ hist = static_cast<const float*>(c.hist) + row * c.hist_stride;
     const float* __restrict__ in = static_cast<const float*>(c.in) + row * c.in_stride;
-    if (tile == n_tiles) {
+    if (group == n_groups) {
         carry_row(hist, c.hist_len, in, c.n_in, static_cast<float*>(c.hist_out) + row * c.hist_out_stride, c.drop,
                   c.new_hist_len);
         return;
     }
-    const int j0 = tile * TJ;
-    const int tj = min(TJ, c.n_pos - j0);
-    const int g0 = c.first + j0 * M;
-    const int need = (tj - 1) * M + c.taps;
+    const int t_first = group * tiles_per_block;
+    const int nt = min(tiles_per_block, n_tiles - t_first);
 
-    int a = 0;
-    bool bulk = false;
-    {
-        const int gi = g0 - c.hist_len;
-        if (gi >= 0) {
-            const uintptr_t addr = reinterpret_cast<uintptr_t>(in + gi);
-            const int mis = (int)((addr & 15u) / sizeof(float));
-            const int words = ((need + mis + 3) / 4) * 4;
-            if (gi - mis >= 0 && gi - mis + words <= c.n_in && words <= xlen) {
-                bulk = true;
-                a = mis;
-            }
+    // Leading pad `a` (same for every tile of the row because the tile stride is a multiple of 16 bytes): the
+    // window of a tile starts `a` samples early so that its global address is 16-byte aligned for the TMA
+    // bulk copy; the filter is shifted by `a` zero taps to compensate.
+    const int a = (int)(((reinterpret_cast<uintptr_t>(in) >> 2) + (uintptr_t)(int64_t)(c.first - c.hist_len)) & 3u);
+    const int need_full = (TJ - 1) * M + c.taps;
+    auto tile_geom = [&](const int t, int& g0a, int& words, bool& bulk) {
+        const int j0 = t * TJ;
+        const int tj = min(TJ, c.n_pos - j0);
+        g0a = c.first + j0 * M - a;                       // virtual index of xs[0]
+        words = (((tj - 1) * M + c.taps + a + 3) / 4) * 4;  // samples the tile reads, rounded to 16 bytes
+        const int gi = g0a - c.hist_len;                  // index into `in`
+        bulk = gi >= 0 && gi + words <= c.n_in && words <= xlen;
+    };
+    auto issue_bulk = [&](const int t, const int buf) {  // one thread
+        int g0a, words;
+        bool bulk;
+        tile_geom(t, g0a, words, bulk);
+        if (bulk) {
+            mbar_expect_tx(bar + buf, (uint32_t)(words * sizeof(float)));
+            bulk_g2s(xs0 + buf * xlen, in + (g0a - c.hist_len), (uint32_t)(words * sizeof(float)), bar + buf);
         }
+    };
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
     }
-    if (bulk) {
-        const int gi = g0 - c.hist_len - a;
-        const int words = ((need + a + 3) / 4) * 4;
-        if (tid == 0) mbar_init(bar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            mbar_expect_tx(bar, (uint32_t)(words * sizeof(float)));
-            bulk_g2s(xs, in + gi, (uint32_t)(words * sizeof(float)), bar);
-        }
-        for (int i = words + tid; i < xlen; i += NT) xs[i] = 0.f;
-    } else {
-        for (int i = tid; i < xlen; i += NT) xs[i] = i < need ? vload(hist, c.hist_len, in, c.n_in, g0 + i) : 0.f;
-    }
+    // both window buffers start as zeros: whatever a later, shorter tile leaves behind is finite
+    for (int i = tid; i < 2 * xlen; i += NT) xs0[i] = 0.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before async-proxy (TMA) writes
     {
         const float* __restrict__ bank = static_cast<const float*>(c.bank);
 #pragma unroll
@@ -332,117 +334,141 @@ __global__ void __launch_bounds__(NT, 5) fir_f32x2_kernel(const FirCall c, const
                 }
     }
     __syncthreads();
-    if (bulk) {
-        while (!mbar_try_wait(bar, 0)) {
-        }
-    }
+    if (tid == 0) issue_bulk(t_first, 0);
+    uint32_t phase0 = 0u, phase1 = 0u;
 
     const int n_iter = (c.taps + a + (NS - 1) + 3) / 4;
-    const float* xt = xs + M * R * tid;
-    u64 xw[NCH * 2];
-    u64 acc[R][NF];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int p = 0; p < NF; ++p) acc[r][p] = 0ull;
-    bool first_fold = true;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xt + ch * 4);
-        xw[ch * 2] = v.x;
-        xw[ch * 2 + 1] = v.y;
-    }
-    auto step = [&](const int u, const int it) {
-        u64 cv[NF][NS][2];
-#pragma unroll
-        for (int p = 0; p < NF; ++p)
-#pragma unroll
-            for (int sh = 0; sh < NS; ++sh) {
-                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(cs + (p * NS + sh) * cp + it * 4);
-                cv[p][sh][0] = v.x;
-                cv[p][sh][1] = v.y;
+    const int itf0 = ((c.taps - 1) / 2 + a) / 4, itf1 = itf0 + 2;  // centre-of-main-lobe folds (see fir_tiled_kernel)
+    constexpr int FOLD_BODIES = 8;
+    float* __restrict__ out = static_cast<float*>(c.out) + row * c.out_stride;
+
+    for (int k = 0; k < nt; ++k) {
+        const int t = t_first + k;
+        const int buf = k & 1;
+        float* xs = xs0 + buf * xlen;
+        int g0a, words;
+        bool bulk;
+        tile_geom(t, g0a, words, bulk);
+        // prefetch the next tile into the other buffer (free since the __syncthreads that ended tile k-1)
+        if (tid == 0 && k + 1 < nt) issue_bulk(t + 1, buf ^ 1);
+        if (bulk) {
+            const uint32_t ph = buf ? phase1 : phase0;
+            while (!mbar_try_wait(bar + buf, ph)) {
             }
-#pragma unroll
-        for (int q = 0; q < 2; ++q)
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                constexpr int dummy = 0;
-                (void)dummy;
-                const int sh = (M * r) & 1;
-                const int eh = (M * r - sh) / 2;
-                const u64 xv = xw[(u * 2 + q + eh) % (NCH * 2)];
-#pragma unroll
-                for (int p = 0; p < NF; ++p) {
-                    u64 d;
-                    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(xv), "l"(cv[p][NS == 2 ? sh : 0][q]), "l"(acc[r][p]));
-                    acc[r][p] = d;
-                }
-            }
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xt + (it + NCH) * 4);
-        xw[(u % NCH) * 2] = v.x;
-        xw[(u % NCH) * 2 + 1] = v.y;
-    };
-    auto fold = [&]() {
+            if (buf) phase1 ^= 1u;
+            else phase0 ^= 1u;
+        } else {  // edge tile (touches the carried tail or the end of the row): guarded loads
+            for (int i = tid; i < xlen; i += NT)
+                xs[i] = i < words ? vload(hist, c.hist_len, in, c.n_in, g0a + i) : 0.f;
+            __syncthreads();
+        }
+
+        // ---- register-tiled sliding window on packed FMAs ----
+        const float* xt = xs + M * R * tid;
+        u64 xw[NCH * 2];
+        u64 acc[R][NF];
+        double tot[R][NF];
 #pragma unroll
         for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int p = 0; p < NF; ++p) {
-                const float lo = __uint_as_float((unsigned)(acc[r][p] & 0xffffffffull));
-                const float hi = __uint_as_float((unsigned)(acc[r][p] >> 32));
-                const double s = (double)lo + (double)hi;
-                double* t = tots + (r * NF + p) * NT;
-                *t = first_fold ? s : *t + s;
                 acc[r][p] = 0ull;
+                tot[r][p] = 0.0;
             }
-        first_fold = false;
-    };
-    // centre-of-main-lobe folds + sparse periodic folds: see fir_tiled_kernel
-    const int itf0 = ((c.taps - 1) / 2 + a) / 4, itf1 = itf0 + 2;
-    constexpr int FOLD_BODIES = 8;
-    int it0 = 0, since_fold = 0;
-    for (; it0 + NCH <= n_iter; it0 += NCH) {
-        if (it0 <= itf1 && it0 + NCH > itf0) {
 #pragma unroll
-            for (int u = 0; u < NCH; ++u) {
+        for (int ch = 0; ch < NCH; ++ch) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xt + ch * 4);
+            xw[ch * 2] = v.x;
+            xw[ch * 2 + 1] = v.y;
+        }
+        auto step = [&](const int u, const int it) {
+            u64 cv[NF][NS][2];
+#pragma unroll
+            for (int p = 0; p < NF; ++p)
+#pragma unroll
+                for (int sh = 0; sh < NS; ++sh) {
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(cs + (p * NS + sh) * cp + it * 4);
+                    cv[p][sh][0] = v.x;
+                    cv[p][sh][1] = v.y;
+                }
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int sh = (M * r) & 1;
+                    const int eh = (M * r - sh) / 2;
+                    const u64 xv = xw[(u * 2 + q + eh) % (NCH * 2)];
+#pragma unroll
+                    for (int p = 0; p < NF; ++p) {
+                        u64 d;
+                        asm("fma.rn.f32x2 %0, %1, %2, %3;"
+                            : "=l"(d)
+                            : "l"(xv), "l"(cv[p][NS == 2 ? sh : 0][q]), "l"(acc[r][p]));
+                        acc[r][p] = d;
+                    }
+                }
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xt + (it + NCH) * 4);
+            xw[(u % NCH) * 2] = v.x;
+            xw[(u % NCH) * 2 + 1] = v.y;
+        };
+        auto fold = [&]() {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int p = 0; p < NF; ++p) {
+                    const float lo = __uint_as_float((unsigned)(acc[r][p] & 0xffffffffull));
+                    const float hi = __uint_as_float((unsigned)(acc[r][p] >> 32));
+                    tot[r][p] += (double)lo + (double)hi;
+                    acc[r][p] = 0ull;
+                }
+        };
+        int it0 = 0, since_fold = 0;
+        for (; it0 + NCH <= n_iter; it0 += NCH) {
+            if (it0 <= itf1 && it0 + NCH > itf0) {
+#pragma unroll
+                for (int u = 0; u < NCH; ++u) {
+                    step(u, it0 + u);
+                    if (it0 + u >= itf0 && it0 + u <= itf1) fold();
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < NCH; ++u) step(u, it0 + u);
+            }
+            if (++since_fold == FOLD_BODIES) {
+                fold();
+                since_fold = 0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NCH; ++u)
+            if (it0 + u < n_iter) {
                 step(u, it0 + u);
                 if (it0 + u >= itf0 && it0 + u <= itf1) fold();
             }
+        fold();
+
+        // ---- vectorised store ----
+        const int jb = t * TJ + R * tid;
+        float* op = out + (int64_t)jb * NF;
+        if (jb + R <= c.n_pos && (R * NF) % 4 == 0 && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {
+#pragma unroll
+            for (int q = 0; q < R * NF / 4; ++q) {
+                float4 v;
+                v.x = (float)tot[(q * 4 + 0) / NF][(q * 4 + 0) % NF];
+                v.y = (float)tot[(q * 4 + 1) / NF][(q * 4 + 1) % NF];
+                v.z = (float)tot[(q * 4 + 2) / NF][(q * 4 + 2) % NF];
+                v.w = (float)tot[(q * 4 + 3) / NF][(q * 4 + 3) % NF];
+                reinterpret_cast<float4*>(op)[q] = v;
+            }
         } else {
 #pragma unroll
-            for (int u = 0; u < NCH; ++u) step(u, it0 + u);
+            for (int r = 0; r < R; ++r)
+                if (jb + r < c.n_pos) {
+#pragma unroll
+                    for (int p = 0; p < NF; ++p) op[r * NF + p] = (float)tot[r][p];
+                }
         }
-        if (++since_fold == FOLD_BODIES) {
-            fold();
-            since_fold = 0;
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < NCH; ++u)
-        if (it0 + u < n_iter) {
-            step(u, it0 + u);
-            if (it0 + u >= itf0 && it0 + u <= itf1) fold();
-        }
-    fold();
-    float res[R][NF];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int p = 0; p < NF; ++p) res[r][p] = (float)tots[(r * NF + p) * NT];
-
-    float* __restrict__ out = static_cast<float*>(c.out) + row * c.out_stride;
-    const int jb = j0 + R * tid;
-    float* op = out + (int64_t)jb * NF;
-    if (jb + R <= c.n_pos && (R * NF) % 4 == 0 && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {
-        const float* flat = &res[0][0];
-#pragma unroll
-        for (int q = 0; q < R * NF / 4; ++q) reinterpret_cast<float4*>(op)[q] = vec_pack(flat + q * 4);
-    } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (jb + r < c.n_pos) {
-#pragma unroll
-                for (int p = 0; p < NF; ++p) op[r * NF + p] = res[r][p];
-            }
+        __syncthreads();  // every thread is done with xs[buf] before the next prefetch overwrites it
     }
 }
 
@@ -657,18 +683,28 @@ void launch_fir_f32x2(const FirCall& c, cudaStream_t s) {
     constexpr int TJ = NT * R;
     const int cp = ((c.taps + 3 + (NS - 1) + 3) / 4) * 4;
     const int xlen = M * R * (NT - 1) + (cp / 4 + NCH + 1) * 4;
-    const size_t smem = 16 + sizeof(double) * R * NF * NT + (size_t)(NF * NS * cp + xlen) * sizeof(float);
+    const size_t smem = 16 + (size_t)(NF * NS * cp + 2 * xlen) * sizeof(float);
     const int n_tiles = (c.n_pos + TJ - 1) / TJ;
+    // tiles per block: long runs amortise the per-block filter load and let the TMA prefetch hide under the
+    // FMAs, but keep >= ~8 blocks per SM-slot in flight for balance
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    static int sm_count[64] = {0};
+    if (!sm_count[dev & 63]) cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    sms = sm_count[dev & 63] > 0 ? sm_count[dev & 63] : 148;
+    const int64_t total_tiles = (int64_t)n_tiles * c.n_streams;
+    int tpb = (int)(total_tiles / ((int64_t)sms * 4 * 8));
+    tpb = tpb < 1 ? 1 : (tpb > 16 ? 16 : tpb);
+    if (tpb > n_tiles) tpb = n_tiles;
+    const int n_groups = (n_tiles + tpb - 1) / tpb;
     auto k = fir_f32x2_kernel<M, NF, R, NT>;
     static size_t configured[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
     if (smem > configured[dev & 63]) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured[dev & 63] = smem;
     }
-    const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
-    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, cp, xlen);
+    const int64_t blocks = (int64_t)(n_groups + 1) * c.n_streams;
+    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, tpb, n_groups, cp, xlen);
     count_launch();
 }
 
