@@ -296,7 +296,6 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
     // window of a tile starts `a` samples early so that its global address is 16-byte aligned for the TMA
     // bulk copy; the filter is shifted by `a` zero taps to compensate.
     const int a = (int)(((reinterpret_cast<uintptr_t>(in) >> 2) + (uintptr_t)(int64_t)(c.first - c.hist_len)) & 3u);
-    const int need_full = (TJ - 1) * M + c.taps;
     auto tile_geom = [&](const int t, int& g0a, int& words, bool& bulk) {
         const int j0 = t * TJ;
         const int tj = min(TJ, c.n_pos - j0);
@@ -339,7 +338,7 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
 
     const int n_iter = (c.taps + a + (NS - 1) + 3) / 4;
     const int itf0 = ((c.taps - 1) / 2 + a) / 4, itf1 = itf0 + 2;  // centre-of-main-lobe folds (see fir_tiled_kernel)
-    constexpr int FOLD_BODIES = 8;
+    constexpr int FOLD_BODIES = 32;  // ~1150 taps: with the centre folds and the even/odd lane split the tails stay small
     float* __restrict__ out = static_cast<float*>(c.out) + row * c.out_stride;
 
     for (int k = 0; k < nt; ++k) {

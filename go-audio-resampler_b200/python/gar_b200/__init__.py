@@ -269,6 +269,62 @@ class _Handle:
                 "Latency": info.latency, "MemoryUsage": info.memory_usage, "SIMDEnabled": bool(info.simd_enabled),
                 "SIMDType": info.simd_type.decode()}
 
+    # --- batched rows (all channels x n_streams rows advance in lock step) ---
+    def _native_dtype(self):
+        return getattr(self, "dtype", np.float64)
+
+    def _io_code(self, io_dtype):
+        dt = np.dtype(io_dtype if io_dtype is not None else self._native_dtype())
+        return F32 if dt == np.float32 else F64
+
+    def next_output_count(self, n_in):
+        return int(lib().gar_next_output_count(self._h, 0, int(n_in)))
+
+    def next_flush_count(self):
+        return int(lib().gar_next_flush_count(self._h, 0))
+
+    def ProcessBatch(self, x2d, out2d=None, io_dtype=None):
+        """x2d: host [n_streams, n_in] (row stride in elements may exceed n_in). Returns ([n_streams, n_out] view, n_out)."""
+        io_dtype = x2d.dtype
+        assert x2d.shape[0] == self.rows and x2d.strides[1] == x2d.itemsize
+        n_in = x2d.shape[1]
+        if out2d is None:
+            out2d = np.empty((self.rows, self.EstimateOutput(n_in)), dtype=io_dtype)
+        n = C.c_int64(0)
+        st = lib().gar_process_batch(self._h, self._io_code(io_dtype), _ptr(x2d), x2d.strides[0] // x2d.itemsize, n_in,
+                                     _ptr(out2d), out2d.strides[0] // out2d.itemsize, out2d.shape[1], C.byref(n))
+        if st != OK:
+            _raise(st, self._h)
+        return out2d[:, :n.value], n.value
+
+    def FlushBatch(self, out2d=None, io_dtype=None):
+        if out2d is None:
+            out2d = np.empty((self.rows, max(self.next_flush_count(), 1)), dtype=io_dtype or self._native_dtype())
+        io_dtype = out2d.dtype
+        n = C.c_int64(0)
+        st = lib().gar_flush_batch(self._h, self._io_code(io_dtype), _ptr(out2d), out2d.strides[0] // out2d.itemsize,
+                                   out2d.shape[1], C.byref(n))
+        if st != OK:
+            _raise(st, self._h)
+        return out2d[:, :n.value], n.value
+
+    # device-pointer variants (torch tensors or raw pointers); enqueue only
+    def process_batch_dev(self, d_in, in_stride, n_in, d_out, out_stride, out_cap, stream=0, io_dtype=None):
+        n = C.c_int64(0)
+        st = lib().gar_process_batch_dev(self._h, self._io_code(io_dtype), C.c_void_p(d_in), in_stride, n_in, C.c_void_p(d_out),
+                                         out_stride, out_cap, C.byref(n), C.c_void_p(stream))
+        if st != OK:
+            _raise(st, self._h)
+        return n.value
+
+    def flush_batch_dev(self, d_out, out_stride, out_cap, stream=0, io_dtype=None):
+        n = C.c_int64(0)
+        st = lib().gar_flush_batch_dev(self._h, self._io_code(io_dtype), C.c_void_p(d_out), out_stride, out_cap, C.byref(n),
+                                       C.c_void_p(stream))
+        if st != OK:
+            _raise(st, self._h)
+        return n.value
+
     def _process(self, ch, x, dtype, out=None):
         fn = lib().gar_process_f32 if dtype == np.float32 else lib().gar_process_f64
         x = np.ascontiguousarray(x, dtype=dtype)
@@ -434,53 +490,7 @@ class BatchResampler(SimpleResampler):
     def __init__(self, input_rate, output_rate, quality, n_streams, dtype=np.float32, device=0, engine_quality=-1):
         super().__init__(input_rate, output_rate, quality, dtype, engine_quality, device, n_streams)
         self.n_streams = int(n_streams)
-        self._code = F32 if self.dtype == np.float32 else F64
 
-    def next_output_count(self, n_in):
-        return int(lib().gar_next_output_count(self._h, 0, int(n_in)))
-
-    def next_flush_count(self):
-        return int(lib().gar_next_flush_count(self._h, 0))
-
-    def ProcessBatch(self, x2d, out2d=None):
-        """x2d: host [n_streams, n_in] (row stride in elements may exceed n_in). Returns ([n_streams, n_out] view, n_out)."""
-        assert x2d.dtype == self.dtype and x2d.shape[0] == self.rows and x2d.strides[1] == x2d.itemsize
-        n_in = x2d.shape[1]
-        if out2d is None:
-            out2d = np.empty((self.rows, self.EstimateOutput(n_in)), dtype=self.dtype)
-        n = C.c_int64(0)
-        st = lib().gar_process_batch(self._h, self._code, _ptr(x2d), x2d.strides[0] // x2d.itemsize, n_in,
-                                     _ptr(out2d), out2d.strides[0] // out2d.itemsize, out2d.shape[1], C.byref(n))
-        if st != OK:
-            _raise(st, self._h)
-        return out2d[:, :n.value], n.value
-
-    def FlushBatch(self, out2d=None):
-        if out2d is None:
-            out2d = np.empty((self.rows, max(self.next_flush_count(), 1)), dtype=self.dtype)
-        n = C.c_int64(0)
-        st = lib().gar_flush_batch(self._h, self._code, _ptr(out2d), out2d.strides[0] // out2d.itemsize,
-                                   out2d.shape[1], C.byref(n))
-        if st != OK:
-            _raise(st, self._h)
-        return out2d[:, :n.value], n.value
-
-    # device-pointer variants (torch tensors or raw pointers); enqueue only
-    def process_batch_dev(self, d_in, in_stride, n_in, d_out, out_stride, out_cap, stream=0):
-        n = C.c_int64(0)
-        st = lib().gar_process_batch_dev(self._h, self._code, C.c_void_p(d_in), in_stride, n_in, C.c_void_p(d_out),
-                                         out_stride, out_cap, C.byref(n), C.c_void_p(stream))
-        if st != OK:
-            _raise(st, self._h)
-        return n.value
-
-    def flush_batch_dev(self, d_out, out_stride, out_cap, stream=0):
-        n = C.c_int64(0)
-        st = lib().gar_flush_batch_dev(self._h, self._code, C.c_void_p(d_out), out_stride, out_cap, C.byref(n),
-                                       C.c_void_p(stream))
-        if st != OK:
-            _raise(st, self._h)
-        return n.value
 
 
 def NewBatch(input_rate, output_rate, quality, n_streams, dtype=np.float32, **kw):
