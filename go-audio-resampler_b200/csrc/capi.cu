@@ -275,6 +275,12 @@ int32_t gar_upload_bank(gar_handle* h, int32_t stage, int32_t which, const doubl
     return h->eng.set_bank(stage, which, coef, n, h->err);
 }
 
+int32_t gar_set_fusion(gar_handle* h, int32_t enabled) {
+    if (!h) return GAR_INVALID_CONFIG;
+    h->eng.set_fuse(enabled != 0);
+    return GAR_OK;
+}
+
 int64_t gar_kernel_launches(const gar_handle* h, int32_t reset) {
     (void)h;  // process-wide counter: every <<<>>> of this library
     return (int64_t)launch_count(reset != 0);

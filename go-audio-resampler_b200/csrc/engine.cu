@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace gar {
@@ -101,6 +102,7 @@ int Engine::init(const Chain& chain, int rows, int compute_dtype, int device, st
     ibuf_.assign(chain_.engines.size() * 2, nullptr);
     ibuf_cap_.assign(chain_.engines.size() * 2, 0);
     streams_.assign((size_t)rows, StreamState{});
+    if (const char* e = std::getenv("GAR_NO_FUSE")) fuse_ = !(e[0] && e[0] != '0');
     reset_state();
     return 0;
 }
@@ -494,10 +496,46 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
         return (char*)ibuf_[(size_t)op.dst_buf] + ((size_t)row0 * (size_t)stride + (size_t)op.dst_off) * esz_;
     };
 
-    for (const Op& op : P.ops) {
+    for (size_t oi = 0; oi < P.ops.size(); ++oi) {
+        const Op& op = P.ops[oi];
         int64_t sstride = 0, dstride = 0;
         const void* sp = src_ptr(op, sstride);
         void* dp = dst_ptr(op, dstride);
+        // K4: an x2 stage whose whole output is consumed by the polyphase stage of the same engine runs as
+        // ONE fused launch; the intermediate-rate samples never reach HBM.
+        if (fuse_ && op.stage >= 0 && oi + 1 < P.ops.size()) {
+            const Op& nx = P.ops[oi + 1];
+            const StageDesign& su = chain_.stages[(size_t)op.stage];
+            if (nx.stage == op.stage + 1 && su.kind == STAGE_UP && su.factor == 2 && op.n_out > 0 &&
+                chain_.stages[(size_t)nx.stage].kind == STAGE_POLY && nx.src_buf == op.dst_buf && op.dst_buf >= 0 &&
+                nx.n_in == op.n_out && chain_.stages[(size_t)nx.stage].engine_index == su.engine_index) {
+                const StageDesign& spd = chain_.stages[(size_t)nx.stage];
+                const StageDev& du = dev_[(size_t)op.stage];
+                const StageDev& dpv = dev_[(size_t)nx.stage];
+                int64_t ostride = 0;
+                void* optr = dst_ptr(nx, ostride);
+                FusedCall f{};
+                f.hist_u = (const char*)du.hist[op.parity_in] + (size_t)row0 * (size_t)du.hist_cap * esz_;
+                f.hist_u_stride = du.hist_cap; f.hu = (int32_t)op.hist_len;
+                f.in = sp; f.in_stride = sstride; f.n_in = (int32_t)op.n_in;
+                f.hist_u_out = (char*)du.hist[op.parity_in ^ 1] + (size_t)row0 * (size_t)du.hist_cap * esz_;
+                f.hist_u_out_stride = du.hist_cap; f.drop_u = (int32_t)op.drop; f.new_hu = (int32_t)op.new_hist_len;
+                f.bank_u = du.bank[0]; f.t1 = su.taps; f.np = (int32_t)(op.n_out / 2);
+                f.hist_p = (const char*)dpv.hist[nx.parity_in] + (size_t)row0 * (size_t)dpv.hist_cap * esz_;
+                f.hist_p_stride = dpv.hist_cap; f.hp = (int32_t)nx.hist_len;
+                f.hist_p_out = (char*)dpv.hist[nx.parity_in ^ 1] + (size_t)row0 * (size_t)dpv.hist_cap * esz_;
+                f.hist_p_out_stride = dpv.hist_cap; f.drop_p = (int32_t)nx.drop; f.new_hp = (int32_t)nx.new_hist_len;
+                f.bank_a = dpv.bank[0]; f.bank_b = dpv.bank[1]; f.bank_c = dpv.bank[2]; f.bank_d = dpv.bank[3];
+                f.t2 = spd.taps; f.L = spd.factor; f.at0 = nx.first; f.step = spd.step;
+                f.n_out = (int32_t)nx.n_out; f.interp = nx.interp ? 1 : 0;
+                f.out = optr; f.out_stride = ostride; f.n_streams = count;
+                if (launch_fused_up2_poly(f, dtype_, s)) {
+                    ++launches_;
+                    ++oi;  // the polyphase op is done too
+                    continue;
+                }
+            }
+        }
         if (op.stage < 0) {
             launch_cast(sp, sstride, dtype_, dp, dstride, dtype_, (int32_t)op.n_in, count, s);
             ++launches_;

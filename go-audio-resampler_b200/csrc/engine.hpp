@@ -89,6 +89,7 @@ class Engine {
     const StreamState& state(int row) const { return streams_[(size_t)row]; }
     const StageDev& stage_dev(int s) const { return dev_[(size_t)s]; }
     int64_t launches() const { return launches_; }
+    void set_fuse(bool on) { fuse_ = on; }
     void reset_launches() { launches_ = 0; }
     int64_t device_bytes() const { return device_bytes_; }
 
@@ -134,6 +135,7 @@ class Engine {
     int32_t* d_cubic_idx_ = nullptr;
     double* d_cubic_phase_ = nullptr;
     int64_t cubic_cap_ = 0;
+    bool fuse_ = true;  // K4 fused x2 -> polyphase launches (GAR_NO_FUSE=1 disables, for A/B tests)
     int64_t launches_ = 0;
     int64_t device_bytes_ = 0;
 };

@@ -76,6 +76,92 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
+// Register-tiled sliding-window FIR core shared by the stand-alone and the fused kernels: R adjacent positions
+// (window stride M) x NF filters per thread, `xt` = this thread's window in shared memory (16-byte aligned),
+// `cs` = [NF][cp] taps shifted by the pad `a`. One LDS.128 of samples + one broadcast LDS.128 per filter feed
+// VEC*R*NF FMAs.
+template <typename T, int M, int NF, int R>
+__device__ __forceinline__ void fir_tile_accumulate(const T* __restrict__ xt, const T* __restrict__ cs, const int cp,
+                                                    const int taps, const int a, T (&res)[R][NF]) {
+    using V = typename VecOf<T>::type;
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int NCH = (M * (R - 1) + VEC - 1) / VEC + 1;  // 16-byte chunks spanned by one step's window
+    constexpr int WREG = NCH * VEC;
+    const int n_iter = (taps + a + VEC - 1) / VEC;
+    T xr[WREG];
+    T acc[R][NF];
+    double tot[R][NF];  // f32: short f32 partial sums are folded into f64 totals (|err| ~ 1e-7, SURVEY H5)
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < NF; ++p) {
+            acc[r][p] = T(0);
+            tot[r][p] = 0.0;
+        }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) vec_unpack(*reinterpret_cast<const V*>(xt + ch * VEC), xr + ch * VEC);
+
+    auto step = [&](const int u, const int it) {
+        T cv[NF][VEC];
+#pragma unroll
+        for (int p = 0; p < NF; ++p) vec_unpack(*reinterpret_cast<const V*>(cs + p * cp + it * VEC), cv[p]);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const T xv = xr[(u * VEC + i + M * r) % WREG];
+#pragma unroll
+                for (int p = 0; p < NF; ++p) acc[r][p] = fma(xv, cv[p][i], acc[r][p]);
+            }
+        // the oldest chunk is dead now: refill its slot with chunk it+NCH (needed from the next step on)
+        vec_unpack(*reinterpret_cast<const V*>(xt + (it + NCH) * VEC), xr + (u % NCH) * VEC);
+    };
+    auto fold = [&]() {
+        if (sizeof(T) == 4) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int p = 0; p < NF; ++p) {
+                    tot[r][p] += (double)acc[r][p];
+                    acc[r][p] = T(0);
+                }
+        }
+    };
+
+    // f32 only: the three iterations that hold the centre of the main lobe are folded one by one, so the
+    // many small terms that follow are never added to an O(1) float32 partial sum (keeps |err| ~ 1.5e-7).
+    const int itf0 = ((taps - 1) / 2 + a) / VEC, itf1 = itf0 + 2;
+    constexpr int FOLD_BODIES = 8;  // periodic fold every 8*NCH*VEC taps (F2F.F64.F32 is ~10x an FFMA slot)
+    int it0 = 0, since_fold = 0;
+    for (; it0 + NCH <= n_iter; it0 += NCH) {
+        if (sizeof(T) == 4 && it0 <= itf1 && it0 + NCH > itf0) {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) {
+                step(u, it0 + u);
+                if (it0 + u >= itf0 && it0 + u <= itf1) fold();
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) step(u, it0 + u);
+        }
+        if (++since_fold == FOLD_BODIES) {
+            fold();
+            since_fold = 0;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NCH; ++u)
+        if (it0 + u < n_iter) {
+            step(u, it0 + u);
+            if (sizeof(T) == 4 && it0 + u >= itf0 && it0 + u <= itf1) fold();
+        }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < NF; ++p) res[r][p] = (T)(tot[r][p] + (double)acc[r][p]);
+
+}
+
 // =============================================================================================
 // Tiled strided multi-filter FIR.
 //   M  = window stride between adjacent outputs (1 for the up-sampler, the decimation factor else)
@@ -91,8 +177,6 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
                                                        const int xlen) {
     using V = typename VecOf<T>::type;
     constexpr int VEC = VecOf<T>::N;
-    constexpr int NCH = (M * (R - 1) + VEC - 1) / VEC + 1;  // 16-byte chunks spanned by one step's window
-    constexpr int WREG = NCH * VEC;
     constexpr int TJ = NT * R;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -160,80 +244,8 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
     }
 
     // ---- register-tiled sliding-window FIR ----
-    const int n_iter = (c.taps + a + VEC - 1) / VEC;
-    const T* xt = xs + M * R * tid;
-    T xr[WREG];
-    T acc[R][NF];
-    double tot[R][NF];  // f32: short f32 partial sums are folded into f64 totals (|err| ~ 1e-7, SURVEY H5)
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int p = 0; p < NF; ++p) {
-            acc[r][p] = T(0);
-            tot[r][p] = 0.0;
-        }
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) vec_unpack(*reinterpret_cast<const V*>(xt + ch * VEC), xr + ch * VEC);
-
-    auto step = [&](const int u, const int it) {
-        T cv[NF][VEC];
-#pragma unroll
-        for (int p = 0; p < NF; ++p) vec_unpack(*reinterpret_cast<const V*>(cs + p * cp + it * VEC), cv[p]);
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const T xv = xr[(u * VEC + i + M * r) % WREG];
-#pragma unroll
-                for (int p = 0; p < NF; ++p) acc[r][p] = fma(xv, cv[p][i], acc[r][p]);
-            }
-        // the oldest chunk is dead now: refill its slot with chunk it+NCH (needed from the next step on)
-        vec_unpack(*reinterpret_cast<const V*>(xt + (it + NCH) * VEC), xr + (u % NCH) * VEC);
-    };
-    auto fold = [&]() {
-        if (sizeof(T) == 4) {
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int p = 0; p < NF; ++p) {
-                    tot[r][p] += (double)acc[r][p];
-                    acc[r][p] = T(0);
-                }
-        }
-    };
-
-    // f32 only: the three iterations that hold the centre of the main lobe are folded one by one, so the
-    // many small terms that follow are never added to an O(1) float32 partial sum (keeps |err| ~ 1.5e-7).
-    const int itf0 = ((c.taps - 1) / 2 + a) / VEC, itf1 = itf0 + 2;
-    constexpr int FOLD_BODIES = 8;  // periodic fold every 8*NCH*VEC taps (F2F.F64.F32 is ~10x an FFMA slot)
-    int it0 = 0, since_fold = 0;
-    for (; it0 + NCH <= n_iter; it0 += NCH) {
-        if (sizeof(T) == 4 && it0 <= itf1 && it0 + NCH > itf0) {
-#pragma unroll
-            for (int u = 0; u < NCH; ++u) {
-                step(u, it0 + u);
-                if (it0 + u >= itf0 && it0 + u <= itf1) fold();
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < NCH; ++u) step(u, it0 + u);
-        }
-        if (++since_fold == FOLD_BODIES) {
-            fold();
-            since_fold = 0;
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < NCH; ++u)
-        if (it0 + u < n_iter) {
-            step(u, it0 + u);
-            if (sizeof(T) == 4 && it0 + u >= itf0 && it0 + u <= itf1) fold();
-        }
     T res[R][NF];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int p = 0; p < NF; ++p) res[r][p] = (T)(tot[r][p] + (double)acc[r][p]);
+    fir_tile_accumulate<T, M, NF, R>(xs + M * R * tid, cs, cp, c.taps, a, res);
 
     // ---- interleaved, vectorised store: out[(j*NF + p)] ----
     T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
@@ -468,6 +480,176 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
                 }
         }
         __syncthreads();  // every thread is done with xs[buf] before the next prefetch overwrites it
+    }
+}
+
+
+// =============================================================================================
+// K4 — fused x2 up-sampler + polyphase stage. One block = one tile of MT = 2*NT*R intermediate samples:
+//   1. stage the input window (TMA bulk copy when regular) and the x2 bank in shared memory,
+//   2. run the register-tiled FIR core and write the tile's intermediate samples to SHARED memory,
+//   3. produce every polyphase output whose T2-sample window lies in the tile (tiles overlap by T2-1
+//      intermediate samples, recomputed rather than exchanged: 4 % for T2 = 64).
+// Block 0 of a row also sees the polyphase stage's carried tail in front of its tile. The last block of
+// every row writes both carried tails (the polyphase tail needs the last few intermediate samples, which
+// it recomputes directly).
+// =============================================================================================
+template <typename T, bool INTERP, int R, int NT>
+__global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, const int n_tiles, const int ms,
+                                                            const int cp, const int xlen, const int hpf,
+                                                            const int bank_pitch /*0: read banks through L1*/) {
+    using V = typename VecOf<T>::type;
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int NF = 2;
+    constexpr int TP = NT * R;      // positions per tile
+    constexpr int MT = TP * NF;     // intermediate samples per tile
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    T* cs = reinterpret_cast<T*>(smem_raw + 16);  // [2][cp]
+    T* xs = cs + NF * cp;                         // [xlen]
+    T* vp = xs + xlen;                            // [hpf + MT] polyphase input: (tail |) intermediate tile
+    T* pbank = vp + hpf + MT;                     // [L][bank_pitch] a-bank copy (optional)
+
+    const int tile = blockIdx.x % (n_tiles + 1);
+    const int64_t row = blockIdx.x / (n_tiles + 1);
+    const int tid = threadIdx.x;
+    const T* __restrict__ hist_u = static_cast<const T*>(c.hist_u) + row * c.hist_u_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    const T* __restrict__ hist_p = static_cast<const T*>(c.hist_p) + row * c.hist_p_stride;
+    const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
+    const int n_mid = c.np * NF;
+
+    if (tile == n_tiles) {  // ---- carried tails ----
+        carry_row(hist_u, c.hu, in, c.n_in, static_cast<T*>(c.hist_u_out) + row * c.hist_u_out_stride, c.drop_u,
+                  c.new_hu);
+        T* hp_out = static_cast<T*>(c.hist_p_out) + row * c.hist_p_out_stride;
+        for (int i = tid; i < c.new_hp; i += NT) {
+            const int idx = c.drop_p + i;  // index into vp = hist_p ++ mid
+            T v;
+            if (idx < c.hp) {
+                v = hist_p[idx];
+            } else {
+                const int j = idx - c.hp;
+                const T* __restrict__ bk = bank_u + (j & 1) * c.t1;
+                if (sizeof(T) == 8) {  // same strictly sequential chain as the tile core: bit-identical
+                    T acc = 0;
+                    for (int t = 0; t < c.t1; ++t)
+                        acc = fma(vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), bk[t], acc);
+                    v = acc;
+                } else {
+                    double acc = 0;
+                    for (int t = 0; t < c.t1; ++t)
+                        acc = fma((double)vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), (double)bk[t], acc);
+                    v = (T)acc;
+                }
+            }
+            hp_out[i] = v;
+        }
+        return;
+    }
+
+    // ---- 1. stage the x2 stage's input window ----
+    const int p0 = (tile * ms) >> 1;  // first position of the tile (ms is even)
+    const int tp = min(TP, c.np - p0);
+    const int need = tp > 0 ? tp - 1 + c.t1 : 0;
+    int a = 0;
+    bool bulk = false;
+    {
+        const int gi = p0 - c.hu;
+        if (gi >= 0 && need > 0) {
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(in + gi);
+            const int mis = (int)((addr & 15u) / sizeof(T));
+            const int words = ((need + mis + VEC - 1) / VEC) * VEC;
+            if (gi - mis >= 0 && gi - mis + words <= c.n_in && words <= xlen) {
+                bulk = true;
+                a = mis;
+            }
+        }
+    }
+    if (bulk) {
+        const int gi = p0 - c.hu - a;
+        const int words = ((need + a + VEC - 1) / VEC) * VEC;
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)(words * sizeof(T)));
+            bulk_g2s(xs, in + gi, (uint32_t)(words * sizeof(T)), bar);
+        }
+        for (int i = words + tid; i < xlen; i += NT) xs[i] = T(0);
+    } else {
+        for (int i = tid; i < xlen; i += NT) xs[i] = i < need ? vload(hist_u, c.hu, in, c.n_in, p0 + i) : T(0);
+    }
+    for (int i = tid; i < NF * cp; i += NT) {
+        const int p = i / cp, k = i % cp - a;
+        cs[i] = (k >= 0 && k < c.t1) ? bank_u[p * c.t1 + k] : T(0);
+    }
+    // polyphase side: carried tail right-aligned in front of tile 0 (the tile itself starts 16-byte aligned),
+    // optional a-bank copy (odd pitch: conflict-free rows)
+    const int front = tile == 0 ? hpf : 0;
+    if (tile == 0)
+        for (int i = tid; i < c.hp; i += NT) vp[hpf - c.hp + i] = hist_p[i];
+    if (bank_pitch > 0) {
+        const T* __restrict__ ba = static_cast<const T*>(c.bank_a);
+        for (int i = tid; i < c.L * c.t2; i += NT) pbank[(i / c.t2) * bank_pitch + (i % c.t2)] = ba[i];
+    }
+    __syncthreads();
+    if (bulk) {
+        while (!mbar_try_wait(bar, 0)) {
+        }
+    }
+
+    // ---- 2. x2 FIR core -> intermediate tile in shared memory ----
+    {
+        T res[R][NF];
+        fir_tile_accumulate<T, 1, NF, R>(xs + R * tid, cs, cp, c.t1, a, res);
+        T* mp = vp + front + (size_t)R * NF * tid;
+#pragma unroll
+        for (int q = 0; q < R * NF / VEC; ++q) reinterpret_cast<V*>(mp)[q] = vec_pack(&res[0][0] + q * VEC);
+    }
+    __syncthreads();
+
+    // ---- 3. polyphase outputs whose window starts in [lo, hi) of vp = hist_p ++ mid ----
+    const int64_t Lq = (int64_t)c.L << 16;
+    const int64_t lo = tile == 0 ? 0 : (int64_t)c.hp + (int64_t)tile * ms;
+    const int64_t hi = (int64_t)c.hp + (int64_t)(tile + 1) * ms;
+    auto first_n = [&](const int64_t d) -> int64_t {  // smallest n with div_n >= d
+        const int64_t need_at = d * Lq - c.at0;
+        return need_at <= 0 ? 0 : (need_at + c.step - 1) / c.step;
+    };
+    const int64_t n_lo = min((int64_t)c.n_out, first_n(lo));
+    const int64_t n_hi = tile == n_tiles - 1 ? (int64_t)c.n_out : min((int64_t)c.n_out, first_n(hi));
+    // virtual vp index d lives at shared-memory element d - vbase
+    const int64_t vbase = tile == 0 ? (int64_t)c.hp - hpf : lo;
+    T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+    const T* __restrict__ ga = static_cast<const T*>(c.bank_a);
+    const T* __restrict__ gb = static_cast<const T*>(c.bank_b);
+    const T* __restrict__ gc = static_cast<const T*>(c.bank_c);
+    const T* __restrict__ gd = static_cast<const T*>(c.bank_d);
+    (void)n_mid;
+    for (int64_t n = n_lo + tid; n < n_hi; n += NT) {
+        const int64_t at = c.at0 + n * c.step;
+        const int64_t full = at >> 16;
+        const int64_t div = full / c.L;
+        const int phase = (int)(full - div * c.L);
+        const T* h = vp + (div - vbase);
+        double acc0 = 0, acc1 = 0;
+        if (INTERP) {
+            const T x = (T)(int)(at & 0xFFFF) * (T)(1.0 / 65536.0);
+            const int64_t co = (int64_t)phase * c.t2;
+            for (int k = 0; k < c.t2; ++k) {
+                const T coef = fma(x, fma(x, fma(x, gd[co + k], gc[co + k]), gb[co + k]), ga[co + k]);
+                if (k & 1) acc1 = fma((double)h[k], (double)coef, acc1);
+                else acc0 = fma((double)h[k], (double)coef, acc0);
+            }
+        } else {
+            const T* __restrict__ ca = bank_pitch > 0 ? pbank + phase * bank_pitch : ga + (int64_t)phase * c.t2;
+            for (int k = 0; k < c.t2; ++k) {
+                if (k & 1) acc1 = fma((double)h[k], (double)ca[k], acc1);
+                else acc0 = fma((double)h[k], (double)ca[k], acc0);
+            }
+        }
+        out[n] = (T)(acc0 + acc1);
     }
 }
 
@@ -807,6 +989,55 @@ const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s) {
     LAUNCH(double, false);
     return "poly_f64";
 #undef LAUNCH
+}
+
+
+template <typename T, bool INTERP>
+static bool launch_fused_t(const FusedCall& c, cudaStream_t s) {
+    constexpr int NT = 128;
+    constexpr int R = sizeof(T) == 8 ? 6 : 12;
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int NCH = (R - 1 + VEC - 1) / VEC + 1;
+    constexpr int MT = NT * R * 2;
+    const int ms = (MT - (c.t2 - 1)) & ~1;  // tile stride in intermediate samples
+    const int hpf = (c.hp + VEC - 1) / VEC * VEC;
+    if (ms < MT / 2 || c.hp > 1024 || c.np <= 0) return false;
+    const int n_mid = c.np * 2;
+    const int n_tiles = (n_mid + ms - 1) / ms;
+    const int cp = ((c.t1 + VEC - 1 + VEC - 1) / VEC) * VEC;
+    const int xlen = R * (NT - 1) + (cp / VEC + NCH + 1) * VEC;
+    size_t words = (size_t)2 * cp + xlen + hpf + MT;
+    int bank_pitch = 0;
+    if (!INTERP) {
+        const int pitch = c.t2 | 1;
+        if (((size_t)c.L * pitch + words) * sizeof(T) + 16 <= 100 * 1024) {
+            bank_pitch = pitch;
+            words += (size_t)c.L * pitch;
+        }
+    }
+    const size_t smem = 16 + words * sizeof(T);
+    auto k = fused_up2_poly_kernel<T, INTERP, R, NT>;
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
+    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, ms, cp, xlen, hpf, bank_pitch);
+    count_launch();
+    return true;
+}
+
+const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s) {
+    if (c.n_streams <= 0) return "none";
+    if (dtype == DT_F32) {
+        if (c.interp) return launch_fused_t<float, true>(c, s) ? "fused_up2_poly_f32_interp" : nullptr;
+        return launch_fused_t<float, false>(c, s) ? "fused_up2_poly_f32" : nullptr;
+    }
+    if (c.interp) return launch_fused_t<double, true>(c, s) ? "fused_up2_poly_f64_interp" : nullptr;
+    return launch_fused_t<double, false>(c, s) ? "fused_up2_poly_f64" : nullptr;
 }
 
 const char* launch_cubic(const CubicCall& c, int dtype, cudaStream_t s) {

@@ -43,6 +43,29 @@ struct PolyCall {
     int32_t n_streams;
 };
 
+// K4: x2 up-sampler fused with the polyphase stage that follows it inside one engine.Resampler
+// (resampler.go:97-121,142-175). The intermediate-rate samples of a tile live only in shared memory.
+//   mid[j]  = sum_t vu[(j>>1) + t] * bank_u[j&1][t]            vu = hist_u ++ in,      j < 2*np
+//   out[n]  = sum_k vp[div_n + k] * coef(phase_n, x_n)[k]      vp = hist_p ++ mid
+struct FusedCall {
+    // x2 stage
+    const void* hist_u;   int64_t hist_u_stride;   int32_t hu;
+    const void* in;       int64_t in_stride;       int32_t n_in;
+    void* hist_u_out;     int64_t hist_u_out_stride;
+    int32_t drop_u;       int32_t new_hu;
+    const void* bank_u;   int32_t t1;              int32_t np;       // positions; 2*np intermediate samples
+    // polyphase stage
+    const void* hist_p;   int64_t hist_p_stride;   int32_t hp;
+    void* hist_p_out;     int64_t hist_p_out_stride;
+    int32_t drop_p;       int32_t new_hp;
+    const void* bank_a;   const void* bank_b;      const void* bank_c;   const void* bank_d;
+    int32_t t2;           int32_t L;
+    int64_t at0;          int64_t step;
+    int32_t n_out;        int32_t interp;
+    void* out;            int64_t out_stride;
+    int32_t n_streams;
+};
+
 // cubic.go:33-90 — indices/phases precomputed on the host by the exact float64 recurrence
 struct CubicCall {
     const void* hist;     int64_t hist_stride;                         // 3 previous samples (zeros at start)
@@ -59,6 +82,8 @@ enum Dtype : int { DT_F64 = 0, DT_F32 = 1 };
 const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s);
 const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s);
 const char* launch_cubic(const CubicCall& c, int dtype, cudaStream_t s);
+// returns nullptr when the pair cannot be fused (caller falls back to the two stand-alone launches)
+const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s);
 // carry only (a call that produced no output but appended to the tail)
 void launch_carry(const void* hist, int64_t hist_stride, int32_t hist_len, const void* in, int64_t in_stride,
                   int32_t n_in, void* hist_out, int64_t hist_out_stride, int32_t drop, int32_t new_len,

@@ -118,6 +118,7 @@ SYMBOLS = {
     "gar_host_alloc": (_vp, [C.c_size_t]),
     "gar_host_free": (None, [_vp]),
     "gar_device_count": (_i32, []),
+    "gar_set_fusion": (_i32, [_vp, _i32]),
     "gar_kernel_launches": (_i64, [_vp, _i32]),
     "gar_stage_kernel_name": (C.c_char_p, [_vp, _i32]),
     "gar_measure_fma_peak": (_i32, [_i32, _i32, C.POINTER(C.c_double)]),
@@ -233,6 +234,10 @@ class _Handle:
 
     def kernel_names(self):
         return [lib().gar_stage_kernel_name(self._h, s).decode() for s in range(lib().gar_num_stages(self._h))]
+
+    def set_fusion(self, enabled: bool):
+        """Enable/disable the fused x2 -> polyphase kernel (K4)."""
+        lib().gar_set_fusion(self._h, 1 if enabled else 0)
 
     def plan_types(self):
         return [lib().gar_plan_stage_type(self._h, e) for e in range(lib().gar_num_engines(self._h))]

@@ -198,6 +198,8 @@ int32_t gar_flush_batch_dev(gar_handle* h, int32_t io_dtype, void* d_out, int64_
 void* gar_host_alloc(size_t bytes);
 void gar_host_free(void* p);
 int32_t gar_device_count(void);
+/* Enable (default) / disable the fused x2 -> polyphase launch (K4); results agree to rounding, used for A/B tests. */
+int32_t gar_set_fusion(gar_handle* h, int32_t enabled);
 /* Number of this library's kernels launched through the handle since creation / last reset of the counter. */
 int64_t gar_kernel_launches(const gar_handle* h, int32_t reset);
 /* Name of the dominant kernel variant chosen for stage `stage` (for bench/ncu filters). */

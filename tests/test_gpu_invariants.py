@@ -187,3 +187,37 @@ def test_uploaded_bank_replaces_host_design():
     r.upload_bank(0, 0, bank * 0.5)
     half = r.Process(x)
     assert np.max(np.abs(half - 0.5 * base)) <= 1e-15
+
+
+@pytest.mark.parametrize("ir,orr,dt", [(44100, 48000, np.float64), (48000, 44100, np.float64),
+                                       (44100, 47999, np.float64), (8000, 12000, np.float64),
+                                       (48000, 44100, np.float32), (44100, 48000, np.float32)])
+def test_fused_x2_polyphase_kernel_equals_unfused(ir, orr, dt):
+    """K4: the fused launch keeps the intermediate-rate samples in shared memory; float64 results are
+    bit-identical to the two stand-alone launches (same summation order), float32 to rounding."""
+    x = _noise(60000, 21, dt)
+    a = G.SimpleResampler(ir, orr, G.QualityHigh, dt)
+    b = G.SimpleResampler(ir, orr, G.QualityHigh, dt)
+    b.set_fusion(False)
+    rng = np.random.default_rng(5)
+    i, la, lb = 0, 0, 0
+    G.kernel_launches(reset=True)
+    while i < len(x):
+        n = int(rng.integers(1, 9000))
+        k0 = G.kernel_launches()
+        ya = a.Process(x[i:i + n])
+        k1 = G.kernel_launches()
+        yb = b.Process(x[i:i + n])
+        k2 = G.kernel_launches()
+        la, lb = la + (k1 - k0), lb + (k2 - k1)
+        if dt == np.float64:
+            np.testing.assert_array_equal(ya, yb)
+        else:
+            assert len(ya) == len(yb) and (len(ya) == 0 or np.max(np.abs(ya - yb)) <= 2e-7)
+        i += n
+    fa, fb = a.Flush(), b.Flush()
+    if dt == np.float64:
+        np.testing.assert_array_equal(fa, fb)
+    else:
+        assert len(fa) == len(fb) and np.max(np.abs(fa - fb)) <= 2e-7
+    assert la < lb  # fewer launches when fused
