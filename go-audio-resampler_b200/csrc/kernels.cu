@@ -173,98 +173,119 @@ __device__ __forceinline__ void fir_tile_accumulate(const T* __restrict__ xt, co
 // grid.x = rows * (n_tiles + 1): the extra block of every row writes the carried tail.
 // =============================================================================================
 template <typename T, int M, int NF, int R, int NT>
-__global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const int n_tiles, const int cp /*padded taps*/,
+__global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const int n_tiles, const int tiles_per_block,
+                                                       const int n_groups, const int cp /*padded taps*/,
                                                        const int xlen) {
     using V = typename VecOf<T>::type;
     constexpr int VEC = VecOf<T>::N;
     constexpr int TJ = NT * R;
+    static_assert((TJ * M * sizeof(T)) % 16 == 0, "tile stride must keep the 16-byte alignment of the window");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    T* cs = reinterpret_cast<T*>(smem_raw + 16);  // [NF][cp]
-    T* xs = cs + NF * cp;                         // [xlen]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // two mbarriers, one per window buffer
+    T* cs = reinterpret_cast<T*>(smem_raw + 16);            // [NF][cp]
+    T* xs0 = cs + NF * cp;                                  // [2][xlen] double-buffered sample window
 
-    const int tile = blockIdx.x % (n_tiles + 1);
-    const int64_t row = blockIdx.x / (n_tiles + 1);
+    // grid.x = rows * (n_groups + 1): a block owns `tiles_per_block` consecutive tiles of one row (filter
+    // loaded once, TMA prefetch of tile k+1 under the FMAs of tile k); the extra block writes the carried tail.
+    const int group = blockIdx.x % (n_groups + 1);
+    const int64_t row = blockIdx.x / (n_groups + 1);
     const int tid = threadIdx.x;
 
     const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
     const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
 
-    if (tile == n_tiles) {  // carry block
+    if (group == n_groups) {  // carry block
         carry_row(hist, c.hist_len, in, c.n_in, static_cast<T*>(c.hist_out) + row * c.hist_out_stride, c.drop,
                   c.new_hist_len);
         return;
     }
+    const int t_first = group * tiles_per_block;
+    const int nt = min(tiles_per_block, n_tiles - t_first);
 
-    const int j0 = tile * TJ;
-    const int tj = min(TJ, c.n_pos - j0);
-    const int g0 = c.first + j0 * M;        // virtual index of the tile's first window sample
-    const int need = (tj - 1) * M + c.taps;  // samples the tile reads
+    // leading pad so that every tile's bulk source address is 16-byte aligned (constant along the row)
+    const int a = (int)(((reinterpret_cast<uintptr_t>(in) / sizeof(T)) + (uintptr_t)(int64_t)(c.first - c.hist_len)) &
+                        (uintptr_t)(VEC - 1));
+    auto tile_geom = [&](const int t, int& g0a, int& words, bool& bulk) {
+        const int j0 = t * TJ;
+        const int tj = min(TJ, c.n_pos - j0);
+        g0a = c.first + j0 * M - a;                                   // virtual index of xs[0]
+        words = (((tj - 1) * M + c.taps + a + VEC - 1) / VEC) * VEC;  // samples the tile reads (16-byte units)
+        const int gi = g0a - c.hist_len;                              // index into `in`
+        bulk = gi >= 0 && gi + words <= c.n_in && words <= xlen;
+    };
+    auto issue_bulk = [&](const int t, const int buf) {  // one thread
+        int g0a, words;
+        bool bulk;
+        tile_geom(t, g0a, words, bulk);
+        if (bulk) {
+            mbar_expect_tx(bar + buf, (uint32_t)(words * sizeof(T)));
+            bulk_g2s(xs0 + buf * xlen, in + (g0a - c.hist_len), (uint32_t)(words * sizeof(T)), bar + buf);
+        }
+    };
 
-    // ---- stage the window: TMA bulk copy when the tile is regular, guarded loads otherwise ----
-    int a = 0;  // leading pad so that the bulk source address is 16-byte aligned
-    bool bulk = false;
-    {
-        const int gi = g0 - c.hist_len;  // index into `in`
-        if (gi >= 0) {
-            const uintptr_t addr = reinterpret_cast<uintptr_t>(in + gi);
-            const int mis = (int)((addr & 15u) / sizeof(T));
-            const int words = ((need + mis + VEC - 1) / VEC) * VEC;
-            if (gi - mis >= 0 && gi - mis + words <= c.n_in && words <= xlen) {
-                bulk = true;
-                a = mis;
-            }
-        }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
     }
-    if (bulk) {
-        const int gi = g0 - c.hist_len - a;
-        const int words = ((need + a + VEC - 1) / VEC) * VEC;
-        if (tid == 0) mbar_init(bar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            mbar_expect_tx(bar, (uint32_t)(words * sizeof(T)));
-            bulk_g2s(xs, in + gi, (uint32_t)(words * sizeof(T)), bar);
-        }
-        for (int i = words + tid; i < xlen; i += NT) xs[i] = T(0);
-    } else {
-        for (int i = tid; i < xlen; i += NT) xs[i] = i < need ? vload(hist, c.hist_len, in, c.n_in, g0 + i) : T(0);
-    }
+    for (int i = tid; i < 2 * xlen; i += NT) xs0[i] = T(0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before async-proxy (TMA) writes
     {  // filter bank, shifted by the pad, zero elsewhere
         const T* __restrict__ bank = static_cast<const T*>(c.bank);
-        for (int i = tid; i < NF * cp; i += NT) {
-            const int p = i / cp, k = i % cp - a;
-            cs[i] = (k >= 0 && k < c.taps) ? bank[p * c.taps + k] : T(0);
-        }
-    }
-    __syncthreads();
-    if (bulk) {
-        while (!mbar_try_wait(bar, 0)) {
-        }
-    }
-
-    // ---- register-tiled sliding-window FIR ----
-    T res[R][NF];
-    fir_tile_accumulate<T, M, NF, R>(xs + M * R * tid, cs, cp, c.taps, a, res);
-
-    // ---- interleaved, vectorised store: out[(j*NF + p)] ----
-    T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
-    const int jb = j0 + R * tid;
-    T* op = out + (int64_t)jb * NF;
-    if (jb + R <= c.n_pos && (R * NF) % VEC == 0 && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {
-        const T* flat = &res[0][0];
 #pragma unroll
-        for (int q = 0; q < R * NF / VEC; ++q) reinterpret_cast<V*>(op)[q] = vec_pack(flat + q * VEC);
-    } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (jb + r < c.n_pos) {
-#pragma unroll
-                for (int p = 0; p < NF; ++p) op[r * NF + p] = res[r][p];
+        for (int p = 0; p < NF; ++p)
+            for (int kk = tid; kk < cp; kk += NT) {
+                const int k = kk - a;
+                cs[p * cp + kk] = (k >= 0 && k < c.taps) ? bank[p * c.taps + k] : T(0);
             }
     }
-}
+    __syncthreads();
+    if (tid == 0) issue_bulk(t_first, 0);
+    uint32_t phase0 = 0u, phase1 = 0u;
+    T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
 
+    for (int k = 0; k < nt; ++k) {
+        const int t = t_first + k;
+        const int buf = k & 1;
+        T* xs = xs0 + buf * xlen;
+        int g0a, words;
+        bool bulk;
+        tile_geom(t, g0a, words, bulk);
+        if (tid == 0 && k + 1 < nt) issue_bulk(t + 1, buf ^ 1);  // prefetch (buffer free since the last barrier)
+        if (bulk) {
+            const uint32_t ph = buf ? phase1 : phase0;
+            while (!mbar_try_wait(bar + buf, ph)) {
+            }
+            if (buf) phase1 ^= 1u;
+            else phase0 ^= 1u;
+        } else {  // edge tile (touches the carried tail or the end of the row): guarded loads
+            for (int i = tid; i < xlen; i += NT)
+                xs[i] = i < words ? vload(hist, c.hist_len, in, c.n_in, g0a + i) : T(0);
+            __syncthreads();
+        }
+
+        // ---- register-tiled sliding-window FIR ----
+        T res[R][NF];
+        fir_tile_accumulate<T, M, NF, R>(xs + M * R * tid, cs, cp, c.taps, a, res);
+
+        // ---- interleaved, vectorised store: out[(j*NF + p)] ----
+        const int jb = t * TJ + R * tid;
+        T* op = out + (int64_t)jb * NF;
+        if (jb + R <= c.n_pos && (R * NF) % VEC == 0 && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {
+            const T* flat = &res[0][0];
+#pragma unroll
+            for (int q = 0; q < R * NF / VEC; ++q) reinterpret_cast<V*>(op)[q] = vec_pack(flat + q * VEC);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (jb + r < c.n_pos) {
+#pragma unroll
+                    for (int p = 0; p < NF; ++p) op[r * NF + p] = res[r][p];
+                }
+        }
+        __syncthreads();  // every thread is done with xs[buf] before the next prefetch overwrites it
+    }
+}
 
 // =============================================================================================
 // float32 decimator with packed FMAs (PTX fma.rn.f32x2 -> SASS FFMA2, new on sm_100).
@@ -832,6 +853,22 @@ struct FirVariant {
     const char* name;
 };
 
+// tiles per block: long runs amortise the per-block filter load and hide the TMA prefetch under the FMAs,
+// but keep >= ~8 blocks per resident slot in flight for balance
+static int pick_tiles_per_block(int n_tiles, int n_streams, int* n_groups) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static int sm_count[64] = {0};
+    if (!sm_count[dev & 63]) cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count[dev & 63] > 0 ? sm_count[dev & 63] : 148;
+    const int64_t total_tiles = (int64_t)n_tiles * n_streams;
+    int tpb = (int)(total_tiles / ((int64_t)sms * 4 * 8));
+    tpb = tpb < 1 ? 1 : (tpb > 16 ? 16 : tpb);
+    if (tpb > n_tiles) tpb = n_tiles;
+    *n_groups = (n_tiles + tpb - 1) / tpb;
+    return tpb;
+}
+
 template <typename T, int M, int NF, int R>
 void launch_fir_tiled(const FirCall& c, cudaStream_t s) {
     constexpr int NT = 128;
@@ -840,8 +877,10 @@ void launch_fir_tiled(const FirCall& c, cudaStream_t s) {
     constexpr int TJ = NT * R;
     const int cp = ((c.taps + VEC - 1 + VEC - 1) / VEC) * VEC;  // room for any alignment pad
     const int xlen = M * R * (NT - 1) + (cp / VEC + NCH + 1) * VEC;
-    const size_t smem = 16 + (size_t)(NF * cp + xlen) * sizeof(T);
+    const size_t smem = 16 + (size_t)(NF * cp + 2 * xlen) * sizeof(T);
     const int n_tiles = (c.n_pos + TJ - 1) / TJ;
+    int n_groups = 1;
+    const int tpb = pick_tiles_per_block(n_tiles, c.n_streams, &n_groups);
     auto k = fir_tiled_kernel<T, M, NF, R, NT>;
     static size_t configured[64] = {0};  // per instantiation, per device
     int dev = 0;
@@ -850,8 +889,8 @@ void launch_fir_tiled(const FirCall& c, cudaStream_t s) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured[dev & 63] = smem;
     }
-    const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
-    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, cp, xlen);
+    const int64_t blocks = (int64_t)(n_groups + 1) * c.n_streams;
+    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, tpb, n_groups, cp, xlen);
     count_launch();
 }
 
@@ -866,18 +905,10 @@ void launch_fir_f32x2(const FirCall& c, cudaStream_t s) {
     const int xlen = M * R * (NT - 1) + (cp / 4 + NCH + 1) * 4;
     const size_t smem = 16 + (size_t)(NF * NS * cp + 2 * xlen) * sizeof(float);
     const int n_tiles = (c.n_pos + TJ - 1) / TJ;
-    // tiles per block: long runs amortise the per-block filter load and let the TMA prefetch hide under the
-    // FMAs, but keep >= ~8 blocks per SM-slot in flight for balance
-    int dev = 0, sms = 148;
+    int n_groups = 1;
+    const int tpb = pick_tiles_per_block(n_tiles, c.n_streams, &n_groups);
+    int dev = 0;
     cudaGetDevice(&dev);
-    static int sm_count[64] = {0};
-    if (!sm_count[dev & 63]) cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
-    sms = sm_count[dev & 63] > 0 ? sm_count[dev & 63] : 148;
-    const int64_t total_tiles = (int64_t)n_tiles * c.n_streams;
-    int tpb = (int)(total_tiles / ((int64_t)sms * 4 * 8));
-    tpb = tpb < 1 ? 1 : (tpb > 16 ? 16 : tpb);
-    if (tpb > n_tiles) tpb = n_tiles;
-    const int n_groups = (n_tiles + tpb - 1) / tpb;
     auto k = fir_f32x2_kernel<M, NF, R, NT>;
     static size_t configured[64] = {0};
     if (smem > configured[dev & 63]) {
