@@ -854,7 +854,7 @@ struct FirVariant {
 };
 
 // tiles per block: long runs amortise the per-block filter load and hide the TMA prefetch under the FMAs,
-// but keep >= ~8 blocks per resident slot in flight for balance
+// but keep >= ~3 blocks per resident slot in flight for balance
 static int pick_tiles_per_block(int n_tiles, int n_streams, int* n_groups) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -862,7 +862,7 @@ static int pick_tiles_per_block(int n_tiles, int n_streams, int* n_groups) {
     if (!sm_count[dev & 63]) cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     const int sms = sm_count[dev & 63] > 0 ? sm_count[dev & 63] : 148;
     const int64_t total_tiles = (int64_t)n_tiles * n_streams;
-    int tpb = (int)(total_tiles / ((int64_t)sms * 4 * 8));
+    int tpb = (int)(total_tiles / ((int64_t)sms * 4 * 3));
     tpb = tpb < 1 ? 1 : (tpb > 16 ? 16 : tpb);
     if (tpb > n_tiles) tpb = n_tiles;
     *n_groups = (n_tiles + tpb - 1) / tpb;
