@@ -371,7 +371,6 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
 
     const int n_iter = (c.taps + a + (NS - 1) + 3) / 4;
     const int itf0 = ((c.taps - 1) / 2 + a) / 4, itf1 = itf0 + 2;  // centre-of-main-lobe folds (see fir_tiled_kernel)
-    constexpr int FOLD_BODIES = 32;  // ~1150 taps: with the centre folds and the even/odd lane split the tails stay small
     float* __restrict__ out = static_cast<float*>(c.out) + row * c.out_stride;
 
     for (int k = 0; k < nt; ++k) {
@@ -414,6 +413,8 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
             xw[ch * 2 + 1] = v.y;
         }
         auto step = [&](const int u, const int it) {
+            // (tools/probe_fma_patterns2.cu: FFMA2 loses ~15 % when one coefficient pair feeds 6 FMAs in a row;
+            //  duplicating the pair with a second, unmergeable ld.shared cost more than it gained — measured)
             u64 cv[NF][NS][2];
 #pragma unroll
             for (int p = 0; p < NF; ++p)
@@ -454,23 +455,29 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
                     acc[r][p] = 0ull;
                 }
         };
-        int it0 = 0, since_fold = 0;
-        for (; it0 + NCH <= n_iter; it0 += NCH) {
-            if (it0 <= itf1 && it0 + NCH > itf0) {
+        // three straight loops (plain bodies, the one or two bodies holding the centre, plain bodies): no
+        // per-body bookkeeping; float32 partial sums are folded into float64 only around the centre of the
+        // main lobe and at the loop boundaries (the tails stay small, see fir_tile_accumulate)
+        const int nb = n_iter / NCH;
+        const int bs0 = min(nb, itf0 / NCH), bs1 = min(nb, itf1 / NCH + 1);
+        int b = 0;
+        for (; b < bs0; ++b) {
 #pragma unroll
-                for (int u = 0; u < NCH; ++u) {
-                    step(u, it0 + u);
-                    if (it0 + u >= itf0 && it0 + u <= itf1) fold();
-                }
-            } else {
+            for (int u = 0; u < NCH; ++u) step(u, b * NCH + u);
+        }
+        fold();
+        for (; b < bs1; ++b) {
 #pragma unroll
-                for (int u = 0; u < NCH; ++u) step(u, it0 + u);
-            }
-            if (++since_fold == FOLD_BODIES) {
-                fold();
-                since_fold = 0;
+            for (int u = 0; u < NCH; ++u) {
+                step(u, b * NCH + u);
+                if (b * NCH + u >= itf0 && b * NCH + u <= itf1) fold();
             }
         }
+        for (; b < nb; ++b) {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) step(u, b * NCH + u);
+        }
+        const int it0 = nb * NCH;
 #pragma unroll
         for (int u = 0; u < NCH; ++u)
             if (it0 + u < n_iter) {
