@@ -274,6 +274,18 @@ def main():
     out_per_rank = rows * (n1 + n2)
     value = out_per_rank * world / (ms_step_max * 1e-3) / 1e6
 
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this very workload
+    # (profiles/r1_traffic.json); null when the launch shape differs (other --streams/--seconds/--gpus)
+    traffic = None
+    try:
+        tj = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+        if tj.get("algorithmic_bytes_per_launch") == rows * (n_in + n1) * 4 and tj.get("kernel") == kname:
+            traffic = {"bytes_per_launch": tj["traffic_bytes_per_launch"],
+                       "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"],
+                       "ratio": round(tj["traffic_bytes_per_launch"] / tj["algorithmic_bytes_per_launch"], 4),
+                       "source": tj["source"]}
+    except Exception:
+        traffic = None
     achieved_tf = rows * n1 * flops_per_out / (k_ms * 1e-3) / 1e12
     bytes_alg = rows * (n_in + n1) * 4.0
     roofline = {"bound": "fma", "kernel": kname, "achieved": round(achieved_tf, 3), "peak": round(peak32, 3),
@@ -281,7 +293,7 @@ def main():
                 "peak_source": "dependent-FMA fp32 probe (gar_measure_fma_peak) run in this job; MEASURED_PEAKS.json "
                                "holds only HBM and bf16-tensor peaks, neither bounds this fp32-FMA kernel",
                 "flops_per_output": flops_per_out, "kernel_ms": round(k_ms, 4), "flush_ms": round(f_ms, 4),
-                "traffic": None,
+                "traffic": traffic,
                 "hbm": {"achieved": round(bytes_alg / (k_ms * 1e-3) / 1e9, 1), "peak": 6446.9, "unit": "GB/s",
                         "frac": round(bytes_alg / (k_ms * 1e-3) / 1e9 / 6446.9, 4),
                         "algorithmic_bytes_per_output": 16}}
