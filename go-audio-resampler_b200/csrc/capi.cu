@@ -628,6 +628,80 @@ int32_t gar_flush_batch(gar_handle* h, int32_t io_dtype, void* out, int64_t out_
     return batch_host(h, io_dtype, nullptr, 0, 0, out, out_stride, out_cap, n_out, true);
 }
 
+
+// ---- interleaved / integer-PCM boundary (N1) -------------------------------------------------------
+static size_t fmt_size(int fmt) {
+    switch (fmt) {
+        case GAR_FMT_F64: case GAR_FMT_I64: return 8;
+        case GAR_FMT_F32: case GAR_FMT_I32: return 4;
+        default: return 2;
+    }
+}
+static double pcm_max(int bit_depth) {  // cmd/resample-wav/main.go:54-56,429-440
+    switch (bit_depth) {
+        case 24: return 8388607.0;
+        case 32: return 2147483647.0;
+        default: return 32767.0;
+    }
+}
+
+static int interleaved_call(gar_handle* h, int fmt, int bit_depth, const void* in, int64_t n_frames, void* out,
+                            int64_t out_cap, int64_t* n_frames_out, bool flush) {
+    Engine& E = h->eng;
+    if (fmt < GAR_FMT_F64 || fmt > GAR_FMT_I64) return fail(h, GAR_INVALID_CONFIG, "unknown sample format");
+    if (E.device() < 0) return fail(h, GAR_CUDA_ERROR, "geometry-only handle (device = -1) cannot process samples");
+    const int C = h->rows;
+    if (E.lockstep_run(0, C) != C) return fail(h, GAR_NOT_SUPPORTED, "channels are not in lock step");
+    const int64_t want = flush ? gar_next_flush_count(h, 0) : gar_next_output_count(h, 0, n_frames);
+    if (n_frames_out) *n_frames_out = 0;
+    if (!flush && out_cap < gar_estimate_output(h, n_frames)) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
+    if (want > out_cap) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
+    if (!flush && n_frames == 0) return GAR_OK;
+    cudaSetDevice(E.device());
+    cudaStream_t s = E.stream();
+    const size_t isz = fmt_size(fmt), csz = dsize(h->compute_dtype);
+    const bool is_int = fmt >= GAR_FMT_I16;
+    const double maxv = is_int ? pcm_max(bit_depth) : 0.0;
+    const int64_t is = (n_frames + 3) & ~int64_t(3), os = (want + 3) & ~int64_t(3);
+    char *d_il_in = nullptr, *d_pl_in = nullptr, *d_pl_out = nullptr, *d_il_out = nullptr;
+    if (!flush) {
+        d_il_in = (char*)E.scratch(0, (size_t)C * (size_t)n_frames * isz, h->err);
+        d_pl_in = (char*)E.scratch(1, (size_t)C * (size_t)is * csz, h->err);
+        if (!d_il_in || !d_pl_in) return GAR_CUDA_ERROR;
+        cudaMemcpyAsync(d_il_in, in, (size_t)C * (size_t)n_frames * isz, cudaMemcpyHostToDevice, s);
+        launch_deinterleave(d_il_in, fmt, C, n_frames, d_pl_in, is, h->compute_dtype, is_int ? 1.0 / maxv : 0.0, s);
+    }
+    if (want > 0) {
+        d_pl_out = (char*)E.scratch(2, (size_t)C * (size_t)os * csz, h->err);
+        d_il_out = (char*)E.scratch(3, (size_t)C * (size_t)want * isz, h->err);
+        if (!d_pl_out || !d_il_out) return GAR_CUDA_ERROR;
+    }
+    int64_t got = 0;
+    int rc = E.run(0, C, d_pl_in, is, flush ? 0 : n_frames, d_pl_out, os, os, flush, s, &got, h->err);
+    if (rc) return rc;
+    if (got > 0) {
+        launch_interleave(d_pl_out, os, h->compute_dtype, C, got, d_il_out, fmt, maxv, s);
+        cudaMemcpyAsync(out, d_il_out, (size_t)C * (size_t)got * isz, cudaMemcpyDeviceToHost, s);
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fail(h, GAR_CUDA_ERROR, std::string("stream sync: ") + cudaGetErrorString(e));
+    if (n_frames_out) *n_frames_out = got;
+    return GAR_OK;
+}
+
+int32_t gar_process_interleaved(gar_handle* h, int32_t fmt, int32_t bit_depth, const void* in, int64_t n_frames,
+                                void* out, int64_t out_cap_frames, int64_t* n_frames_out) {
+    if (!h) return GAR_INVALID_CONFIG;
+    if (n_frames < 0) return fail(h, GAR_INVALID_CONFIG, "negative input length");
+    return interleaved_call(h, fmt, bit_depth, in, n_frames, out, out_cap_frames, n_frames_out, false);
+}
+
+int32_t gar_flush_interleaved(gar_handle* h, int32_t fmt, int32_t bit_depth, void* out, int64_t out_cap_frames,
+                              int64_t* n_frames_out) {
+    if (!h) return GAR_INVALID_CONFIG;
+    return interleaved_call(h, fmt, bit_depth, nullptr, 0, out, out_cap_frames, n_frames_out, true);
+}
+
 // ---- utilities ---------------------------------------------------------------------------------
 void* gar_host_alloc(size_t bytes) {
     void* p = nullptr;

@@ -91,6 +91,14 @@ void launch_carry(const void* hist, int64_t hist_stride, int32_t hist_len, const
 // row-wise dtype casts between I/O and compute precision (constant.go:171-178,195-197)
 void launch_cast(const void* src, int64_t src_stride, int src_dtype, void* dst, int64_t dst_stride, int dst_dtype,
                  int32_t n, int32_t n_rows, cudaStream_t s);
+// N1 boundary kernels (cmd/resample-wav/main.go:358-520, convenience.go:261-282,463-486):
+//   deinterleave: planar[ch][i] = T(double(interleaved[i*C+ch]) * inv_max)   (inv_max == 0: plain cast, float I/O)
+//   interleave:   interleaved[i*C+ch] = int(clamp(double(planar[ch][i]), -1, 1) * max_val)  (truncating; max_val == 0: cast)
+// fmt: 0 f64, 1 f32, 2 int16, 3 int32, 4 int64 containers
+void launch_deinterleave(const void* in, int fmt, int channels, int64_t n_frames, void* planar, int64_t stride,
+                         int dtype, double inv_max, cudaStream_t s);
+void launch_interleave(const void* planar, int64_t stride, int dtype, int channels, int64_t n_frames, void* out, int fmt,
+                       double max_val, cudaStream_t s);
 // dependent-FMA probe; returns elapsed ms for `iters` iterations, flops in *flops
 float run_fma_probe(int dtype, int iters, double* flops, cudaStream_t s);
 // kernels launched by this library in this process (optionally resetting the counter)

@@ -115,6 +115,8 @@ SYMBOLS = {
     "gar_flush_batch": (_i32, [_vp, _i32, _vp, _i64, _i64, _pi64]),
     "gar_process_batch_dev": (_i32, [_vp, _i32, _vp, _i64, _i64, _vp, _i64, _i64, _pi64, _vp]),
     "gar_flush_batch_dev": (_i32, [_vp, _i32, _vp, _i64, _i64, _pi64, _vp]),
+    "gar_process_interleaved": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _i64, _pi64]),
+    "gar_flush_interleaved": (_i32, [_vp, _i32, _i32, _vp, _i64, _pi64]),
     "gar_host_alloc": (_vp, [C.c_size_t]),
     "gar_host_free": (None, [_vp]),
     "gar_device_count": (_i32, []),
@@ -329,6 +331,33 @@ class _Handle:
         if st != OK:
             _raise(st, self._h)
         return n.value
+
+    # --- interleaved / integer-PCM boundary (cmd/resample-wav/main.go:358-520) ---
+    _FMT = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int16): 2, np.dtype(np.int32): 3,
+            np.dtype(np.int64): 4}
+
+    def ProcessInterleaved(self, frames, bit_depth=16):
+        """frames: [n_frames, channels] (or flat interleaved) float32/float64/int16/int32/int64; returns same layout."""
+        x = np.ascontiguousarray(frames)
+        fmt = self._FMT[x.dtype]
+        n = x.size // self.rows
+        cap = max(self.EstimateOutput(n), int(lib().gar_next_output_count(self._h, 0, n)), 1)
+        out = np.empty((cap, self.rows), dtype=x.dtype)
+        got = C.c_int64(0)
+        st = lib().gar_process_interleaved(self._h, fmt, int(bit_depth), _ptr(x), n, _ptr(out), cap, C.byref(got))
+        if st != OK:
+            _raise(st, self._h)
+        return out[:got.value].copy()
+
+    def FlushInterleaved(self, dtype, bit_depth=16):
+        dt = np.dtype(dtype)
+        cap = max(int(lib().gar_next_flush_count(self._h, 0)), 1)
+        out = np.empty((cap, self.rows), dtype=dt)
+        got = C.c_int64(0)
+        st = lib().gar_flush_interleaved(self._h, self._FMT[dt], int(bit_depth), _ptr(out), cap, C.byref(got))
+        if st != OK:
+            _raise(st, self._h)
+        return out[:got.value].copy()
 
     def _process(self, ch, x, dtype, out=None):
         fn = lib().gar_process_f32 if dtype == np.float32 else lib().gar_process_f64

@@ -192,6 +192,27 @@ int32_t gar_flush_batch(gar_handle* h, int32_t io_dtype, void* out, int64_t out_
 int32_t gar_process_batch_dev(gar_handle* h, int32_t io_dtype, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride, int64_t out_cap, int64_t* n_out, void* cuda_stream);
 int32_t gar_flush_batch_dev(gar_handle* h, int32_t io_dtype, void* d_out, int64_t out_stride, int64_t out_cap, int64_t* n_out, void* cuda_stream);
 
+/* ---- interleaved / integer-PCM boundary -------------------------------------- */
+
+/* Sample container of an interleaved buffer (frame-major: all channels of frame i are adjacent). */
+typedef enum gar_sample_format {
+    GAR_FMT_F64 = 0, GAR_FMT_F32 = 1, /* InterleaveToStereo/DeinterleaveFromStereo[Float32] (convenience.go:261-282,463-486) */
+    GAR_FMT_I16 = 2,                  /* packed int16 PCM */
+    GAR_FMT_I32 = 3,                  /* 16/24/32-bit PCM in int32 containers */
+    GAR_FMT_I64 = 4                   /* Go `[]int` (go-audio IntBuffer.Data) on 64-bit platforms */
+} gar_sample_format;
+
+/* One block of the resample-wav loop (cmd/resample-wav/helpers.go:77-334) in one call: deinterleave + normalise
+ * (`F(float64(v) * (1/maxVal))`, main.go:444-470), resample every channel (rows = channels * n_streams, lock step),
+ * clamp to [-1,1] + `int(sample * maxVal)` + interleave (main.go:474-520) — conversions run on the device around
+ * the kernels, so the host copies one contiguous block each way. bit_depth 16/24/32 selects maxVal
+ * 32767 / 8388607 / 2147483647 (anything else: 32767, like the reference's default); ignored for float formats. */
+int32_t gar_process_interleaved(gar_handle* h, int32_t fmt, int32_t bit_depth, const void* in, int64_t n_frames,
+                                void* out, int64_t out_cap_frames, int64_t* n_frames_out);
+/* flushAndPadChannels (cmd/resample-wav/helpers.go:293-334). */
+int32_t gar_flush_interleaved(gar_handle* h, int32_t fmt, int32_t bit_depth, void* out, int64_t out_cap_frames,
+                              int64_t* n_frames_out);
+
 /* ---- utilities --------------------------------------------------------------------------- */
 
 /* Pinned host memory for callers that want full PCIe rate (Go slices are pageable). */
