@@ -1,4 +1,5 @@
 // capi.cu — the C ABI declared in include/gar.h on top of gar::Engine.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -284,6 +285,21 @@ int32_t gar_set_fusion(gar_handle* h, int32_t enabled) {
 int64_t gar_kernel_launches(const gar_handle* h, int32_t reset) {
     (void)h;  // process-wide counter: every <<<>>> of this library
     return (int64_t)launch_count(reset != 0);
+}
+
+int32_t gar_kernels_used(const gar_handle* h, char* buf, int32_t cap) {
+    if (!h) return 0;
+    std::string all;
+    for (const char* k : h->eng.kernels_used()) {
+        if (!all.empty()) all += ",";
+        all += k;
+    }
+    if (buf && cap > 0) {
+        const size_t n = std::min<size_t>(all.size(), (size_t)cap - 1);
+        std::memcpy(buf, all.data(), n);
+        buf[n] = 0;
+    }
+    return (int32_t)all.size();
 }
 
 const char* gar_stage_kernel_name(const gar_handle* h, int32_t stage) {

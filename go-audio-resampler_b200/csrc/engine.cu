@@ -107,6 +107,13 @@ int Engine::init(const Chain& chain, int rows, int compute_dtype, int device, st
     return 0;
 }
 
+void Engine::note_kernel(const char* name) {
+    if (!name) return;
+    for (const char* k : kernels_used_)
+        if (k == name || std::strcmp(k, name) == 0) return;
+    kernels_used_.push_back(name);
+}
+
 void Engine::name_kernels() {
     for (size_t s = 0; s < chain_.stages.size(); ++s) {
         const StageDesign& sd = chain_.stages[s];
@@ -529,7 +536,8 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
                 f.t2 = spd.taps; f.L = spd.factor; f.at0 = nx.first; f.step = spd.step;
                 f.n_out = (int32_t)nx.n_out; f.interp = nx.interp ? 1 : 0;
                 f.out = optr; f.out_stride = ostride; f.n_streams = count;
-                if (launch_fused_up2_poly(f, dtype_, s)) {
+                if (const char* kn = launch_fused_up2_poly(f, dtype_, s)) {
+                    note_kernel(kn);
                     ++launches_;
                     ++oi;  // the polyphase op is done too
                     continue;
@@ -562,7 +570,7 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
                     c.stride = sd.factor; c.nf = 1; c.first = (int32_t)op.first; c.n_pos = (int32_t)op.n_out;
                 }
                 c.n_streams = count;
-                launch_fir(c, dtype_, s);
+                note_kernel(launch_fir(c, dtype_, s));
                 break;
             }
             case STAGE_POLY: {
@@ -576,7 +584,7 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
                 c.taps = sd.taps; c.L = sd.factor; c.at0 = op.first; c.step = sd.step;
                 c.n_out = (int32_t)op.n_out; c.interp = op.interp ? 1 : 0;
                 c.n_streams = count;
-                launch_poly(c, dtype_, s);
+                note_kernel(launch_poly(c, dtype_, s));
                 break;
             }
             case STAGE_CUBIC: {
@@ -587,7 +595,7 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
                 c.hist_out = hout; c.hist_out_stride = dv.hist_cap;
                 c.idx = d_cubic_idx_ + op.table_off; c.phase = d_cubic_phase_ + op.table_off;
                 c.n_out = (int32_t)op.n_out; c.n_streams = count;
-                launch_cubic(c, dtype_, s);
+                note_kernel(launch_cubic(c, dtype_, s));
                 break;
             }
         }

@@ -92,6 +92,8 @@ class Engine {
     void set_fuse(bool on) { fuse_ = on; }
     void reset_launches() { launches_ = 0; }
     int64_t device_bytes() const { return device_bytes_; }
+    // distinct kernel variants this engine has launched so far (names are static strings)
+    const std::vector<const char*>& kernels_used() const { return kernels_used_; }
 
     // Planning (pure integer; mutates `st`). flush=false: Process(n_in). flush=true: Flush().
     // pipeline_mode: path A semantics (constant.go) vs single engine (resampler.go).
@@ -137,6 +139,8 @@ class Engine {
     int64_t cubic_cap_ = 0;
     bool fuse_ = true;  // K4 fused x2 -> polyphase launches (GAR_NO_FUSE=1 disables, for A/B tests)
     int64_t launches_ = 0;
+    std::vector<const char*> kernels_used_;
+    void note_kernel(const char* name);
     int64_t device_bytes_ = 0;
 };
 

@@ -18,6 +18,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 
 namespace gar {
 namespace {
@@ -512,6 +513,42 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
 }
 
 
+
+// Carried tails of a fused x2 -> polyphase call (one block per row): the x2 stage's new tail is a plain copy,
+// the polyphase stage's new tail needs the last few intermediate samples, recomputed here with the same
+// strictly sequential chain as the tile core (bit-identical in float64).
+template <typename T>
+__device__ __forceinline__ void fused_carry_tails_rt(const FusedCall& c, const int64_t row) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const T* __restrict__ hist_u = static_cast<const T*>(c.hist_u) + row * c.hist_u_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    const T* __restrict__ hist_p = static_cast<const T*>(c.hist_p) + row * c.hist_p_stride;
+    const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
+    carry_row(hist_u, c.hu, in, c.n_in, static_cast<T*>(c.hist_u_out) + row * c.hist_u_out_stride, c.drop_u, c.new_hu);
+    T* hp_out = static_cast<T*>(c.hist_p_out) + row * c.hist_p_out_stride;
+    for (int i = tid; i < c.new_hp; i += NT) {
+        const int idx = c.drop_p + i;  // index into vp = hist_p ++ mid
+        T v;
+        if (idx < c.hp) {
+            v = hist_p[idx];
+        } else {
+            const int j = idx - c.hp;
+            const T* __restrict__ bk = bank_u + (j & 1) * c.t1;
+            if (sizeof(T) == 8) {
+                T acc = 0;
+                for (int t = 0; t < c.t1; ++t) acc = fma(vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), bk[t], acc);
+                v = acc;
+            } else {
+                double acc = 0;
+                for (int t = 0; t < c.t1; ++t)
+                    acc = fma((double)vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), (double)bk[t], acc);
+                v = (T)acc;
+            }
+        }
+        hp_out[i] = v;
+    }
+}
+
 // =============================================================================================
 // K4 — fused x2 up-sampler + polyphase stage. One block = one tile of MT = 2*NT*R intermediate samples:
 //   1. stage the input window (TMA bulk copy when regular) and the x2 bank in shared memory,
@@ -549,31 +586,7 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
     const int n_mid = c.np * NF;
 
     if (tile == n_tiles) {  // ---- carried tails ----
-        carry_row(hist_u, c.hu, in, c.n_in, static_cast<T*>(c.hist_u_out) + row * c.hist_u_out_stride, c.drop_u,
-                  c.new_hu);
-        T* hp_out = static_cast<T*>(c.hist_p_out) + row * c.hist_p_out_stride;
-        for (int i = tid; i < c.new_hp; i += NT) {
-            const int idx = c.drop_p + i;  // index into vp = hist_p ++ mid
-            T v;
-            if (idx < c.hp) {
-                v = hist_p[idx];
-            } else {
-                const int j = idx - c.hp;
-                const T* __restrict__ bk = bank_u + (j & 1) * c.t1;
-                if (sizeof(T) == 8) {  // same strictly sequential chain as the tile core: bit-identical
-                    T acc = 0;
-                    for (int t = 0; t < c.t1; ++t)
-                        acc = fma(vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), bk[t], acc);
-                    v = acc;
-                } else {
-                    double acc = 0;
-                    for (int t = 0; t < c.t1; ++t)
-                        acc = fma((double)vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), (double)bk[t], acc);
-                    v = (T)acc;
-                }
-            }
-            hp_out[i] = v;
-        }
+        fused_carry_tails_rt<T>(c, row);
         return;
     }
 
@@ -667,17 +680,357 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
             const int64_t co = (int64_t)phase * c.t2;
             for (int k = 0; k < c.t2; ++k) {
                 const T coef = fma(x, fma(x, fma(x, gd[co + k], gc[co + k]), gb[co + k]), ga[co + k]);
-                if (k & 1) acc1 = fma((double)h[k], (double)coef, acc1);
+                if ((k & 1) && sizeof(T) == 4) acc1 = fma((double)h[k], (double)coef, acc1);
                 else acc0 = fma((double)h[k], (double)coef, acc0);
             }
         } else {
             const T* __restrict__ ca = bank_pitch > 0 ? pbank + phase * bank_pitch : ga + (int64_t)phase * c.t2;
             for (int k = 0; k < c.t2; ++k) {
-                if (k & 1) acc1 = fma((double)h[k], (double)ca[k], acc1);
+                if ((k & 1) && sizeof(T) == 4) acc1 = fma((double)h[k], (double)ca[k], acc1);
                 else acc0 = fma((double)h[k], (double)ca[k], acc0);
             }
         }
         out[n] = (T)(acc0 + acc1);
+    }
+}
+
+// =============================================================================================
+// K4r — fused x2 up-sampler + polyphase stage for RATIONAL ratios (step and phase accumulator have no
+// fractional bits: 44.1k<->48k, 8k->12k, ... every ratio whose L/M is exact), register-tiled.
+//
+// The polyphase stage is periodic: L outputs consume exactly Mi = step>>16 intermediate samples, and output
+// n + L uses the same phase filter as output n on a window Mi samples later. A tile is P such periods of one
+// row (P = 16 or 32). Work on a tile has two kinds of items:
+//   x2 chunk   32 thread tasks of the register-tiled x2 core (fir_tile_accumulate, FMA-bound): R positions each,
+//              input window staged by a TMA bulk copy, results written to the tile's intermediate buffer in
+//              SHARED memory (period j at pitch Mi + PAD; PAD = 1 when Mi is even keeps the period lanes on
+//              different banks);
+//   poly task  a warp owns RN adjacent outputs of the period pattern and its LANES are the periods, so all
+//              lanes use the same phase filters -> every coefficient read is a shared-memory BROADCAST, and a
+//              lane slides a register window over its period: per tap, 1 sample LDS + RN broadcast coefficient
+//              LDS feed RN FMAs (the stand-alone kernel needs 2 loads per FMA). Output i of a thread sits at a
+//              STATIC window slot i*S (S = ceil(Mi/L)); the true offset lags the slot by e_i in [0, D] samples,
+//              absorbed by reading its filter row (stored with D zero taps on both sides) e_i taps early.
+//              Sums run strictly in tap order (zero taps are exact no-ops): float64 results are bit-identical
+//              to the stand-alone kernels.
+// The intermediate buffer is double-buffered and a block is persistent over consecutive tiles of a row: in one
+// iteration its warps pull items from ONE queue holding the poly tasks of tile t-1 and the x2 chunks of tile t,
+// so the shared-memory-bound and the FMA-bound work overlap, quantisation of either kind is absorbed by the
+// other, and there is one barrier per tile. The extra block of every row writes both carried tails.
+// =============================================================================================
+struct RatGeom {
+    int32_t Mi, P, D, tp, gpitch, vlen, G;  // see launch_fused_rat_t
+    int32_t cp, xlen, xbufs, nv;            // x2 filter (padded), input window capacity, window / intermediate buffers
+    int32_t n_tiles, tiles_per_block, n_groups;
+};
+
+constexpr int RAT_MAXT = 16;                 // tiles per block (pick_tiles_per_block caps at 16)
+constexpr int RAT_CTL_INTS = 8 + 6 * (RAT_MAXT + 4);
+constexpr int RAT_CTL_BYTES = ((RAT_CTL_INTS * 4 + 15) / 16) * 16;
+
+template <typename T, int S, int RN, int PAD>
+__global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c, const RatGeom g) {
+    using V = typename VecOf<T>::type;
+    constexpr int VEC = VecOf<T>::N;
+    static_assert(RN % VEC == 0, "a coefficient vector load covers whole outputs");
+    constexpr int NF = 2;
+    constexpr int R = sizeof(T) == 8 ? 6 : 12;  // x2 core: positions per thread task
+    constexpr int WN = (RN - 1) * S + 1;        // register window of the polyphase phase
+    const int NT = blockDim.x;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // [2] one mbarrier per input window buffer
+    int* ctl = reinterpret_cast<int*>(smem_raw + 16);
+    int* qhead = ctl;                                        // work-queue head
+    int* in_done = ctl + 8;                                  // [t] input item of local tile t finished
+    int* up_done = in_done + RAT_MAXT + 4;                   // [t] x2 chunks of tile t finished
+    int* po_done = up_done + RAT_MAXT + 4;                   // [t] poly tasks of tile t finished
+    int* gstart = po_done + RAT_MAXT + 4;                    // [k] first queue item of group k
+    int* nchunk = gstart + RAT_MAXT + 4;                     // [t] x2 chunks of tile t
+    int* tflags = nchunk + RAT_MAXT + 4;                     // [t] bit0: bulk input, bit1: mbarrier parity
+    T* cs = reinterpret_cast<T*>(smem_raw + 16 + RAT_CTL_BYTES);  // [2][cp]       x2 bank
+    T* xs0 = cs + NF * g.cp;                                      // [xbufs][xlen] x2 input windows
+    T* vs0 = xs0 + g.xbufs * g.xlen;                              // [nv][vlen]    intermediate samples of a tile
+    T* cg = vs0 + g.nv * g.vlen;  // [G][gpitch] polyphase coefficients, one tile [tap][RN outputs] per output group
+    int* goff = reinterpret_cast<int*>(cg + (size_t)g.G * g.gpitch);  // [G] window offset of the group
+    int* gtab = goff + g.G;                                            // [G*RN] phase << 8 | lag of every output
+
+    const int group = blockIdx.x % (g.n_groups + 1);
+    const int64_t row = blockIdx.x / (g.n_groups + 1);
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (group == g.n_groups) {
+        fused_carry_tails_rt<T>(c, row);
+        return;
+    }
+    const T* __restrict__ hist_u = static_cast<const T*>(c.hist_u) + row * c.hist_u_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    const T* __restrict__ hist_p = static_cast<const T*>(c.hist_p) + row * c.hist_p_stride;
+    T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+
+    const int Mi = g.Mi, P = g.P, D = g.D, L = c.L;
+    const int FM = D + 1;  // front margin of the intermediate buffer (window starts up to D + PAD before w = 0)
+    const int qM = Mi / L, rM = Mi - qM * L;
+    const int F0 = (int)(c.at0 >> 16);  // < L: full_n of output 0; tile t starts at output t*P*L, same phase pattern
+    const int64_t total_vp = (int64_t)c.hp + 2 * (int64_t)c.np;
+    const int t_first = group * g.tiles_per_block;
+    const int nt = min(g.tiles_per_block, g.n_tiles - t_first);
+    const int gpw = 32 / P, jl = lane & (P - 1), gsub = lane / P;
+    const int n_wt = (g.G + gpw - 1) / gpw;
+
+    // geometry of tile t: x2 positions [i_lo, i_lo + n_pos) feed vp[m0, m0 + wend)
+    auto tile_geom = [&](const int t, int64_t& m0, int& wend, int64_t& i_lo, int& n_pos, bool& bulk, int& words) {
+        m0 = (int64_t)t * P * Mi;
+        wend = (int)min((int64_t)P * Mi + c.t2 - 1, total_vp - m0);
+        const int64_t j_lo = max((int64_t)0, m0 - c.hp), j_hi = m0 + wend - c.hp;
+        i_lo = j_lo >> 1;
+        const int64_t i_hi = (j_hi + 1) >> 1;
+        n_pos = i_hi > i_lo ? (int)(i_hi - i_lo) : 0;
+        bulk = false;
+        words = 0;
+        int64_t gi = i_lo - c.hu;
+        if (gi >= 0 && n_pos > 0) {
+            const int mis = (int)((reinterpret_cast<uintptr_t>(in + gi) & 15u) / sizeof(T));
+            if (gi - mis >= 0) {  // start `mis` positions early: 16-byte aligned source, results below w = 0 are dropped
+                gi -= mis;
+                const int w = ((n_pos + mis - 1 + c.t1 + VEC - 1) / VEC) * VEC;
+                if (gi + w <= c.n_in && w <= g.xlen) {
+                    bulk = true;
+                    words = w;
+                    i_lo -= mis;
+                    n_pos += mis;
+                }
+            }
+        }
+    };
+
+    // ---- block set-up: control words, queue layout, zeroed buffers, banks ----
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        *qhead = 0;
+        int npar0 = 0, npar1 = 0;
+        for (int k = 0; k < nt; ++k) {
+            int64_t m0, i_lo;
+            int wend, n_pos, words;
+            bool bulk;
+            tile_geom(t_first + k, m0, wend, i_lo, n_pos, bulk, words);
+            nchunk[k] = ((n_pos + R - 1) / R + 31) / 32;
+            const int xb = g.xbufs == 2 ? (k & 1) : 0;
+            tflags[k] = (bulk ? 1 : 0) | (((xb ? npar1 : npar0) & 1) << 1);
+            if (bulk) {
+                if (xb) ++npar1;
+                else ++npar0;
+            }
+            in_done[k] = 0;
+            up_done[k] = 0;
+            po_done[k] = 0;
+        }
+        // queue order: group 0 = {I(0), I(1), U(0)*}; group k = {I(k+1), U(k)*, P(k-1)*}; group nt = {P(nt-1)*}
+        int at = 0;
+        for (int k = 0; k <= nt; ++k) {
+            gstart[k] = at;
+            if (k == 0) at += 1 + (nt > 1 ? 1 : 0) + nchunk[0];
+            else if (k < nt) at += (k + 1 < nt ? 1 : 0) + nchunk[k] + n_wt;
+            else at += n_wt;
+        }
+        gstart[nt + 1] = at;
+    }
+    for (int i = tid; i < g.xbufs * g.xlen + g.nv * g.vlen; i += NT) xs0[i] = T(0);  // xs and vs are adjacent
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    {
+        const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
+        for (int i = tid; i < NF * g.cp; i += NT) {
+            const int p = i / g.cp, k = i - p * g.cp;
+            cs[i] = k < c.t1 ? bank_u[p * c.t1 + k] : T(0);
+        }
+    }
+    // Polyphase pattern of a period (identical for every tile: tile t starts at output t*P*L, whose full_n is F0 past the
+    // tile origin): group gi = outputs [gi*RN, gi*RN + RN) of the period. Output i sits at window slot i*S; its true
+    // offset lags by e_i = o_i - i*S + Dg taps, so its phase filter is stored e_i taps late in the group's tile.
+    for (int gi = tid; gi < g.G; gi += NT) {
+        const unsigned rf = (unsigned)(F0 + gi * RN * Mi);
+        const int div0 = (int)(rf / (unsigned)L);
+        int ph = (int)rf - div0 * L, dv = 0, Dg = 0;
+        int o[RN], php[RN];
+#pragma unroll
+        for (int i = 0; i < RN; ++i) {
+            o[i] = dv;
+            php[i] = ph;
+            Dg = max(Dg, i * S - dv);
+            ph += rM;
+            dv += qM;
+            if (ph >= L) {
+                ph -= L;
+                ++dv;
+            }
+        }
+        goff[gi] = div0 - Dg;  // >= -D
+#pragma unroll
+        for (int i = 0; i < RN; ++i) gtab[gi * RN + i] = (php[i] << 8) | (o[i] - i * S + Dg);
+    }
+    __syncthreads();
+    {
+        const T* __restrict__ ba = static_cast<const T*>(c.bank_a);
+        const int per = g.tp * RN;
+        for (int idx = tid; idx < g.G * per; idx += NT) {
+            const int gi = idx / per, rem = idx - gi * per;
+            const int kk = rem / RN, i = rem - kk * RN;
+            const int pe = gtab[gi * RN + i];
+            const int k = kk - (pe & 255);
+            cg[(size_t)gi * g.gpitch + rem] = (k >= 0 && k < c.t2) ? ba[(pe >> 8) * c.t2 + k] : T(0);
+        }
+    }
+    __syncthreads();  // the only block-wide barrier: from here on warps synchronise through the counters
+
+    auto wait_ge = [&](int* cnt, const int target) {  // whole warp, all lanes poll (a broadcast read), then reconverge
+        while (*reinterpret_cast<volatile int*>(cnt) < target) __nanosleep(200);
+        __threadfence_block();
+        __syncwarp();
+    };
+    auto signal = [&](int* cnt) {  // whole warp: everything this warp wrote is visible before the count moves
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicAdd(cnt, 1);
+        __syncwarp();
+    };
+
+    int gk = 0;  // group of the last item this warp took (items come in increasing order)
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(qhead, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= gstart[nt + 1]) break;
+        while (item >= gstart[gk + 1]) ++gk;
+        int sub = item - gstart[gk];
+        // decode: kind 0 = input item I(k), 1 = x2 chunk U(k, sub), 2 = poly task P(k, sub)
+        int kind, k;
+        if (gk == 0) {
+            const int ni = 1 + (nt > 1 ? 1 : 0);
+            if (sub < ni) { kind = 0; k = sub; }
+            else { kind = 1; k = 0; sub -= ni; }
+        } else if (gk < nt) {
+            const int ni = gk + 1 < nt ? 1 : 0;
+            if (sub < ni) { kind = 0; k = gk + 1; }
+            else if (sub - ni < nchunk[gk]) { kind = 1; k = gk; sub -= ni; }
+            else { kind = 2; k = gk - 1; sub -= ni + nchunk[gk]; }
+        } else {
+            kind = 2;
+            k = nt - 1;
+        }
+        const int t = t_first + k;
+        const int xb = g.xbufs == 2 ? (k & 1) : 0;
+
+        if (kind == 2) {
+            // ---- poly task: RN adjacent outputs of the period pattern, lanes = periods ----
+            wait_ge(in_done + k, 1);
+            wait_ge(up_done + k, nchunk[k]);
+            const T* __restrict__ vr = vs0 + (k % g.nv) * g.vlen;
+            const int gi = sub * gpw + gsub;
+            if (gi < g.G) {
+                const int64_t n_lo = (int64_t)t * P * L;  // first output of the tile; its full_n is F0 past the tile origin
+                const int64_t n_hi = min((int64_t)c.n_out, n_lo + (int64_t)P * L);
+                const int iota0 = gi * RN;
+                // window slot x of lane jl is sample w = jl*Mi + off + x, stored at FM + w + PAD*floor(w/Mi)
+                const int off = goff[gi];
+                const int c0 = off < 0 ? -1 : off / Mi;
+                const int xc0 = (c0 + 1) * Mi - off, xc1 = xc0 + Mi;  // slots at which the walk enters the next period
+                const T* __restrict__ sp = vr + FM + jl * (Mi + PAD) + off + (PAD ? c0 : 0);
+                const T* __restrict__ cp0 = cg + (size_t)gi * g.gpitch;  // [tap][RN], 16-byte aligned
+                T W[WN], acc[RN];
+#pragma unroll
+                for (int x = 0; x < WN; ++x) W[x] = sp[x + (PAD ? (x >= xc0) + (x >= xc1) : 0)];
+#pragma unroll
+                for (int i = 0; i < RN; ++i) acc[i] = T(0);
+                auto tap = [&](const int u, const int kk) {  // u = kk % WN (compile-time in the unrolled bodies)
+                    T cf[RN];
+#pragma unroll
+                    for (int q = 0; q < RN / VEC; ++q)
+                        vec_unpack(*reinterpret_cast<const V*>(cp0 + kk * RN + q * VEC), cf + q * VEC);
+#pragma unroll
+                    for (int i = 0; i < RN; ++i) acc[i] = fma(W[(u + i * S) % WN], cf[i], acc[i]);
+                    const int x = kk + WN;
+                    W[u] = sp[x + (PAD ? (x >= xc0) + (x >= xc1) : 0)];
+                };
+                int it0 = 0;
+                for (; it0 + WN <= g.tp; it0 += WN) {  // branch-free bodies: the loads of the next taps overlap the FMAs
+#pragma unroll
+                    for (int u = 0; u < WN; ++u) tap(u, it0 + u);
+                }
+#pragma unroll
+                for (int u = 0; u < WN; ++u)
+                    if (it0 + u < g.tp) tap(u, it0 + u);
+                const int64_t nb = n_lo + (int64_t)jl * L + iota0;
+#pragma unroll
+                for (int i = 0; i < RN; ++i)
+                    if (iota0 + i < L && nb + i < n_hi) out[nb + i] = acc[i];
+            }
+            signal(po_done + k);
+            continue;
+        }
+
+        int64_t m0, i_lo;
+        int wend, n_pos, words;
+        bool bulk;
+        tile_geom(t, m0, wend, i_lo, n_pos, bulk, words);
+        T* __restrict__ xs = xs0 + xb * g.xlen;
+        T* __restrict__ vw = vs0 + (k % g.nv) * g.vlen;
+
+        if (kind == 0) {
+            // ---- input item: stage the x2 input window of tile k (TMA bulk copy when regular) and the part of
+            //      the tile that is the polyphase stage's carried tail ----
+            const int kprev = g.xbufs == 2 ? k - 2 : k - 1;  // last user of this window buffer
+            if (kprev >= 0) wait_ge(up_done + kprev, nchunk[kprev]);
+            if (k >= g.nv) wait_ge(po_done + (k - g.nv), n_wt);  // the intermediate buffer is free
+            if (bulk) {
+                if (lane == 0) {
+                    mbar_expect_tx(bar + xb, (uint32_t)(words * sizeof(T)));
+                    bulk_g2s(xs, in + (i_lo - c.hu), (uint32_t)(words * sizeof(T)), bar + xb);
+                }
+            } else {  // edge tile (touches the carried tail or the end of the row): guarded loads
+                const int need = n_pos > 0 ? n_pos - 1 + c.t1 : 0;
+                for (int i = lane; i < g.xlen; i += 32)
+                    xs[i] = i < need ? vload(hist_u, c.hu, in, c.n_in, (int)i_lo + i) : T(0);
+            }
+            for (int64_t d = m0 + lane; d < min((int64_t)c.hp, m0 + wend); d += 32) {
+                const int w = (int)(d - m0);
+                vw[FM + w + (PAD ? w / Mi : 0)] = hist_p[d];
+            }
+            signal(in_done + k);
+            continue;
+        }
+
+        // ---- x2 chunk: 32 thread tasks of the register-tiled FIR core -> intermediate buffer ----
+        wait_ge(in_done + k, 1);
+        if (k >= g.nv) wait_ge(po_done + (k - g.nv), n_wt);
+        if (bulk) {
+            const uint32_t par = (uint32_t)(tflags[k] >> 1) & 1u;
+            while (!mbar_try_wait(bar + xb, par)) {
+            }
+            __syncwarp();  // lanes leave the poll loop at different times: reconverge before the FIR core
+        }
+        const int n_tasks = (n_pos + R - 1) / R;
+        const int task = sub * 32 + lane;
+        if (task < n_tasks) {
+            const int woff = (int)((int64_t)c.hp + 2 * i_lo - m0);  // w of the first sample of position i_lo
+            T res[R][NF];
+            fir_tile_accumulate<T, 1, NF, R>(xs + R * task, cs, g.cp, c.t1, 0, res);
+            int w = woff + 2 * R * task;
+            int j = (w + Mi) / Mi - 1, r = w - j * Mi;  // floor division (w >= -Mi)
+            T* __restrict__ vp = vw + FM + w + (PAD ? j : 0);
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+#pragma unroll
+                for (int h = 0; h < NF; ++h) {
+                    if (w >= 0 && w < wend && R * task + q < n_pos) *vp = res[q][h];
+                    ++w;
+                    ++vp;
+                    if (++r == Mi) {
+                        r = 0;
+                        if (PAD) ++vp;
+                    }
+                }
+        }
+        signal(up_done + k);
     }
 }
 
@@ -750,14 +1103,16 @@ __global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_
     const T* __restrict__ cb = static_cast<const T*>(c.bank_b) + co;
     const T* __restrict__ cc = static_cast<const T*>(c.bank_c) + co;
     const T* __restrict__ cd = static_cast<const T*>(c.bank_d) + co;
-    // products of two float32 are exact in float64, so the float32 path only rounds once, at the store
+    // products of two float32 are exact in float64, so the float32 path only rounds once, at the store (two
+    // interleaved chains); float64 sums strictly in tap order, like every other float64 kernel here, so the
+    // fused kernels reproduce the stand-alone launches bit for bit
     double acc0 = 0, acc1 = 0;
     const int base = div - div0;
     for (int k = 0; k < c.taps; ++k) {
         T coef = ca[k];
         if (INTERP) coef = fma(x, fma(x, fma(x, cd[k], cc[k]), cb[k]), coef);
         const T h = staged ? xs[base + k] : vload(hist, c.hist_len, in, c.n_in, div + k);
-        if (k & 1) acc1 = fma((double)h, (double)coef, acc1);
+        if ((k & 1) && sizeof(T) == 4) acc1 = fma((double)h, (double)coef, acc1);
         else acc0 = fma((double)h, (double)coef, acc0);
     }
     (static_cast<T*>(c.out) + row * c.out_stride)[n] = (T)(acc0 + acc1);
@@ -1098,6 +1453,96 @@ static bool launch_fused_t(const FusedCall& c, cudaStream_t s) {
     return true;
 }
 
+// K4r launcher: picks the geometry; returns false when the pair is not a rational-ratio case it covers.
+template <typename T, int S, int RN, int PAD>
+static bool launch_fused_rat_t(const FusedCall& c, cudaStream_t s) {
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int R = sizeof(T) == 8 ? 6 : 12;
+    constexpr int NCH = (R - 1 + VEC - 1) / VEC + 1;
+    constexpr int WN = (RN - 1) * S + 1;
+    RatGeom g{};
+    g.Mi = (int32_t)(c.step >> 16);
+    const int Mi = g.Mi, L = c.L;
+    g.D = (RN - 1) * S - (RN - 1) * Mi / L;  // worst lag of a static window slot behind the true offset
+    g.tp = c.t2 + g.D;
+    g.G = (L + RN - 1) / RN;
+    g.cp = ((c.t1 + VEC - 1 + VEC - 1) / VEC) * VEC;
+    if (g.tp + 2 * WN > 2 * Mi) return false;  // the window walk may enter at most two further periods
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int64_t div_last = ((c.at0 >> 16) + (int64_t)(c.n_out - 1) * Mi) / L;
+    // configurations in order of preference: two 256-thread blocks per SM, else one 512-thread block
+    struct Opt { int P, nt, xbufs, nv; size_t lim; };
+    Opt opts[] = {{16, 256, 2, 2, 113 * 1024}, {32, 512, 2, 2, 227 * 1024}, {16, 512, 2, 2, 227 * 1024},
+                  {16, 512, 1, 2, 227 * 1024}};
+    static const int* forced = [] {  // tuning override: GAR_RAT_OPT="P,threads,xbufs,nv"
+        static int v[4];
+        const char* e = std::getenv("GAR_RAT_OPT");
+        return (e && std::sscanf(e, "%d,%d,%d,%d", v, v + 1, v + 2, v + 3) == 4) ? v : (const int*)nullptr;
+    }();
+    if (forced) opts[0] = Opt{forced[0], forced[1], forced[2], forced[3], 227 * 1024};
+    size_t smem = 0;
+    int nthreads = 0;
+    for (const Opt& o : opts) {
+        const int n_pos_max = (o.P * Mi + c.t2) / 2 + 2 + VEC;
+        const int tasks = (n_pos_max + R - 1) / R;
+        const int xlen = R * (tasks - 1) + (g.cp / VEC + NCH + 1) * VEC;
+        const int vlen = (((g.D + 1) + o.P * (Mi + PAD) + g.tp + 2 * WN + 4) + 1) & ~1;
+        // one coefficient tile [tp][RN] per output group; with two groups per warp (P = 16) the two broadcast reads of a
+        // tap must fall into different banks: tile pitch = 64 bytes mod 128
+        int gpitch = g.tp * RN;
+        while ((gpitch * (int)sizeof(T)) % 128 != 64) gpitch += VEC;
+        const size_t need = 16 + RAT_CTL_BYTES +
+                            ((size_t)2 * g.cp + (size_t)o.xbufs * xlen + (size_t)o.nv * vlen + (size_t)g.G * gpitch) * sizeof(T) +
+                            (size_t)g.G * (RN + 1) * sizeof(int);
+        if (need <= o.lim) {
+            g.P = o.P;
+            g.xlen = xlen;
+            g.xbufs = o.xbufs;
+            g.nv = o.nv;
+            g.vlen = vlen;
+            g.gpitch = gpitch;
+            smem = need;
+            nthreads = o.nt;
+            break;
+        }
+    }
+    if (!nthreads) return false;
+    g.n_tiles = (int32_t)(div_last / ((int64_t)g.P * Mi)) + 1;
+    g.tiles_per_block = pick_tiles_per_block(g.n_tiles, c.n_streams, &g.n_groups);
+    auto k = fused_up2_rat_kernel<T, S, RN, PAD>;
+    static size_t configured[64] = {0};
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)(g.n_groups + 1) * c.n_streams;
+    k<<<(unsigned)blocks, nthreads, smem, s>>>(c, g);
+    count_launch();
+    return true;
+}
+
+// A/B toggle (GAR_NO_RAT=1): fall back to the one-thread-per-output fused kernel
+static const bool g_fused_rat = [] {
+    const char* e = std::getenv("GAR_NO_RAT");
+    return !(e && e[0] && e[0] != '0');
+}();
+
+template <typename T>
+static bool launch_fused_rat(const FusedCall& c, cudaStream_t s) {
+    if (!g_fused_rat || c.interp || ((c.step | c.at0) & 0xFFFF) != 0 || c.n_out <= 0 || c.np <= 0) return false;
+    const int64_t Mi = c.step >> 16;
+    if (Mi <= c.L || Mi > 4 * (int64_t)c.L || Mi > 4096 || c.t2 > 512) return false;
+    const int S = (int)((Mi + c.L - 1) / c.L);
+    const bool pad = (Mi & 1) == 0;  // even period length: pad the period pitch to keep the lanes on distinct banks
+    switch (S) {
+        case 2: return pad ? launch_fused_rat_t<T, 2, 8, 1>(c, s) : launch_fused_rat_t<T, 2, 8, 0>(c, s);
+        case 3: return pad ? launch_fused_rat_t<T, 3, 6, 1>(c, s) : launch_fused_rat_t<T, 3, 6, 0>(c, s);
+        case 4: return pad ? launch_fused_rat_t<T, 4, 6, 1>(c, s) : launch_fused_rat_t<T, 4, 6, 0>(c, s);
+    }
+    return false;
+}
+
 const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s) {
     if (c.n_streams <= 0) return "none";
     if (dtype == DT_F32) {
@@ -1105,6 +1550,7 @@ const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s)
         return launch_fused_t<float, false>(c, s) ? "fused_up2_poly_f32" : nullptr;
     }
     if (c.interp) return launch_fused_t<double, true>(c, s) ? "fused_up2_poly_f64_interp" : nullptr;
+    if (launch_fused_rat<double>(c, s)) return "fused_up2_rat_f64";
     return launch_fused_t<double, false>(c, s) ? "fused_up2_poly_f64" : nullptr;
 }
 

@@ -123,6 +123,7 @@ SYMBOLS = {
     "gar_set_fusion": (_i32, [_vp, _i32]),
     "gar_kernel_launches": (_i64, [_vp, _i32]),
     "gar_stage_kernel_name": (C.c_char_p, [_vp, _i32]),
+    "gar_kernels_used": (_i32, [_vp, C.c_char_p, _i32]),
     "gar_measure_fma_peak": (_i32, [_i32, _i32, C.POINTER(C.c_double)]),
     "gar_version": (C.c_char_p, []),
 }
@@ -236,6 +237,12 @@ class _Handle:
 
     def kernel_names(self):
         return [lib().gar_stage_kernel_name(self._h, s).decode() for s in range(lib().gar_num_stages(self._h))]
+
+    def last_kernels(self):
+        """Distinct kernel variants launched through this handle so far."""
+        buf = C.create_string_buffer(1024)
+        lib().gar_kernels_used(self._h, buf, 1024)
+        return [k for k in buf.value.decode().split(",") if k]
 
     def set_fusion(self, enabled: bool):
         """Enable/disable the fused x2 -> polyphase kernel (K4)."""

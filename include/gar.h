@@ -225,6 +225,9 @@ int32_t gar_set_fusion(gar_handle* h, int32_t enabled);
 int64_t gar_kernel_launches(const gar_handle* h, int32_t reset);
 /* Name of the dominant kernel variant chosen for stage `stage` (for bench/ncu filters). */
 const char* gar_stage_kernel_name(const gar_handle* h, int32_t stage);
+/* Comma-separated names of the distinct kernel variants the handle has launched so far (fused launches appear
+ * under their own names), written to buf (NUL-terminated, truncated to cap). Returns the untruncated length. */
+int32_t gar_kernels_used(const gar_handle* h, char* buf, int32_t cap);
 /* Dependent-FMA micro-benchmark on `device`: achieved FMA TFLOP/s for dtype (roofline denominator). */
 int32_t gar_measure_fma_peak(int32_t device, int32_t dtype, double* tflops);
 const char* gar_version(void);

@@ -221,3 +221,36 @@ def test_fused_x2_polyphase_kernel_equals_unfused(ir, orr, dt):
     else:
         assert len(fa) == len(fb) and np.max(np.abs(fa - fb)) <= 2e-7
     assert la < lb  # fewer launches when fused
+
+
+@pytest.mark.parametrize("ir,orr,rows,n,kernel", [
+    (44100, 48000, 200, 60000, "fused_up2_rat_f64"),   # Mi/L = 147/80  -> slot stride 2, persistent multi-tile blocks
+    (48000, 44100, 40, 70000, "fused_up2_rat_f64"),    # 320/147 -> slot stride 3
+    (48000, 30000, 24, 50000, "fused_up2_rat_f64"),    # 3.2     -> slot stride 4
+    (8000, 12000, 33, 20000, "fused_up2_rat_f64"),     # 4/3
+    (44100, 32000, 16, 41000, "fused_up2_rat_f64"),
+])
+def test_rational_fused_kernel_batched_rows_vs_unfused_and_oracle(ir, orr, rows, n, kernel):
+    """K4r (register-tiled rational-ratio fused kernel): many lock-step rows, ragged chunking (every carried
+    phase/tail state), flush. Bit-identical to the stand-alone launches; <= 1e-12 against the oracle."""
+    rng = np.random.default_rng(77)
+    x = (0.5 * np.sin(2 * np.pi * rng.random((rows, 1)) * 0.05 * np.arange(n)[None, :]) +
+         0.4 * (rng.random((rows, n)) - 0.5))
+    a = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float64)
+    b = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float64)
+    b.set_fusion(False)
+    cuts = [0, 7, 7 + 311, n // 3, n - 1234, n]
+    ya, yb = [], []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        xa = np.ascontiguousarray(x[:, lo:hi])
+        ya.append(a.ProcessBatch(xa)[0].copy())
+        yb.append(b.ProcessBatch(xa)[0].copy())
+    ya.append(a.FlushBatch()[0].copy())
+    yb.append(b.FlushBatch()[0].copy())
+    assert kernel in a.last_kernels(), a.last_kernels()
+    ya, yb = np.concatenate(ya, axis=1), np.concatenate(yb, axis=1)
+    np.testing.assert_array_equal(ya, yb)
+    pick = sorted(set([0, 1, rows // 2, rows - 1]))
+    want, counts = O.batch_resample(x[pick], ir, orr, O.Q_HIGH, n_threads=4)
+    assert np.all(counts == ya.shape[1])
+    assert np.max(np.abs(ya[pick] - want[:, :ya.shape[1]])) <= 1e-12
