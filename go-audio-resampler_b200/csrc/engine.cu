@@ -21,6 +21,7 @@ Engine::~Engine() {
     for (auto& d : dev_) {
         for (auto& b : d.bank) if (b) cudaFree(b);
         for (auto& h : d.hist) if (h) cudaFree(h);
+        if (d.rat_cache.dev) cudaFree(d.rat_cache.dev);
     }
     for (void* b : ibuf_) if (b) cudaFree(b);
     if (zeros_) cudaFree(zeros_);
@@ -32,6 +33,7 @@ Engine::~Engine() {
 
 int Engine::upload_bank(int stage, int which, const std::vector<double>& v, std::string& err) {
     StageDev& d = dev_[(size_t)stage];
+    d.rat_cache.built.assign(d.rat_cache.built.size(), 0);  // tiles derive from the bank
     if (d.bank[which]) {
         cudaFree(d.bank[which]);
         d.bank[which] = nullptr;
@@ -518,7 +520,7 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
                 nx.n_in == op.n_out && chain_.stages[(size_t)nx.stage].engine_index == su.engine_index) {
                 const StageDesign& spd = chain_.stages[(size_t)nx.stage];
                 const StageDev& du = dev_[(size_t)op.stage];
-                const StageDev& dpv = dev_[(size_t)nx.stage];
+                StageDev& dpv = dev_[(size_t)nx.stage];
                 int64_t ostride = 0;
                 void* optr = dst_ptr(nx, ostride);
                 FusedCall f{};
@@ -536,7 +538,7 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
                 f.t2 = spd.taps; f.L = spd.factor; f.at0 = nx.first; f.step = spd.step;
                 f.n_out = (int32_t)nx.n_out; f.interp = nx.interp ? 1 : 0;
                 f.out = optr; f.out_stride = ostride; f.n_streams = count;
-                if (const char* kn = launch_fused_up2_poly(f, dtype_, s)) {
+                if (const char* kn = launch_fused_up2_poly(f, dtype_, s, &dpv.rat_cache)) {
                     note_kernel(kn);
                     ++launches_;
                     ++oi;  // the polyphase op is done too
@@ -550,7 +552,7 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
             continue;
         }
         const StageDesign& sd = chain_.stages[(size_t)op.stage];
-        const StageDev& dv = dev_[(size_t)op.stage];
+        StageDev& dv = dev_[(size_t)op.stage];
         const void* hin = (const char*)dv.hist[op.parity_in] + (size_t)row0 * (size_t)dv.hist_cap * esz_;
         void* hout = (char*)dv.hist[op.parity_in ^ 1] + (size_t)row0 * (size_t)dv.hist_cap * esz_;
         switch (sd.kind) {
@@ -584,7 +586,7 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
                 c.taps = sd.taps; c.L = sd.factor; c.at0 = op.first; c.step = sd.step;
                 c.n_out = (int32_t)op.n_out; c.interp = op.interp ? 1 : 0;
                 c.n_streams = count;
-                note_kernel(launch_poly(c, dtype_, s));
+                note_kernel(launch_poly(c, dtype_, s, &dv.rat_cache));
                 break;
             }
             case STAGE_CUBIC: {

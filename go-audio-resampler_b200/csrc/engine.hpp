@@ -69,6 +69,7 @@ struct StageDev {
     void* hist[2] = {nullptr, nullptr};
     int64_t hist_cap = 0;
     const char* kernel = "";
+    RatCache rat_cache;  // POLY stages: coefficient tiles of the fused rational-ratio kernel
 };
 
 class Engine {

@@ -77,6 +77,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 
+// per-thread asynchronous global -> shared copy of one element (SASS LDGSTS); completion via cp.async.wait_all
+__device__ __forceinline__ void cp_async_elem(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // Register-tiled sliding-window FIR core shared by the stand-alone and the fused kernels: R adjacent positions
 // (window stride M) x NF filters per thread, `xt` = this thread's window in shared memory (16-byte aligned),
 // `cs` = [NF][cp] taps shifted by the pad `a`. One LDS.128 of samples + one broadcast LDS.128 per filter feed
@@ -722,132 +731,21 @@ struct RatGeom {
     int32_t Mi, P, D, tp, gpitch, vlen, G;  // see launch_fused_rat_t
     int32_t cp, xlen, xbufs, nv;            // x2 filter (padded), input window capacity, window / intermediate buffers
     int32_t n_tiles, tiles_per_block, n_groups;
+    const void* cg_src;  // this launch's coefficient tile in global memory ([G][gpitch] T, then goff[G] ints)
+    uint32_t cg_bytes;   // its size, a multiple of 16
 };
 
-constexpr int RAT_MAXT = 16;                 // tiles per block (pick_tiles_per_block caps at 16)
-constexpr int RAT_CTL_INTS = 8 + 6 * (RAT_MAXT + 4);
-constexpr int RAT_CTL_BYTES = ((RAT_CTL_INTS * 4 + 15) / 16) * 16;
-
-template <typename T, int S, int RN, int PAD>
-__global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c, const RatGeom g) {
-    using V = typename VecOf<T>::type;
-    constexpr int VEC = VecOf<T>::N;
-    static_assert(RN % VEC == 0, "a coefficient vector load covers whole outputs");
-    constexpr int NF = 2;
-    constexpr int R = sizeof(T) == 8 ? 6 : 12;  // x2 core: positions per thread task
-    constexpr int WN = (RN - 1) * S + 1;        // register window of the polyphase phase
-    const int NT = blockDim.x;
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // [2] one mbarrier per input window buffer
-    int* ctl = reinterpret_cast<int*>(smem_raw + 16);
-    int* qhead = ctl;                                        // work-queue head
-    int* in_done = ctl + 8;                                  // [t] input item of local tile t finished
-    int* up_done = in_done + RAT_MAXT + 4;                   // [t] x2 chunks of tile t finished
-    int* po_done = up_done + RAT_MAXT + 4;                   // [t] poly tasks of tile t finished
-    int* gstart = po_done + RAT_MAXT + 4;                    // [k] first queue item of group k
-    int* nchunk = gstart + RAT_MAXT + 4;                     // [t] x2 chunks of tile t
-    int* tflags = nchunk + RAT_MAXT + 4;                     // [t] bit0: bulk input, bit1: mbarrier parity
-    T* cs = reinterpret_cast<T*>(smem_raw + 16 + RAT_CTL_BYTES);  // [2][cp]       x2 bank
-    T* xs0 = cs + NF * g.cp;                                      // [xbufs][xlen] x2 input windows
-    T* vs0 = xs0 + g.xbufs * g.xlen;                              // [nv][vlen]    intermediate samples of a tile
-    T* cg = vs0 + g.nv * g.vlen;  // [G][gpitch] polyphase coefficients, one tile [tap][RN outputs] per output group
-    int* goff = reinterpret_cast<int*>(cg + (size_t)g.G * g.gpitch);  // [G] window offset of the group
-    int* gtab = goff + g.G;                                            // [G*RN] phase << 8 | lag of every output
-
-    const int group = blockIdx.x % (g.n_groups + 1);
-    const int64_t row = blockIdx.x / (g.n_groups + 1);
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (group == g.n_groups) {
-        fused_carry_tails_rt<T>(c, row);
-        return;
-    }
-    const T* __restrict__ hist_u = static_cast<const T*>(c.hist_u) + row * c.hist_u_stride;
-    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
-    const T* __restrict__ hist_p = static_cast<const T*>(c.hist_p) + row * c.hist_p_stride;
-    T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
-
-    const int Mi = g.Mi, P = g.P, D = g.D, L = c.L;
-    const int FM = D + 1;  // front margin of the intermediate buffer (window starts up to D + PAD before w = 0)
+// Builds the coefficient tile of one start phase F0 (RatCache): for output group gi = outputs [gi*RN, gi*RN + RN) of the
+// period, tile[gi][tap][i] = a-bank[phase_i][tap - e_i] (zero outside the filter), then goff[gi] = window offset.
+// Output i sits at window slot i*S; its true offset lags the slot by e_i = o_i - i*S + Dg taps.
+template <typename T, int S, int RN>
+__global__ void __launch_bounds__(256) rat_build_tile_kernel(const T* __restrict__ bank_a, const int t2, const int L,
+                                                             const int Mi, const int F0, const int G, const int tp,
+                                                             const int gpitch, T* __restrict__ tile) {
+    extern __shared__ int gtab_s[];  // [G*RN] phase << 8 | lag
+    int* goff = reinterpret_cast<int*>(tile + (size_t)G * gpitch);
     const int qM = Mi / L, rM = Mi - qM * L;
-    const int F0 = (int)(c.at0 >> 16);  // < L: full_n of output 0; tile t starts at output t*P*L, same phase pattern
-    const int64_t total_vp = (int64_t)c.hp + 2 * (int64_t)c.np;
-    const int t_first = group * g.tiles_per_block;
-    const int nt = min(g.tiles_per_block, g.n_tiles - t_first);
-    const int gpw = 32 / P, jl = lane & (P - 1), gsub = lane / P;
-    const int n_wt = (g.G + gpw - 1) / gpw;
-
-    // geometry of tile t: x2 positions [i_lo, i_lo + n_pos) feed vp[m0, m0 + wend)
-    auto tile_geom = [&](const int t, int64_t& m0, int& wend, int64_t& i_lo, int& n_pos, bool& bulk, int& words) {
-        m0 = (int64_t)t * P * Mi;
-        wend = (int)min((int64_t)P * Mi + c.t2 - 1, total_vp - m0);
-        const int64_t j_lo = max((int64_t)0, m0 - c.hp), j_hi = m0 + wend - c.hp;
-        i_lo = j_lo >> 1;
-        const int64_t i_hi = (j_hi + 1) >> 1;
-        n_pos = i_hi > i_lo ? (int)(i_hi - i_lo) : 0;
-        bulk = false;
-        words = 0;
-        int64_t gi = i_lo - c.hu;
-        if (gi >= 0 && n_pos > 0) {
-            const int mis = (int)((reinterpret_cast<uintptr_t>(in + gi) & 15u) / sizeof(T));
-            if (gi - mis >= 0) {  // start `mis` positions early: 16-byte aligned source, results below w = 0 are dropped
-                gi -= mis;
-                const int w = ((n_pos + mis - 1 + c.t1 + VEC - 1) / VEC) * VEC;
-                if (gi + w <= c.n_in && w <= g.xlen) {
-                    bulk = true;
-                    words = w;
-                    i_lo -= mis;
-                    n_pos += mis;
-                }
-            }
-        }
-    };
-
-    // ---- block set-up: control words, queue layout, zeroed buffers, banks ----
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_init(bar + 1, 1);
-        *qhead = 0;
-        int npar0 = 0, npar1 = 0;
-        for (int k = 0; k < nt; ++k) {
-            int64_t m0, i_lo;
-            int wend, n_pos, words;
-            bool bulk;
-            tile_geom(t_first + k, m0, wend, i_lo, n_pos, bulk, words);
-            nchunk[k] = ((n_pos + R - 1) / R + 31) / 32;
-            const int xb = g.xbufs == 2 ? (k & 1) : 0;
-            tflags[k] = (bulk ? 1 : 0) | (((xb ? npar1 : npar0) & 1) << 1);
-            if (bulk) {
-                if (xb) ++npar1;
-                else ++npar0;
-            }
-            in_done[k] = 0;
-            up_done[k] = 0;
-            po_done[k] = 0;
-        }
-        // queue order: group 0 = {I(0), I(1), U(0)*}; group k = {I(k+1), U(k)*, P(k-1)*}; group nt = {P(nt-1)*}
-        int at = 0;
-        for (int k = 0; k <= nt; ++k) {
-            gstart[k] = at;
-            if (k == 0) at += 1 + (nt > 1 ? 1 : 0) + nchunk[0];
-            else if (k < nt) at += (k + 1 < nt ? 1 : 0) + nchunk[k] + n_wt;
-            else at += n_wt;
-        }
-        gstart[nt + 1] = at;
-    }
-    for (int i = tid; i < g.xbufs * g.xlen + g.nv * g.vlen; i += NT) xs0[i] = T(0);  // xs and vs are adjacent
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    {
-        const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
-        for (int i = tid; i < NF * g.cp; i += NT) {
-            const int p = i / g.cp, k = i - p * g.cp;
-            cs[i] = k < c.t1 ? bank_u[p * c.t1 + k] : T(0);
-        }
-    }
-    // Polyphase pattern of a period (identical for every tile: tile t starts at output t*P*L, whose full_n is F0 past the
-    // tile origin): group gi = outputs [gi*RN, gi*RN + RN) of the period. Output i sits at window slot i*S; its true
-    // offset lags by e_i = o_i - i*S + Dg taps, so its phase filter is stored e_i taps late in the group's tile.
-    for (int gi = tid; gi < g.G; gi += NT) {
+    for (int gi = threadIdx.x; gi < G; gi += blockDim.x) {
         const unsigned rf = (unsigned)(F0 + gi * RN * Mi);
         const int div0 = (int)(rf / (unsigned)L);
         int ph = (int)rf - div0 * L, dv = 0, Dg = 0;
@@ -866,20 +764,165 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
         }
         goff[gi] = div0 - Dg;  // >= -D
 #pragma unroll
-        for (int i = 0; i < RN; ++i) gtab[gi * RN + i] = (php[i] << 8) | (o[i] - i * S + Dg);
+        for (int i = 0; i < RN; ++i) gtab_s[gi * RN + i] = (php[i] << 8) | (o[i] - i * S + Dg);
     }
     __syncthreads();
-    {
-        const T* __restrict__ ba = static_cast<const T*>(c.bank_a);
-        const int per = g.tp * RN;
-        for (int idx = tid; idx < g.G * per; idx += NT) {
-            const int gi = idx / per, rem = idx - gi * per;
+    for (int idx = threadIdx.x; idx < G * gpitch; idx += blockDim.x) {
+        const int gi = idx / gpitch, rem = idx - gi * gpitch;
+        T v = T(0);
+        if (rem < tp * RN) {
             const int kk = rem / RN, i = rem - kk * RN;
-            const int pe = gtab[gi * RN + i];
+            const int pe = gtab_s[gi * RN + i];
             const int k = kk - (pe & 255);
-            cg[(size_t)gi * g.gpitch + rem] = (k >= 0 && k < c.t2) ? ba[(pe >> 8) * c.t2 + k] : T(0);
+            if (k >= 0 && k < t2) v = bank_a[(pe >> 8) * t2 + k];
+        }
+        tile[idx] = v;
+    }
+}
+
+constexpr int RAT_MAXT = 16;                 // tiles per block (pick_tiles_per_block caps at 16)
+constexpr int RAT_CTL_INTS = 8 + 11 * (RAT_MAXT + 4);
+constexpr int RAT_CTL_BYTES = ((RAT_CTL_INTS * 4 + 15) / 16) * 16;
+
+template <typename T, int S, int RN, int PAD, bool FUSED>
+__global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c, const RatGeom g) {
+    using V = typename VecOf<T>::type;
+    constexpr int VEC = VecOf<T>::N;
+    static_assert(RN % VEC == 0, "a coefficient vector load covers whole outputs");
+    constexpr int NF = 2;
+    constexpr int R = sizeof(T) == 8 ? 6 : 12;  // x2 core: positions per thread task
+    constexpr int WN = (RN - 1) * S + 1;        // register window of the polyphase phase
+    const int NT = blockDim.x;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // [4] one mbarrier per input window buffer, [4]: the tile
+    int* ctl = reinterpret_cast<int*>(smem_raw + 48);
+    int* qhead = ctl;                                        // work-queue head
+    int* in_done = ctl + 8;                                  // [t] input item of local tile t finished
+    int* up_done = in_done + RAT_MAXT + 4;                   // [t] x2 chunks of tile t finished
+    int* po_done = up_done + RAT_MAXT + 4;                   // [t] poly tasks of tile t finished
+    int* gstart = po_done + RAT_MAXT + 4;                    // [k] first queue item of group k
+    int* nchunk = gstart + RAT_MAXT + 4;                     // [t] x2 chunks of tile t
+    int* tflags = nchunk + RAT_MAXT + 4;                     // [t] bit0: bulk input, bit1: mbarrier parity
+    int* tg_src = tflags + RAT_MAXT + 4;                     // [t] tile geometry: i_lo - hu (index into `in`)
+    int* tg_npos = tg_src + RAT_MAXT + 4;                    // [t] x2 positions
+    int* tg_wend = tg_npos + RAT_MAXT + 4;                   // [t] samples of vp the tile covers
+    int* tg_words = tg_wend + RAT_MAXT + 4;                  // [t] bulk-copy length in samples
+    int* tg_woff = tg_words + RAT_MAXT + 4;                  // [t] w of the first sample of the first position
+    T* cs = reinterpret_cast<T*>(smem_raw + 48 + RAT_CTL_BYTES);  // [2][cp]       x2 bank
+    T* xs0 = cs + NF * g.cp;                                      // [xbufs][xlen] x2 input windows
+    T* vs0 = xs0 + (FUSED ? g.xbufs * g.xlen : 0);                // [nv][vlen]    intermediate samples of a tile
+    T* cg = vs0 + g.nv * g.vlen;  // [G][gpitch] polyphase coefficients, one tile [tap][RN outputs] per output group
+    int* goff = reinterpret_cast<int*>(cg + (size_t)g.G * g.gpitch);  // [G] window offset of the group (part of the tile)
+
+    const int group = blockIdx.x % (g.n_groups + 1);
+    const int64_t row = blockIdx.x / (g.n_groups + 1);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const T* __restrict__ hist_u = static_cast<const T*>(c.hist_u) + row * c.hist_u_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    const T* __restrict__ hist_p = static_cast<const T*>(c.hist_p) + row * c.hist_p_stride;
+    T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+    if (group == g.n_groups) {  // carried tails
+        if (FUSED) fused_carry_tails_rt<T>(c, row);
+        else carry_row(hist_p, c.hp, in, c.n_in, static_cast<T*>(c.hist_p_out) + row * c.hist_p_out_stride, c.drop_p, c.new_hp);
+        return;
+    }
+
+    const int Mi = g.Mi, P = g.P, D = g.D, L = c.L;
+    const int FM = D + 1;  // front margin of the intermediate buffer (window starts up to D + PAD before w = 0)
+    // polyphase input vp = carried tail ++ (FUSED: the x2 stage's 2*np outputs, made here; else the stage's input `in`)
+    const int64_t total_vp = (int64_t)c.hp + (FUSED ? 2 * (int64_t)c.np : (int64_t)c.n_in);
+    const int t_first = group * g.tiles_per_block;
+    const int nt = min(g.tiles_per_block, g.n_tiles - t_first);
+    const int gpw = 32 / P, jl = lane & (P - 1), gsub = lane / P;
+    const int n_wt = (g.G + gpw - 1) / gpw;
+
+    // geometry of tile t: x2 positions [i_lo, i_lo + n_pos) feed vp[m0, m0 + wend)
+    auto tile_geom = [&](const int t, int64_t& m0, int& wend, int64_t& i_lo, int& n_pos, bool& bulk, int& words) {
+        m0 = (int64_t)t * P * Mi;
+        wend = (int)min((int64_t)P * Mi + c.t2 - 1, total_vp - m0);
+        i_lo = 0;
+        n_pos = 0;
+        bulk = false;
+        words = 0;
+        if (!FUSED) return;
+        const int64_t j_lo = max((int64_t)0, m0 - c.hp), j_hi = m0 + wend - c.hp;
+        i_lo = j_lo >> 1;
+        const int64_t i_hi = (j_hi + 1) >> 1;
+        n_pos = i_hi > i_lo ? (int)(i_hi - i_lo) : 0;
+        int64_t gi = i_lo - c.hu;
+        if (gi >= 0 && n_pos > 0) {
+            const int mis = (int)((reinterpret_cast<uintptr_t>(in + gi) & 15u) / sizeof(T));
+            if (gi - mis >= 0) {  // start `mis` positions early: 16-byte aligned source, results below w = 0 are dropped
+                gi -= mis;
+                const int w = ((n_pos + mis - 1 + c.t1 + VEC - 1) / VEC) * VEC;
+                if (gi + w <= c.n_in && w <= g.xlen) {
+                    bulk = true;
+                    words = w;
+                    i_lo -= mis;
+                    n_pos += mis;
+                }
+            }
+        }
+    };
+
+    // ---- block set-up: control words, queue layout, zeroed buffers, banks ----
+    const int NX = FUSED ? g.xbufs : g.nv;  // input prefetch depth (poly-only: the input lands in the tile buffers)
+    if (tid == 0) {
+        for (int b = 0; b < 5; ++b) mbar_init(bar + b, 1);
+        *qhead = 0;
+        // this launch's coefficient tile (built once per start phase, RatCache): one bulk copy, overlapped with the set-up
+        mbar_expect_tx(bar + 4, g.cg_bytes);
+        bulk_g2s(cg, g.cg_src, g.cg_bytes, bar + 4);
+    }
+    if (tid < nt) {  // geometry of the block's tiles, one thread each
+        const int k = tid;
+        int64_t m0, i_lo;
+        int wend, n_pos, words;
+        bool bulk;
+        tile_geom(t_first + k, m0, wend, i_lo, n_pos, bulk, words);
+        nchunk[k] = ((n_pos + R - 1) / R + 31) / 32;
+        tflags[k] = bulk ? 1 : 0;
+        tg_src[k] = (int)(i_lo - c.hu);
+        tg_npos[k] = n_pos;
+        tg_wend[k] = wend;
+        tg_words[k] = words;
+        tg_woff[k] = (int)((int64_t)c.hp + 2 * i_lo - m0);
+        in_done[k] = 0;
+        up_done[k] = 0;
+        po_done[k] = 0;
+    }
+    for (int i = tid; i < (FUSED ? g.xbufs * g.xlen : 0) + g.nv * g.vlen; i += NT) xs0[i] = T(0);  // xs, vs adjacent
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (FUSED) {
+        const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
+        for (int i = tid; i < NF * g.cp; i += NT) {
+            const int p = i / g.cp, k = i - p * g.cp;
+            cs[i] = k < c.t1 ? bank_u[p * c.t1 + k] : T(0);
         }
     }
+    __syncthreads();
+    if (tid == 0) {
+        // mbarrier parities and the queue: group 0 = {I(0..NX-1), U(0)*}; group k = {I(k+NX-1), U(k)*, P(k-1)*};
+        // group nt = {P(nt-1)*}
+        unsigned parbits = 0u;  // current mbarrier parity of every window buffer
+        int at = 0;
+        for (int k = 0; k <= nt; ++k) {
+            gstart[k] = at;
+            if (k < nt) {
+                const int xb = k % NX;
+                if (tflags[k] & 1) {
+                    tflags[k] |= (int)(((parbits >> xb) & 1u) << 1);
+                    parbits ^= 1u << xb;
+                }
+            }
+            if (k == 0) at += min(NX, nt) + nchunk[0];
+            else if (k < nt) at += (k + NX - 1 < nt ? 1 : 0) + nchunk[k] + n_wt;
+            else at += n_wt;
+        }
+        gstart[nt + 1] = at;
+    }
+    while (!mbar_try_wait(bar + 4, 0)) __nanosleep(20);  // the coefficient tile has landed
     __syncthreads();  // the only block-wide barrier: from here on warps synchronise through the counters
 
     auto wait_ge = [&](int* cnt, const int target) {  // whole warp, all lanes poll (a broadcast read), then reconverge
@@ -905,12 +948,12 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
         // decode: kind 0 = input item I(k), 1 = x2 chunk U(k, sub), 2 = poly task P(k, sub)
         int kind, k;
         if (gk == 0) {
-            const int ni = 1 + (nt > 1 ? 1 : 0);
+            const int ni = min(NX, nt);
             if (sub < ni) { kind = 0; k = sub; }
             else { kind = 1; k = 0; sub -= ni; }
         } else if (gk < nt) {
-            const int ni = gk + 1 < nt ? 1 : 0;
-            if (sub < ni) { kind = 0; k = gk + 1; }
+            const int ni = gk + NX - 1 < nt ? 1 : 0;
+            if (sub < ni) { kind = 0; k = gk + NX - 1; }
             else if (sub - ni < nchunk[gk]) { kind = 1; k = gk; sub -= ni; }
             else { kind = 2; k = gk - 1; sub -= ni + nchunk[gk]; }
         } else {
@@ -918,7 +961,7 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
             k = nt - 1;
         }
         const int t = t_first + k;
-        const int xb = g.xbufs == 2 ? (k & 1) : 0;
+        const int xb = k % NX;
 
         if (kind == 2) {
             // ---- poly task: RN adjacent outputs of the period pattern, lanes = periods ----
@@ -968,29 +1011,54 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
             continue;
         }
 
-        int64_t m0, i_lo;
-        int wend, n_pos, words;
-        bool bulk;
-        tile_geom(t, m0, wend, i_lo, n_pos, bulk, words);
+        const int n_pos = tg_npos[k], wend = tg_wend[k];
+        const bool bulk = (tflags[k] & 1) != 0;
         T* __restrict__ xs = xs0 + xb * g.xlen;
         T* __restrict__ vw = vs0 + (k % g.nv) * g.vlen;
 
         if (kind == 0) {
             // ---- input item: stage the x2 input window of tile k (TMA bulk copy when regular) and the part of
             //      the tile that is the polyphase stage's carried tail ----
-            const int kprev = g.xbufs == 2 ? k - 2 : k - 1;  // last user of this window buffer
+            const int kprev = k - NX;  // last user of this window buffer
             if (kprev >= 0) wait_ge(up_done + kprev, nchunk[kprev]);
             if (k >= g.nv) wait_ge(po_done + (k - g.nv), n_wt);  // the intermediate buffer is free
+            if (!FUSED) {
+                // poly-only: the tile's samples come straight from the carried tail / the stage input, one asynchronous
+                // element copy each (period j at pitch Mi + PAD)
+                const int64_t m0 = (int64_t)t * P * Mi;
+                for (int j = 0; j * Mi < wend; ++j) {
+                    T* __restrict__ dst = vw + FM + j * (Mi + PAD);
+                    const int64_t d0 = m0 + (int64_t)j * Mi;
+                    const int rn = min(Mi, wend - j * Mi);
+                    for (int r = lane; r < rn; r += 32) {
+                        const int64_t d = d0 + r;
+                        if (d < c.hp) dst[r] = hist_p[d];
+                        else cp_async_elem(dst + r, in + (d - c.hp));
+                    }
+                }
+                cp_async_wait_all();
+                signal(in_done + k);
+                continue;
+            }
             if (bulk) {
                 if (lane == 0) {
-                    mbar_expect_tx(bar + xb, (uint32_t)(words * sizeof(T)));
-                    bulk_g2s(xs, in + (i_lo - c.hu), (uint32_t)(words * sizeof(T)), bar + xb);
+                    const uint32_t bytes = (uint32_t)(tg_words[k] * sizeof(T));
+                    mbar_expect_tx(bar + xb, bytes);
+                    bulk_g2s(xs, in + tg_src[k], bytes, bar + xb);
                 }
             } else {  // edge tile (touches the carried tail or the end of the row): guarded loads
                 const int need = n_pos > 0 ? n_pos - 1 + c.t1 : 0;
-                for (int i = lane; i < g.xlen; i += 32)
-                    xs[i] = i < need ? vload(hist_u, c.hu, in, c.n_in, (int)i_lo + i) : T(0);
+                const int i_lo = tg_src[k] + c.hu;
+                const int tot = c.hu + c.n_in;
+#pragma unroll 8
+                for (int i = lane; i < g.xlen; i += 32) {  // independent predicated loads: eight in flight per lane
+                    const int gidx = i_lo + i;
+                    const bool ok = i < need && gidx >= 0 && gidx < tot;
+                    const T* __restrict__ src = gidx < c.hu ? hist_u + gidx : in + (gidx - c.hu);
+                    xs[i] = ok ? *src : T(0);
+                }
             }
+            const int64_t m0 = (int64_t)t * P * Mi;
             for (int64_t d = m0 + lane; d < min((int64_t)c.hp, m0 + wend); d += 32) {
                 const int w = (int)(d - m0);
                 vw[FM + w + (PAD ? w / Mi : 0)] = hist_p[d];
@@ -1004,14 +1072,13 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
         if (k >= g.nv) wait_ge(po_done + (k - g.nv), n_wt);
         if (bulk) {
             const uint32_t par = (uint32_t)(tflags[k] >> 1) & 1u;
-            while (!mbar_try_wait(bar + xb, par)) {
-            }
+            while (!mbar_try_wait(bar + xb, par)) __nanosleep(20);
             __syncwarp();  // lanes leave the poll loop at different times: reconverge before the FIR core
         }
         const int n_tasks = (n_pos + R - 1) / R;
         const int task = sub * 32 + lane;
         if (task < n_tasks) {
-            const int woff = (int)((int64_t)c.hp + 2 * i_lo - m0);  // w of the first sample of position i_lo
+            const int woff = tg_woff[k];  // w of the first sample of the tile's first position
             T res[R][NF];
             fir_tile_accumulate<T, 1, NF, R>(xs + R * task, cs, g.cp, c.t1, 0, res);
             int w = woff + 2 * R * task;
@@ -1380,12 +1447,25 @@ const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s) {
     return "fir_f64_generic";
 }
 
-const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s) {
+template <typename T, bool FUSED>
+static bool launch_rat(const FusedCall& c, cudaStream_t s, RatCache* cache);
+
+const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* cache) {
     if (c.n_streams <= 0) return "none";
     if (c.n_out <= 0) {
         launch_carry(c.hist, c.hist_stride, c.hist_len, c.in, c.in_stride, c.n_in, c.hist_out, c.hist_out_stride, c.drop,
                      c.new_hist_len, c.n_streams, dtype, s);
         return "carry";
+    }
+    if (dtype == DT_F64 && !c.interp && cache && c.n_out >= 64) {  // K3r: register-tiled rational-ratio kernel
+        FusedCall f{};
+        f.in = c.in; f.in_stride = c.in_stride; f.n_in = c.n_in;
+        f.hist_p = c.hist; f.hist_p_stride = c.hist_stride; f.hp = c.hist_len;
+        f.hist_p_out = c.hist_out; f.hist_p_out_stride = c.hist_out_stride;
+        f.drop_p = c.drop; f.new_hp = c.new_hist_len;
+        f.bank_a = c.bank_a; f.t2 = c.taps; f.L = c.L; f.at0 = c.at0; f.step = c.step;
+        f.n_out = c.n_out; f.interp = 0; f.out = c.out; f.out_stride = c.out_stride; f.n_streams = c.n_streams;
+        if (launch_rat<double, false>(f, s, cache)) return "poly_rat_f64";
     }
     constexpr int TO = 128;
     const int n_tiles = (c.n_out + TO - 1) / TO;
@@ -1453,9 +1533,11 @@ static bool launch_fused_t(const FusedCall& c, cudaStream_t s) {
     return true;
 }
 
-// K4r launcher: picks the geometry; returns false when the pair is not a rational-ratio case it covers.
-template <typename T, int S, int RN, int PAD>
-static bool launch_fused_rat_t(const FusedCall& c, cudaStream_t s) {
+// K4r / K3r launcher: picks the geometry; returns false when the call is not a rational-ratio case it covers.
+// FUSED: x2 stage + polyphase stage (FusedCall as documented). !FUSED: polyphase stage alone; the call carries the
+// stage in its polyphase fields and `in`/`n_in` = the stage input.
+template <typename T, int S, int RN, int PAD, bool FUSED>
+static bool launch_rat_t(const FusedCall& c, cudaStream_t s, RatCache* cache) {
     constexpr int VEC = VecOf<T>::N;
     constexpr int R = sizeof(T) == 8 ? 6 : 12;
     constexpr int NCH = (R - 1 + VEC - 1) / VEC + 1;
@@ -1466,42 +1548,51 @@ static bool launch_fused_rat_t(const FusedCall& c, cudaStream_t s) {
     g.D = (RN - 1) * S - (RN - 1) * Mi / L;  // worst lag of a static window slot behind the true offset
     g.tp = c.t2 + g.D;
     g.G = (L + RN - 1) / RN;
-    g.cp = ((c.t1 + VEC - 1 + VEC - 1) / VEC) * VEC;
+    g.cp = FUSED ? ((c.t1 + VEC - 1 + VEC - 1) / VEC) * VEC : 0;
     if (g.tp + 2 * WN > 2 * Mi) return false;  // the window walk may enter at most two further periods
     int dev = 0;
     cudaGetDevice(&dev);
     const int64_t div_last = ((c.at0 >> 16) + (int64_t)(c.n_out - 1) * Mi) / L;
+    // one coefficient tile [tp][RN] per output group; with two groups per warp (P = 16) the two broadcast reads of a
+    // tap must fall into different banks: tile pitch = 64 bytes mod 128
+    int gpitch = g.tp * RN;
+    while ((gpitch * (int)sizeof(T)) % 128 != 64) gpitch += VEC;
+    g.gpitch = gpitch;
+    const size_t tile_bytes = (size_t)g.G * gpitch * sizeof(T) + (((size_t)g.G * sizeof(int) + 15) & ~(size_t)15);
     // configurations in order of preference: two 256-thread blocks per SM, else one 512-thread block
     struct Opt { int P, nt, xbufs, nv; size_t lim; };
-    Opt opts[] = {{16, 256, 2, 2, 113 * 1024}, {32, 512, 2, 2, 227 * 1024}, {16, 512, 2, 2, 227 * 1024},
-                  {16, 512, 1, 2, 227 * 1024}};
+    Opt opts[4] = {{16, 256, 2, 2, 113 * 1024}, {32, 512, 2, 2, 227 * 1024}, {16, 512, 2, 2, 227 * 1024},
+                   {16, 512, 1, 2, 227 * 1024}};
+    if (!FUSED) {
+        opts[0] = Opt{16, 256, 0, 3, 113 * 1024};
+        opts[1] = Opt{16, 256, 0, 2, 113 * 1024};
+        opts[2] = Opt{32, 512, 0, 3, 227 * 1024};
+        opts[3] = Opt{16, 512, 0, 2, 227 * 1024};
+    }
     static const int* forced = [] {  // tuning override: GAR_RAT_OPT="P,threads,xbufs,nv"
         static int v[4];
         const char* e = std::getenv("GAR_RAT_OPT");
         return (e && std::sscanf(e, "%d,%d,%d,%d", v, v + 1, v + 2, v + 3) == 4) ? v : (const int*)nullptr;
     }();
-    if (forced) opts[0] = Opt{forced[0], forced[1], forced[2], forced[3], 227 * 1024};
+    if (forced) opts[0] = Opt{forced[0], forced[1], FUSED ? forced[2] : 0, forced[3], 227 * 1024};
     size_t smem = 0;
     int nthreads = 0;
     for (const Opt& o : opts) {
-        const int n_pos_max = (o.P * Mi + c.t2) / 2 + 2 + VEC;
-        const int tasks = (n_pos_max + R - 1) / R;
-        const int xlen = R * (tasks - 1) + (g.cp / VEC + NCH + 1) * VEC;
+        int xlen = 0;
+        if (FUSED) {
+            const int n_pos_max = (o.P * Mi + c.t2) / 2 + 2 + VEC;
+            const int tasks = (n_pos_max + R - 1) / R;
+            xlen = R * (tasks - 1) + (g.cp / VEC + NCH + 1) * VEC;
+        }
         const int vlen = (((g.D + 1) + o.P * (Mi + PAD) + g.tp + 2 * WN + 4) + 1) & ~1;
-        // one coefficient tile [tp][RN] per output group; with two groups per warp (P = 16) the two broadcast reads of a
-        // tap must fall into different banks: tile pitch = 64 bytes mod 128
-        int gpitch = g.tp * RN;
-        while ((gpitch * (int)sizeof(T)) % 128 != 64) gpitch += VEC;
-        const size_t need = 16 + RAT_CTL_BYTES +
-                            ((size_t)2 * g.cp + (size_t)o.xbufs * xlen + (size_t)o.nv * vlen + (size_t)g.G * gpitch) * sizeof(T) +
-                            (size_t)g.G * (RN + 1) * sizeof(int);
+        const size_t need = 48 + RAT_CTL_BYTES +
+                            ((size_t)2 * g.cp + (size_t)o.xbufs * xlen + (size_t)o.nv * vlen) * sizeof(T) + tile_bytes;
         if (need <= o.lim) {
             g.P = o.P;
             g.xlen = xlen;
             g.xbufs = o.xbufs;
             g.nv = o.nv;
             g.vlen = vlen;
-            g.gpitch = gpitch;
             smem = need;
             nthreads = o.nt;
             break;
@@ -1510,7 +1601,42 @@ static bool launch_fused_rat_t(const FusedCall& c, cudaStream_t s) {
     if (!nthreads) return false;
     g.n_tiles = (int32_t)(div_last / ((int64_t)g.P * Mi)) + 1;
     g.tiles_per_block = pick_tiles_per_block(g.n_tiles, c.n_streams, &g.n_groups);
-    auto k = fused_up2_rat_kernel<T, S, RN, PAD>;
+    if (const char* e = std::getenv("GAR_RAT_TPB")) {  // tuning override
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= RAT_MAXT) {
+            g.tiles_per_block = v < g.n_tiles ? v : g.n_tiles;
+            g.n_groups = (g.n_tiles + g.tiles_per_block - 1) / g.tiles_per_block;
+        }
+    }
+    {  // coefficient tile of this call's start phase: built on first use, cached per polyphase stage
+        const int F0 = (int)(c.at0 >> 16);
+        const int key = (int)sizeof(T) * 1000003 + S * 100003 + RN * 10007 + g.tp * 131 + g.gpitch * 7 + L;
+        if (!cache->dev || cache->tile_bytes != tile_bytes || cache->key != key || (int)cache->built.size() != L) {
+            if (cache->dev) {
+                cudaStreamSynchronize(s);
+                cudaFree(cache->dev);
+                cache->dev = nullptr;
+            }
+            if (cudaMalloc(&cache->dev, tile_bytes * (size_t)L) != cudaSuccess) {
+                cache->dev = nullptr;
+                cudaGetLastError();
+                return false;
+            }
+            cache->tile_bytes = tile_bytes;
+            cache->key = key;
+            cache->built.assign((size_t)L, 0);
+        }
+        T* tile = reinterpret_cast<T*>(static_cast<char*>(cache->dev) + (size_t)F0 * tile_bytes);
+        if (!cache->built[(size_t)F0]) {
+            rat_build_tile_kernel<T, S, RN><<<1, 256, (size_t)g.G * RN * sizeof(int), s>>>(
+                static_cast<const T*>(c.bank_a), c.t2, L, Mi, F0, g.G, g.tp, g.gpitch, tile);
+            count_launch();
+            cache->built[(size_t)F0] = 1;
+        }
+        g.cg_src = tile;
+        g.cg_bytes = (uint32_t)tile_bytes;
+    }
+    auto k = fused_up2_rat_kernel<T, S, RN, PAD, FUSED>;
     static size_t configured[64] = {0};
     if (smem > configured[dev & 63]) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1528,29 +1654,30 @@ static const bool g_fused_rat = [] {
     return !(e && e[0] && e[0] != '0');
 }();
 
-template <typename T>
-static bool launch_fused_rat(const FusedCall& c, cudaStream_t s) {
-    if (!g_fused_rat || c.interp || ((c.step | c.at0) & 0xFFFF) != 0 || c.n_out <= 0 || c.np <= 0) return false;
+template <typename T, bool FUSED>
+static bool launch_rat(const FusedCall& c, cudaStream_t s, RatCache* cache) {
+    if (!cache || !g_fused_rat || c.interp || ((c.step | c.at0) & 0xFFFF) != 0 || c.n_out <= 0) return false;
+    if (FUSED && c.np <= 0) return false;
     const int64_t Mi = c.step >> 16;
-    if (Mi <= c.L || Mi > 4 * (int64_t)c.L || Mi > 4096 || c.t2 > 512) return false;
+    if (Mi <= c.L || Mi > 4 * (int64_t)c.L || Mi > 4096 || c.t2 > 512 || c.L > 255) return false;
     const int S = (int)((Mi + c.L - 1) / c.L);
     const bool pad = (Mi & 1) == 0;  // even period length: pad the period pitch to keep the lanes on distinct banks
     switch (S) {
-        case 2: return pad ? launch_fused_rat_t<T, 2, 8, 1>(c, s) : launch_fused_rat_t<T, 2, 8, 0>(c, s);
-        case 3: return pad ? launch_fused_rat_t<T, 3, 6, 1>(c, s) : launch_fused_rat_t<T, 3, 6, 0>(c, s);
-        case 4: return pad ? launch_fused_rat_t<T, 4, 6, 1>(c, s) : launch_fused_rat_t<T, 4, 6, 0>(c, s);
+        case 2: return pad ? launch_rat_t<T, 2, 8, 1, FUSED>(c, s, cache) : launch_rat_t<T, 2, 8, 0, FUSED>(c, s, cache);
+        case 3: return pad ? launch_rat_t<T, 3, 6, 1, FUSED>(c, s, cache) : launch_rat_t<T, 3, 6, 0, FUSED>(c, s, cache);
+        case 4: return pad ? launch_rat_t<T, 4, 6, 1, FUSED>(c, s, cache) : launch_rat_t<T, 4, 6, 0, FUSED>(c, s, cache);
     }
     return false;
 }
 
-const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s) {
+const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s, RatCache* cache) {
     if (c.n_streams <= 0) return "none";
     if (dtype == DT_F32) {
         if (c.interp) return launch_fused_t<float, true>(c, s) ? "fused_up2_poly_f32_interp" : nullptr;
         return launch_fused_t<float, false>(c, s) ? "fused_up2_poly_f32" : nullptr;
     }
     if (c.interp) return launch_fused_t<double, true>(c, s) ? "fused_up2_poly_f64_interp" : nullptr;
-    if (launch_fused_rat<double>(c, s)) return "fused_up2_rat_f64";
+    if (launch_rat<double, true>(c, s, cache)) return "fused_up2_rat_f64";
     return launch_fused_t<double, false>(c, s) ? "fused_up2_poly_f64" : nullptr;
 }
 

@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <vector>
 
 namespace gar {
 
@@ -66,6 +67,17 @@ struct FusedCall {
     int32_t n_streams;
 };
 
+// Per polyphase stage, device-resident cache of the K4r kernel's coefficient tiles: for every start phase
+// F0 = at0 >> 16 (< L) the phase filters of a period, pre-shifted and grouped the way the kernel's warps read
+// them (see fused_up2_rat_kernel). A tile is built by a small kernel the first time its F0 is seen and then
+// bulk-copied into shared memory by every block. Owned by the engine; invalidated when a bank is replaced.
+struct RatCache {
+    void* dev = nullptr;        // [L][tile_bytes]
+    size_t tile_bytes = 0;
+    int key = 0;                // geometry the tiles were built for (dtype/S/RN/tp/pitch hash)
+    std::vector<uint8_t> built; // [L]
+};
+
 // cubic.go:33-90 — indices/phases precomputed on the host by the exact float64 recurrence
 struct CubicCall {
     const void* hist;     int64_t hist_stride;                         // 3 previous samples (zeros at start)
@@ -80,10 +92,10 @@ enum Dtype : int { DT_F64 = 0, DT_F32 = 1 };
 
 // launchers (kernels.cu). Return the name of the kernel variant used.
 const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s);
-const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s);
+const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* cache);
 const char* launch_cubic(const CubicCall& c, int dtype, cudaStream_t s);
 // returns nullptr when the pair cannot be fused (caller falls back to the two stand-alone launches)
-const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s);
+const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s, RatCache* cache);
 // carry only (a call that produced no output but appended to the tail)
 void launch_carry(const void* hist, int64_t hist_stride, int32_t hist_len, const void* in, int64_t in_stride,
                   int32_t n_in, void* hist_out, int64_t hist_out_stride, int32_t drop, int32_t new_len,
