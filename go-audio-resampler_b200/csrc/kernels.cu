@@ -16,6 +16,7 @@
 //  fma_probe_kernel   dependent-FMA micro-benchmark for the roofline denominator.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -81,7 +82,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void cp_async_elem(double* dst, const double* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_elem(float* dst, const float* src) {
+[[maybe_unused]] __device__ __forceinline__ void cp_async_elem(float* dst, const float* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
@@ -888,6 +889,28 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
         tg_wend[k] = wend;
         tg_words[k] = words;
         tg_woff[k] = (int)((int64_t)c.hp + 2 * i_lo - m0);
+        if (!FUSED) {
+            // poly-only: samples w in [w0, wend) come from `in`. With an unpadded period pitch they are one contiguous
+            // run: a TMA bulk copy moves the 16-byte aligned middle (the tile's front margin absorbs the parity between
+            // source and destination), single elements at either end are copied by hand.
+            int w0 = (int)max((int64_t)0, (int64_t)c.hp - m0);
+            int fm = FM, nb = 0;
+            int64_t e0 = m0 + w0 - c.hp;
+            if (PAD == 0 && sizeof(T) == 8 && w0 < wend) {
+                if (reinterpret_cast<uintptr_t>(in + e0) & 15u) {
+                    ++w0;
+                    ++e0;
+                }
+                fm = FM + ((FM + w0) & 1);
+                nb = (wend - w0) & ~1;
+                if (nb < 0) nb = 0;
+            }
+            tflags[k] = nb > 0 ? 1 : 0;
+            tg_src[k] = (int)e0;  // first bulk element of `in`
+            tg_words[k] = nb;     // bulk elements
+            tg_woff[k] = w0;      // w of the first bulk element
+            tg_npos[k] = fm;      // front margin of this tile's buffer
+        }
         in_done[k] = 0;
         up_done[k] = 0;
         po_done[k] = 0;
@@ -967,6 +990,12 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
             // ---- poly task: RN adjacent outputs of the period pattern, lanes = periods ----
             wait_ge(in_done + k, 1);
             wait_ge(up_done + k, nchunk[k]);
+            if (!FUSED && (tflags[k] & 1)) {  // poly-only: the bulk part of the tile has landed
+                const uint32_t par = (uint32_t)(tflags[k] >> 1) & 1u;
+                while (!mbar_try_wait(bar + xb, par)) __nanosleep(20);
+                __syncwarp();
+            }
+            const int FMk = FUSED ? FM : tg_npos[k];
             const T* __restrict__ vr = vs0 + (k % g.nv) * g.vlen;
             const int gi = sub * gpw + gsub;
             if (gi < g.G) {
@@ -977,7 +1006,7 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
                 const int off = goff[gi];
                 const int c0 = off < 0 ? -1 : off / Mi;
                 const int xc0 = (c0 + 1) * Mi - off, xc1 = xc0 + Mi;  // slots at which the walk enters the next period
-                const T* __restrict__ sp = vr + FM + jl * (Mi + PAD) + off + (PAD ? c0 : 0);
+                const T* __restrict__ sp = vr + FMk + jl * (Mi + PAD) + off + (PAD ? c0 : 0);
                 const T* __restrict__ cp0 = cg + (size_t)gi * g.gpitch;  // [tap][RN], 16-byte aligned
                 T W[WN], acc[RN];
 #pragma unroll
@@ -1023,18 +1052,23 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
             if (kprev >= 0) wait_ge(up_done + kprev, nchunk[kprev]);
             if (k >= g.nv) wait_ge(po_done + (k - g.nv), n_wt);  // the intermediate buffer is free
             if (!FUSED) {
-                // poly-only: the tile's samples come straight from the carried tail / the stage input, one asynchronous
-                // element copy each (period j at pitch Mi + PAD)
+                // poly-only: the tile's samples come straight from the carried tail / the stage input (period j at pitch
+                // Mi + PAD): one TMA bulk copy when the periods are contiguous, else asynchronous element copies
                 const int64_t m0 = (int64_t)t * P * Mi;
-                for (int j = 0; j * Mi < wend; ++j) {
-                    T* __restrict__ dst = vw + FM + j * (Mi + PAD);
-                    const int64_t d0 = m0 + (int64_t)j * Mi;
-                    const int rn = min(Mi, wend - j * Mi);
-                    for (int r = lane; r < rn; r += 32) {
-                        const int64_t d = d0 + r;
-                        if (d < c.hp) dst[r] = hist_p[d];
-                        else cp_async_elem(dst + r, in + (d - c.hp));
-                    }
+                const int fm = tg_npos[k], nb = tg_words[k], wb = tg_woff[k];
+                if (nb > 0 && lane == 0) {
+                    const uint32_t bytes = (uint32_t)(nb * sizeof(T));
+                    mbar_expect_tx(bar + xb, bytes);
+                    bulk_g2s(vw + fm + wb, in + tg_src[k], bytes, bar + xb);
+                }
+                // elements outside the bulk range: [0, wb) and [wb + nb, wend)
+                const int n_head = nb > 0 ? wb : wend, n_rest = nb > 0 ? wend - (wb + nb) : 0;
+                for (int q = lane; q < n_head + n_rest; q += 32) {
+                    const int w = q < n_head ? q : wb + nb + (q - n_head);
+                    const int64_t d = m0 + w;
+                    T* dst = vw + fm + w + (PAD ? w / Mi : 0);
+                    if (d < c.hp) *dst = hist_p[d];
+                    else cp_async_elem(dst, in + (d - c.hp));
                 }
                 cp_async_wait_all();
                 signal(in_done + k);
@@ -1566,7 +1600,7 @@ static bool launch_rat_t(const FusedCall& c, cudaStream_t s, RatCache* cache) {
     if (!FUSED) {
         opts[0] = Opt{16, 256, 0, 3, 113 * 1024};
         opts[1] = Opt{16, 256, 0, 2, 113 * 1024};
-        opts[2] = Opt{32, 512, 0, 3, 227 * 1024};
+        opts[2] = Opt{16, 512, 0, 3, 227 * 1024};
         opts[3] = Opt{16, 512, 0, 2, 227 * 1024};
     }
     static const int* forced = [] {  // tuning override: GAR_RAT_OPT="P,threads,xbufs,nv"
@@ -1584,7 +1618,7 @@ static bool launch_rat_t(const FusedCall& c, cudaStream_t s, RatCache* cache) {
             const int tasks = (n_pos_max + R - 1) / R;
             xlen = R * (tasks - 1) + (g.cp / VEC + NCH + 1) * VEC;
         }
-        const int vlen = (((g.D + 1) + o.P * (Mi + PAD) + g.tp + 2 * WN + 4) + 1) & ~1;
+        const int vlen = (((g.D + 2) + o.P * (Mi + PAD) + g.tp + 2 * WN + 4) + 1) & ~1;
         const size_t need = 48 + RAT_CTL_BYTES +
                             ((size_t)2 * g.cp + (size_t)o.xbufs * xlen + (size_t)o.nv * vlen) * sizeof(T) + tile_bytes;
         if (need <= o.lim) {
@@ -1600,7 +1634,20 @@ static bool launch_rat_t(const FusedCall& c, cudaStream_t s, RatCache* cache) {
     }
     if (!nthreads) return false;
     g.n_tiles = (int32_t)(div_last / ((int64_t)g.P * Mi)) + 1;
-    g.tiles_per_block = pick_tiles_per_block(g.n_tiles, c.n_streams, &g.n_groups);
+    {  // tiles per block, measured on the batched 44.1k<->48k chains: ~12 (fused) / ~6 (poly-only) blocks per resident
+        // slot, at least 3 / 6 tiles (set-up amortisation) unless that would leave resident slots empty; longer blocks
+        // lose more to the drain of their last tile than they save in set-up
+        static int sms = 0;
+        if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t slots = (int64_t)(sms > 0 ? sms : 148) * 2;
+        const int64_t total_tiles = (int64_t)g.n_tiles * c.n_streams;
+        int64_t tpb = total_tiles / (slots * (FUSED ? 12 : 6));
+        tpb = std::max<int64_t>(tpb, FUSED ? 3 : 6);
+        tpb = std::min<int64_t>(tpb, std::max<int64_t>(1, total_tiles / slots));
+        tpb = std::min<int64_t>(std::min<int64_t>(tpb, RAT_MAXT), g.n_tiles);
+        g.tiles_per_block = (int32_t)tpb;
+        g.n_groups = (g.n_tiles + g.tiles_per_block - 1) / g.tiles_per_block;
+    }
     if (const char* e = std::getenv("GAR_RAT_TPB")) {  // tuning override
         const int v = std::atoi(e);
         if (v >= 1 && v <= RAT_MAXT) {
