@@ -1491,7 +1491,7 @@ const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* 
                      c.new_hist_len, c.n_streams, dtype, s);
         return "carry";
     }
-    if (dtype == DT_F64 && !c.interp && cache && c.n_out >= 64) {  // K3r: register-tiled rational-ratio kernel
+    if (dtype == DT_F64 && !c.interp && cache) {  // K3r: register-tiled rational-ratio kernel (large calls)
         FusedCall f{};
         f.in = c.in; f.in_stride = c.in_stride; f.n_in = c.n_in;
         f.hist_p = c.hist; f.hist_p_stride = c.hist_stride; f.hp = c.hist_len;
@@ -1704,6 +1704,8 @@ static const bool g_fused_rat = [] {
 template <typename T, bool FUSED>
 static bool launch_rat(const FusedCall& c, cudaStream_t s, RatCache* cache) {
     if (!cache || !g_fused_rat || c.interp || ((c.step | c.at0) & 0xFFFF) != 0 || c.n_out <= 0) return false;
+    // small calls (streaming chunks) are latency-bound: the simpler kernels have far less per-block set-up
+    if ((int64_t)c.n_out * c.n_streams < 65536) return false;
     if (FUSED && c.np <= 0) return false;
     const int64_t Mi = c.step >> 16;
     if (Mi <= c.L || Mi > 4 * (int64_t)c.L || Mi > 4096 || c.t2 > 512 || c.L > 255) return false;
