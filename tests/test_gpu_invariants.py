@@ -248,9 +248,37 @@ def test_rational_fused_kernel_batched_rows_vs_unfused_and_oracle(ir, orr, rows,
     ya.append(a.FlushBatch()[0].copy())
     yb.append(b.FlushBatch()[0].copy())
     assert kernel in a.last_kernels(), a.last_kernels()
+    assert "poly_rat_f64" in b.last_kernels(), b.last_kernels()  # K3r: the stand-alone stage uses the same tiling
     ya, yb = np.concatenate(ya, axis=1), np.concatenate(yb, axis=1)
     np.testing.assert_array_equal(ya, yb)
     pick = sorted(set([0, 1, rows // 2, rows - 1]))
     want, counts = O.batch_resample(x[pick], ir, orr, O.Q_HIGH, n_threads=4)
     assert np.all(counts == ya.shape[1])
     assert np.max(np.abs(ya[pick] - want[:, :ya.shape[1]])) <= 1e-12
+
+
+def test_rational_kernels_random_geometry_stress():
+    """Many random (rows, length, chunking) cases through the barrier-free K4r / K3r pipelines: fused, unfused and
+    one-shot runs must agree bit for bit (float64 sums are strictly sequential in every kernel)."""
+    rng = np.random.default_rng(2024)
+    for case in range(12):
+        ir, orr = [(44100, 48000), (48000, 44100), (8000, 12000), (48000, 30000)][case % 4]
+        rows = int(rng.integers(1, 70))
+        n = int(rng.integers(3000, 90000))
+        x = rng.standard_normal((rows, n))
+        a = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float64)
+        b = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float64)
+        c = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float64)
+        b.set_fusion(False)
+        cuts = np.unique(np.concatenate([[0, n], rng.integers(0, n, size=int(rng.integers(0, 4)))]))
+        ya, yb = [], []
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            xa = np.ascontiguousarray(x[:, lo:hi])
+            ya.append(a.ProcessBatch(xa)[0].copy())
+            yb.append(b.ProcessBatch(xa)[0].copy())
+        ya.append(a.FlushBatch()[0].copy())
+        yb.append(b.FlushBatch()[0].copy())
+        yc = np.concatenate([c.ProcessBatch(x)[0].copy(), c.FlushBatch()[0].copy()], axis=1)
+        ya, yb = np.concatenate(ya, axis=1), np.concatenate(yb, axis=1)
+        np.testing.assert_array_equal(ya, yb, err_msg=f"case {case}: fused vs unfused")
+        np.testing.assert_array_equal(ya, yc, err_msg=f"case {case}: chunked vs one-shot")
