@@ -1050,7 +1050,11 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
             //      the tile that is the polyphase stage's carried tail ----
             const int kprev = k - NX;  // last user of this window buffer
             if (kprev >= 0) wait_ge(up_done + kprev, nchunk[kprev]);
-            if (k >= g.nv) wait_ge(po_done + (k - g.nv), n_wt);  // the intermediate buffer is free
+            // The intermediate buffer is written here only by the poly-only tile load and by the carried-tail copy (first
+            // tile of a row). A fused input item must NOT wait for it otherwise: P(k - nv) sits later in the queue, and the
+            // prefetch of tile k would be held back until those tasks have run.
+            const bool writes_tile = !FUSED || (int64_t)t * P * Mi < (int64_t)c.hp;
+            if (writes_tile && k >= g.nv) wait_ge(po_done + (k - g.nv), n_wt);
             if (!FUSED) {
                 // poly-only: the tile's samples come straight from the carried tail / the stage input (period j at pitch
                 // Mi + PAD): one TMA bulk copy when the periods are contiguous, else asynchronous element copies
