@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
 // the polyphase stage's new tail needs the last few intermediate samples, recomputed here with the same
 // strictly sequential chain as the tile core (bit-identical in float64).
 template <typename T>
-__device__ __forceinline__ void fused_carry_tails_rt(const FusedCall& c, const int64_t row) {
+__device__ __forceinline__ void fused_carry_tails_rt(const FusedCall& c, const int64_t row, T* scratch, const int scratch_cap) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const T* __restrict__ hist_u = static_cast<const T*>(c.hist_u) + row * c.hist_u_stride;
     const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
@@ -536,6 +536,20 @@ __device__ __forceinline__ void fused_carry_tails_rt(const FusedCall& c, const i
     const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
     carry_row(hist_u, c.hu, in, c.n_in, static_cast<T*>(c.hist_u_out) + row * c.hist_u_out_stride, c.drop_u, c.new_hu);
     T* hp_out = static_cast<T*>(c.hist_p_out) + row * c.hist_p_out_stride;
+    // intermediate samples [j_lo, j_hi) are needed: stage their input span and the x2 bank in shared memory first, so the
+    // strictly sequential chains below run on shared-memory latency instead of one global round trip per tap (this block
+    // is on the critical path of every streaming-size call)
+    const int j_lo = max(0, c.drop_p - c.hp), j_hi = c.drop_p + c.new_hp - c.hp;
+    const int p_lo = j_lo >> 1;
+    const int span = j_hi > j_lo ? (((j_hi - 1) >> 1) - p_lo) + c.t1 : 0;
+    const bool staged = span > 0 && span + 2 * c.t1 <= scratch_cap;
+    T* xb = scratch;
+    T* bk = scratch + span;
+    if (staged) {
+        for (int i = tid; i < span; i += NT) xb[i] = vload(hist_u, c.hu, in, c.n_in, p_lo + i);
+        for (int i = tid; i < 2 * c.t1; i += NT) bk[i] = bank_u[i];
+        __syncthreads();
+    }
     for (int i = tid; i < c.new_hp; i += NT) {
         const int idx = c.drop_p + i;  // index into vp = hist_p ++ mid
         T v;
@@ -543,16 +557,30 @@ __device__ __forceinline__ void fused_carry_tails_rt(const FusedCall& c, const i
             v = hist_p[idx];
         } else {
             const int j = idx - c.hp;
-            const T* __restrict__ bk = bank_u + (j & 1) * c.t1;
-            if (sizeof(T) == 8) {
-                T acc = 0;
-                for (int t = 0; t < c.t1; ++t) acc = fma(vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), bk[t], acc);
-                v = acc;
+            if (staged) {
+                const T* __restrict__ xx = xb + ((j >> 1) - p_lo);
+                const T* __restrict__ cc = bk + (j & 1) * c.t1;
+                if (sizeof(T) == 8) {  // same order as the tile core: bit-identical
+                    T acc = 0;
+                    for (int t = 0; t < c.t1; ++t) acc = fma(xx[t], cc[t], acc);
+                    v = acc;
+                } else {
+                    double acc = 0;
+                    for (int t = 0; t < c.t1; ++t) acc = fma((double)xx[t], (double)cc[t], acc);
+                    v = (T)acc;
+                }
             } else {
-                double acc = 0;
-                for (int t = 0; t < c.t1; ++t)
-                    acc = fma((double)vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), (double)bk[t], acc);
-                v = (T)acc;
+                const T* __restrict__ bkg = bank_u + (j & 1) * c.t1;
+                if (sizeof(T) == 8) {
+                    T acc = 0;
+                    for (int t = 0; t < c.t1; ++t) acc = fma(vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), bkg[t], acc);
+                    v = acc;
+                } else {
+                    double acc = 0;
+                    for (int t = 0; t < c.t1; ++t)
+                        acc = fma((double)vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), (double)bkg[t], acc);
+                    v = (T)acc;
+                }
             }
         }
         hp_out[i] = v;
@@ -596,7 +624,7 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
     const int n_mid = c.np * NF;
 
     if (tile == n_tiles) {  // ---- carried tails ----
-        fused_carry_tails_rt<T>(c, row);
+        fused_carry_tails_rt<T>(c, row, xs, xlen + hpf + MT);
         return;
     }
 
@@ -642,7 +670,8 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
         for (int i = tid; i < c.hp; i += NT) vp[hpf - c.hp + i] = hist_p[i];
     if (bank_pitch > 0) {
         const T* __restrict__ ba = static_cast<const T*>(c.bank_a);
-        for (int i = tid; i < c.L * c.t2; i += NT) pbank[(i / c.t2) * bank_pitch + (i % c.t2)] = ba[i];
+#pragma unroll 8
+        for (int i = tid; i < c.L * c.t2; i += NT) pbank[(i / c.t2) * bank_pitch + (i % c.t2)] = ba[i];  // 8 loads in flight
     }
     __syncthreads();
     if (bulk) {
@@ -824,7 +853,7 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
     const T* __restrict__ hist_p = static_cast<const T*>(c.hist_p) + row * c.hist_p_stride;
     T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
     if (group == g.n_groups) {  // carried tails
-        if (FUSED) fused_carry_tails_rt<T>(c, row);
+        if (FUSED) fused_carry_tails_rt<T>(c, row, xs0, g.xbufs * g.xlen + g.nv * g.vlen);
         else carry_row(hist_p, c.hp, in, c.n_in, static_cast<T*>(c.hist_p_out) + row * c.hist_p_out_stride, c.drop_p, c.new_hp);
         return;
     }
@@ -1533,10 +1562,9 @@ const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* 
 }
 
 
-template <typename T, bool INTERP>
-static bool launch_fused_t(const FusedCall& c, cudaStream_t s) {
+template <typename T, bool INTERP, int R>
+static bool launch_fused_r(const FusedCall& c, cudaStream_t s) {
     constexpr int NT = 128;
-    constexpr int R = sizeof(T) == 8 ? 6 : 12;
     constexpr int VEC = VecOf<T>::N;
     constexpr int NCH = (R - 1 + VEC - 1) / VEC + 1;
     constexpr int MT = NT * R * 2;
@@ -1569,6 +1597,16 @@ static bool launch_fused_t(const FusedCall& c, cudaStream_t s) {
     k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, ms, cp, xlen, hpf, bank_pitch);
     count_launch();
     return true;
+}
+
+// Tile size by call size: big tiles (R = 6 / 12 positions per thread) keep the FIR core FMA-bound; a streaming-size call
+// has only a handful of them, so its critical path is one tile long — small tiles (R = 2 / 4) spread it over more SMs.
+template <typename T, bool INTERP>
+static bool launch_fused_t(const FusedCall& c, cudaStream_t s) {
+    constexpr int RBIG = sizeof(T) == 8 ? 6 : 12, RSMALL = sizeof(T) == 8 ? 2 : 4;
+    const int64_t big_tiles = ((int64_t)c.np * 2 + 128 * RBIG * 2 - 1) / (128 * RBIG * 2) * c.n_streams;
+    if (big_tiles < 148 && c.t2 - 1 < 128 * RSMALL) return launch_fused_r<T, INTERP, RSMALL>(c, s);
+    return launch_fused_r<T, INTERP, RBIG>(c, s);
 }
 
 // K4r / K3r launcher: picks the geometry; returns false when the call is not a rational-ratio case it covers.
