@@ -282,6 +282,8 @@ int32_t gar_set_fusion(gar_handle* h, int32_t enabled) {
     return GAR_OK;
 }
 
+void gar_set_tiled_polyphase(int32_t enabled) { gar::set_tiled_polyphase(enabled != 0); }
+
 int64_t gar_kernel_launches(const gar_handle* h, int32_t reset) {
     (void)h;  // process-wide counter: every <<<>>> of this library
     return (int64_t)launch_count(reset != 0);

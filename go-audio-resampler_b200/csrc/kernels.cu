@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -1168,6 +1169,211 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
     }
 }
 
+// =============================================================================================
+// K3i — polyphase stage for ANY ratio over a batch of lock-step rows, register-tiled (the batched form of
+// polyphase_stage.go:186-312 with cubic coefficient interpolation).
+//
+// With an irrational ratio no two outputs of a stream share their coefficients, but the rows of a lock-step batch do:
+// output n of every row uses the same phase and the same fraction x. So the LANES are 16 rows, and a half-warp task is
+// RN adjacent outputs of those rows:
+//   1. the half-warp evaluates the interpolated coefficients a + x(b + x(c + x d)) of its RN outputs ONCE (the three
+//      Horner FMAs per tap amortise over the rows) into a per-task tile [tap][RN] in shared memory, each output's filter
+//      e_i taps late (static window slots, as in the rational kernel: e_i = o_i - i*S + Dg, zero taps are exact no-ops);
+//   2. every lane slides a register window over its row (rows at an odd pitch: conflict-free LDS.64): per tap one sample
+//      LDS + RN/2 broadcast LDS.128 feed RN FMAs, sums strictly in tap order (bit-identical to poly_kernel in float64).
+// A block = 16 rows x one tile of 16*RN outputs (8 warps x 2 tasks); samples are staged with asynchronous element
+// copies; two blocks per SM overlap each other's load and compute phases. Trailing blocks write the carried tails.
+// =============================================================================================
+struct RowsGeom {
+    int32_t TO, span, pitch, tp, D, n_tiles, n_rb;  // outputs per tile, staged samples per row (max), row pitch, taps walked
+};
+
+template <typename T, int S, int RN>
+__global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, const RowsGeom g) {
+    using V = typename VecOf<T>::type;
+    constexpr int VEC = VecOf<T>::N;
+    static_assert(RN % VEC == 0, "a coefficient vector load covers whole outputs");
+    constexpr int RB = 16;                 // rows per block = lanes of a half-warp task
+    constexpr int WN = (RN - 1) * S + 1;   // register window
+    constexpr int NTASK = 16;              // half-warp tasks per block (8 warps x 2)
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* xs = reinterpret_cast<T*>(smem_raw);                      // [RB][pitch] staged samples
+    T* ct = xs + RB * g.pitch + (RB * g.pitch & 1);              // [NTASK][tp*RN] coefficient tiles
+    int* pat = reinterpret_cast<int*>(ct + NTASK * g.tp * RN);   // [NTASK][RN][4] phase row offset, lag, x bits
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_work = g.n_tiles * g.n_rb;
+    if ((int)blockIdx.x >= n_work) {  // carried tail of one row
+        const int64_t row = (int)blockIdx.x - n_work;
+        carry_row(static_cast<const T*>(c.hist) + row * c.hist_stride, c.hist_len,
+                  static_cast<const T*>(c.in) + row * c.in_stride, c.n_in,
+                  static_cast<T*>(c.hist_out) + row * c.hist_out_stride, c.drop, c.new_hist_len);
+        return;
+    }
+    const int tile = blockIdx.x % g.n_tiles;
+    const int row0 = (blockIdx.x / g.n_tiles) * RB;
+    const int64_t L = c.L;
+    const int n0 = tile * g.TO;
+    const int n1 = min(c.n_out, n0 + g.TO);  // outputs [n0, n1)
+    // first staged sample: D before the window of output n0
+    const int64_t d_base = (((c.at0 + (int64_t)n0 * c.step) >> 16) / L) - g.D;
+    const int64_t d_last = (((c.at0 + (int64_t)(n1 - 1) * c.step) >> 16) / L);
+    const int span_t = min((int)(d_last - d_base) + g.tp + 2 * WN + 2, g.span);
+    const int64_t total = (int64_t)c.hist_len + c.n_in;
+
+    // ---- stage the rows' samples: warp w copies rows w, w+8 (coalesced along the row) ----
+    for (int r = warp; r < RB; r += 8) {
+        const int64_t row = row0 + r;
+        T* __restrict__ dst = xs + r * g.pitch;
+        const bool live = row < c.n_streams;
+        const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
+        const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+        for (int i = lane; i < span_t; i += 32) {
+            const int64_t d = d_base + i;
+            if (!live || d < 0 || d >= total) dst[i] = T(0);
+            else if (d < c.hist_len) dst[i] = hist[d];
+            else cp_async_elem(dst + i, in + (d - c.hist_len));
+        }
+    }
+
+    // ---- pattern + coefficient tile of this half-warp's task (overlaps the copies above) ----
+    const int hl = lane & 15, half = lane >> 4;
+    const int task = warp * 2 + half;
+    const int nf = n0 + task * RN;  // first output of the task
+    const unsigned hmask = 0xFFFFu << (half * 16);
+    T* __restrict__ ctile = ct + task * g.tp * RN;
+    int* __restrict__ ptask = pat + task * RN * 4;
+    int div0 = 0, Dg = 0;
+    {
+        // lane i < RN: geometry of output nf + i (polyphase_stage.go:260-264)
+        const int i = hl < RN ? hl : RN - 1;
+        const int64_t at = c.at0 + (int64_t)(nf + i) * c.step;
+        const int64_t full = at >> 16;
+        const int64_t dv = full / L;
+        const int ph = (int)(full - dv * L);
+        const int dv0 = __shfl_sync(hmask, (int)(dv - d_base), half * 16);  // window offsets are relative to the tile
+        const int o = (int)(dv - d_base) - dv0;
+        int lag = i * S - o;  // >= 0 would-be lag of the static slot
+        int m = lag;
+#pragma unroll
+        for (int sft = 8; sft >= 1; sft >>= 1) m = max(m, __shfl_xor_sync(hmask, m, sft));
+        Dg = m;
+        div0 = dv0;
+        if (hl < RN) {
+            ptask[i * 4 + 0] = ph * c.taps;
+            ptask[i * 4 + 1] = o - i * S + Dg;  // e_i in [0, D]
+            ptask[i * 4 + 2] = (int)(at & 0xFFFF);
+        }
+    }
+    __syncwarp();
+    {
+        const T* __restrict__ ga = static_cast<const T*>(c.bank_a);
+        const T* __restrict__ gb = static_cast<const T*>(c.bank_b);
+        const T* __restrict__ gc = static_cast<const T*>(c.bank_c);
+        const T* __restrict__ gd = static_cast<const T*>(c.bank_d);
+#pragma unroll 4
+        for (int idx = hl; idx < g.tp * RN; idx += 16) {
+            const int kk = idx / RN, i = idx - kk * RN;
+            const int k = kk - ptask[i * 4 + 1];
+            T v = T(0);
+            if (k >= 0 && k < c.taps && nf + i < n1) {
+                const int co = ptask[i * 4 + 0] + k;
+                v = ga[co];
+                if (c.interp) {
+                    const T x = (T)ptask[i * 4 + 2] * (T)(1.0 / 65536.0);
+                    v = fma(x, fma(x, fma(x, gd[co], gc[co]), gb[co]), v);
+                }
+            }
+            ctile[idx] = v;
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- tap loop: lane = row, RN adjacent outputs, static window slots ----
+    if (nf < n1) {
+        const T* __restrict__ sp = xs + hl * g.pitch + (div0 - Dg);  // window slot 0 (div0 >= D >= Dg)
+        T W[WN], acc[RN];
+#pragma unroll
+        for (int x = 0; x < WN; ++x) W[x] = sp[x];
+#pragma unroll
+        for (int i = 0; i < RN; ++i) acc[i] = T(0);
+        auto tap = [&](const int u, const int kk) {
+            T cf[RN];
+#pragma unroll
+            for (int q = 0; q < RN / VEC; ++q)
+                vec_unpack(*reinterpret_cast<const V*>(ctile + kk * RN + q * VEC), cf + q * VEC);
+#pragma unroll
+            for (int i = 0; i < RN; ++i) acc[i] = fma(W[(u + i * S) % WN], cf[i], acc[i]);
+            W[u] = sp[kk + WN];
+        };
+        int it0 = 0;
+        for (; it0 + WN <= g.tp; it0 += WN) {
+#pragma unroll
+            for (int u = 0; u < WN; ++u) tap(u, it0 + u);
+        }
+#pragma unroll
+        for (int u = 0; u < WN; ++u)
+            if (it0 + u < g.tp) tap(u, it0 + u);
+        const int64_t row = row0 + hl;
+        if (row < c.n_streams) {
+            T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+#pragma unroll
+            for (int i = 0; i < RN; ++i)
+                if (nf + i < n1) out[nf + i] = acc[i];
+        }
+    }
+}
+
+template <typename T, int S, int RN>
+static bool launch_poly_rows_t(const PolyCall& c, cudaStream_t s) {
+    constexpr int WN = (RN - 1) * S + 1;
+    RowsGeom g{};
+    g.TO = 16 * RN;
+    // intermediate samples per output r = step / (L * 65536); worst lag of a static slot behind the true offset
+    const double r = (double)c.step / ((double)c.L * 65536.0);
+    g.D = (RN - 1) * S - (int)std::floor((RN - 1) * r) + 1;
+    if (g.D < 0 || g.D > 200) return false;
+    g.tp = c.taps + g.D;
+    g.span = (int)std::ceil((g.TO - 1) * r) + g.D + g.tp + 2 * WN + 4;
+    g.pitch = g.span | 1;
+    g.n_tiles = (c.n_out + g.TO - 1) / g.TO;
+    g.n_rb = (c.n_streams + 15) / 16;
+    const size_t smem = ((size_t)16 * g.pitch + 1 + (size_t)16 * g.tp * RN) * sizeof(T) + (size_t)16 * RN * 4 * sizeof(int);
+    if (smem > 113 * 1024) return false;
+    auto k = poly_rows_kernel<T, S, RN>;
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)g.n_tiles * g.n_rb + c.n_streams;
+    k<<<(unsigned)blocks, 256, smem, s>>>(c, g);
+    count_launch();
+    return true;
+}
+
+// K3i dispatch: batches of at least 8 lock-step rows with enough outputs; S = ceil(samples per output)
+template <typename T>
+static bool launch_poly_rows(const PolyCall& c, cudaStream_t s) {
+    if (c.n_streams < 8 || (int64_t)c.n_out * c.n_streams < 65536 || c.L > 4096 || c.taps > 1024) return false;
+    const double r = (double)c.step / ((double)c.L * 65536.0);
+    if (!(r > 0.0) || r > 8.0) return false;
+    const int S = (int)std::ceil(r - 1e-12);
+    switch (S) {
+        case 1: return launch_poly_rows_t<T, 1, 8>(c, s);
+        case 2: return launch_poly_rows_t<T, 2, 8>(c, s);
+        case 3: return launch_poly_rows_t<T, 3, 6>(c, s);
+        case 4: return launch_poly_rows_t<T, 4, 6>(c, s);
+        case 5:
+        case 6: return launch_poly_rows_t<T, 6, 4>(c, s);
+        default: return launch_poly_rows_t<T, 8, 4>(c, s);
+    }
+}
+
 // Fallback: one thread per output element, operands straight from global/L1.
 template <typename T>
 __global__ void __launch_bounds__(256) fir_generic_kernel(const FirCall c, const int n_tiles) {
@@ -1514,6 +1720,13 @@ const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s) {
     return "fir_f64_generic";
 }
 
+// A/B toggle (GAR_NO_RAT=1 or set_tiled_polyphase(false)): fall back to the one-thread-per-output kernels (no K4r / K3r / K3i)
+static bool g_fused_rat = [] {
+    const char* e = std::getenv("GAR_NO_RAT");
+    return !(e && e[0] && e[0] != '0');
+}();
+void set_tiled_polyphase(bool on) { g_fused_rat = on; }
+
 template <typename T, bool FUSED>
 static bool launch_rat(const FusedCall& c, cudaStream_t s, RatCache* cache);
 
@@ -1534,6 +1747,7 @@ const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* 
         f.n_out = c.n_out; f.interp = 0; f.out = c.out; f.out_stride = c.out_stride; f.n_streams = c.n_streams;
         if (launch_rat<double, false>(f, s, cache)) return "poly_rat_f64";
     }
+    if (dtype == DT_F64 && g_fused_rat && launch_poly_rows<double>(c, s)) return c.interp ? "poly_rows_f64_interp" : "poly_rows_f64";
     constexpr int TO = 128;
     const int n_tiles = (c.n_out + TO - 1) / TO;
     const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
@@ -1737,12 +1951,6 @@ static bool launch_rat_t(const FusedCall& c, cudaStream_t s, RatCache* cache) {
     return true;
 }
 
-// A/B toggle (GAR_NO_RAT=1): fall back to the one-thread-per-output fused kernel
-static const bool g_fused_rat = [] {
-    const char* e = std::getenv("GAR_NO_RAT");
-    return !(e && e[0] && e[0] != '0');
-}();
-
 template <typename T, bool FUSED>
 static bool launch_rat(const FusedCall& c, cudaStream_t s, RatCache* cache) {
     if (!cache || !g_fused_rat || c.interp || ((c.step | c.at0) & 0xFFFF) != 0 || c.n_out <= 0) return false;
@@ -1767,8 +1975,16 @@ const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s,
         if (c.interp) return launch_fused_t<float, true>(c, s) ? "fused_up2_poly_f32_interp" : nullptr;
         return launch_fused_t<float, false>(c, s) ? "fused_up2_poly_f32" : nullptr;
     }
+    if (!c.interp && launch_rat<double, true>(c, s, cache)) return "fused_up2_rat_f64";
+    // a large lock-step batch that the rational kernel does not cover runs as two launches: the stand-alone x2 kernel and
+    // K3i (lanes = rows, interpolated coefficients evaluated once per batch) beat the one-thread-per-output fused kernel
+    {
+        const double r = (double)c.step / ((double)c.L * 65536.0);
+        if (g_fused_rat && c.n_streams >= 8 && (int64_t)c.n_out * c.n_streams >= 65536 && r > 0.0 && r <= 8.0 &&
+            c.L <= 4096 && c.t2 <= 1024)
+            return nullptr;
+    }
     if (c.interp) return launch_fused_t<double, true>(c, s) ? "fused_up2_poly_f64_interp" : nullptr;
-    if (launch_rat<double, true>(c, s, cache)) return "fused_up2_rat_f64";
     return launch_fused_t<double, false>(c, s) ? "fused_up2_poly_f64" : nullptr;
 }
 

@@ -115,6 +115,8 @@ void launch_interleave(const void* planar, int64_t stride, int dtype, int channe
 float run_fma_probe(int dtype, int iters, double* flops, cudaStream_t s);
 // kernels launched by this library in this process (optionally resetting the counter)
 long long launch_count(bool reset);
+// process-wide A/B switch for the register-tiled polyphase kernels (K4r / K3r / K3i); on by default
+void set_tiled_polyphase(bool on);
 // name the tiled FIR variant that launch_fir would pick (no launch)
 const char* fir_variant_name(int dtype, int stride, int nf, int taps, int64_t n_pos, int n_streams);
 

@@ -282,3 +282,37 @@ def test_rational_kernels_random_geometry_stress():
         ya, yb = np.concatenate(ya, axis=1), np.concatenate(yb, axis=1)
         np.testing.assert_array_equal(ya, yb, err_msg=f"case {case}: fused vs unfused")
         np.testing.assert_array_equal(ya, yc, err_msg=f"case {case}: chunked vs one-shot")
+
+
+@pytest.mark.parametrize("ir,orr,rows,n", [
+    (44100, 47999, 40, 50000),    # BASELINE config 5b's ratio: cubic coefficient interpolation live, 1.84 samples/output
+    (48000, 44099, 24, 60000),    # irrational down-conversion, 2.18 samples/output
+    (8000, 22050, 19, 30000),     # fewer than one intermediate sample per output (window slot stride 1)
+    (44100, 16000, 17, 70000),    # rational, 5.5 samples/output: beyond the rational kernel's slot strides
+])
+def test_rows_kernel_batched_any_ratio_vs_thread_per_output_kernels_and_oracle(ir, orr, rows, n):
+    """K3i (lanes = lock-step rows, interpolated coefficients evaluated once per batch): bit-identical to the
+    one-thread-per-output kernels (same float64 summation order), <= 1e-12 against the oracle."""
+    rng = np.random.default_rng(31)
+    x = 0.5 * rng.standard_normal((rows, n))
+    cuts = [0, 5, n // 2 + 3, n]
+
+    def run(tiled):
+        G.set_tiled_polyphase(tiled)
+        try:
+            h = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float64)
+            ys = [h.ProcessBatch(np.ascontiguousarray(x[:, lo:hi]))[0].copy() for lo, hi in zip(cuts[:-1], cuts[1:])]
+            ys.append(h.FlushBatch()[0].copy())
+            return np.concatenate(ys, axis=1), h.last_kernels()
+        finally:
+            G.set_tiled_polyphase(True)
+
+    ya, ka = run(True)
+    yb, kb = run(False)
+    assert any(k.startswith("poly_rows_f64") for k in ka), ka
+    assert not any(k.startswith(("poly_rows", "poly_rat", "fused_up2_rat")) for k in kb), kb
+    np.testing.assert_array_equal(ya, yb)
+    pick = sorted(set([0, rows // 2, rows - 1]))
+    want, counts = O.batch_resample(x[pick], ir, orr, O.Q_HIGH, n_threads=4)
+    assert np.all(counts == ya.shape[1])
+    assert np.max(np.abs(ya[pick] - want[:, :ya.shape[1]])) <= 1e-12
