@@ -1181,11 +1181,13 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
 //      e_i taps late (static window slots, as in the rational kernel: e_i = o_i - i*S + Dg, zero taps are exact no-ops);
 //   2. every lane slides a register window over its row (rows at an odd pitch: conflict-free LDS.64): per tap one sample
 //      LDS + RN/2 broadcast LDS.128 feed RN FMAs, sums strictly in tap order (bit-identical to poly_kernel in float64).
-// A block = 16 rows x one tile of 16*RN outputs (8 warps x 2 tasks); samples are staged with asynchronous element
-// copies; two blocks per SM overlap each other's load and compute phases. Trailing blocks write the carried tails.
+// A block = one tile of 16*RN outputs (8 warps x 2 tasks) for up to 4 x 16 rows: the coefficient tiles are evaluated
+// once and reused for every 16-row block, whose samples are staged in turn with asynchronous element copies; two
+// blocks per SM overlap each other's load and compute phases. Trailing blocks write the carried tails.
 // =============================================================================================
 struct RowsGeom {
-    int32_t TO, span, pitch, tp, D, n_tiles, n_rb;  // outputs per tile, staged samples per row (max), row pitch, taps walked
+    int32_t TO, span, pitch, tp, D, n_tiles, nrb;  // outputs per tile, staged samples per row (max), row pitch, taps
+                                                   // walked, tiles per row, 16-row blocks per thread block
 };
 
 template <typename T, int S, int RN>
@@ -1203,7 +1205,8 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
     int* pat = reinterpret_cast<int*>(ct + NTASK * g.tp * RN);   // [NTASK][RN][4] phase row offset, lag, x bits
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_work = g.n_tiles * g.n_rb;
+    const int n_rg = (c.n_streams + RB * g.nrb - 1) / (RB * g.nrb);  // row groups
+    const int n_work = g.n_tiles * n_rg;
     if ((int)blockIdx.x >= n_work) {  // carried tail of one row
         const int64_t row = (int)blockIdx.x - n_work;
         carry_row(static_cast<const T*>(c.hist) + row * c.hist_stride, c.hist_len,
@@ -1212,7 +1215,7 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
         return;
     }
     const int tile = blockIdx.x % g.n_tiles;
-    const int row0 = (blockIdx.x / g.n_tiles) * RB;
+    const int rows_base = (blockIdx.x / g.n_tiles) * RB * g.nrb;
     const int64_t L = c.L;
     const int n0 = tile * g.TO;
     const int n1 = min(c.n_out, n0 + g.TO);  // outputs [n0, n1)
@@ -1222,20 +1225,23 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
     const int span_t = min((int)(d_last - d_base) + g.tp + 2 * WN + 2, g.span);
     const int64_t total = (int64_t)c.hist_len + c.n_in;
 
-    // ---- stage the rows' samples: warp w copies rows w, w+8 (coalesced along the row) ----
-    for (int r = warp; r < RB; r += 8) {
-        const int64_t row = row0 + r;
-        T* __restrict__ dst = xs + r * g.pitch;
-        const bool live = row < c.n_streams;
-        const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
-        const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
-        for (int i = lane; i < span_t; i += 32) {
-            const int64_t d = d_base + i;
-            if (!live || d < 0 || d >= total) dst[i] = T(0);
-            else if (d < c.hist_len) dst[i] = hist[d];
-            else cp_async_elem(dst + i, in + (d - c.hist_len));
+    // ---- stage the samples of 16 rows: warp w copies rows w, w+8 (coalesced along the row) ----
+    auto stage_rows = [&](const int row0) {
+        for (int r = warp; r < RB; r += 8) {
+            const int64_t row = row0 + r;
+            T* __restrict__ dst = xs + r * g.pitch;
+            const bool live = row < c.n_streams;
+            const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
+            const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+            for (int i = lane; i < span_t; i += 32) {
+                const int64_t d = d_base + i;
+                if (!live || d < 0 || d >= total) dst[i] = T(0);
+                else if (d < c.hist_len) dst[i] = hist[d];
+                else cp_async_elem(dst + i, in + (d - c.hist_len));
+            }
         }
-    }
+    };
+    stage_rows(rows_base);
 
     // ---- pattern + coefficient tile of this half-warp's task (overlaps the copies above) ----
     const int hl = lane & 15, half = lane >> 4;
@@ -1272,8 +1278,8 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
         const T* __restrict__ gb = static_cast<const T*>(c.bank_b);
         const T* __restrict__ gc = static_cast<const T*>(c.bank_c);
         const T* __restrict__ gd = static_cast<const T*>(c.bank_d);
-#pragma unroll 4
-        for (int idx = hl; idx < g.tp * RN; idx += 16) {
+#pragma unroll 6
+        for (int idx = hl; idx < g.tp * RN; idx += 16) {  // six independent (4-load) evaluations in flight per lane
             const int kk = idx / RN, i = idx - kk * RN;
             const int k = kk - ptask[i * 4 + 1];
             T v = T(0);
@@ -1288,40 +1294,47 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
             ctile[idx] = v;
         }
     }
-    cp_async_wait_all();
-    __syncthreads();
-
-    // ---- tap loop: lane = row, RN adjacent outputs, static window slots ----
-    if (nf < n1) {
-        const T* __restrict__ sp = xs + hl * g.pitch + (div0 - Dg);  // window slot 0 (div0 >= D >= Dg)
-        T W[WN], acc[RN];
-#pragma unroll
-        for (int x = 0; x < WN; ++x) W[x] = sp[x];
-#pragma unroll
-        for (int i = 0; i < RN; ++i) acc[i] = T(0);
-        auto tap = [&](const int u, const int kk) {
-            T cf[RN];
-#pragma unroll
-            for (int q = 0; q < RN / VEC; ++q)
-                vec_unpack(*reinterpret_cast<const V*>(ctile + kk * RN + q * VEC), cf + q * VEC);
-#pragma unroll
-            for (int i = 0; i < RN; ++i) acc[i] = fma(W[(u + i * S) % WN], cf[i], acc[i]);
-            W[u] = sp[kk + WN];
-        };
-        int it0 = 0;
-        for (; it0 + WN <= g.tp; it0 += WN) {
-#pragma unroll
-            for (int u = 0; u < WN; ++u) tap(u, it0 + u);
+    // ---- tap loops: lane = row, RN adjacent outputs, static window slots; one 16-row block after the other ----
+    for (int j = 0; j < g.nrb; ++j) {
+        const int row0 = rows_base + j * RB;
+        if (row0 >= c.n_streams) break;
+        if (j > 0) {
+            __syncthreads();  // everyone is done with the previous rows' samples
+            stage_rows(row0);
         }
+        cp_async_wait_all();
+        __syncthreads();
+        if (nf < n1) {
+            const T* __restrict__ sp = xs + hl * g.pitch + (div0 - Dg);  // window slot 0 (div0 >= D >= Dg)
+            T W[WN], acc[RN];
 #pragma unroll
-        for (int u = 0; u < WN; ++u)
-            if (it0 + u < g.tp) tap(u, it0 + u);
-        const int64_t row = row0 + hl;
-        if (row < c.n_streams) {
-            T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+            for (int x = 0; x < WN; ++x) W[x] = sp[x];
 #pragma unroll
-            for (int i = 0; i < RN; ++i)
-                if (nf + i < n1) out[nf + i] = acc[i];
+            for (int i = 0; i < RN; ++i) acc[i] = T(0);
+            auto tap = [&](const int u, const int kk) {
+                T cf[RN];
+#pragma unroll
+                for (int q = 0; q < RN / VEC; ++q)
+                    vec_unpack(*reinterpret_cast<const V*>(ctile + kk * RN + q * VEC), cf + q * VEC);
+#pragma unroll
+                for (int i = 0; i < RN; ++i) acc[i] = fma(W[(u + i * S) % WN], cf[i], acc[i]);
+                W[u] = sp[kk + WN];
+            };
+            int it0 = 0;
+            for (; it0 + WN <= g.tp; it0 += WN) {
+#pragma unroll
+                for (int u = 0; u < WN; ++u) tap(u, it0 + u);
+            }
+#pragma unroll
+            for (int u = 0; u < WN; ++u)
+                if (it0 + u < g.tp) tap(u, it0 + u);
+            const int64_t row = row0 + hl;
+            if (row < c.n_streams) {
+                T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+#pragma unroll
+                for (int i = 0; i < RN; ++i)
+                    if (nf + i < n1) out[nf + i] = acc[i];
+            }
         }
     }
 }
@@ -1339,7 +1352,10 @@ static bool launch_poly_rows_t(const PolyCall& c, cudaStream_t s) {
     g.span = (int)std::ceil((g.TO - 1) * r) + g.D + g.tp + 2 * WN + 4;
     g.pitch = g.span | 1;
     g.n_tiles = (c.n_out + g.TO - 1) / g.TO;
-    g.n_rb = (c.n_streams + 15) / 16;
+    // 16-row blocks per thread block: reuse every coefficient tile as often as possible while the grid still fills the GPU
+    const int n_rb = (c.n_streams + 15) / 16;
+    g.nrb = 1;
+    while (g.nrb < 4 && g.nrb * 2 <= n_rb && (int64_t)g.n_tiles * ((n_rb + g.nrb * 2 - 1) / (g.nrb * 2)) >= 4 * 148) g.nrb *= 2;
     const size_t smem = ((size_t)16 * g.pitch + 1 + (size_t)16 * g.tp * RN) * sizeof(T) + (size_t)16 * RN * 4 * sizeof(int);
     if (smem > 113 * 1024) return false;
     auto k = poly_rows_kernel<T, S, RN>;
@@ -1350,7 +1366,7 @@ static bool launch_poly_rows_t(const PolyCall& c, cudaStream_t s) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured[dev & 63] = smem;
     }
-    const int64_t blocks = (int64_t)g.n_tiles * g.n_rb + c.n_streams;
+    const int64_t blocks = (int64_t)g.n_tiles * ((c.n_streams + 16 * g.nrb - 1) / (16 * g.nrb)) + c.n_streams;
     k<<<(unsigned)blocks, 256, smem, s>>>(c, g);
     count_launch();
     return true;
@@ -1359,7 +1375,7 @@ static bool launch_poly_rows_t(const PolyCall& c, cudaStream_t s) {
 // K3i dispatch: batches of at least 8 lock-step rows with enough outputs; S = ceil(samples per output)
 template <typename T>
 static bool launch_poly_rows(const PolyCall& c, cudaStream_t s) {
-    if (c.n_streams < 8 || (int64_t)c.n_out * c.n_streams < 65536 || c.L > 4096 || c.taps > 1024) return false;
+    if (c.n_streams < 8 || (int64_t)c.n_out * c.n_streams < 16384 || c.L > 4096 || c.taps > 1024) return false;
     const double r = (double)c.step / ((double)c.L * 65536.0);
     if (!(r > 0.0) || r > 8.0) return false;
     const int S = (int)std::ceil(r - 1e-12);
@@ -1980,7 +1996,7 @@ const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s,
     // K3i (lanes = rows, interpolated coefficients evaluated once per batch) beat the one-thread-per-output fused kernel
     {
         const double r = (double)c.step / ((double)c.L * 65536.0);
-        if (g_fused_rat && c.n_streams >= 8 && (int64_t)c.n_out * c.n_streams >= 65536 && r > 0.0 && r <= 8.0 &&
+        if (g_fused_rat && c.n_streams >= 8 && (int64_t)c.n_out * c.n_streams >= 16384 && r > 0.0 && r <= 8.0 &&
             c.L <= 4096 && c.t2 <= 1024)
             return nullptr;
     }
