@@ -1174,20 +1174,21 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
 // polyphase_stage.go:186-312 with cubic coefficient interpolation).
 //
 // With an irrational ratio no two outputs of a stream share their coefficients, but the rows of a lock-step batch do:
-// output n of every row uses the same phase and the same fraction x. So the LANES are 16 rows, and a half-warp task is
-// RN adjacent outputs of those rows:
-//   1. the half-warp evaluates the interpolated coefficients a + x(b + x(c + x d)) of its RN outputs ONCE (the three
-//      Horner FMAs per tap amortise over the rows) into a per-task tile [tap][RN] in shared memory, each output's filter
-//      e_i taps late (static window slots, as in the rational kernel: e_i = o_i - i*S + Dg, zero taps are exact no-ops);
+// output n of every row uses the same phase and the same fraction x. So the LANES of a warp are 32 rows, and a warp
+// task is RN adjacent outputs of those rows:
+//   1. the warp evaluates the interpolated coefficients a + x(b + x(c + x d)) of its RN outputs ONCE (the three Horner
+//      FMAs per tap amortise over the rows) into a per-task tile [tap][RN] in shared memory, each output's filter e_i
+//      taps late (static window slots, as in the rational kernel: e_i = o_i - i*S + Dg, zero taps are exact no-ops);
 //   2. every lane slides a register window over its row (rows at an odd pitch: conflict-free LDS.64): per tap one sample
-//      LDS + RN/2 broadcast LDS.128 feed RN FMAs, sums strictly in tap order (bit-identical to poly_kernel in float64).
-// A block = one tile of 16*RN outputs (8 warps x 2 tasks) for up to 4 x 16 rows: the coefficient tiles are evaluated
-// once and reused for every 16-row block, whose samples are staged in turn with asynchronous element copies; two
-// blocks per SM overlap each other's load and compute phases. Trailing blocks write the carried tails.
+//      LDS + RN/2 single-wavefront broadcast LDS.128 feed RN FMAs, sums strictly in tap order (bit-identical to
+//      poly_kernel in float64).
+// A block = one tile of 8*RN outputs (8 warp tasks) for up to 4 x 32 rows: the coefficient tiles are evaluated once
+// and reused for every 32-row block, whose samples are staged in turn with asynchronous element copies; two blocks
+// per SM overlap each other's load and compute phases. Trailing blocks write the carried tails.
 // =============================================================================================
 struct RowsGeom {
     int32_t TO, span, pitch, tp, D, n_tiles, nrb;  // outputs per tile, staged samples per row (max), row pitch, taps
-                                                   // walked, tiles per row, 16-row blocks per thread block
+                                                   // walked, tiles per row, 32-row blocks per thread block
 };
 
 template <typename T, int S, int RN>
@@ -1195,13 +1196,13 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
     using V = typename VecOf<T>::type;
     constexpr int VEC = VecOf<T>::N;
     static_assert(RN % VEC == 0, "a coefficient vector load covers whole outputs");
-    constexpr int RB = 16;                 // rows per block = lanes of a half-warp task
+    constexpr int RB = 32;                 // rows per pass = lanes of a warp task
     constexpr int WN = (RN - 1) * S + 1;   // register window
-    constexpr int NTASK = 16;              // half-warp tasks per block (8 warps x 2)
+    constexpr int NTASK = 8;               // warp tasks per block
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* xs = reinterpret_cast<T*>(smem_raw);                      // [RB][pitch] staged samples
-    T* ct = xs + RB * g.pitch + (RB * g.pitch & 1);              // [NTASK][tp*RN] coefficient tiles
+    T* ct = xs + RB * g.pitch;                                   // [NTASK][tp*RN] coefficient tiles
     int* pat = reinterpret_cast<int*>(ct + NTASK * g.tp * RN);   // [NTASK][RN][4] phase row offset, lag, x bits
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1225,7 +1226,7 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
     const int span_t = min((int)(d_last - d_base) + g.tp + 2 * WN + 2, g.span);
     const int64_t total = (int64_t)c.hist_len + c.n_in;
 
-    // ---- stage the samples of 16 rows: warp w copies rows w, w+8 (coalesced along the row) ----
+    // ---- stage the samples of 32 rows: warp w copies rows w, w+8, ... (coalesced along the row) ----
     auto stage_rows = [&](const int row0) {
         for (int r = warp; r < RB; r += 8) {
             const int64_t row = row0 + r;
@@ -1243,30 +1244,26 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
     };
     stage_rows(rows_base);
 
-    // ---- pattern + coefficient tile of this half-warp's task (overlaps the copies above) ----
-    const int hl = lane & 15, half = lane >> 4;
-    const int task = warp * 2 + half;
-    const int nf = n0 + task * RN;  // first output of the task
-    const unsigned hmask = 0xFFFFu << (half * 16);
-    T* __restrict__ ctile = ct + task * g.tp * RN;
-    int* __restrict__ ptask = pat + task * RN * 4;
+    // ---- pattern + coefficient tile of this warp's task (overlaps the copies above) ----
+    const int nf = n0 + warp * RN;  // first output of the task
+    T* __restrict__ ctile = ct + warp * g.tp * RN;
+    int* __restrict__ ptask = pat + warp * RN * 4;
     int div0 = 0, Dg = 0;
     {
         // lane i < RN: geometry of output nf + i (polyphase_stage.go:260-264)
-        const int i = hl < RN ? hl : RN - 1;
+        const int i = lane < RN ? lane : RN - 1;
         const int64_t at = c.at0 + (int64_t)(nf + i) * c.step;
         const int64_t full = at >> 16;
         const int64_t dv = full / L;
         const int ph = (int)(full - dv * L);
-        const int dv0 = __shfl_sync(hmask, (int)(dv - d_base), half * 16);  // window offsets are relative to the tile
+        const int dv0 = __shfl_sync(0xffffffffu, (int)(dv - d_base), 0);  // window offsets are relative to the tile
         const int o = (int)(dv - d_base) - dv0;
-        int lag = i * S - o;  // >= 0 would-be lag of the static slot
-        int m = lag;
+        int m = i * S - o;  // lag of the static slot behind the true offset
 #pragma unroll
-        for (int sft = 8; sft >= 1; sft >>= 1) m = max(m, __shfl_xor_sync(hmask, m, sft));
+        for (int sft = 16; sft >= 1; sft >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, sft));
         Dg = m;
         div0 = dv0;
-        if (hl < RN) {
+        if (lane < RN) {
             ptask[i * 4 + 0] = ph * c.taps;
             ptask[i * 4 + 1] = o - i * S + Dg;  // e_i in [0, D]
             ptask[i * 4 + 2] = (int)(at & 0xFFFF);
@@ -1279,7 +1276,7 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
         const T* __restrict__ gc = static_cast<const T*>(c.bank_c);
         const T* __restrict__ gd = static_cast<const T*>(c.bank_d);
 #pragma unroll 6
-        for (int idx = hl; idx < g.tp * RN; idx += 16) {  // six independent (4-load) evaluations in flight per lane
+        for (int idx = lane; idx < g.tp * RN; idx += 32) {  // six independent (4-load) evaluations in flight per lane
             const int kk = idx / RN, i = idx - kk * RN;
             const int k = kk - ptask[i * 4 + 1];
             T v = T(0);
@@ -1294,7 +1291,8 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
             ctile[idx] = v;
         }
     }
-    // ---- tap loops: lane = row, RN adjacent outputs, static window slots; one 16-row block after the other ----
+
+    // ---- tap loops: lane = row, RN adjacent outputs, static window slots; one 32-row block after the other ----
     for (int j = 0; j < g.nrb; ++j) {
         const int row0 = rows_base + j * RB;
         if (row0 >= c.n_streams) break;
@@ -1305,7 +1303,7 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
         cp_async_wait_all();
         __syncthreads();
         if (nf < n1) {
-            const T* __restrict__ sp = xs + hl * g.pitch + (div0 - Dg);  // window slot 0 (div0 >= D >= Dg)
+            const T* __restrict__ sp = xs + lane * g.pitch + (div0 - Dg);  // window slot 0 (div0 >= D >= Dg)
             T W[WN], acc[RN];
 #pragma unroll
             for (int x = 0; x < WN; ++x) W[x] = sp[x];
@@ -1328,7 +1326,7 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
 #pragma unroll
             for (int u = 0; u < WN; ++u)
                 if (it0 + u < g.tp) tap(u, it0 + u);
-            const int64_t row = row0 + hl;
+            const int64_t row = row0 + lane;
             if (row < c.n_streams) {
                 T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
 #pragma unroll
@@ -1343,7 +1341,7 @@ template <typename T, int S, int RN>
 static bool launch_poly_rows_t(const PolyCall& c, cudaStream_t s) {
     constexpr int WN = (RN - 1) * S + 1;
     RowsGeom g{};
-    g.TO = 16 * RN;
+    g.TO = 8 * RN;
     // intermediate samples per output r = step / (L * 65536); worst lag of a static slot behind the true offset
     const double r = (double)c.step / ((double)c.L * 65536.0);
     g.D = (RN - 1) * S - (int)std::floor((RN - 1) * r) + 1;
@@ -1352,11 +1350,11 @@ static bool launch_poly_rows_t(const PolyCall& c, cudaStream_t s) {
     g.span = (int)std::ceil((g.TO - 1) * r) + g.D + g.tp + 2 * WN + 4;
     g.pitch = g.span | 1;
     g.n_tiles = (c.n_out + g.TO - 1) / g.TO;
-    // 16-row blocks per thread block: reuse every coefficient tile as often as possible while the grid still fills the GPU
-    const int n_rb = (c.n_streams + 15) / 16;
+    // 32-row blocks per thread block: reuse every coefficient tile as often as possible while the grid still fills the GPU
+    const int n_rb = (c.n_streams + 31) / 32;
     g.nrb = 1;
     while (g.nrb < 4 && g.nrb * 2 <= n_rb && (int64_t)g.n_tiles * ((n_rb + g.nrb * 2 - 1) / (g.nrb * 2)) >= 4 * 148) g.nrb *= 2;
-    const size_t smem = ((size_t)16 * g.pitch + 1 + (size_t)16 * g.tp * RN) * sizeof(T) + (size_t)16 * RN * 4 * sizeof(int);
+    const size_t smem = ((size_t)32 * g.pitch + (size_t)8 * g.tp * RN) * sizeof(T) + (size_t)8 * RN * 4 * sizeof(int);
     if (smem > 113 * 1024) return false;
     auto k = poly_rows_kernel<T, S, RN>;
     static size_t configured[64] = {0};
@@ -1366,7 +1364,7 @@ static bool launch_poly_rows_t(const PolyCall& c, cudaStream_t s) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured[dev & 63] = smem;
     }
-    const int64_t blocks = (int64_t)g.n_tiles * ((c.n_streams + 16 * g.nrb - 1) / (16 * g.nrb)) + c.n_streams;
+    const int64_t blocks = (int64_t)g.n_tiles * ((c.n_streams + 32 * g.nrb - 1) / (32 * g.nrb)) + c.n_streams;
     k<<<(unsigned)blocks, 256, smem, s>>>(c, g);
     count_launch();
     return true;
