@@ -1227,19 +1227,26 @@ __global__ void __launch_bounds__(256, 2) poly_rows_kernel(const PolyCall c, con
     const int64_t total = (int64_t)c.hist_len + c.n_in;
 
     // ---- stage the samples of 32 rows: warp w copies rows w, w+8, ... (coalesced along the row) ----
+    // staged index i is sample d_base + i: zeros before the stream, [i0, i1) from the carried tail, [i1, i2) from `in`
+    // (asynchronous element copies), zeros behind the end
+    const int i0 = (int)min((int64_t)span_t, max((int64_t)0, -d_base));
+    const int i1 = (int)min((int64_t)span_t, max((int64_t)i0, (int64_t)c.hist_len - d_base));
+    const int i2 = (int)min((int64_t)span_t, max((int64_t)i1, total - d_base));
     auto stage_rows = [&](const int row0) {
         for (int r = warp; r < RB; r += 8) {
             const int64_t row = row0 + r;
             T* __restrict__ dst = xs + r * g.pitch;
-            const bool live = row < c.n_streams;
-            const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
-            const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
-            for (int i = lane; i < span_t; i += 32) {
-                const int64_t d = d_base + i;
-                if (!live || d < 0 || d >= total) dst[i] = T(0);
-                else if (d < c.hist_len) dst[i] = hist[d];
-                else cp_async_elem(dst + i, in + (d - c.hist_len));
+            if (row >= c.n_streams) {
+                for (int i = lane; i < span_t; i += 32) dst[i] = T(0);
+                continue;
             }
+            const T* __restrict__ hsrc = static_cast<const T*>(c.hist) + row * c.hist_stride + d_base;
+            const T* __restrict__ isrc = static_cast<const T*>(c.in) + row * c.in_stride + (d_base - c.hist_len);
+            for (int i = lane; i < i0; i += 32) dst[i] = T(0);
+            for (int i = i0 + lane; i < i1; i += 32) dst[i] = hsrc[i];
+#pragma unroll 4
+            for (int i = i1 + lane; i < i2; i += 32) cp_async_elem(dst + i, isrc + i);
+            for (int i = i2 + lane; i < span_t; i += 32) dst[i] = T(0);
         }
     };
     stage_rows(rows_base);
