@@ -117,6 +117,8 @@ float run_fma_probe(int dtype, int iters, double* flops, cudaStream_t s);
 long long launch_count(bool reset);
 // process-wide A/B switch for the register-tiled polyphase kernels (K4r / K3r / K3i); on by default
 void set_tiled_polyphase(bool on);
+// process-wide A/B switch for the FP64 tensor-core FIR kernels (DMMA); on by default
+void set_tensor_fir(bool on);
 // name the tiled FIR variant that launch_fir would pick (no launch)
 const char* fir_variant_name(int dtype, int stride, int nf, int taps, int64_t n_pos, int n_streams);
 

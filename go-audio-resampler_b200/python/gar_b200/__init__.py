@@ -125,6 +125,7 @@ SYMBOLS = {
     "gar_stage_kernel_name": (C.c_char_p, [_vp, _i32]),
     "gar_kernels_used": (_i32, [_vp, C.c_char_p, _i32]),
     "gar_set_tiled_polyphase": (None, [_i32]),
+    "gar_set_tensor_fir": (None, [_i32]),
     "gar_measure_fma_peak": (_i32, [_i32, _i32, C.POINTER(C.c_double)]),
     "gar_version": (C.c_char_p, []),
 }
@@ -562,6 +563,11 @@ def device_count():
 def set_tiled_polyphase(enabled: bool):
     """Process-wide A/B switch for the register-tiled polyphase kernels (K4r / K3r / K3i)."""
     lib().gar_set_tiled_polyphase(1 if enabled else 0)
+
+
+def set_tensor_fir(enabled: bool):
+    """Process-wide A/B switch for the FP64 tensor-core (DMMA) FIR kernels."""
+    lib().gar_set_tensor_fir(1 if enabled else 0)
 
 
 def kernel_launches(reset=False):

@@ -224,6 +224,9 @@ int32_t gar_set_fusion(gar_handle* h, int32_t enabled);
 /* Process-wide A/B switch (tests, profiling): 0 routes every polyphase stage through the one-thread-per-output
  * kernels instead of the register-tiled ones (K4r / K3r / K3i). Results are bit-identical in float64. Default 1. */
 void gar_set_tiled_polyphase(int32_t enabled);
+/* Process-wide A/B switch: 0 routes the float64 integer-factor FIR stages of >= 8-row batches through the vector-FMA
+ * kernels instead of the FP64 tensor-core (DMMA) kernels. The two differ in the last bits (taps grouped in fours). Default 1. */
+void gar_set_tensor_fir(int32_t enabled);
 /* Number of this library's kernels launched through the handle since creation / last reset of the counter. */
 int64_t gar_kernel_launches(const gar_handle* h, int32_t reset);
 /* Name of the dominant kernel variant chosen for stage `stage` (for bench/ncu filters). */

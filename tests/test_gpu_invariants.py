@@ -223,6 +223,15 @@ def test_fused_x2_polyphase_kernel_equals_unfused(ir, orr, dt):
     assert la < lb  # fewer launches when fused
 
 
+@pytest.fixture
+def vector_fir_only():
+    """The bit-for-bit comparisons below are between kernels that sum taps strictly in order; the FP64 tensor-core FIR
+    (taps grouped in fours) is switched off for them and has its own test."""
+    G.set_tensor_fir(False)
+    yield
+    G.set_tensor_fir(True)
+
+
 @pytest.mark.parametrize("ir,orr,rows,n,kernel", [
     (44100, 48000, 200, 60000, "fused_up2_rat_f64"),   # Mi/L = 147/80  -> slot stride 2, persistent multi-tile blocks
     (48000, 44100, 40, 70000, "fused_up2_rat_f64"),    # 320/147 -> slot stride 3
@@ -230,7 +239,7 @@ def test_fused_x2_polyphase_kernel_equals_unfused(ir, orr, dt):
     (8000, 12000, 33, 20000, "fused_up2_rat_f64"),     # 4/3
     (44100, 32000, 16, 41000, "fused_up2_rat_f64"),
 ])
-def test_rational_fused_kernel_batched_rows_vs_unfused_and_oracle(ir, orr, rows, n, kernel):
+def test_rational_fused_kernel_batched_rows_vs_unfused_and_oracle(ir, orr, rows, n, kernel, vector_fir_only):
     """K4r (register-tiled rational-ratio fused kernel): many lock-step rows, ragged chunking (every carried
     phase/tail state), flush. Bit-identical to the stand-alone launches; <= 1e-12 against the oracle."""
     rng = np.random.default_rng(77)
@@ -248,7 +257,8 @@ def test_rational_fused_kernel_batched_rows_vs_unfused_and_oracle(ir, orr, rows,
     ya.append(a.FlushBatch()[0].copy())
     yb.append(b.FlushBatch()[0].copy())
     assert kernel in a.last_kernels(), a.last_kernels()
-    assert "poly_rat_f64" in b.last_kernels(), b.last_kernels()  # K3r: the stand-alone stage uses the same tiling
+    # the stand-alone stage runs K3r (odd period length) or K3i (even period length, >= 8 rows)
+    assert any(k in b.last_kernels() for k in ("poly_rat_f64", "poly_rows_f64")), b.last_kernels()
     ya, yb = np.concatenate(ya, axis=1), np.concatenate(yb, axis=1)
     np.testing.assert_array_equal(ya, yb)
     pick = sorted(set([0, 1, rows // 2, rows - 1]))
@@ -257,7 +267,7 @@ def test_rational_fused_kernel_batched_rows_vs_unfused_and_oracle(ir, orr, rows,
     assert np.max(np.abs(ya[pick] - want[:, :ya.shape[1]])) <= 1e-12
 
 
-def test_rational_kernels_random_geometry_stress():
+def test_rational_kernels_random_geometry_stress(vector_fir_only):
     """Many random (rows, length, chunking) cases through the barrier-free K4r / K3r pipelines: fused, unfused and
     one-shot runs must agree bit for bit (float64 sums are strictly sequential in every kernel)."""
     rng = np.random.default_rng(2024)
@@ -290,7 +300,7 @@ def test_rational_kernels_random_geometry_stress():
     (8000, 22050, 19, 30000),     # fewer than one intermediate sample per output (window slot stride 1)
     (44100, 16000, 17, 70000),    # rational, 5.5 samples/output: beyond the rational kernel's slot strides
 ])
-def test_rows_kernel_batched_any_ratio_vs_thread_per_output_kernels_and_oracle(ir, orr, rows, n):
+def test_rows_kernel_batched_any_ratio_vs_thread_per_output_kernels_and_oracle(ir, orr, rows, n, vector_fir_only):
     """K3i (lanes = lock-step rows, interpolated coefficients evaluated once per batch): bit-identical to the
     one-thread-per-output kernels (same float64 summation order), <= 1e-12 against the oracle."""
     rng = np.random.default_rng(31)
@@ -314,5 +324,44 @@ def test_rows_kernel_batched_any_ratio_vs_thread_per_output_kernels_and_oracle(i
     np.testing.assert_array_equal(ya, yb)
     pick = sorted(set([0, rows // 2, rows - 1]))
     want, counts = O.batch_resample(x[pick], ir, orr, O.Q_HIGH, n_threads=4)
+    assert np.all(counts == ya.shape[1])
+    assert np.max(np.abs(ya[pick] - want[:, :ya.shape[1]])) <= 1e-12
+
+
+@pytest.mark.parametrize("ir,orr,preset,rows,n,kernel", [
+    (22050, 44100, G.QualityHigh, 8, 30000, "fir_f64_mma_up2"),        # x2 up-sampler, 166 taps per phase
+    (96000, 48000, G.QualityVeryHigh, 8, 120000, "fir_f64_mma_s2"),    # /2 (path B maps VeryHigh to the 751-tap High filter)
+    (48000, 16000, G.QualityHigh, 19, 90000, "fir_f64_mma_s3"),        # /3 with a ragged last group of streams
+    (192000, 48000, G.QualityMedium, 9, 100000, "fir_f64_mma_s4"),     # /4
+    (44100, 48000, G.QualityHigh, 24, 40000, "fir_f64_mma_up2"),       # x2 stage in front of the polyphase stage
+])
+def test_tensor_core_fir_matches_vector_kernels_and_oracle(ir, orr, preset, rows, n, kernel):
+    """K1m/K2m (FP64 tensor cores, DMMA): same samples as the vector-FMA kernels to 1e-13 (taps grouped in fours
+    instead of strictly sequential), <= 1e-12 against the oracle, identical counts; ragged chunking exercises the
+    carried tails and the mix with the small-call vector kernels."""
+    rng = np.random.default_rng(9)
+    x = 0.6 * rng.standard_normal((rows, n))
+    cuts = [0, 11, n // 3, n // 3 + 40000 if n // 3 + 40000 < n else n - 7, n]
+
+    def run(tensor, chunks):
+        G.set_tensor_fir(tensor)
+        try:
+            h = G.NewBatch(ir, orr, preset, rows, np.float64)
+            ys = [h.ProcessBatch(np.ascontiguousarray(x[:, lo:hi]))[0].copy() for lo, hi in zip(chunks[:-1], chunks[1:])]
+            ys.append(h.FlushBatch()[0].copy())
+            return np.concatenate(ys, axis=1), h.last_kernels()
+        finally:
+            G.set_tensor_fir(True)
+
+    ya, ka = run(True, [0, n])
+    yb, kb = run(False, [0, n])
+    yc, _ = run(True, cuts)
+    assert kernel in ka, ka
+    assert not any("mma" in k for k in kb), kb
+    assert ya.shape == yb.shape == yc.shape
+    assert np.max(np.abs(ya - yb)) <= 1e-13
+    assert np.max(np.abs(yc - yb)) <= 1e-13
+    pick = sorted(set([0, rows // 2, rows - 1]))
+    want, counts = O.batch_resample(x[pick], ir, orr, O.preset_to_engine_quality(preset), n_threads=4)
     assert np.all(counts == ya.shape[1])
     assert np.max(np.abs(ya[pick] - want[:, :ya.shape[1]])) <= 1e-12
