@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
 // bits (1e-16 relative); identical call sequences are bit-identical.
 // =============================================================================================
 struct MmaGeom {
-    int32_t nk, xlen, pitch, n_tiles, tiles_per_block, n_groups, n_sg;  // k-steps, staged samples per stream, row pitch
+    int32_t nk, xlen, pitch, nbuf, n_tiles, tiles_per_block, n_groups, n_sg;  // k-steps, staged samples per stream, row pitch, window buffers
 };
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, const double b) {
@@ -324,19 +324,23 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, 
                  : "d"(a), "d"(b));
 }
 
-template <int M, int NF, int NW>
+template <int M, int NF, int NW, int MT>
 __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, const MmaGeom g) {
     constexpr int JT = 8 / NF;                // positions per MMA tile
     static_assert(8 % NF == 0 && (JT * M) % 4 == 0, "tile shift must be a whole number of k-steps");
     constexpr int SH = JT * M / 4;            // k-steps between consecutive MMA tiles
-    constexpr int MT = 4;                     // MMA tiles per warp
     constexpr int WA = (MT - 1) * SH + 1;     // rotating A-fragment window
     constexpr int TJ = NW * MT * JT;          // positions per block tile
     constexpr int NT = NW * 32;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* As = reinterpret_cast<double*>(smem_raw);  // [nk][32] A fragments in lane order
-    double* Xs = As + (size_t)g.nk * 32;               // [8][pitch] sample windows of the block's streams
+    // A[(jj,p)][w] = bank[p][w - jj*M] is a shifted copy of the filter in every row, so the A fragment of k-step kk is a
+    // gather from the zero-padded bank with a per-lane offset: no fragment table, the bank itself is all that is staged
+    constexpr int BOFF = (JT - 1) * M;                           // leading zeros: the largest negative offset
+    const int blen = (4 * g.nk + BOFF + 5) & ~1;                 // padded filter length, even: windows stay 16-byte aligned
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);       // [2] mbarriers of the bulk-copied window buffers
+    double* Bs = reinterpret_cast<double*>(smem_raw + 16);       // [NF][blen] zero-padded bank
+    double* Xs0 = Bs + (size_t)NF * blen;                        // [nbuf][8][pitch] sample windows of the block's streams
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_work = g.n_sg * g.n_groups;
@@ -352,61 +356,114 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
     const int t_first = grp * g.tiles_per_block;
     const int nt = min(g.tiles_per_block, g.n_tiles - t_first);
 
-    {  // A fragments: lane l of k-step kk holds A[row = l/4][w = 4*kk + l%4]
+    {
         const double* __restrict__ bank = static_cast<const double*>(c.bank);
-#pragma unroll 4
-        for (int idx = tid; idx < g.nk * 32; idx += NT) {
-            const int kk = idx >> 5, l = idx & 31;
-            const int row = l >> 2, w = 4 * kk + (l & 3);
-            const int jj = row / NF, p = row - jj * NF;
-            const int k = w - jj * M;
-            As[idx] = (k >= 0 && k < c.taps) ? bank[p * c.taps + k] : 0.0;
+        for (int idx = tid; idx < NF * blen; idx += NT) {
+            const int p = idx / blen, k = idx - p * blen - BOFF;
+            Bs[idx] = (k >= 0 && k < c.taps) ? bank[p * c.taps + k] : 0.0;
         }
     }
     const int64_t total = (int64_t)c.hist_len + c.n_in;
-    const double* __restrict__ xrow = Xs + (lane >> 2) * g.pitch + (lane & 3);  // B fragment base of this lane
     const int nq = g.nk + (MT - 1) * SH;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+    }
+    uint32_t ph0 = 0u, ph1 = 0u;
+    // TMA bulk copies need 16-byte aligned sources: all 8 rows share the alignment when the row stride is even
+    const bool rows_bulk = (c.in_stride & 1) == 0 && sbase + 8 <= c.n_streams;
+    const double* __restrict__ in0 = static_cast<const double*>(c.in) + (int64_t)sbase * c.in_stride;
+    const int xbuf = 8 * g.pitch;
+
+    // geometry of local tile kt: first sample v0, staged length, bulk-copy parameters
+    auto tile_geom = [&](const int kt, int64_t& v0, int& len, int& a, int& wlen) -> bool {
+        const int jb0 = (t_first + kt) * TJ;
+        v0 = (int64_t)c.first + (int64_t)jb0 * M;
+        const int npos_t = min(TJ, c.n_pos - jb0);
+        len = min(g.xlen, ((npos_t + JT - 1) / JT * JT - 1) * M + 4 * g.nk + 4);
+        a = 0;
+        wlen = 0;
+        const int64_t gi = v0 - c.hist_len;
+        if (!rows_bulk || gi < 0) return false;
+        a = (int)((reinterpret_cast<uintptr_t>(in0 + gi) & 15u) >> 3);  // start `a` samples early: aligned source
+        wlen = (len + a + 1) & ~1;
+        if (gi - a >= 0 && gi - a + wlen <= c.n_in && wlen <= g.pitch) return true;
+        a = 0;  // element copies start exactly at v0
+        return false;
+    };
+    auto issue = [&](const int kt, const int buf) {  // one thread
+        int64_t v0;
+        int len, a, wlen;
+        if (!tile_geom(kt, v0, len, a, wlen)) return;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar + buf, (uint32_t)(8 * wlen * sizeof(double)));
+        const int64_t gi = v0 - c.hist_len - a;
+        for (int r = 0; r < 8; ++r)
+            bulk_g2s(Xs0 + buf * xbuf + r * g.pitch, in0 + (int64_t)r * c.in_stride + gi, (uint32_t)(wlen * sizeof(double)),
+                     bar + buf);
+    };
 
     for (int kt = 0; kt < nt; ++kt) {
-        const int jb0 = (t_first + kt) * TJ;  // first position of the tile
-        // ---- stage the 8 sample windows: element i of a row is v[first + jb0*M + i] ----
-        const int64_t v0 = (int64_t)c.first + (int64_t)jb0 * M;
-        const int npos_t = min(TJ, c.n_pos - jb0);
-        const int len = min(g.xlen, ((npos_t + JT - 1) / JT * JT - 1) * M + 4 * g.nk + 4);
-        const int i1 = (int)min((int64_t)len, max((int64_t)0, (int64_t)c.hist_len - v0));
-        const int i2 = (int)min((int64_t)len, max((int64_t)i1, total - v0));
-        if (kt > 0) __syncthreads();  // everyone is done with the previous tile's windows
-        for (int r = warp; r < 8; r += NW) {
-            const int64_t row = sbase + r;
-            double* __restrict__ dst = Xs + r * g.pitch;
-            if (row >= c.n_streams) {
-                for (int i = lane; i < len; i += 32) dst[i] = 0.0;
-                continue;
-            }
-            const double* __restrict__ hsrc = static_cast<const double*>(c.hist) + row * c.hist_stride + v0;
-            const double* __restrict__ isrc = static_cast<const double*>(c.in) + row * c.in_stride + (v0 - c.hist_len);
-            for (int i = lane; i < i1; i += 32) dst[i] = hsrc[i];
-#pragma unroll 4
-            for (int i = i1 + lane; i < i2; i += 32) cp_async_elem(dst + i, isrc + i);
-            for (int i = i2 + lane; i < len; i += 32) dst[i] = 0.0;
-        }
-        cp_async_wait_all();
+        const int buf = g.nbuf == 2 ? (kt & 1) : 0;
+        double* __restrict__ Xs = Xs0 + buf * xbuf;
+        int64_t v0;
+        int len, a, wlen;
+        const bool bulk = tile_geom(kt, v0, len, a, wlen);
+        // everyone is done with the windows this iteration overwrites (first tile: the bank and the mbarriers are set)
         __syncthreads();
+        if (tid == 0) {
+            if (g.nbuf == 2) {  // prefetch the next tile under this tile's MMAs
+                if (kt == 0) issue(0, 0);
+                if (kt + 1 < nt) issue(kt + 1, buf ^ 1);
+            } else {
+                issue(kt, 0);
+            }
+        }
+        if (bulk) {
+            const uint32_t ph = buf ? ph1 : ph0;
+            while (!mbar_try_wait(bar + buf, ph)) {
+            }
+            if (buf) ph1 ^= 1u;
+            else ph0 ^= 1u;
+        } else {  // edge tile (touches the carried tail or the end of the rows): element copies
+            const int i1 = (int)min((int64_t)len, max((int64_t)0, (int64_t)c.hist_len - v0));
+            const int i2 = (int)min((int64_t)len, max((int64_t)i1, total - v0));
+            for (int r = warp; r < 8; r += NW) {
+                const int64_t row = sbase + r;
+                double* __restrict__ dst = Xs + r * g.pitch;
+                if (row >= c.n_streams) {
+                    for (int i = lane; i < len; i += 32) dst[i] = 0.0;
+                    continue;
+                }
+                const double* __restrict__ hsrc = static_cast<const double*>(c.hist) + row * c.hist_stride + v0;
+                const double* __restrict__ isrc = static_cast<const double*>(c.in) + row * c.in_stride + (v0 - c.hist_len);
+                for (int i = lane; i < i1; i += 32) dst[i] = hsrc[i];
+#pragma unroll 4
+                for (int i = i1 + lane; i < i2; i += 32) cp_async_elem(dst + i, isrc + i);
+                for (int i = i2 + lane; i < len; i += 32) dst[i] = 0.0;
+            }
+            cp_async_wait_all();
+            __syncthreads();
+        }
 
         // ---- MT MMA tiles per warp; step q loads window chunk Q = warp*MT*SH + q and A fragment q ----
+        const int jb0 = (t_first + kt) * TJ;
+        const int npos_t = min(TJ, c.n_pos - jb0);
         if (warp * MT * JT < npos_t) {
             double acc[MT][2];
 #pragma unroll
             for (int b = 0; b < MT; ++b) acc[b][0] = acc[b][1] = 0.0;
             double Areg[WA];
-            const double* __restrict__ xw = xrow + 4 * (warp * MT * SH);
-            const double* __restrict__ aw = As + lane;
+            // B fragment: lane l reads X[w = 4*Q + l%4][stream l/4]
+            const double* __restrict__ xw = Xs + (lane >> 2) * g.pitch + (lane & 3) + a + 4 * (warp * MT * SH);
+            // A fragment: lane l holds A[row = l/4][w = 4*kk + l%4] = bank[p][4*kk + l%4 - jj*M], row = jj*NF + p
+            const double* __restrict__ aw = Bs + ((lane >> 2) % NF) * blen + BOFF + (lane & 3) - ((lane >> 2) / NF) * M;
             for (int q0 = 0; q0 < nq; q0 += WA) {
 #pragma unroll
                 for (int u = 0; u < WA; ++u) {
                     const int q = q0 + u;
                     if (q < nq) {
-                        Areg[u] = q < g.nk ? aw[q * 32] : 0.0;
+                        Areg[u] = q < g.nk ? aw[4 * q] : 0.0;
                         const double bf = xw[4 * q];
 #pragma unroll
                         for (int b = 0; b < MT; ++b) {
@@ -434,29 +491,35 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
 
 template <int M, int NF>
 static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
-    constexpr int JT = 8 / NF, SH = JT * M / 4, MT = 4;
+    constexpr int JT = 8 / NF, SH = JT * M / 4;
     int dev = 0;
     cudaGetDevice(&dev);
     MmaGeom g{};
     const int kp = c.taps + (JT - 1) * M;
     g.nk = (kp + 3) / 4;
     g.n_sg = (c.n_streams + 7) / 8;
-    auto run = [&](auto kernel, const int NW) -> bool {
+    const size_t bank_bytes = 16 + (size_t)NF * ((4 * g.nk + (JT - 1) * M + 5) & ~1) * sizeof(double);
+    auto run = [&](auto kernel, const int NW, const int MT, const int slot) -> bool {
         const int TJ = NW * MT * JT;
-        g.xlen = (TJ - 1) * M + 4 * g.nk + 4 * (MT - 1) * SH + 8;
+        g.xlen = (TJ - 1) * M + 4 * g.nk + 4 * (MT - 1) * SH + 10;
         g.pitch = ((g.xlen + 15) / 16) * 16 + 4;  // rows 32 bytes apart modulo 128: the 8 x 32-byte B fragment reads tile two wavefronts
-        const size_t smem = ((size_t)g.nk * 32 + (size_t)8 * g.pitch) * sizeof(double);
+        const size_t xbytes = (size_t)8 * g.pitch * sizeof(double);
+        // two window buffers (the next tile is prefetched under the MMAs) when at least two such blocks fit an SM
+        static const int force_nbuf = [] { const char* e = std::getenv("GAR_MMA_NBUF"); return e ? std::atoi(e) : 0; }();
+        g.nbuf = bank_bytes + 2 * xbytes <= 110 * 1024 ? 2 : 1;
+        if (force_nbuf == 1) g.nbuf = 1;
+        const size_t smem = bank_bytes + g.nbuf * xbytes;
         if (smem > 227 * 1024) return false;
         g.n_tiles = (c.n_pos + TJ - 1) / TJ;
-        // persistent over a few tiles (the A fragments are built once per block) while the grid still fills the GPU
+        // persistent over a few tiles (bank staged once, prefetch) while the grid still fills the GPU
         const int64_t blocks_per_sm = std::max<int64_t>(1, (int64_t)(227 * 1024) / (int64_t)(smem + 1024));
         const int64_t slots = 148 * std::min<int64_t>(blocks_per_sm, 2048 / (NW * 32));
         int64_t tpb = (int64_t)g.n_tiles * g.n_sg / (slots * 4);
         tpb = std::max<int64_t>(1, std::min<int64_t>(tpb, 8));
         g.tiles_per_block = (int32_t)std::min<int64_t>(tpb, g.n_tiles);
         g.n_groups = (g.n_tiles + g.tiles_per_block - 1) / g.tiles_per_block;
-        static size_t configured[64][2] = {{0}};
-        size_t& conf = configured[dev & 63][NW == 8 ? 0 : 1];
+        static size_t configured[64][4] = {{0}};
+        size_t& conf = configured[dev & 63][slot];
         if (smem > conf) {
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             conf = smem;
@@ -466,9 +529,14 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
         count_launch();
         return true;
     };
-    // long filters (window dominated by the taps): bigger tiles amortise the staged halo, when they fit
-    if (c.taps > 600 && run(fir_mma_f64_kernel<M, NF, 16>, 16)) return true;
-    return run(fir_mma_f64_kernel<M, NF, 8>, 8);
+    // Measured on B200 (C3: 8 ch x 1223 taps /2; x2 stage of the batched 44.1k->48k chain): 16 warps x 4 tiles for long
+    // filters (one block per SM: the window is dominated by the taps), 8 warps x 4 tiles in several blocks per SM for
+    // short ones; 6 or 8 tiles per warp and smaller blocks were slower. GAR_MMA_CFG = 1 / 3 forces one of the two.
+    static const int forced = [] { const char* e = std::getenv("GAR_MMA_CFG"); return e ? std::atoi(e) : -1; }();
+    if (forced == 1) return run(fir_mma_f64_kernel<M, NF, 16, 4>, 16, 4, 1);
+    if (forced == 3) return run(fir_mma_f64_kernel<M, NF, 8, 4>, 8, 4, 3);
+    if (c.taps > 600) return run(fir_mma_f64_kernel<M, NF, 16, 4>, 16, 4, 1) || run(fir_mma_f64_kernel<M, NF, 8, 4>, 8, 4, 3);
+    return run(fir_mma_f64_kernel<M, NF, 8, 4>, 8, 4, 3);
 }
 
 static bool g_fir_mma = [] {
