@@ -1631,6 +1631,173 @@ static bool launch_poly_rows_t(const PolyCall& c, cudaStream_t s) {
     return true;
 }
 
+// =============================================================================================
+// K3m — K3i on the FP64 tensor cores. A warp task is 8 adjacent outputs x 32 rows:
+//     D[i][s] = sum_w A[i][w] * X[w][s],   A[i][w] = coef_i[w - o_i]  (0 outside the filter),
+// A = the task's interpolated coefficient matrix (8 x K, K = o_7 + taps rounded to 4; evaluated once per task as in K3i,
+// stored [w][i] so that a k-step's fragment is 32 consecutive doubles), X = the rows' sample windows from the first
+// output's offset on. Per k-step one A fragment (LDS.64) and four B fragments (8 rows each) feed four DMMA.8x8x4 —
+// 1024 FMAs for 5 shared-memory loads, against 40 loads in K3i. No static window slots, no per-ratio template variants.
+// 17-24 % of A is structural zeros (o_7 of K), still twice K3i's throughput. DMMA accumulates in window order = tap order.
+// =============================================================================================
+struct RowsMmaGeom {
+    int32_t span, pitch, kp, n_tiles, nrb;  // staged samples per row, row pitch, K (multiple of 4), tiles per row, 32-row blocks
+};
+
+__global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c, const RowsMmaGeom g) {
+    constexpr int RB = 32, RN = 8, NTASK = 8, TO = RN * NTASK;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* xs = reinterpret_cast<double*>(smem_raw);            // [RB][pitch] staged samples
+    double* ct = xs + RB * g.pitch;                              // [NTASK][kp][RN] coefficient matrices
+    int* pat = reinterpret_cast<int*>(ct + NTASK * g.kp * RN);   // [NTASK][RN][4] phase row offset, window offset, x bits
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_rg = (c.n_streams + RB * g.nrb - 1) / (RB * g.nrb);
+    const int n_work = g.n_tiles * n_rg;
+    if ((int)blockIdx.x >= n_work) {  // carried tail of one row
+        const int64_t row = (int)blockIdx.x - n_work;
+        carry_row(static_cast<const double*>(c.hist) + row * c.hist_stride, c.hist_len,
+                  static_cast<const double*>(c.in) + row * c.in_stride, c.n_in,
+                  static_cast<double*>(c.hist_out) + row * c.hist_out_stride, c.drop, c.new_hist_len);
+        return;
+    }
+    const int tile = blockIdx.x % g.n_tiles;
+    const int rows_base = (blockIdx.x / g.n_tiles) * RB * g.nrb;
+    const int64_t L = c.L;
+    const int n0 = tile * TO;
+    const int n1 = min(c.n_out, n0 + TO);
+    const int64_t d_base = ((c.at0 + (int64_t)n0 * c.step) >> 16) / L;  // first staged sample = window of output n0
+    const int64_t d_last = ((c.at0 + (int64_t)(n1 - 1) * c.step) >> 16) / L;
+    const int span_t = min((int)(d_last - d_base) + g.kp + 4, g.span);
+    const int64_t total = (int64_t)c.hist_len + c.n_in;
+    const int i0 = 0;
+    const int i1 = (int)min((int64_t)span_t, max((int64_t)i0, (int64_t)c.hist_len - d_base));
+    const int i2 = (int)min((int64_t)span_t, max((int64_t)i1, total - d_base));
+    auto stage_rows = [&](const int row0) {
+        for (int r = warp; r < RB; r += 8) {
+            const int64_t row = row0 + r;
+            double* __restrict__ dst = xs + r * g.pitch;
+            if (row >= c.n_streams) {
+                for (int i = lane; i < span_t; i += 32) dst[i] = 0.0;
+                continue;
+            }
+            const double* __restrict__ hsrc = static_cast<const double*>(c.hist) + row * c.hist_stride + d_base;
+            const double* __restrict__ isrc = static_cast<const double*>(c.in) + row * c.in_stride + (d_base - c.hist_len);
+            for (int i = i0 + lane; i < i1; i += 32) dst[i] = hsrc[i];
+#pragma unroll 4
+            for (int i = i1 + lane; i < i2; i += 32) cp_async_elem(dst + i, isrc + i);
+            for (int i = i2 + lane; i < span_t; i += 32) dst[i] = 0.0;
+        }
+    };
+    stage_rows(rows_base);
+
+    // ---- geometry + coefficient matrix of this warp's task (overlaps the copies above) ----
+    const int nf = n0 + warp * RN;
+    double* __restrict__ ctile = ct + warp * g.kp * RN;
+    int* __restrict__ ptask = pat + warp * RN * 4;
+    int base = 0;
+    {
+        const int i = lane < RN ? lane : RN - 1;  // lane i: output nf + i (polyphase_stage.go:260-264)
+        const int64_t at = c.at0 + (int64_t)(nf + i) * c.step;
+        const int64_t full = at >> 16;
+        const int64_t dv = full / L;
+        const int ph = (int)(full - dv * L);
+        const int dv0 = __shfl_sync(0xffffffffu, (int)(dv - d_base), 0);
+        base = dv0;
+        if (lane < RN) {
+            ptask[i * 4 + 0] = ph * c.taps;
+            ptask[i * 4 + 1] = (int)(dv - d_base) - dv0;  // o_i
+            ptask[i * 4 + 2] = (int)(at & 0xFFFF);
+        }
+    }
+    __syncwarp();
+    {
+        const double* __restrict__ ga = static_cast<const double*>(c.bank_a);
+        const double* __restrict__ gb = static_cast<const double*>(c.bank_b);
+        const double* __restrict__ gc = static_cast<const double*>(c.bank_c);
+        const double* __restrict__ gd = static_cast<const double*>(c.bank_d);
+#pragma unroll 6
+        for (int idx = lane; idx < g.kp * RN; idx += 32) {
+            const int w = idx >> 3, i = idx & 7;
+            const int k = w - ptask[i * 4 + 1];
+            double v = 0.0;
+            if (k >= 0 && k < c.taps && nf + i < n1) {
+                const int co = ptask[i * 4 + 0] + k;
+                v = ga[co];
+                if (c.interp) {
+                    const double x = (double)ptask[i * 4 + 2] * (1.0 / 65536.0);
+                    v = fma(x, fma(x, fma(x, gd[co], gc[co]), gb[co]), v);
+                }
+            }
+            ctile[idx] = v;
+        }
+    }
+
+    const int nks = g.kp >> 2;
+    for (int j = 0; j < g.nrb; ++j) {
+        const int row0 = rows_base + j * RB;
+        if (row0 >= c.n_streams) break;
+        if (j > 0) {
+            __syncthreads();
+            stage_rows(row0);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (nf < n1) {
+            double acc[4][2];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
+            // A fragment: lane l holds A[i = l/4][w = 4*kk + l%4] = ctile[w][i]; B: X[w = 4*kk + l%4][row 8*t + l/4]
+            const double* __restrict__ ap = ctile + (lane & 3) * RN + (lane >> 2);
+            const double* __restrict__ bp = xs + (lane >> 2) * g.pitch + base + (lane & 3);
+#pragma unroll 2
+            for (int kk = 0; kk < nks; ++kk) {
+                const double a = ap[kk * 4 * RN];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) dmma884(acc[t][0], acc[t][1], a, bp[t * 8 * g.pitch + 4 * kk]);
+            }
+            const int i = lane >> 2;
+            if (nf + i < n1) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int64_t s0 = (int64_t)row0 + t * 8 + 2 * (lane & 3);
+                    if (s0 < c.n_streams) (static_cast<double*>(c.out) + s0 * c.out_stride)[nf + i] = acc[t][0];
+                    if (s0 + 1 < c.n_streams) (static_cast<double*>(c.out) + (s0 + 1) * c.out_stride)[nf + i] = acc[t][1];
+                }
+            }
+        }
+    }
+}
+
+static bool launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
+    if (!g_fir_mma || c.n_streams < 8 || (int64_t)c.n_out * c.n_streams < 16384 || c.L > 4096 || c.taps > 1024) return false;
+    const double r = (double)c.step / ((double)c.L * 65536.0);
+    if (!(r > 0.0) || r > 8.0) return false;
+    RowsMmaGeom g{};
+    const int omax = (int)std::ceil(7 * r) + 1;
+    g.kp = ((omax + c.taps + 3) / 4) * 4;
+    if (g.kp > 2 * c.taps + 8) return false;  // too many structural zeros: K3i
+    g.span = (int)std::ceil(63 * r) + 1 + g.kp + 8;
+    g.pitch = ((g.span + 15) / 16) * 16 + 4;  // rows 32 bytes apart modulo 128 (B fragment reads: two wavefronts)
+    g.n_tiles = (c.n_out + 63) / 64;
+    const int n_rb = (c.n_streams + 31) / 32;
+    g.nrb = 1;
+    while (g.nrb < 4 && g.nrb * 2 <= n_rb && (int64_t)g.n_tiles * ((n_rb + g.nrb * 2 - 1) / (g.nrb * 2)) >= 4 * 148) g.nrb *= 2;
+    const size_t smem = ((size_t)32 * g.pitch + (size_t)8 * g.kp * 8) * sizeof(double) + (size_t)8 * 8 * 4 * sizeof(int);
+    if (smem > 113 * 1024) return false;
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(poly_rows_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)g.n_tiles * ((c.n_streams + 32 * g.nrb - 1) / (32 * g.nrb)) + c.n_streams;
+    poly_rows_mma_kernel<<<(unsigned)blocks, 256, smem, s>>>(c, g);
+    count_launch();
+    return true;
+}
+
 // K3i dispatch: batches of at least 8 lock-step rows with enough outputs; S = ceil(samples per output)
 template <typename T>
 static bool launch_poly_rows(const PolyCall& c, cudaStream_t s) {
@@ -2016,6 +2183,8 @@ const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* 
                      c.new_hist_len, c.n_streams, dtype, s);
         return "carry";
     }
+    // Batches of >= 8 lock-step rows: K3m, the polyphase stage on the FP64 tensor cores (any ratio)
+    if (dtype == DT_F64 && g_fused_rat && launch_poly_rows_mma(c, s)) return c.interp ? "poly_rows_mma_f64_interp" : "poly_rows_mma_f64";
     // Batches of >= 8 rows with an even period length run K3i rather than K3r: K3r then stages its padded periods with
     // element copies from one warp (measured on the batched 48k->44.1k chain: 0.63 ms against 0.78 ms)
     if (dtype == DT_F64 && g_fused_rat && !c.interp && c.n_streams >= 8 && ((c.step >> 16) & 1) == 0 &&

@@ -365,3 +365,40 @@ def test_tensor_core_fir_matches_vector_kernels_and_oracle(ir, orr, preset, rows
     want, counts = O.batch_resample(x[pick], ir, orr, O.preset_to_engine_quality(preset), n_threads=4)
     assert np.all(counts == ya.shape[1])
     assert np.max(np.abs(ya[pick] - want[:, :ya.shape[1]])) <= 1e-12
+
+
+@pytest.mark.parametrize("ir,orr,rows,n", [
+    (44100, 47999, 40, 50000),    # cubic coefficient interpolation live, 1.84 samples/output
+    (48000, 44100, 33, 60000),    # rational 320/147, ragged last group of rows
+    (44100, 48000, 64, 30000),    # rational 147/80
+    (8000, 22050, 19, 30000),     # fewer than one intermediate sample per output
+])
+def test_tensor_core_polyphase_rows_kernel_vs_thread_per_output_kernels_and_oracle(ir, orr, rows, n):
+    """K3m (polyphase stage as 8-output x K coefficient matrices times the rows' windows, DMMA): same samples as the
+    one-thread-per-output kernels to 1e-13, <= 1e-12 against the oracle, ragged chunking + flush."""
+    rng = np.random.default_rng(32)
+    x = 0.5 * rng.standard_normal((rows, n))
+    cuts = [0, 9, n // 2 + 5, n]
+
+    def run(tiled):
+        G.set_tiled_polyphase(tiled)
+        G.set_tensor_fir(tiled)
+        try:
+            h = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float64)
+            ys = [h.ProcessBatch(np.ascontiguousarray(x[:, lo:hi]))[0].copy() for lo, hi in zip(cuts[:-1], cuts[1:])]
+            ys.append(h.FlushBatch()[0].copy())
+            return np.concatenate(ys, axis=1), h.last_kernels()
+        finally:
+            G.set_tiled_polyphase(True)
+            G.set_tensor_fir(True)
+
+    ya, ka = run(True)
+    yb, kb = run(False)
+    assert any(k.startswith("poly_rows_mma_f64") for k in ka), ka
+    assert not any("mma" in k or k.startswith(("poly_rows", "poly_rat", "fused_up2_rat")) for k in kb), kb
+    assert ya.shape == yb.shape
+    assert np.max(np.abs(ya - yb)) <= 1e-13
+    pick = sorted(set([0, rows // 2, rows - 1]))
+    want, counts = O.batch_resample(x[pick], ir, orr, O.Q_HIGH, n_threads=4)
+    assert np.all(counts == ya.shape[1])
+    assert np.max(np.abs(ya[pick] - want[:, :ya.shape[1]])) <= 1e-12
