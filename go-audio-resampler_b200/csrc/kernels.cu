@@ -1647,7 +1647,8 @@ struct RowsMmaGeom {
 __global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c, const RowsMmaGeom g) {
     constexpr int RB = 32, RN = 8, NTASK = 8, TO = RN * NTASK;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* xs = reinterpret_cast<double*>(smem_raw);            // [RB][pitch] staged samples
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);       // mbarrier of the bulk-copied rows
+    double* xs = reinterpret_cast<double*>(smem_raw + 16);       // [RB][pitch] staged samples
     double* ct = xs + RB * g.pitch;                              // [NTASK][kp][RN] coefficient matrices
     int* pat = reinterpret_cast<int*>(ct + NTASK * g.kp * RN);   // [NTASK][RN][4] phase row offset, window offset, x bits
 
@@ -1673,7 +1674,29 @@ __global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c,
     const int i0 = 0;
     const int i1 = (int)min((int64_t)span_t, max((int64_t)i0, (int64_t)c.hist_len - d_base));
     const int i2 = (int)min((int64_t)span_t, max((int64_t)i1, total - d_base));
-    auto stage_rows = [&](const int row0) {
+    // A 32-row block whose staged span lies inside `in` is moved by 32 TMA bulk copies (one thread), started `a` samples
+    // early so that the sources are 16-byte aligned (all rows share the alignment when the row stride is even);
+    // anything else (carried tail, end of the rows, ragged last block) by element copies. Returns the pad.
+    const int64_t gi = d_base - c.hist_len;
+    uint32_t bar_phase = 0u;
+    if (tid == 0) mbar_init(bar, 1);
+    auto stage_rows = [&](const int row0, bool& bulk) -> int {
+        bulk = false;
+        if ((c.in_stride & 1) == 0 && row0 + RB <= c.n_streams && gi >= 0) {
+            const double* __restrict__ src0 = static_cast<const double*>(c.in) + (int64_t)row0 * c.in_stride + gi;
+            const int a = (int)((reinterpret_cast<uintptr_t>(src0) & 15u) >> 3);
+            const int wlen = (span_t + a + 1) & ~1;
+            if (gi - a >= 0 && gi - a + wlen <= c.n_in && wlen <= g.pitch) {
+                bulk = true;
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(bar, (uint32_t)(RB * wlen * sizeof(double)));
+                    for (int r = 0; r < RB; ++r)
+                        bulk_g2s(xs + r * g.pitch, src0 + (int64_t)r * c.in_stride - a, (uint32_t)(wlen * sizeof(double)), bar);
+                }
+                return a;
+            }
+        }
         for (int r = warp; r < RB; r += 8) {
             const int64_t row = row0 + r;
             double* __restrict__ dst = xs + r * g.pitch;
@@ -1688,8 +1711,11 @@ __global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c,
             for (int i = i1 + lane; i < i2; i += 32) cp_async_elem(dst + i, isrc + i);
             for (int i = i2 + lane; i < span_t; i += 32) dst[i] = 0.0;
         }
+        return 0;
     };
-    stage_rows(rows_base);
+    __syncthreads();  // the mbarrier is initialised
+    bool bulk = false;
+    int apad = stage_rows(rows_base, bulk);
 
     // ---- geometry + coefficient matrix of this warp's task (overlaps the copies above) ----
     const int nf = n0 + warp * RN;
@@ -1738,18 +1764,25 @@ __global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c,
         const int row0 = rows_base + j * RB;
         if (row0 >= c.n_streams) break;
         if (j > 0) {
-            __syncthreads();
-            stage_rows(row0);
+            __syncthreads();  // everyone is done with the previous rows' samples
+            apad = stage_rows(row0, bulk);
         }
-        cp_async_wait_all();
-        __syncthreads();
+        if (bulk) {
+            while (!mbar_try_wait(bar, bar_phase)) {
+            }
+            bar_phase ^= 1u;
+            if (j == 0) __syncthreads();  // the coefficient matrices of all tasks are written (they are per warp: __syncwarp would do)
+        } else {
+            cp_async_wait_all();
+            __syncthreads();
+        }
         if (nf < n1) {
             double acc[4][2];
 #pragma unroll
             for (int t = 0; t < 4; ++t) acc[t][0] = acc[t][1] = 0.0;
             // A fragment: lane l holds A[i = l/4][w = 4*kk + l%4] = ctile[w][i]; B: X[w = 4*kk + l%4][row 8*t + l/4]
             const double* __restrict__ ap = ctile + (lane & 3) * RN + (lane >> 2);
-            const double* __restrict__ bp = xs + (lane >> 2) * g.pitch + base + (lane & 3);
+            const double* __restrict__ bp = xs + (lane >> 2) * g.pitch + base + apad + (lane & 3);
 #pragma unroll 2
             for (int kk = 0; kk < nks; ++kk) {
                 const double a = ap[kk * 4 * RN];
@@ -1778,12 +1811,12 @@ static bool launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
     g.kp = ((omax + c.taps + 3) / 4) * 4;
     if (g.kp > 2 * c.taps + 8) return false;  // too many structural zeros: K3i
     g.span = (int)std::ceil(63 * r) + 1 + g.kp + 8;
-    g.pitch = ((g.span + 15) / 16) * 16 + 4;  // rows 32 bytes apart modulo 128 (B fragment reads: two wavefronts)
+    g.pitch = ((g.span + 2 + 15) / 16) * 16 + 4;  // rows 32 bytes apart modulo 128 (B fragment reads: two wavefronts)
     g.n_tiles = (c.n_out + 63) / 64;
     const int n_rb = (c.n_streams + 31) / 32;
     g.nrb = 1;
     while (g.nrb < 4 && g.nrb * 2 <= n_rb && (int64_t)g.n_tiles * ((n_rb + g.nrb * 2 - 1) / (g.nrb * 2)) >= 4 * 148) g.nrb *= 2;
-    const size_t smem = ((size_t)32 * g.pitch + (size_t)8 * g.kp * 8) * sizeof(double) + (size_t)8 * 8 * 4 * sizeof(int);
+    const size_t smem = 16 + ((size_t)32 * g.pitch + (size_t)8 * g.kp * 8) * sizeof(double) + (size_t)8 * 8 * 4 * sizeof(int);
     if (smem > 113 * 1024) return false;
     static size_t configured[64] = {0};
     int dev = 0;
