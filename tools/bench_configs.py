@@ -45,18 +45,18 @@ def configs():
              x=np.stack(sig_c3()), io=np.float64, flops=2446.0, compute="f64", cpu=None),
         dict(name="C4 256 of the 4096 mono streams 48k->16k Medium f32", io=np.float32, flops=1754.0, compute="f32",
              make=lambda: G.NewBatch(48000, 16000, G.QualityMedium, 256, np.float32), x=sig_c4(256, 480000), cpu=None),
-        dict(name="K4 roofline: C1 chain batched x256 streams (44.1k->48k High f64, 1 s each)",
+        dict(name="K4 roofline: C1 chain batched x256 streams (44.1k->48k High f64, 10 s each)",
              make=lambda: G.NewBatch(44100, 48000, G.QualityHigh, 256, np.float64),
-             x=np.tile(sig_c1(44100)[None, :], (256, 1)), io=np.float64, flops=738.0, compute="f64", cpu=None),
-        dict(name="K4 roofline: C2 chain batched x256 streams (48k->44.1k 24Bit f64, 1 s each)",
+             x=np.tile(sig_c1(441000)[None, :], (256, 1)), io=np.float64, flops=738.0, compute="f64", cpu=None),
+        dict(name="K4 roofline: C2 chain batched x256 streams (48k->44.1k 24Bit f64, 10 s each)",
              make=lambda: G.Resampler(cfg(48000, 44100, 1, G.QualityHigh), n_streams=256),
-             x=np.tile(sig_c1(48000)[None, :], (256, 1)), io=np.float64, flops=980.8, compute="f64", cpu=None),
-        dict(name="K4 roofline: C5b chain batched x256 streams (44.1k->47.999k High f64, cubic coefficient interpolation)",
+             x=np.tile(sig_c1(480000)[None, :], (256, 1)), io=np.float64, flops=980.8, compute="f64", cpu=None),
+        dict(name="K4 roofline: C5b chain batched x256 streams (44.1k->47.999k High f64, cubic coefficient interpolation, 10 s each)",
              make=lambda: G.NewBatch(44100, 47999, G.QualityHigh, 256, np.float64),
-             x=np.tile(sig_c1(44100)[None, :], (256, 1)), io=np.float64, flops=692.0, compute="f64", cpu=None),
-        dict(name="K4 roofline: C5a chain batched x64 streams (8k->192k High f64, 1 s each)",
+             x=np.tile(sig_c1(441000)[None, :], (256, 1)), io=np.float64, flops=692.0, compute="f64", cpu=None),
+        dict(name="K4 roofline: C5a chain batched x64 streams (8k->192k High f64, 10 s each)",
              make=lambda: G.Resampler(cfg(8000, 192000, 1, G.QualityHigh), n_streams=64),
-             x=np.tile(sig_c5a()[None, :8000], (64, 1)), io=np.float64, flops=1233.3, compute="f64", cpu=None),
+             x=np.tile(sig_c5a()[None, :], (64, 1)), io=np.float64, flops=1233.3, compute="f64", cpu=None),
         dict(name="C5a 8k->192k High multistage f64", make=lambda: G.New(cfg(8000, 192000, 1, G.QualityHigh)),
              x=sig_c5a()[None, :], io=np.float64, flops=1233.3, compute="f64", cpu=None),
         dict(name="C5b 44.1k->47.999k High f64 (cubic coefficient interpolation)", io=np.float64, flops=692.0,
