@@ -282,6 +282,12 @@ int32_t gar_set_fusion(gar_handle* h, int32_t enabled) {
     return GAR_OK;
 }
 
+int32_t gar_set_slice_budget(gar_handle* h, int64_t bytes) {
+    if (!h) return GAR_INVALID_CONFIG;
+    h->eng.set_slice_budget(bytes < 0 ? 0 : bytes);
+    return GAR_OK;
+}
+
 void gar_set_tiled_polyphase(int32_t enabled) { gar::set_tiled_polyphase(enabled != 0); }
 void gar_set_tensor_fir(int32_t enabled) { gar::set_tensor_fir(enabled != 0); }
 

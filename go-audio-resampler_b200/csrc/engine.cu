@@ -105,6 +105,7 @@ int Engine::init(const Chain& chain, int rows, int compute_dtype, int device, st
     ibuf_cap_.assign(chain_.engines.size() * 2, 0);
     streams_.assign((size_t)rows, StreamState{});
     if (const char* e = std::getenv("GAR_NO_FUSE")) fuse_ = !(e[0] && e[0] != '0');
+    if (const char* e = std::getenv("GAR_L2_SLICE_MB")) slice_budget_ = (int64_t)std::atoll(e) << 20;
     reset_state();
     return 0;
 }
@@ -446,8 +447,53 @@ int Engine::lockstep_run(int row0, int row_end) const {
     return n;
 }
 
+int64_t Engine::slice_length(int row0, int count, int64_t n_in) const {
+    if (slice_budget_ <= 0 || count <= 0 || n_in < 32768 || chain_.stages.size() < 2) return 0;
+    // inter-stage elements per input sample, from a dry run of the state machine on a probe length
+    StreamState st = streams_[(size_t)row0];
+    Plan P;
+    const int64_t probe = std::min<int64_t>(n_in, 1 << 16);
+    plan(st, probe, false, P);
+    int64_t need = 0;
+    for (int64_t b : P.buf_need) need = std::max(need, b);
+    if (need <= 0) return 0;
+    const double per_sample = (double)need / (double)probe * (double)esz_ * (double)count;  // bytes per input sample
+    int64_t len = (int64_t)((double)slice_budget_ / per_sample);
+    len = std::max<int64_t>(len & ~int64_t(4095), 16384);
+    return len < n_in ? len : 0;
+}
+
 int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
                 int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err) {
+    // the slice length is derived from ALL rows of the handle, not from this call's row range: row groups of one batch call
+    // must advance through the same sequence of stage calls to stay in lock step (same tail ping-pong parity)
+    const int64_t slice = flush || device_ < 0 ? 0 : slice_length(row0, rows_, n_in);
+    if (slice <= 0) return run_once(row0, count, d_in, in_stride, n_in, d_out, out_stride, out_cap, flush, s, n_out, err);
+    {   // ErrBufferTooSmall is decided for the whole call, before any state changes (constant.go:107-109)
+        StreamState st = streams_[(size_t)row0];
+        Plan P;
+        plan(st, n_in, false, P);
+        if (n_out) *n_out = P.n_out;
+        if (P.n_out > out_cap) {
+            err = "output buffer too small";
+            return 2;
+        }
+    }
+    int64_t produced = 0;
+    for (int64_t off = 0; off < n_in; off += slice) {
+        const int64_t len = std::min(slice, n_in - off);
+        int64_t k = 0;
+        const int rc = run_once(row0, count, (const char*)d_in + (size_t)off * esz_, in_stride, len,
+                                (char*)d_out + (size_t)produced * esz_, out_stride, out_cap - produced, false, s, &k, err);
+        if (rc) return rc;
+        produced += k;
+    }
+    if (n_out) *n_out = produced;
+    return 0;
+}
+
+int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
+                     int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err) {
     if (count <= 0) return 0;
     if (device_ < 0) {
         err = "geometry-only handle (device = -1) cannot process samples; there is no CPU fallback";

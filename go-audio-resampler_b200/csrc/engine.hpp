@@ -104,6 +104,13 @@ class Engine {
     // compute dtype. Enqueues on `s`; commits the state. Returns status; *n_out per row.
     int run(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
             int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err);
+    // Time slicing of multi-stage calls: a Process call whose inter-stage buffers would exceed `bytes` is run as a
+    // sequence of shorter Process calls (identical samples and counts: every stage is greedy), so that the intermediate-rate
+    // buffers stay small (and, with an L2-sized budget, the intermediate-rate streams stay L2-resident). 0 disables.
+    void set_slice_budget(int64_t bytes) { slice_budget_ = bytes; }
+    int64_t slice_budget() const { return slice_budget_; }
+    // samples of one row a time slice may hold for `count` rows (0: no slicing needed for n_in)
+    int64_t slice_length(int row0, int count, int64_t n_in) const;
 
     // Advance only the integer state of one row (geometry-only use; no samples move).
     int64_t advance(int row, int64_t n_in, bool flush);
@@ -140,6 +147,12 @@ class Engine {
     int64_t cubic_cap_ = 0;
     bool fuse_ = true;  // K4 fused x2 -> polyphase launches (GAR_NO_FUSE=1 disables, for A/B tests)
     int64_t launches_ = 0;
+    // bytes of the largest inter-stage buffer per slice. Default 2 GiB: a memory-footprint guard only. L2-sized slices
+    // (40 MiB) keep the intermediate stream out of HBM but measured 20 % slower on the batched chains (57 launches
+    // instead of 5: every slice pays a launch ramp and tail), and those chains are FMA-bound, not HBM-bound.
+    int64_t slice_budget_ = 2ll << 30;
+    int run_once(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
+                 int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err);
     std::vector<const char*> kernels_used_;
     void note_kernel(const char* name);
     int64_t device_bytes_ = 0;

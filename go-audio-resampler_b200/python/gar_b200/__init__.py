@@ -125,6 +125,7 @@ SYMBOLS = {
     "gar_stage_kernel_name": (C.c_char_p, [_vp, _i32]),
     "gar_kernels_used": (_i32, [_vp, C.c_char_p, _i32]),
     "gar_set_tiled_polyphase": (None, [_i32]),
+    "gar_set_slice_budget": (_i32, [_vp, _i64]),
     "gar_set_tensor_fir": (None, [_i32]),
     "gar_measure_fma_peak": (_i32, [_i32, _i32, C.POINTER(C.c_double)]),
     "gar_version": (C.c_char_p, []),
@@ -245,6 +246,10 @@ class _Handle:
         buf = C.create_string_buffer(1024)
         lib().gar_kernels_used(self._h, buf, 1024)
         return [k for k in buf.value.decode().split(",") if k]
+
+    def set_slice_budget(self, nbytes: int):
+        """Inter-stage buffer budget of one time slice of a long call (0 disables slicing)."""
+        lib().gar_set_slice_budget(self._h, int(nbytes))
 
     def set_fusion(self, enabled: bool):
         """Enable/disable the fused x2 -> polyphase kernel (K4)."""

@@ -221,6 +221,11 @@ void gar_host_free(void* p);
 int32_t gar_device_count(void);
 /* Enable (default) / disable the fused x2 -> polyphase launch (K4); results agree to rounding, used for A/B tests. */
 int32_t gar_set_fusion(gar_handle* h, int32_t enabled);
+/* Time slicing of long multi-stage calls (batch / device entry points and every Process call): a call whose inter-stage
+ * buffers would exceed `bytes` runs as a sequence of shorter calls with identical results, which bounds the device memory
+ * of the inter-stage buffers (default 2 GiB) or, with an L2-sized budget (e.g. 40 MiB), keeps the intermediate-rate
+ * streams out of HBM at the price of more launches. 0 disables. */
+int32_t gar_set_slice_budget(gar_handle* h, int64_t bytes);
 /* Process-wide A/B switch (tests, profiling): 0 routes every polyphase stage through the one-thread-per-output
  * kernels instead of the register-tiled ones (K4r / K3r / K3i). Results are bit-identical in float64. Default 1. */
 void gar_set_tiled_polyphase(int32_t enabled);

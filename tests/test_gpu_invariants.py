@@ -402,3 +402,24 @@ def test_tensor_core_polyphase_rows_kernel_vs_thread_per_output_kernels_and_orac
     want, counts = O.batch_resample(x[pick], ir, orr, O.Q_HIGH, n_threads=4)
     assert np.all(counts == ya.shape[1])
     assert np.max(np.abs(ya[pick] - want[:, :ya.shape[1]])) <= 1e-12
+
+
+@pytest.mark.parametrize("ir,orr,rows", [(44100, 48000, 12), (8000, 192000, 3), (44100, 47999, 9), (48000, 44100, 1)])
+def test_time_sliced_calls_are_bit_identical_to_unsliced(ir, orr, rows):
+    """A long multi-stage call runs as a sequence of shorter ones (inter-stage buffers L2-resident): identical samples
+    and counts, BUFFER_TOO_SMALL still decided for the whole call before any state changes."""
+    rng = np.random.default_rng(3)
+    n = 150000 if orr < 100000 else 40000
+    x = rng.standard_normal((rows, n))
+    a = G.Resampler(_cfg(ir, orr), n_streams=rows)
+    b = G.Resampler(_cfg(ir, orr), n_streams=rows)
+    a.set_slice_budget(1 << 20)   # forces many slices
+    b.set_slice_budget(0)
+    with pytest.raises(G.ErrBufferTooSmall):
+        a.ProcessBatch(x, np.empty((rows, 1000)))
+    ya, na = a.ProcessBatch(x)
+    yb, nb = b.ProcessBatch(x)
+    assert na == nb
+    np.testing.assert_array_equal(ya, yb)
+    fa, fb = a.FlushBatch()[0], b.FlushBatch()[0]
+    np.testing.assert_array_equal(fa, fb)

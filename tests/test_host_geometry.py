@@ -136,3 +136,31 @@ def test_reset_clears_state():
     h.Reset()
     assert product_chain_desc(h) == fresh
     assert h.advance_geometry(4096) == first
+
+
+@pytest.mark.parametrize("ir,orr,preset", [(44100, 48000, G.QualityHigh), (48000, 44100, G.QualityHigh),
+                                          (44100, 47999, G.QualityHigh), (8000, 192000, G.QualityHigh),
+                                          (96000, 48000, G.QualityVeryHigh), (48000, 16000, G.QualityHigh),
+                                          (44100, 16000, G.QualityMedium), (8000, 22050, G.QualityLow)])
+def test_time_sliced_process_produces_the_one_shot_counts_and_state(ir, orr, preset):
+    """The engine runs a long multi-stage Process call as a sequence of shorter ones (inter-stage buffers stay
+    L2-resident). Every stage is greedy, so the summed counts, the carried state and the flush length are those of
+    the single call — checked here on the integer state machine (geometry-only handles, no device)."""
+    n = 1_000_003
+    for make in (lambda: G.New(geometry_config(ir, orr, 1, preset)),
+                 lambda: G.SimpleResampler(ir, orr, preset, np.float64, device=-1)):
+        one, cut = make(), make()
+        total = one.advance_geometry(n)
+        got, off = 0, 0
+        for slice_len in (16384, 20480, 65536, 12288):
+            while off < n and (slice_len != 12288 or True):
+                k = min(slice_len, n - off)
+                got += cut.advance_geometry(k)
+                off += k
+                if slice_len != 12288 and off > n // 2:
+                    break
+            if off >= n:
+                break
+        assert off == n and got == total
+        assert product_chain_desc(one) == product_chain_desc(cut)
+        assert one.advance_geometry(0, flush=True) == cut.advance_geometry(0, flush=True)
