@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--preset", default="medium", choices=list(PRESETS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the float64 side measurements (BASELINE configs 1 and 3)")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="target wall time of the CPU baseline sample")
     return ap.parse_args()
 
@@ -168,6 +169,62 @@ def run_reference(a, rank):
             "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def extra_f64(dev, local, tstream):
+    """Side measurements, not the headline: the float64 kernels of BASELINE configs 1 and 3 on this GPU (CUDA events,
+    inputs resident in HBM, Process + Flush), against the fp64 dependent-FMA probe. Config 1's chain batched over 256
+    streams runs the x2 stage and the polyphase stage on the FP64 tensor cores (K1m + K3m); config 3 is the 8-channel
+    1223-tap /2 decimator (K2m)."""
+    import torch
+
+    import gar_b200 as G
+
+    peak64 = G.measure_fma_peak(np.float64, local)
+    out = {"fp64_fma_peak_tflops": round(peak64, 2)}
+
+    def timed(h, x, flops_per_out, reps=5):
+        rows, n_in = x.shape
+        est = h.EstimateOutput(n_in)
+        ostride = (est + 8192 + 3) & ~3
+        dx = torch.from_numpy(x).to(dev)
+        dy = torch.zeros((rows, ostride), dtype=torch.float64, device=dev)
+
+        def one():
+            h.Reset()
+            n1 = h.process_batch_dev(dx.data_ptr(), n_in, n_in, dy.data_ptr(), ostride, ostride, tstream.cuda_stream, np.float64)
+            n2 = h.flush_batch_dev(dy.data_ptr() + n1 * 8, ostride, ostride - n1, tstream.cuda_stream, np.float64)
+            return n1 + n2
+
+        for _ in range(3):
+            n = one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(tstream)
+        for _ in range(reps):
+            one()
+        e1.record(tstream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        tf = rows * n * flops_per_out / (ms * 1e-3) / 1e12
+        return {"ms": round(ms, 4), "msamples_per_s": round(rows * n / ms / 1e3, 1), "tflops": round(tf, 2),
+                "frac_of_fp64_fma_peak": round(tf / peak64, 4), "kernels": h.last_kernels()}
+
+    t = np.arange(441000) / 44100.0
+    x1 = np.tile(np.sin(2 * np.pi * 1000.0 * t)[None, :], (256, 1))
+    out["c1_chain_x256_streams_10s_f64"] = dict(
+        timed(G.NewBatch(44100, 48000, G.QualityHigh, 256, np.float64), x1, 738.0),
+        workload="BASELINE config 1's chain (44.1k->48k QualityHigh float64) x 256 lock-step streams x 10 s")
+    del x1
+    rng = np.random.default_rng(4242)
+    t3 = np.arange(960000) / 96000.0
+    x3 = np.stack([0.7 * np.sin(2 * np.pi * 440 * t3 + c) + 0.2 * np.sin(2 * np.pi * 1750 * t3) + 0.1 * (rng.random(t3.size) - 0.5)
+                   for c in range(8)])
+    cfg = G.Config(InputRate=96000, OutputRate=48000, Channels=8, Quality=G.QualitySpec(Preset=G.QualityVeryHigh))
+    out["c3_8ch_96k_to_48k_veryhigh_f64"] = dict(
+        timed(G.New(cfg), x3, 2446.0, reps=10),
+        workload="BASELINE config 3: 8 channels x 960000 samples, 96k->48k QualityVeryHigh float64 (1223-tap /2)")
+    return out
 
 
 def main():
@@ -340,6 +397,15 @@ def main():
         xc = xh if xh is not None else x[:min(rows, 512)].cpu().numpy()
         cpu = cpu_baseline(a, xc, os.cpu_count() or 1, a.cpu_seconds)
 
+    extra = None
+    if rank == 0 and world == 1 and not a.no_extra:
+        try:
+            del x, y
+            torch.cuda.empty_cache()
+            extra = extra_f64(dev, local, tstream)
+        except Exception as e:  # side measurement only: never fail the headline line
+            extra = {"error": repr(e)[:200]}
+
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": round(ms_step_max, 4), "higher_is_better": True,
@@ -348,7 +414,7 @@ def main():
                            "l2": "inputs larger than L2 (%.1f GB per GPU per step)" % (rows * n_in * 4 / 1e9),
                            "timer": "CUDA events on the launching stream, max over ranks"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks}
+                "clocks": clocks, "extra_f64": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
