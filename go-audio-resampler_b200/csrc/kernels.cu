@@ -1815,7 +1815,10 @@ static bool launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
     g.n_tiles = (c.n_out + 63) / 64;
     const int n_rb = (c.n_streams + 31) / 32;
     g.nrb = 1;
-    while (g.nrb < 4 && g.nrb * 2 <= n_rb && (int64_t)g.n_tiles * ((n_rb + g.nrb * 2 - 1) / (g.nrb * 2)) >= 4 * 148) g.nrb *= 2;
+    // measured on the batched 44.1k->48k chain (256 rows): 1 / 2 / 4 / 8 row blocks per coefficient evaluation -> 1.93 / 1.45 /
+    // 1.19 / 1.10 ms for the polyphase stage
+    static const int max_nrb = [] { const char* e = std::getenv("GAR_K3M_NRB"); return e ? std::atoi(e) : 8; }();
+    while (g.nrb < max_nrb && g.nrb * 2 <= n_rb && (int64_t)g.n_tiles * ((n_rb + g.nrb * 2 - 1) / (g.nrb * 2)) >= 4 * 148) g.nrb *= 2;
     const size_t smem = 16 + ((size_t)32 * g.pitch + (size_t)8 * g.kp * 8) * sizeof(double) + (size_t)8 * 8 * 4 * sizeof(int);
     if (smem > 113 * 1024) return false;
     static size_t configured[64] = {0};
