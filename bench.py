@@ -33,6 +33,28 @@ METRIC = "output_msamples_per_s"
 UNIT = "Msamples/s"
 
 
+# Exactly ONE line may reach stdout (the driver parses it). Libraries print there too (NCCL's version banner, warnings), so
+# file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to a saved copy of the real stdout.
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,7 +190,7 @@ def run_reference(a, rank):
                                        "(oracle/, AVX2+FMA) — the Go reference cannot be built in this image"},
             "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def extra_f64(dev, local, tstream):
@@ -228,6 +250,7 @@ def extra_f64(dev, local, tstream):
 
 
 def main():
+    _capture_stdout()
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -415,7 +438,7 @@ def main():
                            "timer": "CUDA events on the launching stream, max over ranks"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "extra_f64": extra}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
