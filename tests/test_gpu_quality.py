@@ -1,0 +1,87 @@
+"""The reference's audio-quality regression floors (internal/engine/quality_regression_test.go:26-55,109-290) measured on the
+GPU engine's output with the reference's own procedure (0.9-amplitude 1 kHz sine, 65 536 samples, Process + Flush, Hann
+window over the first 16 384 output samples, harmonics 2..10 / fundamental +-3 bins) — on a single stream (fused /
+one-thread kernels) and on a batch of 8 rows (FP64 tensor-core kernels), next to the oracle's figure."""
+import numpy as np
+import pytest
+
+from helpers import G, O
+
+pytestmark = pytest.mark.gpu
+
+N, FFT = 65536, 16384
+MAX_THD = {O.Q_QUICK: -80.0, O.Q_LOW: -130.0, O.Q_MEDIUM: -129.0, O.Q_HIGH: -140.0, O.Q_VERYHIGH: -140.0}
+MIN_SNR = 35.0
+
+
+def _spectrum(y):
+    w = 0.5 * (1.0 - np.cos(2.0 * np.pi * np.arange(FFT) / (FFT - 1)))
+    seg = np.zeros(FFT)
+    m = min(FFT, len(y))
+    seg[:m] = y[:m]
+    return np.abs(np.fft.fft(seg * w))
+
+
+def thd_db(y, out_rate, f0=1000.0):  # measureTHDInternal, quality_regression_test.go:292-342
+    mag = _spectrum(y)
+    fund = mag[int(f0 / out_rate * FFT)]
+    hp = 0.0
+    for h in range(2, 11):
+        if f0 * h >= out_rate / 2:
+            break
+        b = int(f0 * h / out_rate * FFT)
+        if b < FFT // 2:
+            hp += mag[b] ** 2
+    return 20 * np.log10(np.sqrt(hp) / (fund + 1e-20) + 1e-20)
+
+
+def snr_db(y, out_rate, f0=1000.0):  # measureSNRInternal, quality_regression_test.go:344-425
+    mag = _spectrum(y)
+    fb = int(f0 / out_rate * FFT)
+    sig = sum(mag[fb + b] ** 2 for b in range(-3, 4) if 0 < fb + b < FFT // 2)
+    hbins = [int(f0 * h / out_rate * FFT) for h in range(2, 11) if f0 * h < out_rate / 2]
+    noise = 0.0
+    for b in range(1, FFT // 2):
+        if fb - 3 <= b <= fb + 3 or any(hb - 2 <= b <= hb + 2 for hb in hbins):
+            continue
+        noise += mag[b] ** 2
+    return 10 * np.log10(sig + 1e-20) - 10 * np.log10(noise + 1e-20)
+
+
+def _run(ir, orr, q, rows):
+    x = 0.9 * np.sin(2.0 * np.pi * 1000.0 * np.arange(N) / ir)
+    h = G.SimpleResampler(ir, orr, G.QualityHigh, np.float64, engine_quality=q, n_streams=rows)
+    xx = np.tile(x[None, :], (max(rows, 1), 1))
+    y = np.concatenate([h.ProcessBatch(xx)[0], h.FlushBatch()[0]], axis=1)
+    e = O.Engine(ir, orr, q)
+    want = np.concatenate([e.process(x), e.flush()])
+    return y, want, h.last_kernels()
+
+
+@pytest.mark.parametrize("rows", [1, 8])
+@pytest.mark.parametrize("ir,orr,q", [
+    (44100, 48000, O.Q_VERYHIGH), (48000, 44100, O.Q_VERYHIGH), (48000, 32000, O.Q_VERYHIGH), (48000, 96000, O.Q_VERYHIGH),
+    (44100, 48000, O.Q_HIGH), (48000, 32000, O.Q_HIGH), (44100, 48000, O.Q_MEDIUM), (48000, 32000, O.Q_MEDIUM),
+    (44100, 48000, O.Q_LOW), (48000, 32000, O.Q_LOW), (44100, 48000, O.Q_QUICK), (48000, 32000, O.Q_QUICK)])
+def test_thd_and_snr_floors_of_the_reference(ir, orr, q, rows):  # TestQualityRegression_THD / _SNR
+    y, want, kernels = _run(ir, orr, q, rows)
+    assert y.shape[1] == len(want)
+    for r in range(y.shape[0]):
+        thd, snr = thd_db(y[r], orr), snr_db(y[r], orr)
+        assert thd <= MAX_THD[q], (thd, kernels)
+        assert snr >= MIN_SNR, (snr, kernels)
+    # same figure as the oracle's output, not merely under the floor
+    assert abs(thd_db(y[0], orr) - thd_db(want, orr)) <= 3.0 or thd_db(y[0], orr) <= -150.0
+    if rows >= 8 and q != O.Q_QUICK:
+        assert any("mma" in k for k in kernels), kernels
+
+
+@pytest.mark.parametrize("ir,orr", [(44100, 48000), (48000, 44100), (48000, 32000), (48000, 96000), (96000, 48000)])
+def test_dc_gain_and_output_ratio(ir, orr):  # TestQualityRegression_DCGain / _OutputRatio
+    x = np.full(N, 0.5)
+    for rows in (1, 8):
+        h = G.SimpleResampler(ir, orr, G.QualityHigh, np.float64, engine_quality=O.Q_HIGH, n_streams=rows)
+        y = np.concatenate([h.ProcessBatch(np.tile(x[None, :], (rows, 1)))[0], h.FlushBatch()[0]], axis=1)
+        mid = y[:, y.shape[1] // 4: 3 * y.shape[1] // 4]
+        assert np.max(np.abs(mid.mean(axis=1) / 0.5 - 1.0)) <= 0.001
+        assert abs(y.shape[1] / N - orr / ir) <= 0.02
