@@ -1641,15 +1641,16 @@ static bool launch_poly_rows_t(const PolyCall& c, cudaStream_t s) {
 // 17-24 % of A is structural zeros (o_7 of K), still twice K3i's throughput. DMMA accumulates in window order = tap order.
 // =============================================================================================
 struct RowsMmaGeom {
-    int32_t span, pitch, kp, n_tiles, nrb;  // staged samples per row, row pitch, K (multiple of 4), tiles per row, 32-row blocks
+    int32_t span, pitch, kp, n_tiles, nrb, nbuf;  // staged samples per row, row pitch, K (multiple of 4), tiles per row,
+                                                  // 32-row blocks per thread block, sample buffers (2: prefetch)
 };
 
 __global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c, const RowsMmaGeom g) {
     constexpr int RB = 32, RN = 8, NTASK = 8, TO = RN * NTASK;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);       // mbarrier of the bulk-copied rows
-    double* xs = reinterpret_cast<double*>(smem_raw + 16);       // [RB][pitch] staged samples
-    double* ct = xs + RB * g.pitch;                              // [NTASK][kp][RN] coefficient matrices
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);       // [2] mbarriers of the bulk-copied row buffers
+    double* xs0 = reinterpret_cast<double*>(smem_raw + 16);      // [nbuf][RB][pitch] staged samples
+    double* ct = xs0 + g.nbuf * RB * g.pitch;                    // [NTASK][kp][RN] coefficient matrices
     int* pat = reinterpret_cast<int*>(ct + NTASK * g.kp * RN);   // [NTASK][RN][4] phase row offset, window offset, x bits
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1678,9 +1679,13 @@ __global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c,
     // early so that the sources are 16-byte aligned (all rows share the alignment when the row stride is even);
     // anything else (carried tail, end of the rows, ragged last block) by element copies. Returns the pad.
     const int64_t gi = d_base - c.hist_len;
-    uint32_t bar_phase = 0u;
-    if (tid == 0) mbar_init(bar, 1);
-    auto stage_rows = [&](const int row0, bool& bulk) -> int {
+    uint32_t ph0 = 0u, ph1 = 0u;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+    }
+    auto stage_rows = [&](const int row0, const int buf, bool& bulk) -> int {
+        double* xs = xs0 + buf * RB * g.pitch;
         bulk = false;
         if ((c.in_stride & 1) == 0 && row0 + RB <= c.n_streams && gi >= 0) {
             const double* __restrict__ src0 = static_cast<const double*>(c.in) + (int64_t)row0 * c.in_stride + gi;
@@ -1690,9 +1695,9 @@ __global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c,
                 bulk = true;
                 if (tid == 0) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_expect_tx(bar, (uint32_t)(RB * wlen * sizeof(double)));
+                    mbar_expect_tx(bar + buf, (uint32_t)(RB * wlen * sizeof(double)));
                     for (int r = 0; r < RB; ++r)
-                        bulk_g2s(xs + r * g.pitch, src0 + (int64_t)r * c.in_stride - a, (uint32_t)(wlen * sizeof(double)), bar);
+                        bulk_g2s(xs + r * g.pitch, src0 + (int64_t)r * c.in_stride - a, (uint32_t)(wlen * sizeof(double)), bar + buf);
                 }
                 return a;
             }
@@ -1714,8 +1719,8 @@ __global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c,
         return 0;
     };
     __syncthreads();  // the mbarrier is initialised
-    bool bulk = false;
-    int apad = stage_rows(rows_base, bulk);
+    bool bulk = false, bulk_next = false;
+    int apad = stage_rows(rows_base, 0, bulk), apad_next = 0;
 
     // ---- geometry + coefficient matrix of this warp's task (overlaps the copies above) ----
     const int nf = n0 + warp * RN;
@@ -1763,18 +1768,33 @@ __global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c,
     for (int j = 0; j < g.nrb; ++j) {
         const int row0 = rows_base + j * RB;
         if (row0 >= c.n_streams) break;
+        const int buf = g.nbuf == 2 ? (j & 1) : 0;
+        const double* __restrict__ xs = xs0 + buf * RB * g.pitch;
         if (j > 0) {
-            __syncthreads();  // everyone is done with the previous rows' samples
-            apad = stage_rows(row0, bulk);
+            if (g.nbuf == 2) {  // staged by the previous iteration's prefetch
+                bulk = bulk_next;
+                apad = apad_next;
+            } else {
+                __syncthreads();  // everyone is done with the previous rows' samples
+                apad = stage_rows(row0, 0, bulk);
+            }
         }
         if (bulk) {
-            while (!mbar_try_wait(bar, bar_phase)) {
+            const uint32_t ph = buf ? ph1 : ph0;
+            while (!mbar_try_wait(bar + buf, ph)) {
             }
-            bar_phase ^= 1u;
-            if (j == 0) __syncthreads();  // the coefficient matrices of all tasks are written (they are per warp: __syncwarp would do)
+            if (buf) ph1 ^= 1u;
+            else ph0 ^= 1u;
+            if (j == 0) __syncthreads();  // also orders the first use after the set-up
         } else {
             cp_async_wait_all();
             __syncthreads();
+        }
+        if (g.nbuf == 2 && j + 1 < g.nrb && row0 + RB < c.n_streams) {
+            // prefetch the next 32 rows into the other buffer under this block of MMAs; that buffer was last read two
+            // iterations ago, and every warp has passed this iteration's barrier / mbarrier wait since
+            if (j > 0) __syncthreads();
+            apad_next = stage_rows(row0 + RB, buf ^ 1, bulk_next);
         }
         if (nf < n1) {
             double acc[4][2];
@@ -1819,8 +1839,12 @@ static bool launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
     // 1.19 / 1.10 ms for the polyphase stage
     static const int max_nrb = [] { const char* e = std::getenv("GAR_K3M_NRB"); return e ? std::atoi(e) : 8; }();
     while (g.nrb < max_nrb && g.nrb * 2 <= n_rb && (int64_t)g.n_tiles * ((n_rb + g.nrb * 2 - 1) / (g.nrb * 2)) >= 4 * 148) g.nrb *= 2;
-    const size_t smem = 16 + ((size_t)32 * g.pitch + (size_t)8 * g.kp * 8) * sizeof(double) + (size_t)8 * 8 * 4 * sizeof(int);
-    if (smem > 113 * 1024) return false;
+    static const int force_nbuf = [] { const char* e = std::getenv("GAR_K3M_NBUF"); return e ? std::atoi(e) : 0; }();
+    const size_t fixed = 16 + (size_t)8 * g.kp * 8 * sizeof(double) + (size_t)8 * 8 * 4 * sizeof(int);
+    const size_t xbytes = (size_t)32 * g.pitch * sizeof(double);
+    g.nbuf = force_nbuf ? force_nbuf : 1;
+    const size_t smem = fixed + g.nbuf * xbytes;
+    if (smem > (g.nbuf == 2 ? 227 : 113) * 1024) return false;
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
