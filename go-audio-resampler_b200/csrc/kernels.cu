@@ -1645,8 +1645,9 @@ struct RowsMmaGeom {
                                                   // 32-row blocks per thread block, sample buffers (2: prefetch)
 };
 
-__global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c, const RowsMmaGeom g) {
-    constexpr int RB = 32, RN = 8, NTASK = 8, TO = RN * NTASK;
+template <int NTASK>
+__global__ void __launch_bounds__(NTASK * 32, NTASK == 8 ? 2 : 3) poly_rows_mma_kernel(const PolyCall c, const RowsMmaGeom g) {
+    constexpr int RB = 32, RN = 8, TO = RN * NTASK;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);       // [2] mbarriers of the bulk-copied row buffers
     double* xs0 = reinterpret_cast<double*>(smem_raw + 16);      // [nbuf][RB][pitch] staged samples
@@ -1702,7 +1703,7 @@ __global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c,
                 return a;
             }
         }
-        for (int r = warp; r < RB; r += 8) {
+        for (int r = warp; r < RB; r += NTASK) {
             const int64_t row = row0 + r;
             double* __restrict__ dst = xs + r * g.pitch;
             if (row >= c.n_streams) {
@@ -1822,17 +1823,17 @@ __global__ void __launch_bounds__(256, 2) poly_rows_mma_kernel(const PolyCall c,
     }
 }
 
-static bool launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
-    if (!g_fir_mma || c.n_streams < 8 || (int64_t)c.n_out * c.n_streams < 16384 || c.L > 4096 || c.taps > 1024) return false;
+template <int NTASK>
+static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s) {
+    constexpr int TO = 8 * NTASK;
     const double r = (double)c.step / ((double)c.L * 65536.0);
-    if (!(r > 0.0) || r > 8.0) return false;
     RowsMmaGeom g{};
     const int omax = (int)std::ceil(7 * r) + 1;
     g.kp = ((omax + c.taps + 3) / 4) * 4;
     if (g.kp > 2 * c.taps + 8) return false;  // too many structural zeros: K3i
-    g.span = (int)std::ceil(63 * r) + 1 + g.kp + 8;
+    g.span = (int)std::ceil((TO - 1) * r) + 1 + g.kp + 8;
     g.pitch = ((g.span + 2 + 15) / 16) * 16 + 4;  // rows 32 bytes apart modulo 128 (B fragment reads: two wavefronts)
-    g.n_tiles = (c.n_out + 63) / 64;
+    g.n_tiles = (c.n_out + TO - 1) / TO;
     const int n_rb = (c.n_streams + 31) / 32;
     g.nrb = 1;
     // measured on the batched 44.1k->48k chain (256 rows): 1 / 2 / 4 / 8 row blocks per coefficient evaluation -> 1.93 / 1.45 /
@@ -1840,7 +1841,7 @@ static bool launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
     static const int max_nrb = [] { const char* e = std::getenv("GAR_K3M_NRB"); return e ? std::atoi(e) : 8; }();
     while (g.nrb < max_nrb && g.nrb * 2 <= n_rb && (int64_t)g.n_tiles * ((n_rb + g.nrb * 2 - 1) / (g.nrb * 2)) >= 4 * 148) g.nrb *= 2;
     static const int force_nbuf = [] { const char* e = std::getenv("GAR_K3M_NBUF"); return e ? std::atoi(e) : 0; }();
-    const size_t fixed = 16 + (size_t)8 * g.kp * 8 * sizeof(double) + (size_t)8 * 8 * 4 * sizeof(int);
+    const size_t fixed = 16 + (size_t)NTASK * g.kp * 8 * sizeof(double) + (size_t)NTASK * 8 * 4 * sizeof(int);
     const size_t xbytes = (size_t)32 * g.pitch * sizeof(double);
     g.nbuf = force_nbuf ? force_nbuf : 1;
     const size_t smem = fixed + g.nbuf * xbytes;
@@ -1849,13 +1850,22 @@ static bool launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (smem > configured[dev & 63]) {
-        cudaFuncSetAttribute(poly_rows_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(poly_rows_mma_kernel<NTASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured[dev & 63] = smem;
     }
     const int64_t blocks = (int64_t)g.n_tiles * ((c.n_streams + 32 * g.nrb - 1) / (32 * g.nrb)) + c.n_streams;
-    poly_rows_mma_kernel<<<(unsigned)blocks, 256, smem, s>>>(c, g);
+    poly_rows_mma_kernel<NTASK><<<(unsigned)blocks, NTASK * 32, smem, s>>>(c, g);
     count_launch();
     return true;
+}
+
+static bool launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
+    if (!g_fir_mma || c.n_streams < 8 || (int64_t)c.n_out * c.n_streams < 16384 || c.L > 4096 || c.taps > 1024) return false;
+    const double r = (double)c.step / ((double)c.L * 65536.0);
+    if (!(r > 0.0) || r > 8.0) return false;
+    static const int ntask = [] { const char* e = std::getenv("GAR_K3M_NTASK"); return e ? std::atoi(e) : 8; }();
+    if (ntask == 4) return launch_poly_rows_mma_t<4>(c, s) || launch_poly_rows_mma_t<8>(c, s);
+    return launch_poly_rows_mma_t<8>(c, s) || launch_poly_rows_mma_t<4>(c, s);
 }
 
 // K3i dispatch: batches of at least 8 lock-step rows with enough outputs; S = ceil(samples per output)
