@@ -1,0 +1,179 @@
+// device_common.cuh — device helpers shared by the kernel translation units (vector pack/unpack, the virtual input
+// v = hist ++ in, mbarrier / TMA bulk copy / cp.async wrappers, the register-tiled FIR core, the DMMA wrapper) and the
+// few host-side pieces they share (launch counter, A/B switches, tiles-per-block heuristic).
+#pragma once
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+namespace gar {
+
+// host side, defined in kernels_misc.cu / kernels_fir.cu / kernels_fused.cu
+void count_launch();
+bool tensor_fir_enabled();        // K1m / K2m / K3m (FP64 tensor cores)
+bool tiled_polyphase_enabled();   // K4r / K3r / K3i / K3m
+int pick_tiles_per_block(int n_tiles, int n_streams, int* n_groups);
+// K3r: the rational-ratio kernel without the x2 stage (kernels_fused.cu), used by launch_poly
+bool launch_rat_poly_only_f64(const FusedCall& c, cudaStream_t s, RatCache* cache);
+
+namespace {
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { using type = float4; static constexpr int N = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int N = 2; };
+
+__device__ __forceinline__ void vec_unpack(const float4& v, float* d) { d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+__device__ __forceinline__ void vec_unpack(const double2& v, double* d) { d[0] = v.x; d[1] = v.y; }
+__device__ __forceinline__ float4 vec_pack(const float* d) { return make_float4(d[0], d[1], d[2], d[3]); }
+__device__ __forceinline__ double2 vec_pack(const double* d) { return make_double2(d[0], d[1]); }
+
+// v[g] of the virtual input  hist ++ in  (zero outside)
+template <typename T>
+__device__ __forceinline__ T vload(const T* __restrict__ hist, int hist_len, const T* __restrict__ in, int n_in, int g) {
+    if (g < 0) return T(0);
+    if (g < hist_len) return hist[g];
+    g -= hist_len;
+    return g < n_in ? in[g] : T(0);
+}
+
+template <typename T>
+__device__ __forceinline__ void carry_row(const T* hist, int hist_len, const T* in, int n_in, T* hist_out, int drop,
+                                          int new_len) {
+    for (int i = threadIdx.x; i < new_len; i += blockDim.x) hist_out[i] = vload(hist, hist_len, in, n_in, drop + i);
+}
+
+// ---- mbarrier / TMA bulk-copy helpers (PTX; SASS: SYNCS.*, UBLKCP) ------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// per-thread asynchronous global -> shared copy of one element (SASS LDGSTS); completion via cp.async.wait_all
+__device__ __forceinline__ void cp_async_elem(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+[[maybe_unused]] __device__ __forceinline__ void cp_async_elem(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Register-tiled sliding-window FIR core shared by the stand-alone and the fused kernels: R adjacent positions
+// (window stride M) x NF filters per thread, `xt` = this thread's window in shared memory (16-byte aligned),
+// `cs` = [NF][cp] taps shifted by the pad `a`. One LDS.128 of samples + one broadcast LDS.128 per filter feed
+// VEC*R*NF FMAs.
+template <typename T, int M, int NF, int R>
+__device__ __forceinline__ void fir_tile_accumulate(const T* __restrict__ xt, const T* __restrict__ cs, const int cp,
+                                                    const int taps, const int a, T (&res)[R][NF]) {
+    using V = typename VecOf<T>::type;
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int NCH = (M * (R - 1) + VEC - 1) / VEC + 1;  // 16-byte chunks spanned by one step's window
+    constexpr int WREG = NCH * VEC;
+    const int n_iter = (taps + a + VEC - 1) / VEC;
+    T xr[WREG];
+    T acc[R][NF];
+    double tot[R][NF];  // f32: short f32 partial sums are folded into f64 totals (|err| ~ 1e-7)
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < NF; ++p) {
+            acc[r][p] = T(0);
+            tot[r][p] = 0.0;
+        }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) vec_unpack(*reinterpret_cast<const V*>(xt + ch * VEC), xr + ch * VEC);
+
+    auto step = [&](const int u, const int it) {
+        T cv[NF][VEC];
+#pragma unroll
+        for (int p = 0; p < NF; ++p) vec_unpack(*reinterpret_cast<const V*>(cs + p * cp + it * VEC), cv[p]);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const T xv = xr[(u * VEC + i + M * r) % WREG];
+#pragma unroll
+                for (int p = 0; p < NF; ++p) acc[r][p] = fma(xv, cv[p][i], acc[r][p]);
+            }
+        // the oldest chunk is dead now: refill its slot with chunk it+NCH (needed from the next step on)
+        vec_unpack(*reinterpret_cast<const V*>(xt + (it + NCH) * VEC), xr + (u % NCH) * VEC);
+    };
+    auto fold = [&]() {
+        if (sizeof(T) == 4) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int p = 0; p < NF; ++p) {
+                    tot[r][p] += (double)acc[r][p];
+                    acc[r][p] = T(0);
+                }
+        }
+    };
+
+    // f32 only: the three iterations that hold the centre of the main lobe are folded one by one, so the
+    // many small terms that follow are never added to an O(1) float32 partial sum (keeps |err| ~ 1.5e-7).
+    const int itf0 = ((taps - 1) / 2 + a) / VEC, itf1 = itf0 + 2;
+    constexpr int FOLD_BODIES = 8;  // periodic fold every 8*NCH*VEC taps (F2F.F64.F32 is ~10x an FFMA slot)
+    int it0 = 0, since_fold = 0;
+    for (; it0 + NCH <= n_iter; it0 += NCH) {
+        if (sizeof(T) == 4 && it0 <= itf1 && it0 + NCH > itf0) {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) {
+                step(u, it0 + u);
+                if (it0 + u >= itf0 && it0 + u <= itf1) fold();
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) step(u, it0 + u);
+        }
+        if (++since_fold == FOLD_BODIES) {
+            fold();
+            since_fold = 0;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NCH; ++u)
+        if (it0 + u < n_iter) {
+            step(u, it0 + u);
+            if (sizeof(T) == 4 && it0 + u >= itf0 && it0 + u <= itf1) fold();
+        }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < NF; ++p) res[r][p] = (T)(tot[r][p] + (double)acc[r][p]);
+
+}
+
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+
+}  // namespace
+}  // namespace gar

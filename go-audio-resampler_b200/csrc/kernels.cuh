@@ -90,7 +90,7 @@ struct CubicCall {
 
 enum Dtype : int { DT_F64 = 0, DT_F32 = 1 };
 
-// launchers (kernels.cu). Return the name of the kernel variant used.
+// launchers (kernels_fir.cu, kernels_poly.cu, kernels_fused.cu, kernels_misc.cu). Return the name of the kernel variant used.
 const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s);
 const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* cache);
 const char* launch_cubic(const CubicCall& c, int dtype, cudaStream_t s);

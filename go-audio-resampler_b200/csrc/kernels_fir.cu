@@ -1,0 +1,781 @@
+// kernels_fir.cu — integer-factor FIR stages (dft_stage.go): K1/K2 register-tiled vector kernels (fir_tiled_kernel,
+// fir_f32x2_kernel with packed fma.rn.f32x2), K1m/K2m on the FP64 tensor cores (fir_mma_f64_kernel, DMMA), the generic
+// fallback, and launch_fir.
+#include "device_common.cuh"
+
+namespace gar {
+namespace {
+
+// =============================================================================================
+// Tiled strided multi-filter FIR.
+//   M  = window stride between adjacent outputs (1 for the up-sampler, the decimation factor else)
+//   NF = filters applied to the same window (up-sampling factor; 1 for the decimator)
+//   R  = adjacent output positions per thread; M*R*sizeof(T)/16 is odd for the shipped variants so
+//        the eight threads of a quarter-warp hit eight different 16-byte bank groups (conflict-free
+//        LDS.128)
+//   NT = threads per block; a block produces NT*R positions of one stream row.
+// grid.x = rows * (n_tiles + 1): the extra block of every row writes the carried tail.
+// =============================================================================================
+template <typename T, int M, int NF, int R, int NT>
+__global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const int n_tiles, const int tiles_per_block,
+                                                       const int n_groups, const int cp /*padded taps*/,
+                                                       const int xlen) {
+    using V = typename VecOf<T>::type;
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int TJ = NT * R;
+    static_assert((TJ * M * sizeof(T)) % 16 == 0, "tile stride must keep the 16-byte alignment of the window");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // two mbarriers, one per window buffer
+    T* cs = reinterpret_cast<T*>(smem_raw + 16);            // [NF][cp]
+    T* xs0 = cs + NF * cp;                                  // [2][xlen] double-buffered sample window
+
+    // grid.x = rows * (n_groups + 1): a block owns `tiles_per_block` consecutive tiles of one row (filter
+    // loaded once, TMA prefetch of tile k+1 under the FMAs of tile k); the extra block writes the carried tail.
+    const int group = blockIdx.x % (n_groups + 1);
+    const int64_t row = blockIdx.x / (n_groups + 1);
+    const int tid = threadIdx.x;
+
+    const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+
+    if (group == n_groups) {  // carry block
+        carry_row(hist, c.hist_len, in, c.n_in, static_cast<T*>(c.hist_out) + row * c.hist_out_stride, c.drop,
+                  c.new_hist_len);
+        return;
+    }
+    const int t_first = group * tiles_per_block;
+    const int nt = min(tiles_per_block, n_tiles - t_first);
+
+    // leading pad so that every tile's bulk source address is 16-byte aligned (constant along the row)
+    const int a = (int)(((reinterpret_cast<uintptr_t>(in) / sizeof(T)) + (uintptr_t)(int64_t)(c.first - c.hist_len)) &
+                        (uintptr_t)(VEC - 1));
+    auto tile_geom = [&](const int t, int& g0a, int& words, bool& bulk) {
+        const int j0 = t * TJ;
+        const int tj = min(TJ, c.n_pos - j0);
+        g0a = c.first + j0 * M - a;                                   // virtual index of xs[0]
+        words = (((tj - 1) * M + c.taps + a + VEC - 1) / VEC) * VEC;  // samples the tile reads (16-byte units)
+        const int gi = g0a - c.hist_len;                              // index into `in`
+        bulk = gi >= 0 && gi + words <= c.n_in && words <= xlen;
+    };
+    auto issue_bulk = [&](const int t, const int buf) {  // one thread
+        int g0a, words;
+        bool bulk;
+        tile_geom(t, g0a, words, bulk);
+        if (bulk) {
+            mbar_expect_tx(bar + buf, (uint32_t)(words * sizeof(T)));
+            bulk_g2s(xs0 + buf * xlen, in + (g0a - c.hist_len), (uint32_t)(words * sizeof(T)), bar + buf);
+        }
+    };
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+    }
+    for (int i = tid; i < 2 * xlen; i += NT) xs0[i] = T(0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before async-proxy (TMA) writes
+    {  // filter bank, shifted by the pad, zero elsewhere
+        const T* __restrict__ bank = static_cast<const T*>(c.bank);
+#pragma unroll
+        for (int p = 0; p < NF; ++p)
+            for (int kk = tid; kk < cp; kk += NT) {
+                const int k = kk - a;
+                cs[p * cp + kk] = (k >= 0 && k < c.taps) ? bank[p * c.taps + k] : T(0);
+            }
+    }
+    __syncthreads();
+    if (tid == 0) issue_bulk(t_first, 0);
+    uint32_t phase0 = 0u, phase1 = 0u;
+    T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+
+    for (int k = 0; k < nt; ++k) {
+        const int t = t_first + k;
+        const int buf = k & 1;
+        T* xs = xs0 + buf * xlen;
+        int g0a, words;
+        bool bulk;
+        tile_geom(t, g0a, words, bulk);
+        if (tid == 0 && k + 1 < nt) issue_bulk(t + 1, buf ^ 1);  // prefetch (buffer free since the last barrier)
+        if (bulk) {
+            const uint32_t ph = buf ? phase1 : phase0;
+            while (!mbar_try_wait(bar + buf, ph)) {
+            }
+            if (buf) phase1 ^= 1u;
+            else phase0 ^= 1u;
+        } else {  // edge tile (touches the carried tail or the end of the row): guarded loads
+            for (int i = tid; i < xlen; i += NT)
+                xs[i] = i < words ? vload(hist, c.hist_len, in, c.n_in, g0a + i) : T(0);
+            __syncthreads();
+        }
+
+        // ---- register-tiled sliding-window FIR ----
+        T res[R][NF];
+        fir_tile_accumulate<T, M, NF, R>(xs + M * R * tid, cs, cp, c.taps, a, res);
+
+        // ---- interleaved, vectorised store: out[(j*NF + p)] ----
+        const int jb = t * TJ + R * tid;
+        T* op = out + (int64_t)jb * NF;
+        if (jb + R <= c.n_pos && (R * NF) % VEC == 0 && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {
+            const T* flat = &res[0][0];
+#pragma unroll
+            for (int q = 0; q < R * NF / VEC; ++q) reinterpret_cast<V*>(op)[q] = vec_pack(flat + q * VEC);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (jb + r < c.n_pos) {
+#pragma unroll
+                    for (int p = 0; p < NF; ++p) op[r * NF + p] = res[r][p];
+                }
+        }
+        __syncthreads();  // every thread is done with xs[buf] before the next prefetch overwrites it
+    }
+}
+
+// =============================================================================================
+// K1m/K2m — float64 integer-factor FIR on the FP64 TENSOR cores (PTX mma.sync.m8n8k4.f64, SASS DMMA.8x8x4), for batches
+// of >= 8 lock-step rows.
+//
+// JT = 8/NF consecutive positions x NF phases are the 8 rows of an MMA tile, 8 streams its 8 columns:
+//     D[(jj,p)][s] = sum_w A[(jj,p)][w] * X[w][s],   A[(jj,p)][w] = bank[p][w - jj*M]  (0 outside the filter),
+// X[w][s] = the sample window of stream s. A is a fixed 8 x (taps + (JT-1)*M) block-Toeplitz matrix (2 % zero padding
+// for the x2 stage, 1 % for the 1223-tap /2 decimator): a real dense contraction, 256 FMAs per instruction instead of 32,
+// no register-file or shared-memory pressure (measured: DMMA sustains 36.9 TFLOP/s on this B200, vector DFMA 34.1).
+// A warp owns MT = 4 consecutive MMA tiles (4*JT positions): they see the same sample window shifted by SH = JT*M/4
+// k-steps, so ONE B fragment (LDS.64) and ONE A fragment (LDS.64, kept in a rotating register window) feed 4 MMAs.
+// A block = 8 streams x NW*MT*JT positions; A fragments are laid out per k-step in shared memory in fragment order.
+// Taps are grouped in fours in window order, so results differ from the strictly sequential vector kernels in the last
+// bits (1e-16 relative); identical call sequences are bit-identical.
+// =============================================================================================
+struct MmaGeom {
+    int32_t nk, xlen, pitch, nbuf, n_tiles, tiles_per_block, n_groups, n_sg;  // k-steps, staged samples per stream, row pitch, window buffers
+};
+
+template <int M, int NF, int NW, int MT>
+__global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, const MmaGeom g) {
+    constexpr int JT = 8 / NF;                // positions per MMA tile
+    static_assert(8 % NF == 0 && (JT * M) % 4 == 0, "tile shift must be a whole number of k-steps");
+    constexpr int SH = JT * M / 4;            // k-steps between consecutive MMA tiles
+    constexpr int WA = (MT - 1) * SH + 1;     // rotating A-fragment window
+    constexpr int TJ = NW * MT * JT;          // positions per block tile
+    constexpr int NT = NW * 32;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // A[(jj,p)][w] = bank[p][w - jj*M] is a shifted copy of the filter in every row, so the A fragment of k-step kk is a
+    // gather from the zero-padded bank with a per-lane offset: no fragment table, the bank itself is all that is staged
+    constexpr int BOFF = (JT - 1) * M;                           // leading zeros: the largest negative offset
+    const int blen = (4 * g.nk + BOFF + 5) & ~1;                 // padded filter length, even: windows stay 16-byte aligned
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);       // [2] mbarriers of the bulk-copied window buffers
+    double* Bs = reinterpret_cast<double*>(smem_raw + 16);       // [NF][blen] zero-padded bank
+    double* Xs0 = Bs + (size_t)NF * blen;                        // [nbuf][8][pitch] sample windows of the block's streams
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_work = g.n_sg * g.n_groups;
+    if ((int)blockIdx.x >= n_work) {  // carried tail of one row
+        const int64_t row = (int)blockIdx.x - n_work;
+        carry_row(static_cast<const double*>(c.hist) + row * c.hist_stride, c.hist_len,
+                  static_cast<const double*>(c.in) + row * c.in_stride, c.n_in,
+                  static_cast<double*>(c.hist_out) + row * c.hist_out_stride, c.drop, c.new_hist_len);
+        return;
+    }
+    const int grp = blockIdx.x % g.n_groups;
+    const int sbase = (blockIdx.x / g.n_groups) * 8;
+    const int t_first = grp * g.tiles_per_block;
+    const int nt = min(g.tiles_per_block, g.n_tiles - t_first);
+
+    {
+        const double* __restrict__ bank = static_cast<const double*>(c.bank);
+        for (int idx = tid; idx < NF * blen; idx += NT) {
+            const int p = idx / blen, k = idx - p * blen - BOFF;
+            Bs[idx] = (k >= 0 && k < c.taps) ? bank[p * c.taps + k] : 0.0;
+        }
+    }
+    const int64_t total = (int64_t)c.hist_len + c.n_in;
+    const int nq = g.nk + (MT - 1) * SH;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+    }
+    uint32_t ph0 = 0u, ph1 = 0u;
+    // TMA bulk copies need 16-byte aligned sources: all 8 rows share the alignment when the row stride is even
+    const bool rows_bulk = (c.in_stride & 1) == 0 && sbase + 8 <= c.n_streams;
+    const double* __restrict__ in0 = static_cast<const double*>(c.in) + (int64_t)sbase * c.in_stride;
+    const int xbuf = 8 * g.pitch;
+
+    // geometry of local tile kt: first sample v0, staged length, bulk-copy parameters
+    auto tile_geom = [&](const int kt, int64_t& v0, int& len, int& a, int& wlen) -> bool {
+        const int jb0 = (t_first + kt) * TJ;
+        v0 = (int64_t)c.first + (int64_t)jb0 * M;
+        const int npos_t = min(TJ, c.n_pos - jb0);
+        len = min(g.xlen, ((npos_t + JT - 1) / JT * JT - 1) * M + 4 * g.nk + 4);
+        a = 0;
+        wlen = 0;
+        const int64_t gi = v0 - c.hist_len;
+        if (!rows_bulk || gi < 0) return false;
+        a = (int)((reinterpret_cast<uintptr_t>(in0 + gi) & 15u) >> 3);  // start `a` samples early: aligned source
+        wlen = (len + a + 1) & ~1;
+        if (gi - a >= 0 && gi - a + wlen <= c.n_in && wlen <= g.pitch) return true;
+        a = 0;  // element copies start exactly at v0
+        return false;
+    };
+    auto issue = [&](const int kt, const int buf) {  // one thread
+        int64_t v0;
+        int len, a, wlen;
+        if (!tile_geom(kt, v0, len, a, wlen)) return;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar + buf, (uint32_t)(8 * wlen * sizeof(double)));
+        const int64_t gi = v0 - c.hist_len - a;
+        for (int r = 0; r < 8; ++r)
+            bulk_g2s(Xs0 + buf * xbuf + r * g.pitch, in0 + (int64_t)r * c.in_stride + gi, (uint32_t)(wlen * sizeof(double)),
+                     bar + buf);
+    };
+
+    for (int kt = 0; kt < nt; ++kt) {
+        const int buf = g.nbuf == 2 ? (kt & 1) : 0;
+        double* __restrict__ Xs = Xs0 + buf * xbuf;
+        int64_t v0;
+        int len, a, wlen;
+        const bool bulk = tile_geom(kt, v0, len, a, wlen);
+        // everyone is done with the windows this iteration overwrites (first tile: the bank and the mbarriers are set)
+        __syncthreads();
+        if (tid == 0) {
+            if (g.nbuf == 2) {  // prefetch the next tile under this tile's MMAs
+                if (kt == 0) issue(0, 0);
+                if (kt + 1 < nt) issue(kt + 1, buf ^ 1);
+            } else {
+                issue(kt, 0);
+            }
+        }
+        if (bulk) {
+            const uint32_t ph = buf ? ph1 : ph0;
+            while (!mbar_try_wait(bar + buf, ph)) {
+            }
+            if (buf) ph1 ^= 1u;
+            else ph0 ^= 1u;
+        } else {  // edge tile (touches the carried tail or the end of the rows): element copies
+            const int i1 = (int)min((int64_t)len, max((int64_t)0, (int64_t)c.hist_len - v0));
+            const int i2 = (int)min((int64_t)len, max((int64_t)i1, total - v0));
+            for (int r = warp; r < 8; r += NW) {
+                const int64_t row = sbase + r;
+                double* __restrict__ dst = Xs + r * g.pitch;
+                if (row >= c.n_streams) {
+                    for (int i = lane; i < len; i += 32) dst[i] = 0.0;
+                    continue;
+                }
+                const double* __restrict__ hsrc = static_cast<const double*>(c.hist) + row * c.hist_stride + v0;
+                const double* __restrict__ isrc = static_cast<const double*>(c.in) + row * c.in_stride + (v0 - c.hist_len);
+                for (int i = lane; i < i1; i += 32) dst[i] = hsrc[i];
+#pragma unroll 4
+                for (int i = i1 + lane; i < i2; i += 32) cp_async_elem(dst + i, isrc + i);
+                for (int i = i2 + lane; i < len; i += 32) dst[i] = 0.0;
+            }
+            cp_async_wait_all();
+            __syncthreads();
+        }
+
+        // ---- MT MMA tiles per warp; step q loads window chunk Q = warp*MT*SH + q and A fragment q ----
+        const int jb0 = (t_first + kt) * TJ;
+        const int npos_t = min(TJ, c.n_pos - jb0);
+        if (warp * MT * JT < npos_t) {
+            double acc[MT][2];
+#pragma unroll
+            for (int b = 0; b < MT; ++b) acc[b][0] = acc[b][1] = 0.0;
+            double Areg[WA];
+            // B fragment: lane l reads X[w = 4*Q + l%4][stream l/4]
+            const double* __restrict__ xw = Xs + (lane >> 2) * g.pitch + (lane & 3) + a + 4 * (warp * MT * SH);
+            // A fragment: lane l holds A[row = l/4][w = 4*kk + l%4] = bank[p][4*kk + l%4 - jj*M], row = jj*NF + p
+            const double* __restrict__ aw = Bs + ((lane >> 2) % NF) * blen + BOFF + (lane & 3) - ((lane >> 2) / NF) * M;
+            for (int q0 = 0; q0 < nq; q0 += WA) {
+#pragma unroll
+                for (int u = 0; u < WA; ++u) {
+                    const int q = q0 + u;
+                    if (q < nq) {
+                        Areg[u] = q < g.nk ? aw[4 * q] : 0.0;
+                        const double bf = xw[4 * q];
+#pragma unroll
+                        for (int b = 0; b < MT; ++b) {
+                            const int kk = q - b * SH;
+                            if (kk >= 0 && kk < g.nk) dmma884(acc[b][0], acc[b][1], Areg[((u - b * SH) % WA + WA) % WA], bf);
+                        }
+                    }
+                }
+            }
+            // ---- D[row = lane/4][cols 2*(lane%4), +1]: output jb*NF + row of streams sbase + col ----
+            const int r8 = lane >> 2;
+            const int s0 = sbase + 2 * (lane & 3);
+#pragma unroll
+            for (int b = 0; b < MT; ++b) {
+                const int jb = jb0 + (warp * MT + b) * JT;
+                if (jb + r8 / NF < c.n_pos) {
+                    const int64_t o = (int64_t)jb * NF + r8;
+                    if (s0 < c.n_streams) (static_cast<double*>(c.out) + (int64_t)s0 * c.out_stride)[o] = acc[b][0];
+                    if (s0 + 1 < c.n_streams) (static_cast<double*>(c.out) + (int64_t)(s0 + 1) * c.out_stride)[o] = acc[b][1];
+                }
+            }
+        }
+    }
+}
+
+template <int M, int NF>
+static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
+    constexpr int JT = 8 / NF, SH = JT * M / 4;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    MmaGeom g{};
+    const int kp = c.taps + (JT - 1) * M;
+    g.nk = (kp + 3) / 4;
+    g.n_sg = (c.n_streams + 7) / 8;
+    const size_t bank_bytes = 16 + (size_t)NF * ((4 * g.nk + (JT - 1) * M + 5) & ~1) * sizeof(double);
+    auto run = [&](auto kernel, const int NW, const int MT, const int slot) -> bool {
+        const int TJ = NW * MT * JT;
+        g.xlen = (TJ - 1) * M + 4 * g.nk + 4 * (MT - 1) * SH + 10;
+        g.pitch = ((g.xlen + 15) / 16) * 16 + 4;  // rows 32 bytes apart modulo 128: the 8 x 32-byte B fragment reads tile two wavefronts
+        const size_t xbytes = (size_t)8 * g.pitch * sizeof(double);
+        // two window buffers (the next tile is prefetched under the MMAs) when at least two such blocks fit an SM
+        static const int force_nbuf = [] { const char* e = std::getenv("GAR_MMA_NBUF"); return e ? std::atoi(e) : 0; }();
+        g.nbuf = bank_bytes + 2 * xbytes <= 110 * 1024 ? 2 : 1;
+        if (force_nbuf == 1) g.nbuf = 1;
+        const size_t smem = bank_bytes + g.nbuf * xbytes;
+        if (smem > 227 * 1024) return false;
+        g.n_tiles = (c.n_pos + TJ - 1) / TJ;
+        // persistent over a few tiles (bank staged once, prefetch) while the grid still fills the GPU
+        const int64_t blocks_per_sm = std::max<int64_t>(1, (int64_t)(227 * 1024) / (int64_t)(smem + 1024));
+        const int64_t slots = 148 * std::min<int64_t>(blocks_per_sm, 2048 / (NW * 32));
+        int64_t tpb = (int64_t)g.n_tiles * g.n_sg / (slots * 4);
+        tpb = std::max<int64_t>(1, std::min<int64_t>(tpb, 8));
+        g.tiles_per_block = (int32_t)std::min<int64_t>(tpb, g.n_tiles);
+        g.n_groups = (g.n_tiles + g.tiles_per_block - 1) / g.tiles_per_block;
+        static size_t configured[64][4] = {{0}};
+        size_t& conf = configured[dev & 63][slot];
+        if (smem > conf) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            conf = smem;
+        }
+        const int64_t blocks = (int64_t)g.n_sg * g.n_groups + c.n_streams;
+        kernel<<<(unsigned)blocks, NW * 32, smem, s>>>(c, g);
+        count_launch();
+        return true;
+    };
+    // Measured on B200 (C3: 8 ch x 1223 taps /2; x2 stage of the batched 44.1k->48k chain): 16 warps x 4 tiles for long
+    // filters (one block per SM: the window is dominated by the taps), 8 warps x 4 tiles in several blocks per SM for
+    // short ones; 6 or 8 tiles per warp and smaller blocks were slower. GAR_MMA_CFG = 1 / 3 forces one of the two.
+    static const int forced = [] { const char* e = std::getenv("GAR_MMA_CFG"); return e ? std::atoi(e) : -1; }();
+    if (forced == 1) return run(fir_mma_f64_kernel<M, NF, 16, 4>, 16, 4, 1);
+    if (forced == 3) return run(fir_mma_f64_kernel<M, NF, 8, 4>, 8, 4, 3);
+    if (c.taps > 600) return run(fir_mma_f64_kernel<M, NF, 16, 4>, 16, 4, 1) || run(fir_mma_f64_kernel<M, NF, 8, 4>, 8, 4, 3);
+    return run(fir_mma_f64_kernel<M, NF, 8, 4>, 8, 4, 3);
+}
+
+static bool g_fir_mma = [] {
+    const char* e = std::getenv("GAR_NO_MMA");
+    return !(e && e[0] && e[0] != '0');
+}();
+// float64 FIR on the FP64 tensor cores: batches of >= 8 lock-step rows, x2 up-sampler and /2 /3 /4 decimators
+static const char* launch_fir_mma(const FirCall& c, cudaStream_t s) {
+    if (!g_fir_mma || c.n_streams < 8 || (int64_t)c.n_pos * c.n_streams < 32768 || c.taps < 16) return nullptr;
+    if (c.stride == 1 && c.nf == 2) return launch_fir_mma_t<1, 2>(c, s) ? "fir_f64_mma_up2" : nullptr;
+    if (c.nf == 1 && c.stride == 2) return launch_fir_mma_t<2, 1>(c, s) ? "fir_f64_mma_s2" : nullptr;
+    if (c.nf == 1 && c.stride == 3) return launch_fir_mma_t<3, 1>(c, s) ? "fir_f64_mma_s3" : nullptr;
+    if (c.nf == 1 && c.stride == 4) return launch_fir_mma_t<4, 1>(c, s) ? "fir_f64_mma_s4" : nullptr;
+    return nullptr;
+}
+
+// =============================================================================================
+// float32 decimator with packed FMAs (PTX fma.rn.f32x2 -> SASS FFMA2, new on sm_100).
+// Same tiling as fir_tiled_kernel, but adjacent taps are paired: (x[k],x[k+1]) * (c[k],c[k+1]) is ONE
+// instruction on even/odd register pairs. Pairs always span both register banks, so the bank conflicts that
+// cap the scalar-FFMA version at ~78 % issue utilisation cannot occur, and the FMA work needs half the issue
+// slots. A position whose window offset M*r is odd reads its samples from the even address below and uses a
+// copy of the filter shifted by one tap (c'[k] = c[k-1]); lane .x sums even taps, lane .y odd taps.
+// =============================================================================================
+template <int M, int NF, int R, int NT>
+__global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const int n_tiles, const int tiles_per_block,
+                                                       const int n_groups, const int cp, const int xlen) {
+    typedef unsigned long long u64;
+    constexpr int MAXE = M * (R - 1) - ((M * (R - 1)) & 1);
+    constexpr int NCH = (MAXE + 4 + 3) / 4;
+    constexpr int NS = ((M & 1) && R > 1) ? 2 : 1;  // filter copies: shift 0 (even offsets), shift 1 (odd offsets)
+    constexpr int TJ = NT * R;
+    static_assert((TJ * M) % 4 == 0, "tile stride must keep the 16-byte alignment of the window");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // two mbarriers, one per window buffer
+    float* cs = reinterpret_cast<float*>(smem_raw + 16);    // [NF][NS][cp]
+    float* xs0 = cs + NF * NS * cp;                         // [2][xlen] double-buffered sample window
+
+    // grid.x = rows * (n_groups + 1): a block owns `tiles_per_block` consecutive tiles of one row; the extra
+    // block of every row writes the carried tail.
+    const int group = blockIdx.x % (n_groups + 1);
+    const int64_t row = blockIdx.x / (n_groups + 1);
+    const int tid = threadIdx.x;
+    const float* __restrict__ hist = static_cast<const float*>(c.hist) + row * c.hist_stride;
+    const float* __restrict__ in = static_cast<const float*>(c.in) + row * c.in_stride;
+    if (group == n_groups) {
+        carry_row(hist, c.hist_len, in, c.n_in, static_cast<float*>(c.hist_out) + row * c.hist_out_stride, c.drop,
+                  c.new_hist_len);
+        return;
+    }
+    const int t_first = group * tiles_per_block;
+    const int nt = min(tiles_per_block, n_tiles - t_first);
+
+    // Leading pad `a` (same for every tile of the row because the tile stride is a multiple of 16 bytes): the
+    // window of a tile starts `a` samples early so that its global address is 16-byte aligned for the TMA
+    // bulk copy; the filter is shifted by `a` zero taps to compensate.
+    const int a = (int)(((reinterpret_cast<uintptr_t>(in) >> 2) + (uintptr_t)(int64_t)(c.first - c.hist_len)) & 3u);
+    auto tile_geom = [&](const int t, int& g0a, int& words, bool& bulk) {
+        const int j0 = t * TJ;
+        const int tj = min(TJ, c.n_pos - j0);
+        g0a = c.first + j0 * M - a;                       // virtual index of xs[0]
+        words = (((tj - 1) * M + c.taps + a + 3) / 4) * 4;  // samples the tile reads, rounded to 16 bytes
+        const int gi = g0a - c.hist_len;                  // index into `in`
+        bulk = gi >= 0 && gi + words <= c.n_in && words <= xlen;
+    };
+    auto issue_bulk = [&](const int t, const int buf) {  // one thread
+        int g0a, words;
+        bool bulk;
+        tile_geom(t, g0a, words, bulk);
+        if (bulk) {
+            mbar_expect_tx(bar + buf, (uint32_t)(words * sizeof(float)));
+            bulk_g2s(xs0 + buf * xlen, in + (g0a - c.hist_len), (uint32_t)(words * sizeof(float)), bar + buf);
+        }
+    };
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+    }
+    // both window buffers start as zeros: whatever a later, shorter tile leaves behind is finite
+    for (int i = tid; i < 2 * xlen; i += NT) xs0[i] = 0.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before async-proxy (TMA) writes
+    {
+        const float* __restrict__ bank = static_cast<const float*>(c.bank);
+#pragma unroll
+        for (int p = 0; p < NF; ++p)
+#pragma unroll
+            for (int sh = 0; sh < NS; ++sh)
+                for (int kk = tid; kk < cp; kk += NT) {
+                    const int k = kk - a - sh;
+                    cs[(p * NS + sh) * cp + kk] = (k >= 0 && k < c.taps) ? bank[p * c.taps + k] : 0.f;
+                }
+    }
+    __syncthreads();
+    if (tid == 0) issue_bulk(t_first, 0);
+    uint32_t phase0 = 0u, phase1 = 0u;
+
+    const int n_iter = (c.taps + a + (NS - 1) + 3) / 4;
+    const int itf0 = ((c.taps - 1) / 2 + a) / 4, itf1 = itf0 + 2;  // centre-of-main-lobe folds (see fir_tiled_kernel)
+    float* __restrict__ out = static_cast<float*>(c.out) + row * c.out_stride;
+
+    for (int k = 0; k < nt; ++k) {
+        const int t = t_first + k;
+        const int buf = k & 1;
+        float* xs = xs0 + buf * xlen;
+        int g0a, words;
+        bool bulk;
+        tile_geom(t, g0a, words, bulk);
+        // prefetch the next tile into the other buffer (free since the __syncthreads that ended tile k-1)
+        if (tid == 0 && k + 1 < nt) issue_bulk(t + 1, buf ^ 1);
+        if (bulk) {
+            const uint32_t ph = buf ? phase1 : phase0;
+            while (!mbar_try_wait(bar + buf, ph)) {
+            }
+            if (buf) phase1 ^= 1u;
+            else phase0 ^= 1u;
+        } else {  // edge tile (touches the carried tail or the end of the row): guarded loads
+            for (int i = tid; i < xlen; i += NT)
+                xs[i] = i < words ? vload(hist, c.hist_len, in, c.n_in, g0a + i) : 0.f;
+            __syncthreads();
+        }
+
+        // ---- register-tiled sliding window on packed FMAs ----
+        const float* xt = xs + M * R * tid;
+        u64 xw[NCH * 2];
+        u64 acc[R][NF];
+        double tot[R][NF];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int p = 0; p < NF; ++p) {
+                acc[r][p] = 0ull;
+                tot[r][p] = 0.0;
+            }
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xt + ch * 4);
+            xw[ch * 2] = v.x;
+            xw[ch * 2 + 1] = v.y;
+        }
+        auto step = [&](const int u, const int it) {
+            // (tools/probe_fma_patterns2.cu: FFMA2 loses ~15 % when one coefficient pair feeds 6 FMAs in a row;
+            //  duplicating the pair with a second, unmergeable ld.shared cost more than it gained — measured)
+            u64 cv[NF][NS][2];
+#pragma unroll
+            for (int p = 0; p < NF; ++p)
+#pragma unroll
+                for (int sh = 0; sh < NS; ++sh) {
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(cs + (p * NS + sh) * cp + it * 4);
+                    cv[p][sh][0] = v.x;
+                    cv[p][sh][1] = v.y;
+                }
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int sh = (M * r) & 1;
+                    const int eh = (M * r - sh) / 2;
+                    const u64 xv = xw[(u * 2 + q + eh) % (NCH * 2)];
+#pragma unroll
+                    for (int p = 0; p < NF; ++p) {
+                        u64 d;
+                        asm("fma.rn.f32x2 %0, %1, %2, %3;"
+                            : "=l"(d)
+                            : "l"(xv), "l"(cv[p][NS == 2 ? sh : 0][q]), "l"(acc[r][p]));
+                        acc[r][p] = d;
+                    }
+                }
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xt + (it + NCH) * 4);
+            xw[(u % NCH) * 2] = v.x;
+            xw[(u % NCH) * 2 + 1] = v.y;
+        };
+        auto fold = [&]() {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int p = 0; p < NF; ++p) {
+                    const float lo = __uint_as_float((unsigned)(acc[r][p] & 0xffffffffull));
+                    const float hi = __uint_as_float((unsigned)(acc[r][p] >> 32));
+                    tot[r][p] += (double)lo + (double)hi;
+                    acc[r][p] = 0ull;
+                }
+        };
+        // three straight loops (plain bodies, the one or two bodies holding the centre, plain bodies): no
+        // per-body bookkeeping; float32 partial sums are folded into float64 only around the centre of the
+        // main lobe and at the loop boundaries (the tails stay small, see fir_tile_accumulate)
+        const int nb = n_iter / NCH;
+        const int bs0 = min(nb, itf0 / NCH), bs1 = min(nb, itf1 / NCH + 1);
+        int b = 0;
+        for (; b < bs0; ++b) {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) step(u, b * NCH + u);
+        }
+        fold();
+        for (; b < bs1; ++b) {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) {
+                step(u, b * NCH + u);
+                if (b * NCH + u >= itf0 && b * NCH + u <= itf1) fold();
+            }
+        }
+        for (; b < nb; ++b) {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) step(u, b * NCH + u);
+        }
+        const int it0 = nb * NCH;
+#pragma unroll
+        for (int u = 0; u < NCH; ++u)
+            if (it0 + u < n_iter) {
+                step(u, it0 + u);
+                if (it0 + u >= itf0 && it0 + u <= itf1) fold();
+            }
+        fold();
+
+        // ---- vectorised store ----
+        const int jb = t * TJ + R * tid;
+        float* op = out + (int64_t)jb * NF;
+        if (jb + R <= c.n_pos && (R * NF) % 4 == 0 && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {
+#pragma unroll
+            for (int q = 0; q < R * NF / 4; ++q) {
+                float4 v;
+                v.x = (float)tot[(q * 4 + 0) / NF][(q * 4 + 0) % NF];
+                v.y = (float)tot[(q * 4 + 1) / NF][(q * 4 + 1) % NF];
+                v.z = (float)tot[(q * 4 + 2) / NF][(q * 4 + 2) % NF];
+                v.w = (float)tot[(q * 4 + 3) / NF][(q * 4 + 3) % NF];
+                reinterpret_cast<float4*>(op)[q] = v;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (jb + r < c.n_pos) {
+#pragma unroll
+                    for (int p = 0; p < NF; ++p) op[r * NF + p] = (float)tot[r][p];
+                }
+        }
+        __syncthreads();  // every thread is done with xs[buf] before the next prefetch overwrites it
+    }
+}
+
+
+
+// Fallback: one thread per output element, operands straight from global/L1.
+template <typename T>
+__global__ void __launch_bounds__(256) fir_generic_kernel(const FirCall c, const int n_tiles) {
+    const int tile = blockIdx.x % (n_tiles + 1);
+    const int64_t row = blockIdx.x / (n_tiles + 1);
+    const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    if (tile == n_tiles) {
+        carry_row(hist, c.hist_len, in, c.n_in, static_cast<T*>(c.hist_out) + row * c.hist_out_stride, c.drop,
+                  c.new_hist_len);
+        return;
+    }
+    const int64_t o = (int64_t)tile * 256 + threadIdx.x;
+    if (o >= (int64_t)c.n_pos * c.nf) return;
+    const int j = (int)(o / c.nf), p = (int)(o % c.nf);
+    const int g = c.first + j * c.stride;
+    const T* __restrict__ bank = static_cast<const T*>(c.bank) + (int64_t)p * c.taps;
+    double tot = 0;
+    T acc = 0;
+    const int kc = (c.taps - 1) / 2;
+    for (int k = 0; k < c.taps; ++k) {
+        acc = fma(vload(hist, c.hist_len, in, c.n_in, g + k), bank[k], acc);
+        if (sizeof(T) == 4 && ((k & 255) == 255 || (k >= kc && k < kc + 12 && ((k - kc) & 3) == 3))) {
+            tot += (double)acc;
+            acc = 0;
+        }
+    }
+    (static_cast<T*>(c.out) + row * c.out_stride)[o] = (T)(tot + (double)acc);
+}
+
+template <typename T, int M, int NF, int R>
+void launch_fir_tiled(const FirCall& c, cudaStream_t s) {
+    constexpr int NT = 128;
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int NCH = (M * (R - 1) + VEC - 1) / VEC + 1;
+    constexpr int TJ = NT * R;
+    const int cp = ((c.taps + VEC - 1 + VEC - 1) / VEC) * VEC;  // room for any alignment pad
+    const int xlen = M * R * (NT - 1) + (cp / VEC + NCH + 1) * VEC;
+    const size_t smem = 16 + (size_t)(NF * cp + 2 * xlen) * sizeof(T);
+    const int n_tiles = (c.n_pos + TJ - 1) / TJ;
+    int n_groups = 1;
+    const int tpb = pick_tiles_per_block(n_tiles, c.n_streams, &n_groups);
+    auto k = fir_tiled_kernel<T, M, NF, R, NT>;
+    static size_t configured[64] = {0};  // per instantiation, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)(n_groups + 1) * c.n_streams;
+    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, tpb, n_groups, cp, xlen);
+    count_launch();
+}
+
+template <int M, int NF, int R>
+void launch_fir_f32x2(const FirCall& c, cudaStream_t s) {
+    constexpr int NT = 128;
+    constexpr int MAXE = M * (R - 1) - ((M * (R - 1)) & 1);
+    constexpr int NCH = (MAXE + 4 + 3) / 4;
+    constexpr int NS = ((M & 1) && R > 1) ? 2 : 1;
+    constexpr int TJ = NT * R;
+    const int cp = ((c.taps + 3 + (NS - 1) + 3) / 4) * 4;
+    const int xlen = M * R * (NT - 1) + (cp / 4 + NCH + 1) * 4;
+    const size_t smem = 16 + (size_t)(NF * NS * cp + 2 * xlen) * sizeof(float);
+    const int n_tiles = (c.n_pos + TJ - 1) / TJ;
+    int n_groups = 1;
+    const int tpb = pick_tiles_per_block(n_tiles, c.n_streams, &n_groups);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto k = fir_f32x2_kernel<M, NF, R, NT>;
+    static size_t configured[64] = {0};
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)(n_groups + 1) * c.n_streams;
+    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, tpb, n_groups, cp, xlen);
+    count_launch();
+}
+
+}  // namespace
+
+// tiles per block: long runs amortise the per-block filter load and hide the TMA prefetch under the FMAs,
+// but keep >= ~3 blocks per resident slot in flight for balance
+int pick_tiles_per_block(int n_tiles, int n_streams, int* n_groups) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static int sm_count[64] = {0};
+    if (!sm_count[dev & 63]) cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count[dev & 63] > 0 ? sm_count[dev & 63] : 148;
+    const int64_t total_tiles = (int64_t)n_tiles * n_streams;
+    int tpb = (int)(total_tiles / ((int64_t)sms * 4 * 3));
+    tpb = tpb < 1 ? 1 : (tpb > 16 ? 16 : tpb);
+    if (tpb > n_tiles) tpb = n_tiles;
+    *n_groups = (n_tiles + tpb - 1) / tpb;
+    return tpb;
+}
+
+
+bool tensor_fir_enabled() { return g_fir_mma; }
+
+// float32 decimators on packed FMAs
+#define GAR_FIR_X2_VARIANTS(X)          \
+    X(3, 1, 12, "fir_f32x2_s3_r12")     \
+    X(2, 1, 10, "fir_f32x2_s2_r10")     \
+    X(4, 1, 7, "fir_f32x2_s4_r7")
+
+#define GAR_FIR_VARIANTS(X)                 \
+    X(float, DT_F32, 3, 1, 12, "fir_f32_s3_r12")  \
+    X(float, DT_F32, 2, 1, 10, "fir_f32_s2_r10")  \
+    X(float, DT_F32, 4, 1, 7, "fir_f32_s4_r7")    \
+    X(float, DT_F32, 1, 2, 12, "fir_f32_up2_r12") \
+    X(float, DT_F32, 1, 3, 4, "fir_f32_up3_r4")   \
+    X(float, DT_F32, 1, 4, 4, "fir_f32_up4_r4")   \
+    X(double, DT_F64, 2, 1, 7, "fir_f64_s2_r7")   \
+    X(double, DT_F64, 3, 1, 6, "fir_f64_s3_r6")   \
+    X(double, DT_F64, 4, 1, 5, "fir_f64_s4_r5")   \
+    X(double, DT_F64, 1, 2, 6, "fir_f64_up2_r6")  \
+    X(double, DT_F64, 1, 3, 2, "fir_f64_up3_r2")  \
+    X(double, DT_F64, 1, 4, 2, "fir_f64_up4_r2")
+
+void set_tensor_fir(bool on) { g_fir_mma = on; }
+
+const char* fir_variant_name(int dtype, int stride, int nf, int taps, int64_t n_pos, int n_streams) {
+    (void)taps; (void)n_pos; (void)n_streams;
+#define X(M, NF, R, NAME) \
+    if (dtype == DT_F32 && stride == M && nf == NF) return NAME;
+    GAR_FIR_X2_VARIANTS(X)
+#undef X
+#define X(T, DT, M, NF, R, NAME) \
+    if (dtype == DT && stride == M && nf == NF) return NAME;
+    GAR_FIR_VARIANTS(X)
+#undef X
+    return dtype == DT_F32 ? "fir_f32_generic" : "fir_f64_generic";
+}
+
+const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s) {
+    if (c.n_streams <= 0) return "none";
+    if (c.n_pos <= 0) {
+        launch_carry(c.hist, c.hist_stride, c.hist_len, c.in, c.in_stride, c.n_in, c.hist_out, c.hist_out_stride, c.drop,
+                     c.new_hist_len, c.n_streams, dtype, s);
+        return "carry";
+    }
+    if (dtype == DT_F64)
+        if (const char* nm = launch_fir_mma(c, s)) return nm;
+#define X(M, NF, R, NAME)                                       \
+    if (dtype == DT_F32 && c.stride == M && c.nf == NF) {       \
+        launch_fir_f32x2<M, NF, R>(c, s);                       \
+        return NAME;                                            \
+    }
+    GAR_FIR_X2_VARIANTS(X)
+#undef X
+#define X(T, DT, M, NF, R, NAME)                           \
+    if (dtype == DT && c.stride == M && c.nf == NF) {      \
+        launch_fir_tiled<T, M, NF, R>(c, s);               \
+        return NAME;                                       \
+    }
+    GAR_FIR_VARIANTS(X)
+#undef X
+    const int64_t n_el = (int64_t)c.n_pos * c.nf;
+    const int n_tiles = (int)((n_el + 255) / 256);
+    const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
+    count_launch();
+    if (dtype == DT_F32) {
+        fir_generic_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(c, n_tiles);
+        return "fir_f32_generic";
+    }
+    fir_generic_kernel<double><<<(unsigned)blocks, 256, 0, s>>>(c, n_tiles);
+    return "fir_f64_generic";
+}
+
+
+}  // namespace gar

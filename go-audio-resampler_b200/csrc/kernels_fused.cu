@@ -1,0 +1,886 @@
+// kernels_fused.cu — x2 up-sampler + polyphase stage of one engine.Resampler in one launch (resampler.go:97-121,142-175):
+// K4 (generic, one thread per output), K4r / K3r (rational ratios, lanes = periods, barrier-free item pipeline), the
+// coefficient-tile builder, and launch_fused_up2_poly.
+#include "device_common.cuh"
+
+namespace gar {
+namespace {
+
+// Carried tails of a fused x2 -> polyphase call (one block per row): the x2 stage's new tail is a plain copy,
+// the polyphase stage's new tail needs the last few intermediate samples, recomputed here with the same
+// strictly sequential chain as the tile core (bit-identical in float64).
+template <typename T>
+__device__ __forceinline__ void fused_carry_tails_rt(const FusedCall& c, const int64_t row, T* scratch, const int scratch_cap) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const T* __restrict__ hist_u = static_cast<const T*>(c.hist_u) + row * c.hist_u_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    const T* __restrict__ hist_p = static_cast<const T*>(c.hist_p) + row * c.hist_p_stride;
+    const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
+    carry_row(hist_u, c.hu, in, c.n_in, static_cast<T*>(c.hist_u_out) + row * c.hist_u_out_stride, c.drop_u, c.new_hu);
+    T* hp_out = static_cast<T*>(c.hist_p_out) + row * c.hist_p_out_stride;
+    // intermediate samples [j_lo, j_hi) are needed: stage their input span and the x2 bank in shared memory first, so the
+    // strictly sequential chains below run on shared-memory latency instead of one global round trip per tap (this block
+    // is on the critical path of every streaming-size call)
+    const int j_lo = max(0, c.drop_p - c.hp), j_hi = c.drop_p + c.new_hp - c.hp;
+    const int p_lo = j_lo >> 1;
+    const int span = j_hi > j_lo ? (((j_hi - 1) >> 1) - p_lo) + c.t1 : 0;
+    const bool staged = span > 0 && span + 2 * c.t1 <= scratch_cap;
+    T* xb = scratch;
+    T* bk = scratch + span;
+    if (staged) {
+        for (int i = tid; i < span; i += NT) xb[i] = vload(hist_u, c.hu, in, c.n_in, p_lo + i);
+        for (int i = tid; i < 2 * c.t1; i += NT) bk[i] = bank_u[i];
+        __syncthreads();
+    }
+    for (int i = tid; i < c.new_hp; i += NT) {
+        const int idx = c.drop_p + i;  // index into vp = hist_p ++ mid
+        T v;
+        if (idx < c.hp) {
+            v = hist_p[idx];
+        } else {
+            const int j = idx - c.hp;
+            if (staged) {
+                const T* __restrict__ xx = xb + ((j >> 1) - p_lo);
+                const T* __restrict__ cc = bk + (j & 1) * c.t1;
+                if (sizeof(T) == 8) {  // same order as the tile core: bit-identical
+                    T acc = 0;
+                    for (int t = 0; t < c.t1; ++t) acc = fma(xx[t], cc[t], acc);
+                    v = acc;
+                } else {
+                    double acc = 0;
+                    for (int t = 0; t < c.t1; ++t) acc = fma((double)xx[t], (double)cc[t], acc);
+                    v = (T)acc;
+                }
+            } else {
+                const T* __restrict__ bkg = bank_u + (j & 1) * c.t1;
+                if (sizeof(T) == 8) {
+                    T acc = 0;
+                    for (int t = 0; t < c.t1; ++t) acc = fma(vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), bkg[t], acc);
+                    v = acc;
+                } else {
+                    double acc = 0;
+                    for (int t = 0; t < c.t1; ++t)
+                        acc = fma((double)vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), (double)bkg[t], acc);
+                    v = (T)acc;
+                }
+            }
+        }
+        hp_out[i] = v;
+    }
+}
+
+// =============================================================================================
+// K4 — fused x2 up-sampler + polyphase stage. One block = one tile of MT = 2*NT*R intermediate samples:
+//   1. stage the input window (TMA bulk copy when regular) and the x2 bank in shared memory,
+//   2. run the register-tiled FIR core and write the tile's intermediate samples to SHARED memory,
+//   3. produce every polyphase output whose T2-sample window lies in the tile (tiles overlap by T2-1
+//      intermediate samples, recomputed rather than exchanged: 4 % for T2 = 64).
+// Block 0 of a row also sees the polyphase stage's carried tail in front of its tile. The last block of
+// every row writes both carried tails (the polyphase tail needs the last few intermediate samples, which
+// it recomputes directly).
+// =============================================================================================
+template <typename T, bool INTERP, int R, int NT>
+__global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, const int n_tiles, const int ms,
+                                                            const int cp, const int xlen, const int hpf,
+                                                            const int bank_pitch /*0: read banks through L1*/) {
+    using V = typename VecOf<T>::type;
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int NF = 2;
+    constexpr int TP = NT * R;      // positions per tile
+    constexpr int MT = TP * NF;     // intermediate samples per tile
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    T* cs = reinterpret_cast<T*>(smem_raw + 16);  // [2][cp]
+    T* xs = cs + NF * cp;                         // [xlen]
+    T* vp = xs + xlen;                            // [hpf + MT] polyphase input: (tail |) intermediate tile
+    T* pbank = vp + hpf + MT;                     // [L][bank_pitch] a-bank copy (optional)
+
+    const int tile = blockIdx.x % (n_tiles + 1);
+    const int64_t row = blockIdx.x / (n_tiles + 1);
+    const int tid = threadIdx.x;
+    const T* __restrict__ hist_u = static_cast<const T*>(c.hist_u) + row * c.hist_u_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    const T* __restrict__ hist_p = static_cast<const T*>(c.hist_p) + row * c.hist_p_stride;
+    const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
+    const int n_mid = c.np * NF;
+
+    if (tile == n_tiles) {  // ---- carried tails ----
+        fused_carry_tails_rt<T>(c, row, xs, xlen + hpf + MT);
+        return;
+    }
+
+    // ---- 1. stage the x2 stage's input window ----
+    const int p0 = (tile * ms) >> 1;  // first position of the tile (ms is even)
+    const int tp = min(TP, c.np - p0);
+    const int need = tp > 0 ? tp - 1 + c.t1 : 0;
+    int a = 0;
+    bool bulk = false;
+    {
+        const int gi = p0 - c.hu;
+        if (gi >= 0 && need > 0) {
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(in + gi);
+            const int mis = (int)((addr & 15u) / sizeof(T));
+            const int words = ((need + mis + VEC - 1) / VEC) * VEC;
+            if (gi - mis >= 0 && gi - mis + words <= c.n_in && words <= xlen) {
+                bulk = true;
+                a = mis;
+            }
+        }
+    }
+    if (bulk) {
+        const int gi = p0 - c.hu - a;
+        const int words = ((need + a + VEC - 1) / VEC) * VEC;
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)(words * sizeof(T)));
+            bulk_g2s(xs, in + gi, (uint32_t)(words * sizeof(T)), bar);
+        }
+        for (int i = words + tid; i < xlen; i += NT) xs[i] = T(0);
+    } else {
+        for (int i = tid; i < xlen; i += NT) xs[i] = i < need ? vload(hist_u, c.hu, in, c.n_in, p0 + i) : T(0);
+    }
+    for (int i = tid; i < NF * cp; i += NT) {
+        const int p = i / cp, k = i % cp - a;
+        cs[i] = (k >= 0 && k < c.t1) ? bank_u[p * c.t1 + k] : T(0);
+    }
+    // polyphase side: carried tail right-aligned in front of tile 0 (the tile itself starts 16-byte aligned),
+    // optional a-bank copy (odd pitch: conflict-free rows)
+    const int front = tile == 0 ? hpf : 0;
+    if (tile == 0)
+        for (int i = tid; i < c.hp; i += NT) vp[hpf - c.hp + i] = hist_p[i];
+    if (bank_pitch > 0) {
+        const T* __restrict__ ba = static_cast<const T*>(c.bank_a);
+#pragma unroll 8
+        for (int i = tid; i < c.L * c.t2; i += NT) pbank[(i / c.t2) * bank_pitch + (i % c.t2)] = ba[i];  // 8 loads in flight
+    }
+    __syncthreads();
+    if (bulk) {
+        while (!mbar_try_wait(bar, 0)) {
+        }
+    }
+
+    // ---- 2. x2 FIR core -> intermediate tile in shared memory ----
+    {
+        T res[R][NF];
+        fir_tile_accumulate<T, 1, NF, R>(xs + R * tid, cs, cp, c.t1, a, res);
+        T* mp = vp + front + (size_t)R * NF * tid;
+#pragma unroll
+        for (int q = 0; q < R * NF / VEC; ++q) reinterpret_cast<V*>(mp)[q] = vec_pack(&res[0][0] + q * VEC);
+    }
+    __syncthreads();
+
+    // ---- 3. polyphase outputs whose window starts in [lo, hi) of vp = hist_p ++ mid ----
+    const int64_t Lq = (int64_t)c.L << 16;
+    const int64_t lo = tile == 0 ? 0 : (int64_t)c.hp + (int64_t)tile * ms;
+    const int64_t hi = (int64_t)c.hp + (int64_t)(tile + 1) * ms;
+    auto first_n = [&](const int64_t d) -> int64_t {  // smallest n with div_n >= d
+        const int64_t need_at = d * Lq - c.at0;
+        return need_at <= 0 ? 0 : (need_at + c.step - 1) / c.step;
+    };
+    const int64_t n_lo = min((int64_t)c.n_out, first_n(lo));
+    const int64_t n_hi = tile == n_tiles - 1 ? (int64_t)c.n_out : min((int64_t)c.n_out, first_n(hi));
+    // virtual vp index d lives at shared-memory element d - vbase
+    const int64_t vbase = tile == 0 ? (int64_t)c.hp - hpf : lo;
+    T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+    const T* __restrict__ ga = static_cast<const T*>(c.bank_a);
+    const T* __restrict__ gb = static_cast<const T*>(c.bank_b);
+    const T* __restrict__ gc = static_cast<const T*>(c.bank_c);
+    const T* __restrict__ gd = static_cast<const T*>(c.bank_d);
+    (void)n_mid;
+    for (int64_t n = n_lo + tid; n < n_hi; n += NT) {
+        const int64_t at = c.at0 + n * c.step;
+        const int64_t full = at >> 16;
+        const int64_t div = full / c.L;
+        const int phase = (int)(full - div * c.L);
+        const T* h = vp + (div - vbase);
+        double acc0 = 0, acc1 = 0;
+        if (INTERP) {
+            const T x = (T)(int)(at & 0xFFFF) * (T)(1.0 / 65536.0);
+            const int64_t co = (int64_t)phase * c.t2;
+            for (int k = 0; k < c.t2; ++k) {
+                const T coef = fma(x, fma(x, fma(x, gd[co + k], gc[co + k]), gb[co + k]), ga[co + k]);
+                if ((k & 1) && sizeof(T) == 4) acc1 = fma((double)h[k], (double)coef, acc1);
+                else acc0 = fma((double)h[k], (double)coef, acc0);
+            }
+        } else {
+            const T* __restrict__ ca = bank_pitch > 0 ? pbank + phase * bank_pitch : ga + (int64_t)phase * c.t2;
+            for (int k = 0; k < c.t2; ++k) {
+                if ((k & 1) && sizeof(T) == 4) acc1 = fma((double)h[k], (double)ca[k], acc1);
+                else acc0 = fma((double)h[k], (double)ca[k], acc0);
+            }
+        }
+        out[n] = (T)(acc0 + acc1);
+    }
+}
+
+// =============================================================================================
+// K4r — fused x2 up-sampler + polyphase stage for RATIONAL ratios (step and phase accumulator have no
+// fractional bits: 44.1k<->48k, 8k->12k, ... every ratio whose L/M is exact), register-tiled.
+//
+// The polyphase stage is periodic: L outputs consume exactly Mi = step>>16 intermediate samples, and output
+// n + L uses the same phase filter as output n on a window Mi samples later. A tile is P such periods of one
+// row (P = 16 or 32). Work on a tile has two kinds of items:
+//   x2 chunk   32 thread tasks of the register-tiled x2 core (fir_tile_accumulate, FMA-bound): R positions each,
+//              input window staged by a TMA bulk copy, results written to the tile's intermediate buffer in
+//              SHARED memory (period j at pitch Mi + PAD; PAD = 1 when Mi is even keeps the period lanes on
+//              different banks);
+//   poly task  a warp owns RN adjacent outputs of the period pattern and its LANES are the periods, so all
+//              lanes use the same phase filters -> every coefficient read is a shared-memory BROADCAST, and a
+//              lane slides a register window over its period: per tap, 1 sample LDS + RN broadcast coefficient
+//              LDS feed RN FMAs (the stand-alone kernel needs 2 loads per FMA). Output i of a thread sits at a
+//              STATIC window slot i*S (S = ceil(Mi/L)); the true offset lags the slot by e_i in [0, D] samples,
+//              absorbed by reading its filter row (stored with D zero taps on both sides) e_i taps early.
+//              Sums run strictly in tap order (zero taps are exact no-ops): float64 results are bit-identical
+//              to the stand-alone kernels.
+// The intermediate buffer is double-buffered and a block is persistent over consecutive tiles of a row: in one
+// iteration its warps pull items from ONE queue holding the poly tasks of tile t-1 and the x2 chunks of tile t,
+// so the shared-memory-bound and the FMA-bound work overlap, quantisation of either kind is absorbed by the
+// other, and there is one barrier per tile. The extra block of every row writes both carried tails.
+// =============================================================================================
+struct RatGeom {
+    int32_t Mi, P, D, tp, gpitch, vlen, G;  // see launch_fused_rat_t
+    int32_t cp, xlen, xbufs, nv;            // x2 filter (padded), input window capacity, window / intermediate buffers
+    int32_t n_tiles, tiles_per_block, n_groups;
+    const void* cg_src;  // this launch's coefficient tile in global memory ([G][gpitch] T, then goff[G] ints)
+    uint32_t cg_bytes;   // its size, a multiple of 16
+};
+
+// Builds the coefficient tile of one start phase F0 (RatCache): for output group gi = outputs [gi*RN, gi*RN + RN) of the
+// period, tile[gi][tap][i] = a-bank[phase_i][tap - e_i] (zero outside the filter), then goff[gi] = window offset.
+// Output i sits at window slot i*S; its true offset lags the slot by e_i = o_i - i*S + Dg taps.
+template <typename T, int S, int RN>
+__global__ void __launch_bounds__(256) rat_build_tile_kernel(const T* __restrict__ bank_a, const int t2, const int L,
+                                                             const int Mi, const int F0, const int G, const int tp,
+                                                             const int gpitch, T* __restrict__ tile) {
+    extern __shared__ int gtab_s[];  // [G*RN] phase << 8 | lag
+    int* goff = reinterpret_cast<int*>(tile + (size_t)G * gpitch);
+    const int qM = Mi / L, rM = Mi - qM * L;
+    for (int gi = threadIdx.x; gi < G; gi += blockDim.x) {
+        const unsigned rf = (unsigned)(F0 + gi * RN * Mi);
+        const int div0 = (int)(rf / (unsigned)L);
+        int ph = (int)rf - div0 * L, dv = 0, Dg = 0;
+        int o[RN], php[RN];
+#pragma unroll
+        for (int i = 0; i < RN; ++i) {
+            o[i] = dv;
+            php[i] = ph;
+            Dg = max(Dg, i * S - dv);
+            ph += rM;
+            dv += qM;
+            if (ph >= L) {
+                ph -= L;
+                ++dv;
+            }
+        }
+        goff[gi] = div0 - Dg;  // >= -D
+#pragma unroll
+        for (int i = 0; i < RN; ++i) gtab_s[gi * RN + i] = (php[i] << 8) | (o[i] - i * S + Dg);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < G * gpitch; idx += blockDim.x) {
+        const int gi = idx / gpitch, rem = idx - gi * gpitch;
+        T v = T(0);
+        if (rem < tp * RN) {
+            const int kk = rem / RN, i = rem - kk * RN;
+            const int pe = gtab_s[gi * RN + i];
+            const int k = kk - (pe & 255);
+            if (k >= 0 && k < t2) v = bank_a[(pe >> 8) * t2 + k];
+        }
+        tile[idx] = v;
+    }
+}
+
+constexpr int RAT_MAXT = 16;                 // tiles per block (pick_tiles_per_block caps at 16)
+constexpr int RAT_CTL_INTS = 8 + 11 * (RAT_MAXT + 4);
+constexpr int RAT_CTL_BYTES = ((RAT_CTL_INTS * 4 + 15) / 16) * 16;
+
+template <typename T, int S, int RN, int PAD, bool FUSED>
+__global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c, const RatGeom g) {
+    using V = typename VecOf<T>::type;
+    constexpr int VEC = VecOf<T>::N;
+    static_assert(RN % VEC == 0, "a coefficient vector load covers whole outputs");
+    constexpr int NF = 2;
+    constexpr int R = sizeof(T) == 8 ? 6 : 12;  // x2 core: positions per thread task
+    constexpr int WN = (RN - 1) * S + 1;        // register window of the polyphase phase
+    const int NT = blockDim.x;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // [4] one mbarrier per input window buffer, [4]: the tile
+    int* ctl = reinterpret_cast<int*>(smem_raw + 48);
+    int* qhead = ctl;                                        // work-queue head
+    int* in_done = ctl + 8;                                  // [t] input item of local tile t finished
+    int* up_done = in_done + RAT_MAXT + 4;                   // [t] x2 chunks of tile t finished
+    int* po_done = up_done + RAT_MAXT + 4;                   // [t] poly tasks of tile t finished
+    int* gstart = po_done + RAT_MAXT + 4;                    // [k] first queue item of group k
+    int* nchunk = gstart + RAT_MAXT + 4;                     // [t] x2 chunks of tile t
+    int* tflags = nchunk + RAT_MAXT + 4;                     // [t] bit0: bulk input, bit1: mbarrier parity
+    int* tg_src = tflags + RAT_MAXT + 4;                     // [t] tile geometry: i_lo - hu (index into `in`)
+    int* tg_npos = tg_src + RAT_MAXT + 4;                    // [t] x2 positions
+    int* tg_wend = tg_npos + RAT_MAXT + 4;                   // [t] samples of vp the tile covers
+    int* tg_words = tg_wend + RAT_MAXT + 4;                  // [t] bulk-copy length in samples
+    int* tg_woff = tg_words + RAT_MAXT + 4;                  // [t] w of the first sample of the first position
+    T* cs = reinterpret_cast<T*>(smem_raw + 48 + RAT_CTL_BYTES);  // [2][cp]       x2 bank
+    T* xs0 = cs + NF * g.cp;                                      // [xbufs][xlen] x2 input windows
+    T* vs0 = xs0 + (FUSED ? g.xbufs * g.xlen : 0);                // [nv][vlen]    intermediate samples of a tile
+    T* cg = vs0 + g.nv * g.vlen;  // [G][gpitch] polyphase coefficients, one tile [tap][RN outputs] per output group
+    int* goff = reinterpret_cast<int*>(cg + (size_t)g.G * g.gpitch);  // [G] window offset of the group (part of the tile)
+
+    const int group = blockIdx.x % (g.n_groups + 1);
+    const int64_t row = blockIdx.x / (g.n_groups + 1);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const T* __restrict__ hist_u = static_cast<const T*>(c.hist_u) + row * c.hist_u_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    const T* __restrict__ hist_p = static_cast<const T*>(c.hist_p) + row * c.hist_p_stride;
+    T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+    if (group == g.n_groups) {  // carried tails
+        if (FUSED) fused_carry_tails_rt<T>(c, row, xs0, g.xbufs * g.xlen + g.nv * g.vlen);
+        else carry_row(hist_p, c.hp, in, c.n_in, static_cast<T*>(c.hist_p_out) + row * c.hist_p_out_stride, c.drop_p, c.new_hp);
+        return;
+    }
+
+    const int Mi = g.Mi, P = g.P, D = g.D, L = c.L;
+    const int FM = D + 1;  // front margin of the intermediate buffer (window starts up to D + PAD before w = 0)
+    // polyphase input vp = carried tail ++ (FUSED: the x2 stage's 2*np outputs, made here; else the stage's input `in`)
+    const int64_t total_vp = (int64_t)c.hp + (FUSED ? 2 * (int64_t)c.np : (int64_t)c.n_in);
+    const int t_first = group * g.tiles_per_block;
+    const int nt = min(g.tiles_per_block, g.n_tiles - t_first);
+    const int gpw = 32 / P, jl = lane & (P - 1), gsub = lane / P;
+    const int n_wt = (g.G + gpw - 1) / gpw;
+
+    // geometry of tile t: x2 positions [i_lo, i_lo + n_pos) feed vp[m0, m0 + wend)
+    auto tile_geom = [&](const int t, int64_t& m0, int& wend, int64_t& i_lo, int& n_pos, bool& bulk, int& words) {
+        m0 = (int64_t)t * P * Mi;
+        wend = (int)min((int64_t)P * Mi + c.t2 - 1, total_vp - m0);
+        i_lo = 0;
+        n_pos = 0;
+        bulk = false;
+        words = 0;
+        if (!FUSED) return;
+        const int64_t j_lo = max((int64_t)0, m0 - c.hp), j_hi = m0 + wend - c.hp;
+        i_lo = j_lo >> 1;
+        const int64_t i_hi = (j_hi + 1) >> 1;
+        n_pos = i_hi > i_lo ? (int)(i_hi - i_lo) : 0;
+        int64_t gi = i_lo - c.hu;
+        if (gi >= 0 && n_pos > 0) {
+            const int mis = (int)((reinterpret_cast<uintptr_t>(in + gi) & 15u) / sizeof(T));
+            if (gi - mis >= 0) {  // start `mis` positions early: 16-byte aligned source, results below w = 0 are dropped
+                gi -= mis;
+                const int w = ((n_pos + mis - 1 + c.t1 + VEC - 1) / VEC) * VEC;
+                if (gi + w <= c.n_in && w <= g.xlen) {
+                    bulk = true;
+                    words = w;
+                    i_lo -= mis;
+                    n_pos += mis;
+                }
+            }
+        }
+    };
+
+    // ---- block set-up: control words, queue layout, zeroed buffers, banks ----
+    const int NX = FUSED ? g.xbufs : g.nv;  // input prefetch depth (poly-only: the input lands in the tile buffers)
+    if (tid == 0) {
+        for (int b = 0; b < 5; ++b) mbar_init(bar + b, 1);
+        *qhead = 0;
+        // this launch's coefficient tile (built once per start phase, RatCache): one bulk copy, overlapped with the set-up
+        mbar_expect_tx(bar + 4, g.cg_bytes);
+        bulk_g2s(cg, g.cg_src, g.cg_bytes, bar + 4);
+    }
+    if (tid < nt) {  // geometry of the block's tiles, one thread each
+        const int k = tid;
+        int64_t m0, i_lo;
+        int wend, n_pos, words;
+        bool bulk;
+        tile_geom(t_first + k, m0, wend, i_lo, n_pos, bulk, words);
+        nchunk[k] = ((n_pos + R - 1) / R + 31) / 32;
+        tflags[k] = bulk ? 1 : 0;
+        tg_src[k] = (int)(i_lo - c.hu);
+        tg_npos[k] = n_pos;
+        tg_wend[k] = wend;
+        tg_words[k] = words;
+        tg_woff[k] = (int)((int64_t)c.hp + 2 * i_lo - m0);
+        if (!FUSED) {
+            // poly-only: samples w in [w0, wend) come from `in`. With an unpadded period pitch they are one contiguous
+            // run: a TMA bulk copy moves the 16-byte aligned middle (the tile's front margin absorbs the parity between
+            // source and destination), single elements at either end are copied by hand.
+            int w0 = (int)max((int64_t)0, (int64_t)c.hp - m0);
+            int fm = FM, nb = 0;
+            int64_t e0 = m0 + w0 - c.hp;
+            if (PAD == 0 && sizeof(T) == 8 && w0 < wend) {
+                if (reinterpret_cast<uintptr_t>(in + e0) & 15u) {
+                    ++w0;
+                    ++e0;
+                }
+                fm = FM + ((FM + w0) & 1);
+                nb = (wend - w0) & ~1;
+                if (nb < 0) nb = 0;
+            }
+            tflags[k] = nb > 0 ? 1 : 0;
+            tg_src[k] = (int)e0;  // first bulk element of `in`
+            tg_words[k] = nb;     // bulk elements
+            tg_woff[k] = w0;      // w of the first bulk element
+            tg_npos[k] = fm;      // front margin of this tile's buffer
+        }
+        in_done[k] = 0;
+        up_done[k] = 0;
+        po_done[k] = 0;
+    }
+    for (int i = tid; i < (FUSED ? g.xbufs * g.xlen : 0) + g.nv * g.vlen; i += NT) xs0[i] = T(0);  // xs, vs adjacent
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (FUSED) {
+        const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
+        for (int i = tid; i < NF * g.cp; i += NT) {
+            const int p = i / g.cp, k = i - p * g.cp;
+            cs[i] = k < c.t1 ? bank_u[p * c.t1 + k] : T(0);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // mbarrier parities and the queue: group 0 = {I(0..NX-1), U(0)*}; group k = {I(k+NX-1), U(k)*, P(k-1)*};
+        // group nt = {P(nt-1)*}
+        unsigned parbits = 0u;  // current mbarrier parity of every window buffer
+        int at = 0;
+        for (int k = 0; k <= nt; ++k) {
+            gstart[k] = at;
+            if (k < nt) {
+                const int xb = k % NX;
+                if (tflags[k] & 1) {
+                    tflags[k] |= (int)(((parbits >> xb) & 1u) << 1);
+                    parbits ^= 1u << xb;
+                }
+            }
+            if (k == 0) at += min(NX, nt) + nchunk[0];
+            else if (k < nt) at += (k + NX - 1 < nt ? 1 : 0) + nchunk[k] + n_wt;
+            else at += n_wt;
+        }
+        gstart[nt + 1] = at;
+    }
+    while (!mbar_try_wait(bar + 4, 0)) __nanosleep(20);  // the coefficient tile has landed
+    __syncthreads();  // the only block-wide barrier: from here on warps synchronise through the counters
+
+    auto wait_ge = [&](int* cnt, const int target) {  // whole warp, all lanes poll (a broadcast read), then reconverge
+        while (*reinterpret_cast<volatile int*>(cnt) < target) __nanosleep(200);
+        __threadfence_block();
+        __syncwarp();
+    };
+    auto signal = [&](int* cnt) {  // whole warp: everything this warp wrote is visible before the count moves
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicAdd(cnt, 1);
+        __syncwarp();
+    };
+
+    int gk = 0;  // group of the last item this warp took (items come in increasing order)
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(qhead, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= gstart[nt + 1]) break;
+        while (item >= gstart[gk + 1]) ++gk;
+        int sub = item - gstart[gk];
+        // decode: kind 0 = input item I(k), 1 = x2 chunk U(k, sub), 2 = poly task P(k, sub)
+        int kind, k;
+        if (gk == 0) {
+            const int ni = min(NX, nt);
+            if (sub < ni) { kind = 0; k = sub; }
+            else { kind = 1; k = 0; sub -= ni; }
+        } else if (gk < nt) {
+            const int ni = gk + NX - 1 < nt ? 1 : 0;
+            if (sub < ni) { kind = 0; k = gk + NX - 1; }
+            else if (sub - ni < nchunk[gk]) { kind = 1; k = gk; sub -= ni; }
+            else { kind = 2; k = gk - 1; sub -= ni + nchunk[gk]; }
+        } else {
+            kind = 2;
+            k = nt - 1;
+        }
+        const int t = t_first + k;
+        const int xb = k % NX;
+
+        if (kind == 2) {
+            // ---- poly task: RN adjacent outputs of the period pattern, lanes = periods ----
+            wait_ge(in_done + k, 1);
+            wait_ge(up_done + k, nchunk[k]);
+            if (!FUSED && (tflags[k] & 1)) {  // poly-only: the bulk part of the tile has landed
+                const uint32_t par = (uint32_t)(tflags[k] >> 1) & 1u;
+                while (!mbar_try_wait(bar + xb, par)) __nanosleep(20);
+                __syncwarp();
+            }
+            const int FMk = FUSED ? FM : tg_npos[k];
+            const T* __restrict__ vr = vs0 + (k % g.nv) * g.vlen;
+            const int gi = sub * gpw + gsub;
+            if (gi < g.G) {
+                const int64_t n_lo = (int64_t)t * P * L;  // first output of the tile; its full_n is F0 past the tile origin
+                const int64_t n_hi = min((int64_t)c.n_out, n_lo + (int64_t)P * L);
+                const int iota0 = gi * RN;
+                // window slot x of lane jl is sample w = jl*Mi + off + x, stored at FM + w + PAD*floor(w/Mi)
+                const int off = goff[gi];
+                const int c0 = off < 0 ? -1 : off / Mi;
+                const int xc0 = (c0 + 1) * Mi - off, xc1 = xc0 + Mi;  // slots at which the walk enters the next period
+                const T* __restrict__ sp = vr + FMk + jl * (Mi + PAD) + off + (PAD ? c0 : 0);
+                const T* __restrict__ cp0 = cg + (size_t)gi * g.gpitch;  // [tap][RN], 16-byte aligned
+                T W[WN], acc[RN];
+#pragma unroll
+                for (int x = 0; x < WN; ++x) W[x] = sp[x + (PAD ? (x >= xc0) + (x >= xc1) : 0)];
+#pragma unroll
+                for (int i = 0; i < RN; ++i) acc[i] = T(0);
+                auto tap = [&](const int u, const int kk) {  // u = kk % WN (compile-time in the unrolled bodies)
+                    T cf[RN];
+#pragma unroll
+                    for (int q = 0; q < RN / VEC; ++q)
+                        vec_unpack(*reinterpret_cast<const V*>(cp0 + kk * RN + q * VEC), cf + q * VEC);
+#pragma unroll
+                    for (int i = 0; i < RN; ++i) acc[i] = fma(W[(u + i * S) % WN], cf[i], acc[i]);
+                    const int x = kk + WN;
+                    W[u] = sp[x + (PAD ? (x >= xc0) + (x >= xc1) : 0)];
+                };
+                int it0 = 0;
+                for (; it0 + WN <= g.tp; it0 += WN) {  // branch-free bodies: the loads of the next taps overlap the FMAs
+#pragma unroll
+                    for (int u = 0; u < WN; ++u) tap(u, it0 + u);
+                }
+#pragma unroll
+                for (int u = 0; u < WN; ++u)
+                    if (it0 + u < g.tp) tap(u, it0 + u);
+                const int64_t nb = n_lo + (int64_t)jl * L + iota0;
+#pragma unroll
+                for (int i = 0; i < RN; ++i)
+                    if (iota0 + i < L && nb + i < n_hi) out[nb + i] = acc[i];
+            }
+            signal(po_done + k);
+            continue;
+        }
+
+        const int n_pos = tg_npos[k], wend = tg_wend[k];
+        const bool bulk = (tflags[k] & 1) != 0;
+        T* __restrict__ xs = xs0 + xb * g.xlen;
+        T* __restrict__ vw = vs0 + (k % g.nv) * g.vlen;
+
+        if (kind == 0) {
+            // ---- input item: stage the x2 input window of tile k (TMA bulk copy when regular) and the part of
+            //      the tile that is the polyphase stage's carried tail ----
+            const int kprev = k - NX;  // last user of this window buffer
+            if (kprev >= 0) wait_ge(up_done + kprev, nchunk[kprev]);
+            // The intermediate buffer is written here only by the poly-only tile load and by the carried-tail copy (first
+            // tile of a row). A fused input item must NOT wait for it otherwise: P(k - nv) sits later in the queue, and the
+            // prefetch of tile k would be held back until those tasks have run.
+            const bool writes_tile = !FUSED || (int64_t)t * P * Mi < (int64_t)c.hp;
+            if (writes_tile && k >= g.nv) wait_ge(po_done + (k - g.nv), n_wt);
+            if (!FUSED) {
+                // poly-only: the tile's samples come straight from the carried tail / the stage input (period j at pitch
+                // Mi + PAD): one TMA bulk copy when the periods are contiguous, else asynchronous element copies
+                const int64_t m0 = (int64_t)t * P * Mi;
+                const int fm = tg_npos[k], nb = tg_words[k], wb = tg_woff[k];
+                if (nb > 0 && lane == 0) {
+                    const uint32_t bytes = (uint32_t)(nb * sizeof(T));
+                    mbar_expect_tx(bar + xb, bytes);
+                    bulk_g2s(vw + fm + wb, in + tg_src[k], bytes, bar + xb);
+                }
+                // elements outside the bulk range: [0, wb) and [wb + nb, wend)
+                const int n_head = nb > 0 ? wb : wend, n_rest = nb > 0 ? wend - (wb + nb) : 0;
+                for (int q = lane; q < n_head + n_rest; q += 32) {
+                    const int w = q < n_head ? q : wb + nb + (q - n_head);
+                    const int64_t d = m0 + w;
+                    T* dst = vw + fm + w + (PAD ? w / Mi : 0);
+                    if (d < c.hp) *dst = hist_p[d];
+                    else cp_async_elem(dst, in + (d - c.hp));
+                }
+                cp_async_wait_all();
+                signal(in_done + k);
+                continue;
+            }
+            if (bulk) {
+                if (lane == 0) {
+                    const uint32_t bytes = (uint32_t)(tg_words[k] * sizeof(T));
+                    mbar_expect_tx(bar + xb, bytes);
+                    bulk_g2s(xs, in + tg_src[k], bytes, bar + xb);
+                }
+            } else {  // edge tile (touches the carried tail or the end of the row): guarded loads
+                const int need = n_pos > 0 ? n_pos - 1 + c.t1 : 0;
+                const int i_lo = tg_src[k] + c.hu;
+                const int tot = c.hu + c.n_in;
+#pragma unroll 8
+                for (int i = lane; i < g.xlen; i += 32) {  // independent predicated loads: eight in flight per lane
+                    const int gidx = i_lo + i;
+                    const bool ok = i < need && gidx >= 0 && gidx < tot;
+                    const T* __restrict__ src = gidx < c.hu ? hist_u + gidx : in + (gidx - c.hu);
+                    xs[i] = ok ? *src : T(0);
+                }
+            }
+            const int64_t m0 = (int64_t)t * P * Mi;
+            for (int64_t d = m0 + lane; d < min((int64_t)c.hp, m0 + wend); d += 32) {
+                const int w = (int)(d - m0);
+                vw[FM + w + (PAD ? w / Mi : 0)] = hist_p[d];
+            }
+            signal(in_done + k);
+            continue;
+        }
+
+        // ---- x2 chunk: 32 thread tasks of the register-tiled FIR core -> intermediate buffer ----
+        wait_ge(in_done + k, 1);
+        if (k >= g.nv) wait_ge(po_done + (k - g.nv), n_wt);
+        if (bulk) {
+            const uint32_t par = (uint32_t)(tflags[k] >> 1) & 1u;
+            while (!mbar_try_wait(bar + xb, par)) __nanosleep(20);
+            __syncwarp();  // lanes leave the poll loop at different times: reconverge before the FIR core
+        }
+        const int n_tasks = (n_pos + R - 1) / R;
+        const int task = sub * 32 + lane;
+        if (task < n_tasks) {
+            const int woff = tg_woff[k];  // w of the first sample of the tile's first position
+            T res[R][NF];
+            fir_tile_accumulate<T, 1, NF, R>(xs + R * task, cs, g.cp, c.t1, 0, res);
+            int w = woff + 2 * R * task;
+            int j = (w + Mi) / Mi - 1, r = w - j * Mi;  // floor division (w >= -Mi)
+            T* __restrict__ vp = vw + FM + w + (PAD ? j : 0);
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+#pragma unroll
+                for (int h = 0; h < NF; ++h) {
+                    if (w >= 0 && w < wend && R * task + q < n_pos) *vp = res[q][h];
+                    ++w;
+                    ++vp;
+                    if (++r == Mi) {
+                        r = 0;
+                        if (PAD) ++vp;
+                    }
+                }
+        }
+        signal(up_done + k);
+    }
+}
+
+}  // namespace
+
+// A/B toggle (GAR_NO_RAT=1 or set_tiled_polyphase(false)): fall back to the one-thread-per-output kernels (no K4r / K3r / K3i)
+static bool g_fused_rat = [] {
+    const char* e = std::getenv("GAR_NO_RAT");
+    return !(e && e[0] && e[0] != '0');
+}();
+void set_tiled_polyphase(bool on) { g_fused_rat = on; }
+
+
+bool tiled_polyphase_enabled() { return g_fused_rat; }
+
+template <typename T, bool INTERP, int R>
+static bool launch_fused_r(const FusedCall& c, cudaStream_t s) {
+    constexpr int NT = 128;
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int NCH = (R - 1 + VEC - 1) / VEC + 1;
+    constexpr int MT = NT * R * 2;
+    const int ms = (MT - (c.t2 - 1)) & ~1;  // tile stride in intermediate samples
+    const int hpf = (c.hp + VEC - 1) / VEC * VEC;
+    if (ms < MT / 2 || c.hp > 1024 || c.np <= 0) return false;
+    const int n_mid = c.np * 2;
+    const int n_tiles = (n_mid + ms - 1) / ms;
+    const int cp = ((c.t1 + VEC - 1 + VEC - 1) / VEC) * VEC;
+    const int xlen = R * (NT - 1) + (cp / VEC + NCH + 1) * VEC;
+    size_t words = (size_t)2 * cp + xlen + hpf + MT;
+    int bank_pitch = 0;
+    // a-bank copy in shared memory: pays only when a block's set-up is amortised over many outputs. A streaming-size call
+    // (a few small tiles) reads its coefficients through L1 instead: ncu showed 55 % of such a launch inside the copy.
+    if (!INTERP && (int64_t)n_tiles * c.n_streams >= 2 * 148) {
+        const int pitch = c.t2 | 1;
+        if (((size_t)c.L * pitch + words) * sizeof(T) + 16 <= 100 * 1024) {
+            bank_pitch = pitch;
+            words += (size_t)c.L * pitch;
+        }
+    }
+    const size_t smem = 16 + words * sizeof(T);
+    auto k = fused_up2_poly_kernel<T, INTERP, R, NT>;
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
+    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, ms, cp, xlen, hpf, bank_pitch);
+    count_launch();
+    return true;
+}
+
+// Tile size by call size: big tiles (R = 6 / 12 positions per thread) keep the FIR core FMA-bound; a streaming-size call
+// has only a handful of them, so its critical path is one tile long — small tiles (R = 2 / 4) spread it over more SMs.
+template <typename T, bool INTERP>
+static bool launch_fused_t(const FusedCall& c, cudaStream_t s) {
+    constexpr int RBIG = sizeof(T) == 8 ? 6 : 12, RSMALL = sizeof(T) == 8 ? 2 : 4;
+    const int64_t big_tiles = ((int64_t)c.np * 2 + 128 * RBIG * 2 - 1) / (128 * RBIG * 2) * c.n_streams;
+    if (big_tiles < 148 && c.t2 - 1 < 128 * RSMALL) return launch_fused_r<T, INTERP, RSMALL>(c, s);
+    return launch_fused_r<T, INTERP, RBIG>(c, s);
+}
+
+// K4r / K3r launcher: picks the geometry; returns false when the call is not a rational-ratio case it covers.
+// FUSED: x2 stage + polyphase stage (FusedCall as documented). !FUSED: polyphase stage alone; the call carries the
+// stage in its polyphase fields and `in`/`n_in` = the stage input.
+template <typename T, int S, int RN, int PAD, bool FUSED>
+static bool launch_rat_t(const FusedCall& c, cudaStream_t s, RatCache* cache) {
+    constexpr int VEC = VecOf<T>::N;
+    constexpr int R = sizeof(T) == 8 ? 6 : 12;
+    constexpr int NCH = (R - 1 + VEC - 1) / VEC + 1;
+    constexpr int WN = (RN - 1) * S + 1;
+    RatGeom g{};
+    g.Mi = (int32_t)(c.step >> 16);
+    const int Mi = g.Mi, L = c.L;
+    g.D = (RN - 1) * S - (RN - 1) * Mi / L;  // worst lag of a static window slot behind the true offset
+    g.tp = c.t2 + g.D;
+    g.G = (L + RN - 1) / RN;
+    g.cp = FUSED ? ((c.t1 + VEC - 1 + VEC - 1) / VEC) * VEC : 0;
+    if (g.tp + 2 * WN > 2 * Mi) return false;  // the window walk may enter at most two further periods
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int64_t div_last = ((c.at0 >> 16) + (int64_t)(c.n_out - 1) * Mi) / L;
+    // one coefficient tile [tp][RN] per output group; with two groups per warp (P = 16) the two broadcast reads of a
+    // tap must fall into different banks: tile pitch = 64 bytes mod 128
+    int gpitch = g.tp * RN;
+    while ((gpitch * (int)sizeof(T)) % 128 != 64) gpitch += VEC;
+    g.gpitch = gpitch;
+    const size_t tile_bytes = (size_t)g.G * gpitch * sizeof(T) + (((size_t)g.G * sizeof(int) + 15) & ~(size_t)15);
+    // configurations in order of preference: two 256-thread blocks per SM, else one 512-thread block
+    struct Opt { int P, nt, xbufs, nv; size_t lim; };
+    Opt opts[4] = {{16, 256, 2, 2, 113 * 1024}, {32, 512, 2, 2, 227 * 1024}, {16, 512, 2, 2, 227 * 1024},
+                   {16, 512, 1, 2, 227 * 1024}};
+    if (!FUSED) {
+        opts[0] = Opt{16, 256, 0, 3, 113 * 1024};
+        opts[1] = Opt{16, 256, 0, 2, 113 * 1024};
+        opts[2] = Opt{16, 512, 0, 3, 227 * 1024};
+        opts[3] = Opt{16, 512, 0, 2, 227 * 1024};
+    }
+    static const int* forced = [] {  // tuning override: GAR_RAT_OPT="P,threads,xbufs,nv"
+        static int v[4];
+        const char* e = std::getenv("GAR_RAT_OPT");
+        return (e && std::sscanf(e, "%d,%d,%d,%d", v, v + 1, v + 2, v + 3) == 4) ? v : (const int*)nullptr;
+    }();
+    if (forced) opts[0] = Opt{forced[0], forced[1], FUSED ? forced[2] : 0, forced[3], 227 * 1024};
+    size_t smem = 0;
+    int nthreads = 0;
+    for (const Opt& o : opts) {
+        int xlen = 0;
+        if (FUSED) {
+            const int n_pos_max = (o.P * Mi + c.t2) / 2 + 2 + VEC;
+            const int tasks = (n_pos_max + R - 1) / R;
+            xlen = R * (tasks - 1) + (g.cp / VEC + NCH + 1) * VEC;
+        }
+        const int vlen = (((g.D + 2) + o.P * (Mi + PAD) + g.tp + 2 * WN + 4) + 1) & ~1;
+        const size_t need = 48 + RAT_CTL_BYTES +
+                            ((size_t)2 * g.cp + (size_t)o.xbufs * xlen + (size_t)o.nv * vlen) * sizeof(T) + tile_bytes;
+        if (need <= o.lim) {
+            g.P = o.P;
+            g.xlen = xlen;
+            g.xbufs = o.xbufs;
+            g.nv = o.nv;
+            g.vlen = vlen;
+            smem = need;
+            nthreads = o.nt;
+            break;
+        }
+    }
+    if (!nthreads) return false;
+    g.n_tiles = (int32_t)(div_last / ((int64_t)g.P * Mi)) + 1;
+    {  // tiles per block, measured on the batched 44.1k<->48k chains: ~12 (fused) / ~6 (poly-only) blocks per resident
+        // slot, at least 3 / 6 tiles (set-up amortisation) unless that would leave resident slots empty; longer blocks
+        // lose more to the drain of their last tile than they save in set-up
+        static int sms = 0;
+        if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int64_t slots = (int64_t)(sms > 0 ? sms : 148) * 2;
+        const int64_t total_tiles = (int64_t)g.n_tiles * c.n_streams;
+        int64_t tpb = total_tiles / (slots * (FUSED ? 12 : 6));
+        tpb = std::max<int64_t>(tpb, FUSED ? 3 : 6);
+        tpb = std::min<int64_t>(tpb, std::max<int64_t>(1, total_tiles / slots));
+        tpb = std::min<int64_t>(std::min<int64_t>(tpb, RAT_MAXT), g.n_tiles);
+        g.tiles_per_block = (int32_t)tpb;
+        g.n_groups = (g.n_tiles + g.tiles_per_block - 1) / g.tiles_per_block;
+    }
+    if (const char* e = std::getenv("GAR_RAT_TPB")) {  // tuning override
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= RAT_MAXT) {
+            g.tiles_per_block = v < g.n_tiles ? v : g.n_tiles;
+            g.n_groups = (g.n_tiles + g.tiles_per_block - 1) / g.tiles_per_block;
+        }
+    }
+    {  // coefficient tile of this call's start phase: built on first use, cached per polyphase stage
+        const int F0 = (int)(c.at0 >> 16);
+        const int key = (int)sizeof(T) * 1000003 + S * 100003 + RN * 10007 + g.tp * 131 + g.gpitch * 7 + L;
+        if (!cache->dev || cache->tile_bytes != tile_bytes || cache->key != key || (int)cache->built.size() != L) {
+            if (cache->dev) {
+                cudaStreamSynchronize(s);
+                cudaFree(cache->dev);
+                cache->dev = nullptr;
+            }
+            if (cudaMalloc(&cache->dev, tile_bytes * (size_t)L) != cudaSuccess) {
+                cache->dev = nullptr;
+                cudaGetLastError();
+                return false;
+            }
+            cache->tile_bytes = tile_bytes;
+            cache->key = key;
+            cache->built.assign((size_t)L, 0);
+        }
+        T* tile = reinterpret_cast<T*>(static_cast<char*>(cache->dev) + (size_t)F0 * tile_bytes);
+        if (!cache->built[(size_t)F0]) {
+            rat_build_tile_kernel<T, S, RN><<<1, 256, (size_t)g.G * RN * sizeof(int), s>>>(
+                static_cast<const T*>(c.bank_a), c.t2, L, Mi, F0, g.G, g.tp, g.gpitch, tile);
+            count_launch();
+            cache->built[(size_t)F0] = 1;
+        }
+        g.cg_src = tile;
+        g.cg_bytes = (uint32_t)tile_bytes;
+    }
+    auto k = fused_up2_rat_kernel<T, S, RN, PAD, FUSED>;
+    static size_t configured[64] = {0};
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)(g.n_groups + 1) * c.n_streams;
+    k<<<(unsigned)blocks, nthreads, smem, s>>>(c, g);
+    count_launch();
+    return true;
+}
+
+template <typename T, bool FUSED>
+static bool launch_rat(const FusedCall& c, cudaStream_t s, RatCache* cache) {
+    if (!cache || !g_fused_rat || c.interp || ((c.step | c.at0) & 0xFFFF) != 0 || c.n_out <= 0) return false;
+    // small calls (streaming chunks) are latency-bound: the simpler kernels have far less per-block set-up
+    if ((int64_t)c.n_out * c.n_streams < 65536) return false;
+    if (FUSED && c.np <= 0) return false;
+    const int64_t Mi = c.step >> 16;
+    if (Mi <= c.L || Mi > 4 * (int64_t)c.L || Mi > 4096 || c.t2 > 512 || c.L > 255) return false;
+    const int S = (int)((Mi + c.L - 1) / c.L);
+    const bool pad = (Mi & 1) == 0;  // even period length: pad the period pitch to keep the lanes on distinct banks
+    switch (S) {
+        case 2: return pad ? launch_rat_t<T, 2, 8, 1, FUSED>(c, s, cache) : launch_rat_t<T, 2, 8, 0, FUSED>(c, s, cache);
+        case 3: return pad ? launch_rat_t<T, 3, 6, 1, FUSED>(c, s, cache) : launch_rat_t<T, 3, 6, 0, FUSED>(c, s, cache);
+        case 4: return pad ? launch_rat_t<T, 4, 6, 1, FUSED>(c, s, cache) : launch_rat_t<T, 4, 6, 0, FUSED>(c, s, cache);
+    }
+    return false;
+}
+
+bool launch_rat_poly_only_f64(const FusedCall& c, cudaStream_t s, RatCache* cache) { return launch_rat<double, false>(c, s, cache); }
+
+const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s, RatCache* cache) {
+    if (c.n_streams <= 0) return "none";
+    if (dtype == DT_F32) {
+        if (c.interp) return launch_fused_t<float, true>(c, s) ? "fused_up2_poly_f32_interp" : nullptr;
+        return launch_fused_t<float, false>(c, s) ? "fused_up2_poly_f32" : nullptr;
+    }
+    // Batches of >= 8 lock-step rows run the x2 stage on the FP64 tensor cores (K1m) and the polyphase stage as its own
+    // launch (K3r / K3i): faster than the fused vector-FMA kernel (measured: 0.53 against 0.55 ms on the batched
+    // 44.1k->48k chain, 0.63 against 0.70 ms on 48k->44.1k); the fused kernel serves 1-7 rows.
+    if (tensor_fir_enabled() && g_fused_rat && c.n_streams >= 8 && (int64_t)c.np * c.n_streams >= 32768) return nullptr;
+    if (!c.interp && launch_rat<double, true>(c, s, cache)) return "fused_up2_rat_f64";
+    // a large lock-step batch that the rational kernel does not cover runs as two launches: the stand-alone x2 kernel and
+    // K3i (lanes = rows, interpolated coefficients evaluated once per batch) beat the one-thread-per-output fused kernel
+    {
+        const double r = (double)c.step / ((double)c.L * 65536.0);
+        if (g_fused_rat && c.n_streams >= 8 && (int64_t)c.n_out * c.n_streams >= 16384 && r > 0.0 && r <= 8.0 &&
+            c.L <= 4096 && c.t2 <= 1024)
+            return nullptr;
+    }
+    if (c.interp) return launch_fused_t<double, true>(c, s) ? "fused_up2_poly_f64_interp" : nullptr;
+    return launch_fused_t<double, false>(c, s) ? "fused_up2_poly_f64" : nullptr;
+}
+
+
+}  // namespace gar
