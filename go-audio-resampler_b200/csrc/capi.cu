@@ -579,7 +579,8 @@ static int batch_host(gar_handle* h, int io_dtype, const void* in, int64_t in_st
     // slice size: ~64 MiB of input per slice, at least 1 row, at most all rows
     const int64_t row_bytes = (int64_t)((flush ? 0 : n_in) + want) * (int64_t)iosz;
     int slice = (int)std::max<int64_t>(1, std::min<int64_t>(rows, (64ll << 20) / std::max<int64_t>(row_bytes, 1)));
-    if (rows <= 2) slice = rows;
+    // a handful of long rows stays together (their time segments fill the tensor-core kernels' columns) up to 1 GiB
+    if (rows <= 2 || (rows <= 8 && rows * row_bytes <= (1ll << 30))) slice = rows;
     const size_t need_in = (size_t)slice * (size_t)is * iosz, need_out = (size_t)slice * (size_t)os * iosz;
     if (need_in > h->slot_in_cap) {
         cudaDeviceSynchronize();

@@ -142,12 +142,15 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
 // no register-file or shared-memory pressure (measured: DMMA sustains 36.9 TFLOP/s on this B200, vector DFMA 34.1).
 // A warp owns MT = 4 consecutive MMA tiles (4*JT positions): they see the same sample window shifted by SH = JT*M/4
 // k-steps, so ONE B fragment (LDS.64) and ONE A fragment (LDS.64, kept in a rotating register window) feed 4 MMAs.
-// A block = 8 streams x NW*MT*JT positions; A fragments are laid out per k-step in shared memory in fragment order.
+// Fewer than 8 rows: the columns are TIME SEGMENTS of the rows (virtual stream = row x segment of `ps` positions), so a
+// single long stream fills the 8 columns with 8 of its own segments — A does not depend on the position.
+// A block = 8 (virtual) streams x NW*MT*JT positions; A fragments are laid out per k-step in shared memory in fragment order.
 // Taps are grouped in fours in window order, so results differ from the strictly sequential vector kernels in the last
 // bits (1e-16 relative); identical call sequences are bit-identical.
 // =============================================================================================
 struct MmaGeom {
     int32_t nk, xlen, pitch, nbuf, n_tiles, tiles_per_block, n_groups, n_sg;  // k-steps, staged samples per stream, row pitch, window buffers
+    int32_t nseg, ps, nvs;  // time segments per row, positions per segment, virtual streams = rows x segments (MMA columns)
 };
 
 template <int M, int NF, int NW, int MT>
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
         return;
     }
     const int grp = blockIdx.x % g.n_groups;
-    const int sbase = (blockIdx.x / g.n_groups) * 8;
+    const int sbase = (blockIdx.x / g.n_groups) * 8;  // first virtual stream (row x segment) of the block's 8 MMA columns
     const int t_first = grp * g.tiles_per_block;
     const int nt = min(g.tiles_per_block, g.n_tiles - t_first);
 
@@ -196,45 +199,54 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
         mbar_init(bar + 1, 1);
     }
     uint32_t ph0 = 0u, ph1 = 0u;
-    // TMA bulk copies need 16-byte aligned sources: all 8 rows share the alignment when the row stride is even
-    const bool rows_bulk = (c.in_stride & 1) == 0 && sbase + 8 <= c.n_streams;
-    const double* __restrict__ in0 = static_cast<const double*>(c.in) + (int64_t)sbase * c.in_stride;
+    // TMA bulk copies need 16-byte aligned sources: all 8 columns share the alignment when the row stride and the segment
+    // length in samples are even
+    const bool rows_bulk = (c.in_stride & 1) == 0 && (((int64_t)g.ps * M) & 1) == 0 && sbase + 8 <= g.nvs;
     const int xbuf = 8 * g.pitch;
+    // column r of the block: row, first position of its segment
+    auto col_row = [&](const int r) -> int64_t { return (sbase + r) / g.nseg; };
+    auto col_pos0 = [&](const int r) -> int64_t { return (int64_t)((sbase + r) % g.nseg) * g.ps; };
 
-    // geometry of local tile kt: first sample v0, staged length, bulk-copy parameters
-    auto tile_geom = [&](const int kt, int64_t& v0, int& len, int& a, int& wlen) -> bool {
-        const int jb0 = (t_first + kt) * TJ;
-        v0 = (int64_t)c.first + (int64_t)jb0 * M;
-        const int npos_t = min(TJ, c.n_pos - jb0);
+    // geometry of local tile kt: segment-local first position jb0, staged length, bulk-copy parameters
+    auto tile_geom = [&](const int kt, int& jb0, int& len, int& a, int& wlen) -> bool {
+        jb0 = (t_first + kt) * TJ;
+        const int npos_t = min(TJ, g.ps - jb0);
         len = min(g.xlen, ((npos_t + JT - 1) / JT * JT - 1) * M + 4 * g.nk + 4);
         a = 0;
         wlen = 0;
-        const int64_t gi = v0 - c.hist_len;
-        if (!rows_bulk || gi < 0) return false;
-        a = (int)((reinterpret_cast<uintptr_t>(in0 + gi) & 15u) >> 3);  // start `a` samples early: aligned source
+        if (!rows_bulk) return false;
+        // index into `in` of every column's window start: all must lie inside the rows
+        int64_t gmin = INT64_MAX, gmax = INT64_MIN;
+        for (int r = 0; r < 8; ++r) {
+            const int64_t gi = (int64_t)c.first + (col_pos0(r) + jb0) * M - c.hist_len;
+            gmin = min(gmin, gi);
+            gmax = max(gmax, gi);
+        }
+        if (gmin < 0) return false;
+        const double* src0 = static_cast<const double*>(c.in) + col_row(0) * c.in_stride + ((int64_t)c.first + (col_pos0(0) + jb0) * M - c.hist_len);
+        a = (int)((reinterpret_cast<uintptr_t>(src0) & 15u) >> 3);  // start `a` samples early: aligned sources
         wlen = (len + a + 1) & ~1;
-        if (gi - a >= 0 && gi - a + wlen <= c.n_in && wlen <= g.pitch) return true;
-        a = 0;  // element copies start exactly at v0
+        if (gmin - a >= 0 && gmax - a + wlen <= c.n_in && wlen <= g.pitch) return true;
+        a = 0;  // element copies start exactly at the window
         return false;
     };
     auto issue = [&](const int kt, const int buf) {  // one thread
-        int64_t v0;
-        int len, a, wlen;
-        if (!tile_geom(kt, v0, len, a, wlen)) return;
+        int jb0, len, a, wlen;
+        if (!tile_geom(kt, jb0, len, a, wlen)) return;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar + buf, (uint32_t)(8 * wlen * sizeof(double)));
-        const int64_t gi = v0 - c.hist_len - a;
-        for (int r = 0; r < 8; ++r)
-            bulk_g2s(Xs0 + buf * xbuf + r * g.pitch, in0 + (int64_t)r * c.in_stride + gi, (uint32_t)(wlen * sizeof(double)),
-                     bar + buf);
+        for (int r = 0; r < 8; ++r) {
+            const int64_t gi = (int64_t)c.first + (col_pos0(r) + jb0) * M - c.hist_len - a;
+            bulk_g2s(Xs0 + buf * xbuf + r * g.pitch, static_cast<const double*>(c.in) + col_row(r) * c.in_stride + gi,
+                     (uint32_t)(wlen * sizeof(double)), bar + buf);
+        }
     };
 
     for (int kt = 0; kt < nt; ++kt) {
         const int buf = g.nbuf == 2 ? (kt & 1) : 0;
         double* __restrict__ Xs = Xs0 + buf * xbuf;
-        int64_t v0;
-        int len, a, wlen;
-        const bool bulk = tile_geom(kt, v0, len, a, wlen);
+        int jb0, len, a, wlen;
+        const bool bulk = tile_geom(kt, jb0, len, a, wlen);
         // everyone is done with the windows this iteration overwrites (first tile: the bank and the mbarriers are set)
         __syncthreads();
         if (tid == 0) {
@@ -251,16 +263,17 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
             }
             if (buf) ph1 ^= 1u;
             else ph0 ^= 1u;
-        } else {  // edge tile (touches the carried tail or the end of the rows): element copies
-            const int i1 = (int)min((int64_t)len, max((int64_t)0, (int64_t)c.hist_len - v0));
-            const int i2 = (int)min((int64_t)len, max((int64_t)i1, total - v0));
+        } else {  // edge tile (a column touches the carried tail or the end of its row): element copies
             for (int r = warp; r < 8; r += NW) {
-                const int64_t row = sbase + r;
                 double* __restrict__ dst = Xs + r * g.pitch;
-                if (row >= c.n_streams) {
+                if (sbase + r >= g.nvs) {
                     for (int i = lane; i < len; i += 32) dst[i] = 0.0;
                     continue;
                 }
+                const int64_t row = col_row(r);
+                const int64_t v0 = (int64_t)c.first + (col_pos0(r) + jb0) * M;  // element i of the window is v[v0 + i]
+                const int i1 = (int)min((int64_t)len, max((int64_t)0, (int64_t)c.hist_len - v0));
+                const int i2 = (int)min((int64_t)len, max((int64_t)i1, total - v0));
                 const double* __restrict__ hsrc = static_cast<const double*>(c.hist) + row * c.hist_stride + v0;
                 const double* __restrict__ isrc = static_cast<const double*>(c.in) + row * c.in_stride + (v0 - c.hist_len);
                 for (int i = lane; i < i1; i += 32) dst[i] = hsrc[i];
@@ -273,14 +286,13 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
         }
 
         // ---- MT MMA tiles per warp; step q loads window chunk Q = warp*MT*SH + q and A fragment q ----
-        const int jb0 = (t_first + kt) * TJ;
-        const int npos_t = min(TJ, c.n_pos - jb0);
+        const int npos_t = min(TJ, g.ps - jb0);
         if (warp * MT * JT < npos_t) {
             double acc[MT][2];
 #pragma unroll
             for (int b = 0; b < MT; ++b) acc[b][0] = acc[b][1] = 0.0;
             double Areg[WA];
-            // B fragment: lane l reads X[w = 4*Q + l%4][stream l/4]
+            // B fragment: lane l reads X[w = 4*Q + l%4][column l/4]
             const double* __restrict__ xw = Xs + (lane >> 2) * g.pitch + (lane & 3) + a + 4 * (warp * MT * SH);
             // A fragment: lane l holds A[row = l/4][w = 4*kk + l%4] = bank[p][4*kk + l%4 - jj*M], row = jj*NF + p
             const double* __restrict__ aw = Bs + ((lane >> 2) % NF) * blen + BOFF + (lane & 3) - ((lane >> 2) / NF) * M;
@@ -299,16 +311,19 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
                     }
                 }
             }
-            // ---- D[row = lane/4][cols 2*(lane%4), +1]: output jb*NF + row of streams sbase + col ----
+            // ---- D[row = lane/4][cols 2*(lane%4), +1]: output (pos0 + jb)*NF + row of the columns' rows ----
             const int r8 = lane >> 2;
-            const int s0 = sbase + 2 * (lane & 3);
 #pragma unroll
-            for (int b = 0; b < MT; ++b) {
-                const int jb = jb0 + (warp * MT + b) * JT;
-                if (jb + r8 / NF < c.n_pos) {
-                    const int64_t o = (int64_t)jb * NF + r8;
-                    if (s0 < c.n_streams) (static_cast<double*>(c.out) + (int64_t)s0 * c.out_stride)[o] = acc[b][0];
-                    if (s0 + 1 < c.n_streams) (static_cast<double*>(c.out) + (int64_t)(s0 + 1) * c.out_stride)[o] = acc[b][1];
+            for (int e = 0; e < 2; ++e) {
+                const int col = 2 * (lane & 3) + e;
+                if (sbase + col >= g.nvs) continue;
+                const int64_t pos0 = col_pos0(col);
+                const int64_t plim = min((int64_t)c.n_pos, pos0 + g.ps);  // the column's segment ends here
+                double* __restrict__ orow = static_cast<double*>(c.out) + col_row(col) * c.out_stride;
+#pragma unroll
+                for (int b = 0; b < MT; ++b) {
+                    const int64_t jb = pos0 + jb0 + (warp * MT + b) * JT;
+                    if (jb + r8 / NF < plim) orow[jb * NF + r8] = acc[b][e];
                 }
             }
         }
@@ -323,7 +338,14 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
     MmaGeom g{};
     const int kp = c.taps + (JT - 1) * M;
     g.nk = (kp + 3) / 4;
-    g.n_sg = (c.n_streams + 7) / 8;
+    // fewer than 8 rows: split every row into time segments, the MMA columns are (row, segment) pairs
+    g.nseg = 1;
+    if (c.n_streams < 8) {
+        static const int tbl[8] = {0, 8, 4, 8, 2, 8, 4, 8};  // rows x segments = 8, 8, 24, 8, 40, 24, 56
+        g.nseg = tbl[c.n_streams];
+    }
+    g.nvs = c.n_streams * g.nseg;
+    g.n_sg = (g.nvs + 7) / 8;
     const size_t bank_bytes = 16 + (size_t)NF * ((4 * g.nk + (JT - 1) * M + 5) & ~1) * sizeof(double);
     auto run = [&](auto kernel, const int NW, const int MT, const int slot) -> bool {
         const int TJ = NW * MT * JT;
@@ -336,7 +358,9 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
         if (force_nbuf == 1) g.nbuf = 1;
         const size_t smem = bank_bytes + g.nbuf * xbytes;
         if (smem > 227 * 1024) return false;
-        g.n_tiles = (c.n_pos + TJ - 1) / TJ;
+        g.ps = g.nseg == 1 ? c.n_pos : (((c.n_pos + g.nseg - 1) / g.nseg + TJ - 1) / TJ) * TJ;
+        if (g.nseg > 1 && g.ps < 2 * TJ) return false;  // segments shorter than two tiles: not worth it
+        g.n_tiles = (g.ps + TJ - 1) / TJ;
         // persistent over a few tiles (bank staged once, prefetch) while the grid still fills the GPU
         const int64_t blocks_per_sm = std::max<int64_t>(1, (int64_t)(227 * 1024) / (int64_t)(smem + 1024));
         const int64_t slots = 148 * std::min<int64_t>(blocks_per_sm, 2048 / (NW * 32));
@@ -369,9 +393,13 @@ static bool g_fir_mma = [] {
     const char* e = std::getenv("GAR_NO_MMA");
     return !(e && e[0] && e[0] != '0');
 }();
-// float64 FIR on the FP64 tensor cores: batches of >= 8 lock-step rows, x2 up-sampler and /2 /3 /4 decimators
+// float64 FIR on the FP64 tensor cores: x2 up-sampler and /2 /3 /4 decimators, any number of lock-step rows (fewer than 8:
+// time segments of the rows fill the MMA columns), calls of at least 32768 positions
 static const char* launch_fir_mma(const FirCall& c, cudaStream_t s) {
-    if (!g_fir_mma || c.n_streams < 8 || (int64_t)c.n_pos * c.n_streams < 32768 || c.taps < 16) return nullptr;
+    if (!g_fir_mma || c.n_streams < 1 || (int64_t)c.n_pos * c.n_streams < 32768 || c.taps < 16) return nullptr;
+    // fewer than 8 rows (time-segment columns): only long calls — measured +5 % on 60 s of stereo 96k->48k, but a loss on the
+    // sub-millisecond stages of a single 10 s stream (C5a), which are launch-latency-bound
+    if (c.n_streams < 8 && (int64_t)c.n_pos * c.n_streams < 2000000) return nullptr;
     if (c.stride == 1 && c.nf == 2) return launch_fir_mma_t<1, 2>(c, s) ? "fir_f64_mma_up2" : nullptr;
     if (c.nf == 1 && c.stride == 2) return launch_fir_mma_t<2, 1>(c, s) ? "fir_f64_mma_s2" : nullptr;
     if (c.nf == 1 && c.stride == 3) return launch_fir_mma_t<3, 1>(c, s) ? "fir_f64_mma_s3" : nullptr;

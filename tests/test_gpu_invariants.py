@@ -334,6 +334,12 @@ def test_rows_kernel_batched_any_ratio_vs_thread_per_output_kernels_and_oracle(i
     (48000, 16000, G.QualityHigh, 19, 90000, "fir_f64_mma_s3"),        # /3 with a ragged last group of streams
     (192000, 48000, G.QualityMedium, 9, 100000, "fir_f64_mma_s4"),     # /4
     (44100, 48000, G.QualityHigh, 24, 40000, "fir_f64_mma_up2"),       # x2 stage in front of the polyphase stage
+    # fewer than 8 rows: time segments of the rows are the MMA columns
+    (96000, 48000, G.QualityVeryHigh, 2, 2100000, "fir_f64_mma_s2"),   # stereo, 2 rows x 4 segments
+    (22050, 44100, G.QualityHigh, 1, 2050000, "fir_f64_mma_up2"),      # mono, 8 segments
+    (48000, 16000, G.QualityHigh, 3, 2100003, "fir_f64_mma_s3"),       # 3 rows x 8 segments = 24 columns
+    (192000, 48000, G.QualityMedium, 5, 1700003, "fir_f64_mma_s4"),    # 5 rows x 8 segments, ragged last segment
+    (96000, 48000, G.QualityHigh, 7, 600001, "fir_f64_mma_s2"),        # 7 rows x 8 segments = 56 columns
 ])
 def test_tensor_core_fir_matches_vector_kernels_and_oracle(ir, orr, preset, rows, n, kernel):
     """K1m/K2m (FP64 tensor cores, DMMA): same samples as the vector-FMA kernels to 1e-13 (taps grouped in fours
