@@ -203,9 +203,21 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
     // length in samples are even
     const bool rows_bulk = (c.in_stride & 1) == 0 && (((int64_t)g.ps * M) & 1) == 0 && sbase + 8 <= g.nvs;
     const int xbuf = 8 * g.pitch;
-    // column r of the block: row, first position of its segment
-    auto col_row = [&](const int r) -> int64_t { return (sbase + r) / g.nseg; };
-    auto col_pos0 = [&](const int r) -> int64_t { return (int64_t)((sbase + r) % g.nseg) * g.ps; };
+    // column r of the block: row, first position of its segment — fixed for the block, tabulated once (no divisions per tile)
+    __shared__ int s_col_row[8], s_col_pos0[8];
+    if (tid < 8) {
+        s_col_row[tid] = (sbase + tid) / g.nseg;
+        s_col_pos0[tid] = ((sbase + tid) % g.nseg) * g.ps;
+    }
+    __syncthreads();
+    auto col_row = [&](const int r) -> int64_t { return s_col_row[r]; };
+    auto col_pos0 = [&](const int r) -> int64_t { return s_col_pos0[r]; };
+    int pos0_min = INT32_MAX, pos0_max = 0;
+    for (int r = 0; r < 8; ++r) {
+        pos0_min = min(pos0_min, s_col_pos0[r]);
+        pos0_max = max(pos0_max, s_col_pos0[r]);
+    }
+    const double* __restrict__ col0_in = static_cast<const double*>(c.in) + col_row(0) * c.in_stride + col_pos0(0) * M;
 
     // geometry of local tile kt: segment-local first position jb0, staged length, bulk-copy parameters
     auto tile_geom = [&](const int kt, int& jb0, int& len, int& a, int& wlen) -> bool {
@@ -216,14 +228,10 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
         wlen = 0;
         if (!rows_bulk) return false;
         // index into `in` of every column's window start: all must lie inside the rows
-        int64_t gmin = INT64_MAX, gmax = INT64_MIN;
-        for (int r = 0; r < 8; ++r) {
-            const int64_t gi = (int64_t)c.first + (col_pos0(r) + jb0) * M - c.hist_len;
-            gmin = min(gmin, gi);
-            gmax = max(gmax, gi);
-        }
+        const int64_t g0 = (int64_t)c.first + (int64_t)jb0 * M - c.hist_len;
+        const int64_t gmin = g0 + (int64_t)pos0_min * M, gmax = g0 + (int64_t)pos0_max * M;
         if (gmin < 0) return false;
-        const double* src0 = static_cast<const double*>(c.in) + col_row(0) * c.in_stride + ((int64_t)c.first + (col_pos0(0) + jb0) * M - c.hist_len);
+        const double* src0 = col0_in + g0;
         a = (int)((reinterpret_cast<uintptr_t>(src0) & 15u) >> 3);  // start `a` samples early: aligned sources
         wlen = (len + a + 1) & ~1;
         if (gmin - a >= 0 && gmax - a + wlen <= c.n_in && wlen <= g.pitch) return true;

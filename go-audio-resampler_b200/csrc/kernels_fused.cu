@@ -865,10 +865,18 @@ const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s,
         if (c.interp) return launch_fused_t<float, true>(c, s) ? "fused_up2_poly_f32_interp" : nullptr;
         return launch_fused_t<float, false>(c, s) ? "fused_up2_poly_f32" : nullptr;
     }
-    // Batches of >= 8 lock-step rows run the x2 stage on the FP64 tensor cores (K1m) and the polyphase stage as its own
-    // launch (K3r / K3i): faster than the fused vector-FMA kernel (measured: 0.53 against 0.55 ms on the batched
-    // 44.1k->48k chain, 0.63 against 0.70 ms on 48k->44.1k); the fused kernel serves 1-7 rows.
-    if (tensor_fir_enabled() && g_fused_rat && c.n_streams >= 8 && (int64_t)c.np * c.n_streams >= 32768) return nullptr;
+    // Tensor-core path = two launches: the x2 stage (K1m) and the polyphase stage (K3m) on the FP64 tensor cores.
+    //  * rational ratios: batches of >= 64 lock-step rows. Measured on 21 M input samples of 44.1k->48k (TFLOP/s, tensor path
+    //    against the fused K4r): 8 rows 15.7 / 17.5, 32 rows 15.7 / 17.5, 64 rows 18.3 / 17.9, 256 rows x 10 s 23.3 — K3m
+    //    amortises its coefficient matrices over the rows, K4r is the better kernel for a few long rows;
+    //  * irrational ratios: batches of >= 8 rows (K3m / K3i evaluate the interpolated coefficients once per batch; the fused
+    //    one-thread-per-output kernel is 10x slower there).
+    {
+        const bool rational = !c.interp && ((c.step | c.at0) & 0xFFFF) == 0;
+        if (tensor_fir_enabled() && g_fused_rat && (int64_t)c.np * c.n_streams >= 32768 &&
+            c.n_streams >= (rational ? 64 : 8))
+            return nullptr;
+    }
     if (!c.interp && launch_rat<double, true>(c, s, cache)) return "fused_up2_rat_f64";
     // a large lock-step batch that the rational kernel does not cover runs as two launches: the stand-alone x2 kernel and
     // K3i (lanes = rows, interpolated coefficients evaluated once per batch) beat the one-thread-per-output fused kernel

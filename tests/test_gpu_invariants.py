@@ -297,7 +297,7 @@ def test_rational_kernels_random_geometry_stress(vector_fir_only):
 @pytest.mark.parametrize("ir,orr,rows,n", [
     (44100, 47999, 40, 50000),    # BASELINE config 5b's ratio: cubic coefficient interpolation live, 1.84 samples/output
     (48000, 44099, 24, 60000),    # irrational down-conversion, 2.18 samples/output
-    (8000, 22050, 19, 30000),     # fewer than one intermediate sample per output (window slot stride 1)
+    (8000, 22051, 19, 30000),     # fewer than one intermediate sample per output (window slot stride 1)
     (44100, 16000, 17, 70000),    # rational, 5.5 samples/output: beyond the rational kernel's slot strides
 ])
 def test_rows_kernel_batched_any_ratio_vs_thread_per_output_kernels_and_oracle(ir, orr, rows, n, vector_fir_only):
@@ -333,7 +333,7 @@ def test_rows_kernel_batched_any_ratio_vs_thread_per_output_kernels_and_oracle(i
     (96000, 48000, G.QualityVeryHigh, 8, 120000, "fir_f64_mma_s2"),    # /2 (path B maps VeryHigh to the 751-tap High filter)
     (48000, 16000, G.QualityHigh, 19, 90000, "fir_f64_mma_s3"),        # /3 with a ragged last group of streams
     (192000, 48000, G.QualityMedium, 9, 100000, "fir_f64_mma_s4"),     # /4
-    (44100, 48000, G.QualityHigh, 24, 40000, "fir_f64_mma_up2"),       # x2 stage in front of the polyphase stage
+    (44100, 48000, G.QualityHigh, 70, 16000, "fir_f64_mma_up2"),       # x2 stage in front of the polyphase stage (>= 64 rows: unfused)
     # fewer than 8 rows: time segments of the rows are the MMA columns
     (96000, 48000, G.QualityVeryHigh, 2, 2100000, "fir_f64_mma_s2"),   # stereo, 2 rows x 4 segments
     (22050, 44100, G.QualityHigh, 1, 2050000, "fir_f64_mma_up2"),      # mono, 8 segments
@@ -375,9 +375,9 @@ def test_tensor_core_fir_matches_vector_kernels_and_oracle(ir, orr, preset, rows
 
 @pytest.mark.parametrize("ir,orr,rows,n", [
     (44100, 47999, 40, 50000),    # cubic coefficient interpolation live, 1.84 samples/output
-    (48000, 44100, 33, 60000),    # rational 320/147, ragged last group of rows
+    (48000, 44100, 70, 60000),    # rational 320/147, ragged last group of rows
     (44100, 48000, 64, 30000),    # rational 147/80
-    (8000, 22050, 19, 30000),     # fewer than one intermediate sample per output
+    (8000, 22051, 19, 30000),     # fewer than one intermediate sample per output
 ])
 def test_tensor_core_polyphase_rows_kernel_vs_thread_per_output_kernels_and_oracle(ir, orr, rows, n):
     """K3m (polyphase stage as 8-output x K coefficient matrices times the rows' windows, DMMA): same samples as the
