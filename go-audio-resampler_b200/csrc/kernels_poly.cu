@@ -406,6 +406,223 @@ __global__ void __launch_bounds__(NTASK * 32, NTASK == 8 ? 2 : 3) poly_rows_mma_
     }
 }
 
+// =============================================================================================
+// K3p — K3m as a producer / consumer pipeline. Each of the 8 MMA warps keeps its task's whole coefficient matrix in
+// REGISTERS (lane l holds A[i = l/4][4*kk + l%4] for every k-step: NK doubles, gathered straight from the L2-resident banks,
+// no shared-memory copy), so shared memory holds nothing but two 32-row sample stages. A ninth warp is the producer: it waits
+// for a stage to be released (mbarrier `empty`, one arrival per MMA warp), issues the 32 TMA bulk copies of the next 32 rows
+// (mbarrier `full`, transaction bytes) and runs ahead of the MMA warps by one stage — no block-wide barrier in the loop,
+// the copy latency of row block j+1 hides under the MMAs of row block j, and two such blocks still fit an SM.
+// Per k-step 4 B fragments (LDS.64) feed 4 DMMA.8x8x4 (K3m: 5 loads). Same A values, same accumulation order as K3m:
+// bit-identical results.
+// =============================================================================================
+template <int NK, int RB, int NST>
+__global__ void __launch_bounds__(288, 2) poly_rows_pipe_kernel(const PolyCall c, const RowsMmaGeom g) {
+    constexpr int RN = 8, NTASK = 8, TO = RN * NTASK, NT8 = RB / 8;
+    static_assert(RB == 32 || RB == 16, "a stage is 32 or 16 rows");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);      // [NST] stage filled (producer arrival + TMA bytes)
+    uint64_t* empty = full + NST;                                // [NST] stage released (8 MMA warps)
+    double* xs0 = reinterpret_cast<double*>(smem_raw + 64);      // [NST][RB][pitch] staged samples
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_rg = (c.n_streams + RB * g.nrb - 1) / (RB * g.nrb);
+    const int n_work = g.n_tiles * n_rg;
+    if ((int)blockIdx.x >= n_work) {  // carried tail of one row
+        const int64_t row = (int)blockIdx.x - n_work;
+        carry_row(static_cast<const double*>(c.hist) + row * c.hist_stride, c.hist_len,
+                  static_cast<const double*>(c.in) + row * c.in_stride, c.n_in,
+                  static_cast<double*>(c.hist_out) + row * c.hist_out_stride, c.drop, c.new_hist_len);
+        return;
+    }
+    const int tile = blockIdx.x % g.n_tiles;
+    const int rows_base = (blockIdx.x / g.n_tiles) * RB * g.nrb;
+    const int64_t L = c.L;
+    const int n0 = tile * TO;
+    const int n1 = min(c.n_out, n0 + TO);
+    const int64_t d_base = ((c.at0 + (int64_t)n0 * c.step) >> 16) / L;  // first staged sample = window of output n0
+    const int64_t d_last = ((c.at0 + (int64_t)(n1 - 1) * c.step) >> 16) / L;
+    const int span_t = min((int)(d_last - d_base) + g.kp + 4, g.span);
+    const int64_t total = (int64_t)c.hist_len + c.n_in;
+    const int64_t gi = d_base - c.hist_len;
+    const int nj = min(g.nrb, (c.n_streams - rows_base + RB - 1) / RB);  // 32-row stages of this block
+
+    // stage kind, the same pure function on both sides of the pipeline: a full 32-row block whose span lies inside `in` is
+    // moved by TMA, started `a` samples early (16-byte aligned sources; rows share the alignment when the stride is even)
+    auto stage_is_bulk = [&](const int row0, int& a, int& wlen) -> bool {
+        a = 0;
+        wlen = 0;
+        if ((c.in_stride & 1) != 0 || row0 + RB > c.n_streams || gi < 0) return false;
+        const double* src0 = static_cast<const double*>(c.in) + (int64_t)row0 * c.in_stride + gi;
+        a = (int)((reinterpret_cast<uintptr_t>(src0) & 15u) >> 3);
+        wlen = (span_t + a + 1) & ~1;
+        if (gi - a >= 0 && gi - a + wlen <= c.n_in && wlen <= g.pitch) return true;
+        a = 0;
+        return false;
+    };
+
+    if (tid == 0) {
+        for (int b = 0; b < NST; ++b) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, NTASK);
+        }
+    }
+    __syncthreads();
+
+    if (warp == NTASK) {
+        // ---------------- producer warp ----------------
+        for (int j = 0; j < nj; ++j) {
+            const int buf = j % NST;
+            const int row0 = rows_base + j * RB;
+            double* xs = xs0 + buf * RB * g.pitch;
+            if (j >= NST) {  // the MMA warps have released the stage's previous contents
+                const uint32_t par = (uint32_t)((j / NST - 1) & 1);
+                while (!mbar_try_wait(empty + buf, par)) {
+                }
+                __syncwarp();
+            }
+            int a, wlen;
+            if (stage_is_bulk(row0, a, wlen)) {
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(full + buf, (uint32_t)(RB * wlen * sizeof(double)));
+                }
+                __syncwarp();
+                if (lane < RB)
+                    bulk_g2s(xs + lane * g.pitch, static_cast<const double*>(c.in) + (int64_t)(row0 + lane) * c.in_stride + gi - a,
+                             (uint32_t)(wlen * sizeof(double)), full + buf);
+            } else {  // edge stage (carried tail, end of the rows, ragged last row block): element copies by this warp
+                const int i1 = (int)min((int64_t)span_t, max((int64_t)0, (int64_t)c.hist_len - d_base));
+                const int i2 = (int)min((int64_t)span_t, max((int64_t)i1, total - d_base));
+                for (int r = 0; r < RB; ++r) {
+                    const int64_t row = row0 + r;
+                    double* __restrict__ dst = xs + r * g.pitch;
+                    if (row >= c.n_streams) {
+                        for (int i = lane; i < span_t; i += 32) dst[i] = 0.0;
+                        continue;
+                    }
+                    const double* __restrict__ hsrc = static_cast<const double*>(c.hist) + row * c.hist_stride + d_base;
+                    const double* __restrict__ isrc = static_cast<const double*>(c.in) + row * c.in_stride + (d_base - c.hist_len);
+                    for (int i = lane; i < i1; i += 32) dst[i] = hsrc[i];
+#pragma unroll 4
+                    for (int i = i1 + lane; i < i2; i += 32) cp_async_elem(dst + i, isrc + i);
+                    for (int i = i2 + lane; i < span_t; i += 32) dst[i] = 0.0;
+                }
+                cp_async_wait_all();
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(full + buf)) : "memory");
+            }
+        }
+        return;
+    }
+
+    // ---------------- MMA warps: task = 8 outputs nf .. nf+7 ----------------
+    const int nf = n0 + warp * RN;
+    const int i = lane >> 2;  // this lane's output row of the MMA tile (polyphase_stage.go:260-264)
+    const int64_t at = c.at0 + (int64_t)(nf + i) * c.step;
+    const int64_t fullp = at >> 16;
+    const int64_t dv = fullp / L;
+    const int ph = (int)(fullp - dv * L);
+    const int base = __shfl_sync(0xffffffffu, (int)(dv - d_base), 0);  // window offset of the task's first output
+    const int o_i = (int)(dv - d_base) - base;
+    const bool live = nf + i < n1;
+    const int nks = g.kp >> 2;
+    double A[NK];
+    {
+        const double* __restrict__ ga = static_cast<const double*>(c.bank_a);
+        const double* __restrict__ gb = static_cast<const double*>(c.bank_b);
+        const double* __restrict__ gc = static_cast<const double*>(c.bank_c);
+        const double* __restrict__ gd = static_cast<const double*>(c.bank_d);
+        const double x = (double)(int)(at & 0xFFFF) * (1.0 / 65536.0);
+#pragma unroll
+        for (int kk = 0; kk < NK; ++kk) {
+            const int k = 4 * kk + (lane & 3) - o_i;
+            double v = 0.0;
+            if (kk < nks && live && k >= 0 && k < c.taps) {
+                const int co = ph * c.taps + k;
+                v = ga[co];
+                if (c.interp) v = fma(x, fma(x, fma(x, gd[co], gc[co]), gb[co]), v);
+            }
+            A[kk] = v;
+        }
+    }
+    for (int j = 0; j < nj; ++j) {
+        const int buf = j % NST;
+        const int row0 = rows_base + j * RB;
+        const double* __restrict__ xs = xs0 + buf * RB * g.pitch;
+        int apad, wlen;
+        stage_is_bulk(row0, apad, wlen);
+        const uint32_t par = (uint32_t)((j / NST) & 1);
+        while (!mbar_try_wait(full + buf, par)) {
+        }
+        __syncwarp();
+        if (nf < n1) {
+            double acc[NT8][2];
+#pragma unroll
+            for (int t = 0; t < NT8; ++t) acc[t][0] = acc[t][1] = 0.0;
+            // B fragment: X[w = 4*kk + l%4][row 8*t + l/4]
+            const double* __restrict__ bp = xs + (lane >> 2) * g.pitch + base + apad + (lane & 3);
+#pragma unroll
+            for (int kk = 0; kk < NK; ++kk) {
+                if (kk < nks) {
+#pragma unroll
+                    for (int t = 0; t < NT8; ++t) dmma884(acc[t][0], acc[t][1], A[kk], bp[t * 8 * g.pitch + 4 * kk]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + buf)) : "memory");
+            if (live) {
+#pragma unroll
+                for (int t = 0; t < NT8; ++t) {
+                    const int64_t s0 = (int64_t)row0 + t * 8 + 2 * (lane & 3);
+                    if (s0 < c.n_streams) (static_cast<double*>(c.out) + s0 * c.out_stride)[nf + i] = acc[t][0];
+                    if (s0 + 1 < c.n_streams) (static_cast<double*>(c.out) + (s0 + 1) * c.out_stride)[nf + i] = acc[t][1];
+                }
+            }
+        } else {
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + buf)) : "memory");
+        }
+    }
+}
+
+template <int NK, int RB, int NST>
+static bool launch_poly_rows_pipe_t(const PolyCall& c, cudaStream_t s) {
+    constexpr int TO = 64;
+    const double r = (double)c.step / ((double)c.L * 65536.0);
+    RowsMmaGeom g{};
+    const int omax = (int)std::ceil(7 * r) + 1;
+    g.kp = ((omax + c.taps + 3) / 4) * 4;
+    if (g.kp > 4 * NK || g.kp > 2 * c.taps + 8) return false;
+    g.span = (int)std::ceil((TO - 1) * r) + 1 + g.kp + 8;
+    g.pitch = ((g.span + 2 + 15) / 16) * 16 + 4;  // rows 32 bytes apart modulo 128 (B fragment reads: two wavefronts)
+    g.n_tiles = (c.n_out + TO - 1) / TO;
+    const int n_rb = (c.n_streams + RB - 1) / RB;
+    // stages (of RB rows) per block: the register-resident coefficients are gathered once per block
+    g.nrb = 1;
+    while (g.nrb < 256 / RB && g.nrb * 2 <= n_rb && (int64_t)g.n_tiles * ((n_rb + g.nrb * 2 - 1) / (g.nrb * 2)) >= 4 * 148) g.nrb *= 2;
+    g.nbuf = NST;
+    const size_t smem = 64 + (size_t)NST * RB * g.pitch * sizeof(double);
+    if (smem > 113 * 1024) return false;  // two blocks per SM
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(poly_rows_pipe_kernel<NK, RB, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)g.n_tiles * ((c.n_streams + RB * g.nrb - 1) / (RB * g.nrb)) + c.n_streams;
+    poly_rows_pipe_kernel<NK, RB, NST><<<(unsigned)blocks, 288, smem, s>>>(c, g);
+    count_launch();
+    return true;
+}
+
+// K3p variants: coefficient registers for K <= 80 or <= 112, 2 stages of 32 rows or (long spans) 3 stages of 16 rows
+static bool launch_poly_rows_pipe(const PolyCall& c, cudaStream_t s) {
+    return launch_poly_rows_pipe_t<20, 32, 2>(c, s) || launch_poly_rows_pipe_t<20, 16, 3>(c, s) ||
+           launch_poly_rows_pipe_t<28, 32, 2>(c, s) || launch_poly_rows_pipe_t<28, 16, 3>(c, s);
+}
+
 template <int NTASK>
 static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s) {
     constexpr int TO = 8 * NTASK;
@@ -442,13 +659,17 @@ static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s) {
     return true;
 }
 
-static bool launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
-    if (!tensor_fir_enabled() || c.n_streams < 8 || (int64_t)c.n_out * c.n_streams < 16384 || c.L > 4096 || c.taps > 1024) return false;
+// 0: not taken, 1: K3m, 2: K3p
+static int launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
+    if (!tensor_fir_enabled() || c.n_streams < 8 || (int64_t)c.n_out * c.n_streams < 16384 || c.L > 4096 || c.taps > 1024) return 0;
     const double r = (double)c.step / ((double)c.L * 65536.0);
-    if (!(r > 0.0) || r > 8.0) return false;
+    if (!(r > 0.0) || r > 8.0) return 0;
     static const int ntask = [] { const char* e = std::getenv("GAR_K3M_NTASK"); return e ? std::atoi(e) : 8; }();
-    if (ntask == 4) return launch_poly_rows_mma_t<4>(c, s) || launch_poly_rows_mma_t<8>(c, s);
-    return launch_poly_rows_mma_t<8>(c, s) || launch_poly_rows_mma_t<4>(c, s);
+    static const bool pipe = [] { const char* e = std::getenv("GAR_K3M_PIPE"); return !e || e[0] != '0'; }();
+    static const int pipe_rows = [] { const char* e = std::getenv("GAR_K3M_PIPE_ROWS"); return e ? std::atoi(e) : 64; }();
+    if (pipe && c.n_streams >= pipe_rows && launch_poly_rows_pipe(c, s)) return 2;
+    if (ntask == 4) return (launch_poly_rows_mma_t<4>(c, s) || launch_poly_rows_mma_t<8>(c, s)) ? 1 : 0;
+    return (launch_poly_rows_mma_t<8>(c, s) || launch_poly_rows_mma_t<4>(c, s)) ? 1 : 0;
 }
 
 // K3i dispatch: batches of at least 8 lock-step rows with enough outputs; S = ceil(samples per output)
@@ -533,7 +754,11 @@ const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* 
         return "carry";
     }
     // Batches of >= 8 lock-step rows: K3m, the polyphase stage on the FP64 tensor cores (any ratio)
-    if (dtype == DT_F64 && tiled_polyphase_enabled() && launch_poly_rows_mma(c, s)) return c.interp ? "poly_rows_mma_f64_interp" : "poly_rows_mma_f64";
+    if (dtype == DT_F64 && tiled_polyphase_enabled()) {
+        const int k = launch_poly_rows_mma(c, s);
+        if (k == 2) return c.interp ? "poly_rows_mma_f64_interp_pipe" : "poly_rows_mma_f64_pipe";
+        if (k == 1) return c.interp ? "poly_rows_mma_f64_interp" : "poly_rows_mma_f64";
+    }
     // Batches of >= 8 rows with an even period length run K3i rather than K3r: K3r then stages its padded periods with
     // element copies from one warp (measured on the batched 48k->44.1k chain: 0.63 ms against 0.78 ms)
     if (dtype == DT_F64 && tiled_polyphase_enabled() && !c.interp && c.n_streams >= 8 && ((c.step >> 16) & 1) == 0 &&
