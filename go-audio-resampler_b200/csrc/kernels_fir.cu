@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
 struct MmaGeom {
     int32_t nk, xlen, pitch, nbuf, n_tiles, tiles_per_block, n_groups, n_sg;  // k-steps, staged samples per stream, row pitch, window buffers
     int32_t nseg, ps, nvs;  // time segments per row, positions per segment, virtual streams = rows x segments (MMA columns)
+    int32_t blen;           // zero-padded filter length of the A-fragment gather
 };
 
 template <int M, int NF, int NW, int MT>
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
     // A[(jj,p)][w] = bank[p][w - jj*M] is a shifted copy of the filter in every row, so the A fragment of k-step kk is a
     // gather from the zero-padded bank with a per-lane offset: no fragment table, the bank itself is all that is staged
     constexpr int BOFF = (JT - 1) * M;                           // leading zeros: the largest negative offset
-    const int blen = (4 * g.nk + BOFF + 5) & ~1;                 // padded filter length, even: windows stay 16-byte aligned
+    const int blen = g.blen;                                     // padded filter length, even: windows stay 16-byte aligned
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);       // [2] mbarriers of the bulk-copied window buffers
     double* Bs = reinterpret_cast<double*>(smem_raw + 16);       // [NF][blen] zero-padded bank
     double* Xs0 = Bs + (size_t)NF * blen;                        // [nbuf][8][pitch] sample windows of the block's streams
@@ -354,7 +355,13 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
     }
     g.nvs = c.n_streams * g.nseg;
     g.n_sg = (g.nvs + 7) / 8;
-    const size_t bank_bytes = 16 + (size_t)NF * ((4 * g.nk + (JT - 1) * M + 5) & ~1) * sizeof(double);
+    // Zero-padded filter length. Two phase filters (x2 up-sampler): a half-warp's A-fragment LDS.64 reads a few doubles around
+    // the same offset of BOTH filters; 8 doubles apart modulo the 16 eight-byte banks (length = 8 mod 16) the two groups do
+    // not collide (ncu: the A loads took 4 wavefronts instead of 2 with the unpadded length)
+    g.blen = (4 * g.nk + (JT - 1) * M + 5) & ~1;
+    static const bool pad_bank = [] { const char* e = std::getenv("GAR_MMA_BANKPAD"); return !e || e[0] != '0'; }();
+    if (NF == 2 && pad_bank) g.blen = ((g.blen + 7) & ~15) + 8;
+    const size_t bank_bytes = 16 + (size_t)NF * g.blen * sizeof(double);
     auto run = [&](auto kernel, const int NW, const int MT, const int slot) -> bool {
         const int TJ = NW * MT * JT;
         g.xlen = (TJ - 1) * M + 4 * g.nk + 4 * (MT - 1) * SH + 10;
