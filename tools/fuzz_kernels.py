@@ -45,7 +45,7 @@ def main():
         if not (1 / 64 <= orr / ir <= 64):
             continue
         preset = PRESETS[int(rng.integers(len(PRESETS)))]
-        rows = int(rng.choice([1, 2, 7, 8, 9, 16, 31, 33, 64, 70]))
+        rows = int(rng.choice([1, 2, 7, 8, 9, 16, 31, 33, 64, 70, 96, 130, 257]))
         n = int(rng.integers(2000, 120000))
         if n * rows * max(1.0, orr / ir) > 3e7:
             n = int(3e7 / (rows * max(1.0, orr / ir)))
