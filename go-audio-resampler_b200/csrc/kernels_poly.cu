@@ -594,6 +594,7 @@ static bool launch_poly_rows_pipe_t(const PolyCall& c, cudaStream_t s) {
     const int omax = (int)std::ceil(7 * r) + 1;
     g.kp = ((omax + c.taps + 3) / 4) * 4;
     if (g.kp > 4 * NK || g.kp > 2 * c.taps + 8) return false;
+    if (c.in_stride & 1) return false;  // no TMA (16-byte aligned rows): K3m stages with all of its warps instead
     g.span = (int)std::ceil((TO - 1) * r) + 1 + g.kp + 8;
     g.pitch = ((g.span + 2 + 15) / 16) * 16 + 4;  // rows 32 bytes apart modulo 128 (B fragment reads: two wavefronts)
     g.n_tiles = (c.n_out + TO - 1) / TO;
