@@ -152,9 +152,10 @@ struct MmaGeom {
     int32_t nk, xlen, pitch, nbuf, n_tiles, tiles_per_block, n_groups, n_sg;  // k-steps, staged samples per stream, row pitch, window buffers
     int32_t nseg, ps, nvs;  // time segments per row, positions per segment, virtual streams = rows x segments (MMA columns)
     int32_t blen;           // zero-padded filter length of the A-fragment gather
+    int32_t nkc, nqc;       // window chunks per tile along the taps (long filters), k-steps per chunk (multiple of the A window)
 };
 
-template <int M, int NF, int NW, int MT>
+template <int M, int NF, int NW, int MT, bool KC>
 __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, const MmaGeom g) {
     constexpr int JT = 8 / NF;                // positions per MMA tile
     static_assert(8 % NF == 0 && (JT * M) % 4 == 0, "tile shift must be a whole number of k-steps");
@@ -220,16 +221,21 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
     }
     const double* __restrict__ col0_in = static_cast<const double*>(c.in) + col_row(0) * c.in_stride + col_pos0(0) * M;
 
-    // geometry of local tile kt: segment-local first position jb0, staged length, bulk-copy parameters
-    auto tile_geom = [&](const int kt, int& jb0, int& len, int& a, int& wlen) -> bool {
+    // geometry of iteration `it` = (local tile kt, tap chunk kc): segment-local first position jb0, first k-step qa of the
+    // chunk, staged length (from window sample 4*qa on), bulk-copy parameters
+    auto tile_geom = [&](const int it, int& jb0, int& qa, int& len, int& a, int& wlen) -> bool {
+        const int kt = KC ? it / g.nkc : it, kc = KC ? it - kt * g.nkc : 0;  // KC = false: one chunk, the whole window
         jb0 = (t_first + kt) * TJ;
+        qa = KC ? kc * g.nqc : 0;
         const int npos_t = min(TJ, g.ps - jb0);
-        len = min(g.xlen, ((npos_t + JT - 1) / JT * JT - 1) * M + 4 * g.nk + 4);
+        // the MMA tiles that hold a valid position read window samples below this bound
+        const int len_full = ((npos_t + JT - 1) / JT * JT - 1) * M + 4 * g.nk + 4;
+        len = max(0, min(g.xlen, len_full - 4 * qa));
         a = 0;
         wlen = 0;
-        if (!rows_bulk) return false;
+        if (!rows_bulk || len == 0) return false;
         // index into `in` of every column's window start: all must lie inside the rows
-        const int64_t g0 = (int64_t)c.first + (int64_t)jb0 * M - c.hist_len;
+        const int64_t g0 = (int64_t)c.first + (int64_t)jb0 * M - c.hist_len + 4 * qa;
         const int64_t gmin = g0 + (int64_t)pos0_min * M, gmax = g0 + (int64_t)pos0_max * M;
         if (gmin < 0) return false;
         const double* src0 = col0_in + g0;
@@ -239,31 +245,34 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
         a = 0;  // element copies start exactly at the window
         return false;
     };
-    auto issue = [&](const int kt, const int buf) {  // one thread
-        int jb0, len, a, wlen;
-        if (!tile_geom(kt, jb0, len, a, wlen)) return;
+    auto issue = [&](const int it, const int buf) {  // one thread
+        int jb0, qa, len, a, wlen;
+        if (!tile_geom(it, jb0, qa, len, a, wlen)) return;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar + buf, (uint32_t)(8 * wlen * sizeof(double)));
         for (int r = 0; r < 8; ++r) {
-            const int64_t gi = (int64_t)c.first + (col_pos0(r) + jb0) * M - c.hist_len - a;
+            const int64_t gi = (int64_t)c.first + (col_pos0(r) + jb0) * M - c.hist_len + 4 * qa - a;
             bulk_g2s(Xs0 + buf * xbuf + r * g.pitch, static_cast<const double*>(c.in) + col_row(r) * c.in_stride + gi,
                      (uint32_t)(wlen * sizeof(double)), bar + buf);
         }
     };
 
-    for (int kt = 0; kt < nt; ++kt) {
-        const int buf = g.nbuf == 2 ? (kt & 1) : 0;
+    const int n_it = KC ? nt * g.nkc : nt;
+    double acc[MT][2];
+    double Areg[WA];
+    for (int it = 0; it < n_it; ++it) {
+        const int buf = g.nbuf == 2 ? (it & 1) : 0;
         double* __restrict__ Xs = Xs0 + buf * xbuf;
-        int jb0, len, a, wlen;
-        const bool bulk = tile_geom(kt, jb0, len, a, wlen);
+        int jb0, qa, len, a, wlen;
+        const bool bulk = tile_geom(it, jb0, qa, len, a, wlen);
         // everyone is done with the windows this iteration overwrites (first tile: the bank and the mbarriers are set)
         __syncthreads();
         if (tid == 0) {
-            if (g.nbuf == 2) {  // prefetch the next tile under this tile's MMAs
-                if (kt == 0) issue(0, 0);
-                if (kt + 1 < nt) issue(kt + 1, buf ^ 1);
+            if (g.nbuf == 2) {  // prefetch the next tile / chunk under this one's MMAs
+                if (it == 0) issue(0, 0);
+                if (it + 1 < n_it) issue(it + 1, buf ^ 1);
             } else {
-                issue(kt, 0);
+                issue(it, 0);
             }
         }
         if (bulk) {
@@ -280,7 +289,7 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
                     continue;
                 }
                 const int64_t row = col_row(r);
-                const int64_t v0 = (int64_t)c.first + (col_pos0(r) + jb0) * M;  // element i of the window is v[v0 + i]
+                const int64_t v0 = (int64_t)c.first + (col_pos0(r) + jb0) * M + 4 * qa;  // element i of the window is v[v0 + i]
                 const int i1 = (int)min((int64_t)len, max((int64_t)0, (int64_t)c.hist_len - v0));
                 const int i2 = (int)min((int64_t)len, max((int64_t)i1, total - v0));
                 const double* __restrict__ hsrc = static_cast<const double*>(c.hist) + row * c.hist_stride + v0;
@@ -297,19 +306,20 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
         // ---- MT MMA tiles per warp; step q loads window chunk Q = warp*MT*SH + q and A fragment q ----
         const int npos_t = min(TJ, g.ps - jb0);
         if (warp * MT * JT < npos_t) {
-            double acc[MT][2];
+            if (!KC || qa == 0) {
 #pragma unroll
-            for (int b = 0; b < MT; ++b) acc[b][0] = acc[b][1] = 0.0;
-            double Areg[WA];
-            // B fragment: lane l reads X[w = 4*Q + l%4][column l/4]
-            const double* __restrict__ xw = Xs + (lane >> 2) * g.pitch + (lane & 3) + a + 4 * (warp * MT * SH);
+                for (int b = 0; b < MT; ++b) acc[b][0] = acc[b][1] = 0.0;
+            }
+            const int qb = KC ? min(nq, qa + g.nqc) : nq;
+            // B fragment: lane l reads X[w = 4*Q + l%4][column l/4]; the staged window starts at sample 4*qa of the tile's
+            const double* __restrict__ xw = Xs + (lane >> 2) * g.pitch + (lane & 3) + a + 4 * (warp * MT * SH) - 4 * qa;
             // A fragment: lane l holds A[row = l/4][w = 4*kk + l%4] = bank[p][4*kk + l%4 - jj*M], row = jj*NF + p
             const double* __restrict__ aw = Bs + ((lane >> 2) % NF) * blen + BOFF + (lane & 3) - ((lane >> 2) / NF) * M;
-            for (int q0 = 0; q0 < nq; q0 += WA) {
+            for (int q0 = qa; q0 < qb; q0 += WA) {  // qa is a multiple of WA: the rotating A window carries over
 #pragma unroll
                 for (int u = 0; u < WA; ++u) {
                     const int q = q0 + u;
-                    if (q < nq) {
+                    if (q < qb) {
                         Areg[u] = q < g.nk ? aw[4 * q] : 0.0;
                         const double bf = xw[4 * q];
 #pragma unroll
@@ -320,19 +330,21 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
                     }
                 }
             }
-            // ---- D[row = lane/4][cols 2*(lane%4), +1]: output (pos0 + jb)*NF + row of the columns' rows ----
-            const int r8 = lane >> 2;
+            if (!KC || qb == nq) {
+                // ---- D[row = lane/4][cols 2*(lane%4), +1]: output (pos0 + jb)*NF + row of the columns' rows ----
+                const int r8 = lane >> 2;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int col = 2 * (lane & 3) + e;
-                if (sbase + col >= g.nvs) continue;
-                const int64_t pos0 = col_pos0(col);
-                const int64_t plim = min((int64_t)c.n_pos, pos0 + g.ps);  // the column's segment ends here
-                double* __restrict__ orow = static_cast<double*>(c.out) + col_row(col) * c.out_stride;
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 2 * (lane & 3) + e;
+                    if (sbase + col >= g.nvs) continue;
+                    const int64_t pos0 = col_pos0(col);
+                    const int64_t plim = min((int64_t)c.n_pos, pos0 + g.ps);  // the column's segment ends here
+                    double* __restrict__ orow = static_cast<double*>(c.out) + col_row(col) * c.out_stride;
 #pragma unroll
-                for (int b = 0; b < MT; ++b) {
-                    const int64_t jb = pos0 + jb0 + (warp * MT + b) * JT;
-                    if (jb + r8 / NF < plim) orow[jb * NF + r8] = acc[b][e];
+                    for (int b = 0; b < MT; ++b) {
+                        const int64_t jb = pos0 + jb0 + (warp * MT + b) * JT;
+                        if (jb + r8 / NF < plim) orow[jb * NF + r8] = acc[b][e];
+                    }
                 }
             }
         }
@@ -362,17 +374,25 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
     static const bool pad_bank = [] { const char* e = std::getenv("GAR_MMA_BANKPAD"); return !e || e[0] != '0'; }();
     if (NF == 2 && pad_bank) g.blen = ((g.blen + 7) & ~15) + 8;
     const size_t bank_bytes = 16 + (size_t)NF * g.blen * sizeof(double);
-    auto run = [&](auto kernel, const int NW, const int MT, const int slot) -> bool {
+    // nkc > 1: tap-chunked staging (KC kernels); max_smem: give up when a block needs more (0: whatever fits an SM)
+    auto run = [&](auto kernel, const int NW, const int MT, const int slot, const int nkc, const size_t max_smem) -> bool {
         const int TJ = NW * MT * JT;
-        g.xlen = (TJ - 1) * M + 4 * g.nk + 4 * (MT - 1) * SH + 10;
+        // long filters: the window of a tile is mostly taps; it is staged in `nkc` chunks along the taps (accumulators and
+        // the rotating A window stay in registers), so that smaller / double-buffered stages fit
+        const int WA = (MT - 1) * SH + 1, nq = g.nk + (MT - 1) * SH;
+        g.nkc = nkc;
+        g.nqc = ((nq + g.nkc - 1) / g.nkc + WA - 1) / WA * WA;
+        g.nkc = (nq + g.nqc - 1) / g.nqc;
+        g.xlen = g.nkc == 1 ? (TJ - 1) * M + 4 * g.nk + 4 * (MT - 1) * SH + 10 : 4 * (NW - 1) * MT * SH + 4 * g.nqc + 10;
         g.pitch = ((g.xlen + 15) / 16) * 16 + 4;  // rows 32 bytes apart modulo 128: the 8 x 32-byte B fragment reads tile two wavefronts
         const size_t xbytes = (size_t)8 * g.pitch * sizeof(double);
         // two window buffers (the next tile is prefetched under the MMAs) when at least two such blocks fit an SM
         static const int force_nbuf = [] { const char* e = std::getenv("GAR_MMA_NBUF"); return e ? std::atoi(e) : 0; }();
         g.nbuf = bank_bytes + 2 * xbytes <= 110 * 1024 ? 2 : 1;
         if (force_nbuf == 1) g.nbuf = 1;
+        if (force_nbuf == 2 && bank_bytes + 2 * xbytes <= 227 * 1024) g.nbuf = 2;
         const size_t smem = bank_bytes + g.nbuf * xbytes;
-        if (smem > 227 * 1024) return false;
+        if (smem > 227 * 1024 || (max_smem && smem > max_smem)) return false;
         g.ps = g.nseg == 1 ? c.n_pos : (((c.n_pos + g.nseg - 1) / g.nseg + TJ - 1) / TJ) * TJ;
         if (g.nseg > 1 && g.ps < 2 * TJ) return false;  // segments shorter than two tiles: not worth it
         g.n_tiles = (g.ps + TJ - 1) / TJ;
@@ -394,14 +414,24 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
         count_launch();
         return true;
     };
-    // Measured on B200 (C3: 8 ch x 1223 taps /2; x2 stage of the batched 44.1k->48k chain): 16 warps x 4 tiles for long
-    // filters (one block per SM: the window is dominated by the taps), 8 warps x 4 tiles in several blocks per SM for
-    // short ones; 6 or 8 tiles per warp and smaller blocks were slower. GAR_MMA_CFG = 1 / 3 forces one of the two.
+    // Measured on B200. Short filters (x2 stage of the batched 44.1k->48k chain): 8 warps x 4 tiles, several blocks per SM;
+    // 6 or 8 tiles per warp were slower. Long filters (C3: 8 ch x 1223 taps /2): the window of a tile is mostly taps, so the
+    // 8-warp block is staged in 2-4 chunks along the taps until TWO blocks fit an SM (C3: 0.398 -> 0.374 ms against one
+    // 16-warp block per SM with the whole window; chunking that 16-warp block or double-buffering the chunks was slower).
+    // GAR_MMA_CFG = 1 / 3 forces 16 / 8 warps with the whole window, GAR_MMA_NKC = n the chunk count.
     static const int forced = [] { const char* e = std::getenv("GAR_MMA_CFG"); return e ? std::atoi(e) : -1; }();
-    if (forced == 1) return run(fir_mma_f64_kernel<M, NF, 16, 4>, 16, 4, 1);
-    if (forced == 3) return run(fir_mma_f64_kernel<M, NF, 8, 4>, 8, 4, 3);
-    if (c.taps > 600) return run(fir_mma_f64_kernel<M, NF, 16, 4>, 16, 4, 1) || run(fir_mma_f64_kernel<M, NF, 8, 4>, 8, 4, 3);
-    return run(fir_mma_f64_kernel<M, NF, 8, 4>, 8, 4, 3);
+    static const int nkc_env = [] { const char* e = std::getenv("GAR_MMA_NKC"); return e ? std::atoi(e) : 0; }();
+    if (forced == 1) return run(fir_mma_f64_kernel<M, NF, 16, 4, false>, 16, 4, 1, 1, 0);
+    if (forced == 3) return run(fir_mma_f64_kernel<M, NF, 8, 4, false>, 8, 4, 3, 1, 0);
+    if (c.taps > 600) {
+        constexpr size_t two_per_sm = 113 * 1024;
+        if (nkc_env > 1) return run(fir_mma_f64_kernel<M, NF, 8, 4, true>, 8, 4, 2, nkc_env, 0);
+        if (run(fir_mma_f64_kernel<M, NF, 8, 4, false>, 8, 4, 3, 1, two_per_sm)) return true;
+        for (int nkc = 2; nkc <= 4; ++nkc)
+            if (run(fir_mma_f64_kernel<M, NF, 8, 4, true>, 8, 4, 2, nkc, two_per_sm)) return true;
+        return run(fir_mma_f64_kernel<M, NF, 16, 4, false>, 16, 4, 1, 1, 0) || run(fir_mma_f64_kernel<M, NF, 8, 4, false>, 8, 4, 3, 1, 0);
+    }
+    return run(fir_mma_f64_kernel<M, NF, 8, 4, false>, 8, 4, 3, 1, 0);
 }
 
 static bool g_fir_mma = [] {
