@@ -180,3 +180,38 @@ def test_c4_alt_path_a_float32_io_float64_inside():
     assert _maxerr(out[:n], ref[:m]) <= TOL32
     gf, wf = r.Flush(), p.flush()
     assert len(gf) == 471 and _maxerr(gf, wf) <= TOL64
+
+
+@pytest.mark.parametrize("ir,orr,counts", [(44100, 48000, (479787, 215)), (44100, 47999, (479789, 203))])
+def test_c1_c5b_full_length_batched_on_the_tensor_cores_equals_single_streams_and_oracle(ir, orr, counts):
+    """BASELINE configs 1 and 5b at full length as ONE lock-step batch call on device buffers (128 rows x 441 000 samples:
+    K1m + K3p on the FP64 tensor cores): every row equals the single-stream engine's result for its signal to 1e-13 (rows are
+    independent; the single stream takes the fused vector kernels), counts are the reference's, and the sine row is within
+    1e-12 of the oracle."""
+    import torch
+    rows, n = 128, 441000
+    rng = np.random.default_rng(77)
+    base = [sig_c1(), 0.7 * rng.standard_normal(n), np.where(np.arange(n) % 1000 == 0, 1.0, 0.0), rng.uniform(-1, 1, n)]
+    x = np.empty((rows, n))
+    for r in range(rows):
+        x[r] = base[r % 4]
+    h = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float64)
+    dx = torch.from_numpy(x).cuda()
+    ostride = (h.EstimateOutput(n) + 3) & ~3
+    dy = torch.zeros((rows, ostride), dtype=torch.float64, device="cuda")
+    df = torch.zeros((rows, 1024), dtype=torch.float64, device="cuda")
+    c1 = h.process_batch_dev(dx.data_ptr(), n, n, dy.data_ptr(), ostride, ostride, 0, np.float64)
+    used = set(h.last_kernels())
+    c2 = h.flush_batch_dev(df.data_ptr(), 1024, 1024, 0, np.float64)
+    torch.cuda.synchronize()
+    assert (c1, c2) == counts
+    assert "fir_f64_mma_up2" in used and any(k.startswith("poly_rows_mma_f64") and k.endswith("pipe") for k in used), used
+    got = np.concatenate([dy[:, :c1].cpu().numpy(), df[:, :c2].cpu().numpy()], axis=1)
+    for s in range(4):
+        e = G.NewEngine(ir, orr, G.QualityHigh)
+        single = np.concatenate([e.Process(base[s]), e.Flush()])
+        assert single.shape[0] == got.shape[1]
+        for r in range(s, rows, 4):
+            assert np.max(np.abs(got[r] - single)) <= 1e-13, (s, r)
+    want = O.resample_mono(base[0], ir, orr, O.PRESET_HIGH)
+    assert _maxerr(got[0], want) <= TOL64
