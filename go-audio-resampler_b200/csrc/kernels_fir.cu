@@ -2,6 +2,7 @@
 // fir_f32x2_kernel with packed fma.rn.f32x2), K1m/K2m on the FP64 tensor cores (fir_mma_f64_kernel, DMMA), the generic
 // fallback, and launch_fir.
 #include "device_common.cuh"
+#include <type_traits>
 
 namespace gar {
 namespace {
@@ -315,20 +316,28 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
             const double* __restrict__ xw = Xs + (lane >> 2) * g.pitch + (lane & 3) + a + 4 * (warp * MT * SH) - 4 * qa;
             // A fragment: lane l holds A[row = l/4][w = 4*kk + l%4] = bank[p][4*kk + l%4 - jj*M], row = jj*NF + p
             const double* __restrict__ aw = Bs + ((lane >> 2) % NF) * blen + BOFF + (lane & 3) - ((lane >> 2) / NF) * M;
-            for (int q0 = qa; q0 < qb; q0 += WA) {  // qa is a multiple of WA: the rotating A window carries over
+            // WA steps; CK = false: every step has all MT tiles inside the filter (no predicates, no re-convergence code
+            // around the MMAs) — the steady state between the ramp-up of the first and the ramp-down of the last tiles
+            auto steps = [&](const int q0, auto ck) {
+                constexpr bool CK = decltype(ck)::value;
 #pragma unroll
                 for (int u = 0; u < WA; ++u) {
                     const int q = q0 + u;
-                    if (q < qb) {
-                        Areg[u] = q < g.nk ? aw[4 * q] : 0.0;
+                    if (!CK || q < qb) {
+                        Areg[u] = (!CK || q < g.nk) ? aw[4 * q] : 0.0;
                         const double bf = xw[4 * q];
 #pragma unroll
                         for (int b = 0; b < MT; ++b) {
                             const int kk = q - b * SH;
-                            if (kk >= 0 && kk < g.nk) dmma884(acc[b][0], acc[b][1], Areg[((u - b * SH) % WA + WA) % WA], bf);
+                            if (!CK || (kk >= 0 && kk < g.nk)) dmma884(acc[b][0], acc[b][1], Areg[((u - b * SH) % WA + WA) % WA], bf);
                         }
                     }
                 }
+            };
+            const int q_steady = min(g.nk, qb) - WA;  // last q0 of an all-valid group
+            for (int q0 = qa; q0 < qb; q0 += WA) {  // qa is a multiple of WA: the rotating A window carries over
+                if (q0 >= (MT - 1) * SH && q0 <= q_steady) steps(q0, std::false_type{});
+                else steps(q0, std::true_type{});
             }
             if (!KC || qb == nq) {
                 // ---- D[row = lane/4][cols 2*(lane%4), +1]: output (pos0 + jb)*NF + row of the columns' rows ----

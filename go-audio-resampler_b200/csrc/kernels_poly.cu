@@ -2,6 +2,7 @@
 // K3 (one thread per output), K3i (lanes = lock-step rows, coefficients interpolated once per batch), K3m (the same
 // contraction on the FP64 tensor cores), and launch_poly.
 #include "device_common.cuh"
+#include <type_traits>
 
 namespace gar {
 namespace {
@@ -416,6 +417,14 @@ __global__ void __launch_bounds__(NTASK * 32, NTASK == 8 ? 2 : 3) poly_rows_mma_
 // Per k-step 4 B fragments (LDS.64) feed 4 DMMA.8x8x4 (K3m: 5 loads). Same A values, same accumulation order as K3m:
 // bit-identical results.
 // =============================================================================================
+// calls f(integral_constant<N>) for the N in [LO, HI] equal to n, f(integral_constant<0>) when n is outside the range
+template <int HI, int LO, class F>
+__device__ __forceinline__ void dispatch_count(const int n, F&& f) {
+    if (n == HI) f(std::integral_constant<int, HI>{});
+    else if constexpr (HI > LO) dispatch_count<HI - 1, LO>(n, f);
+    else f(std::integral_constant<int, 0>{});
+}
+
 template <int NK, int RB, int NST>
 __global__ void __launch_bounds__(288, 2) poly_rows_pipe_kernel(const PolyCall c, const RowsMmaGeom g) {
     constexpr int RN = 8, NTASK = 8, TO = RN * NTASK, NT8 = RB / 8;
@@ -563,13 +572,18 @@ __global__ void __launch_bounds__(288, 2) poly_rows_pipe_kernel(const PolyCall c
             for (int t = 0; t < NT8; ++t) acc[t][0] = acc[t][1] = 0.0;
             // B fragment: X[w = 4*kk + l%4][row 8*t + l/4]
             const double* __restrict__ bp = xs + (lane >> 2) * g.pitch + base + apad + (lane & 3);
+            // straight-line MMA block for the launch's k-step count (no predicates or re-convergence code between the MMAs);
+            // N = 0: predicated generic form
+            dispatch_count<NK, (NK > 20 ? 21 : 8)>(nks, [&](auto n_tag) {
+                constexpr int N = decltype(n_tag)::value;
 #pragma unroll
-            for (int kk = 0; kk < NK; ++kk) {
-                if (kk < nks) {
+                for (int kk = 0; kk < (N ? N : NK); ++kk) {
+                    if (N || kk < nks) {
 #pragma unroll
-                    for (int t = 0; t < NT8; ++t) dmma884(acc[t][0], acc[t][1], A[kk], bp[t * 8 * g.pitch + 4 * kk]);
+                        for (int t = 0; t < NT8; ++t) dmma884(acc[t][0], acc[t][1], A[kk], bp[t * 8 * g.pitch + 4 * kk]);
+                    }
                 }
-            }
+            });
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + buf)) : "memory");
             if (live) {
