@@ -2,6 +2,7 @@
 // v = hist ++ in, mbarrier / TMA bulk copy / cp.async wrappers, the register-tiled FIR core, the DMMA wrapper) and the
 // few host-side pieces they share (launch counter, A/B switches, tiles-per-block heuristic).
 #pragma once
+#include <type_traits>
 #include "kernels.cuh"
 
 #include <algorithm>
@@ -43,6 +44,14 @@ template <typename T>
 __device__ __forceinline__ void carry_row(const T* hist, int hist_len, const T* in, int n_in, T* hist_out, int drop,
                                           int new_len) {
     for (int i = threadIdx.x; i < new_len; i += blockDim.x) hist_out[i] = vload(hist, hist_len, in, n_in, drop + i);
+}
+
+// calls f(integral_constant<N>) for the N in [LO, HI] equal to n, f(integral_constant<0>) when n is outside the range
+template <int HI, int LO, class F>
+__device__ __forceinline__ void dispatch_count(const int n, F&& f) {
+    if (n == HI) f(std::integral_constant<int, HI>{});
+    else if constexpr (HI > LO) dispatch_count<HI - 1, LO>(n, f);
+    else f(std::integral_constant<int, 0>{});
 }
 
 // ---- mbarrier / TMA bulk-copy helpers (PTX; SASS: SYNCS.*, UBLKCP) ------------------------

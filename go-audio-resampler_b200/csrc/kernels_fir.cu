@@ -318,26 +318,49 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
             const double* __restrict__ aw = Bs + ((lane >> 2) % NF) * blen + BOFF + (lane & 3) - ((lane >> 2) / NF) * M;
             // WA steps; CK = false: every step has all MT tiles inside the filter (no predicates, no re-convergence code
             // around the MMAs) — the steady state between the ramp-up of the first and the ramp-down of the last tiles
-            auto steps = [&](const int q0, auto ck) {
-                constexpr bool CK = decltype(ck)::value;
+            // MODE 0: every step has all MT tiles inside the filter; MODE 2: the first group (q0 = 0), where which tiles have
+            // started is known at compile time; MODE 1: run-time checks (ramp-down, short filters)
+            auto steps = [&](const int q0, auto mode) {
+                constexpr int MODE = decltype(mode)::value;
 #pragma unroll
                 for (int u = 0; u < WA; ++u) {
-                    const int q = q0 + u;
-                    if (!CK || q < qb) {
-                        Areg[u] = (!CK || q < g.nk) ? aw[4 * q] : 0.0;
+                    const int q = MODE == 2 ? u : q0 + u;
+                    if (MODE != 1 || q < qb) {
+                        Areg[u] = (MODE != 1 || q < g.nk) ? aw[4 * q] : 0.0;
                         const double bf = xw[4 * q];
 #pragma unroll
                         for (int b = 0; b < MT; ++b) {
                             const int kk = q - b * SH;
-                            if (!CK || (kk >= 0 && kk < g.nk)) dmma884(acc[b][0], acc[b][1], Areg[((u - b * SH) % WA + WA) % WA], bf);
+                            const bool on = MODE == 0 ? true : MODE == 2 ? u - b * SH >= 0 : (kk >= 0 && kk < g.nk);
+                            if (on) dmma884(acc[b][0], acc[b][1], Areg[((u - b * SH) % WA + WA) % WA], bf);
                         }
+                    }
+                }
+            };
+            // ramp-down group with D = nk - q0 known at compile time (D + OFF = 1 .. WA - 1 + OFF; short A windows only)
+            constexpr int OFF = (MT - 1) * SH;
+            auto steps_tail = [&](const int q0, auto d_tag) {
+                constexpr int D = decltype(d_tag)::value - OFF;
+#pragma unroll
+                for (int u = 0; u < WA; ++u) {
+                    if (u < D + OFF) {
+                        Areg[u] = u < D ? aw[4 * (q0 + u)] : 0.0;
+                        const double bf = xw[4 * (q0 + u)];
+#pragma unroll
+                        for (int b = 0; b < MT; ++b)
+                            if (u - b * SH < D) dmma884(acc[b][0], acc[b][1], Areg[((u - b * SH) % WA + WA) % WA], bf);
                     }
                 }
             };
             const int q_steady = min(g.nk, qb) - WA;  // last q0 of an all-valid group
             for (int q0 = qa; q0 < qb; q0 += WA) {  // qa is a multiple of WA: the rotating A window carries over
-                if (q0 >= (MT - 1) * SH && q0 <= q_steady) steps(q0, std::false_type{});
-                else steps(q0, std::true_type{});
+                if (q0 >= (MT - 1) * SH && q0 <= q_steady) steps(q0, std::integral_constant<int, 0>{});
+                else if (q0 == 0 && q_steady >= 0) steps(q0, std::integral_constant<int, 2>{});
+                else if (!KC && WA <= 8 && q0 >= OFF && g.nk - q0 + OFF >= 1 && g.nk - q0 < WA)
+                    dispatch_count<WA - 1 + OFF, 1>(g.nk - q0 + OFF, [&](auto t) {
+                        if constexpr (decltype(t)::value != 0) steps_tail(q0, t);
+                    });
+                else steps(q0, std::integral_constant<int, 1>{});
             }
             if (!KC || qb == nq) {
                 // ---- D[row = lane/4][cols 2*(lane%4), +1]: output (pos0 + jb)*NF + row of the columns' rows ----

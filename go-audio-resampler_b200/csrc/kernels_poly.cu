@@ -417,14 +417,6 @@ __global__ void __launch_bounds__(NTASK * 32, NTASK == 8 ? 2 : 3) poly_rows_mma_
 // Per k-step 4 B fragments (LDS.64) feed 4 DMMA.8x8x4 (K3m: 5 loads). Same A values, same accumulation order as K3m:
 // bit-identical results.
 // =============================================================================================
-// calls f(integral_constant<N>) for the N in [LO, HI] equal to n, f(integral_constant<0>) when n is outside the range
-template <int HI, int LO, class F>
-__device__ __forceinline__ void dispatch_count(const int n, F&& f) {
-    if (n == HI) f(std::integral_constant<int, HI>{});
-    else if constexpr (HI > LO) dispatch_count<HI - 1, LO>(n, f);
-    else f(std::integral_constant<int, 0>{});
-}
-
 template <int NK, int RB, int NST>
 __global__ void __launch_bounds__(288, 2) poly_rows_pipe_kernel(const PolyCall c, const RowsMmaGeom g) {
     constexpr int RN = 8, NTASK = 8, TO = RN * NTASK, NT8 = RB / 8;
