@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(NW * 32) fir_mma_f64_kernel(const FirCall c, c
             for (int q0 = qa; q0 < qb; q0 += WA) {  // qa is a multiple of WA: the rotating A window carries over
                 if (q0 >= (MT - 1) * SH && q0 <= q_steady) steps(q0, std::integral_constant<int, 0>{});
                 else if (q0 == 0 && q_steady >= 0) steps(q0, std::integral_constant<int, 2>{});
-                else if (qb == nq && WA <= 13 && q0 >= OFF && g.nk - q0 + OFF >= 1 && g.nk - q0 < WA)
+                else if (qb == nq && WA <= 25 && q0 >= OFF && g.nk - q0 + OFF >= 1 && g.nk - q0 < WA)
                     dispatch_count<WA - 1 + OFF, 1>(g.nk - q0 + OFF, [&](auto t) {
                         if constexpr (decltype(t)::value != 0) steps_tail(q0, t);
                     });
