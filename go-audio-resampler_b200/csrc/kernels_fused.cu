@@ -866,15 +866,17 @@ const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s,
         return launch_fused_t<float, false>(c, s) ? "fused_up2_poly_f32" : nullptr;
     }
     // Tensor-core path = two launches: the x2 stage (K1m) and the polyphase stage (K3m) on the FP64 tensor cores.
-    //  * rational ratios: batches of >= 64 lock-step rows. Measured on 21 M input samples of 44.1k->48k (TFLOP/s, tensor path
-    //    against the fused K4r): 8 rows 15.7 / 17.5, 32 rows 15.7 / 17.5, 64 rows 18.3 / 17.9, 256 rows x 10 s 23.3 — K3m
-    //    amortises its coefficient matrices over the rows, K4r is the better kernel for a few long rows;
+    //  * rational ratios: batches of >= 32 lock-step rows. Measured on 21 M input samples of 44.1k->48k (TFLOP/s, tensor path
+    //    against the fused K4r): 8 rows 9.4 / 17.6, 16 rows 14.6 / 17.6, 24 rows 17.7 / 17.6, 32 rows 19.9 / 17.8, 48 rows
+    //    20.4 / 17.7, 64 rows 23.0, 256 rows x 10 s 28.1 — K3m / K3p amortise their coefficient matrices over the rows, K4r
+    //    is the better kernel for a few long rows (GAR_TENSOR_MIN_ROWS overrides the threshold);
     //  * irrational ratios: batches of >= 8 rows (K3m / K3i evaluate the interpolated coefficients once per batch; the fused
     //    one-thread-per-output kernel is 10x slower there).
     {
         const bool rational = !c.interp && ((c.step | c.at0) & 0xFFFF) == 0;
+        static const int rational_min_rows = [] { const char* e = std::getenv("GAR_TENSOR_MIN_ROWS"); return e ? std::atoi(e) : 32; }();
         if (tensor_fir_enabled() && g_fused_rat && (int64_t)c.np * c.n_streams >= 32768 &&
-            c.n_streams >= (rational ? 64 : 8))
+            c.n_streams >= (rational ? rational_min_rows : 8))
             return nullptr;
     }
     if (!c.interp && launch_rat<double, true>(c, s, cache)) return "fused_up2_rat_f64";

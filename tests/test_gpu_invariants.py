@@ -333,7 +333,7 @@ def test_rows_kernel_batched_any_ratio_vs_thread_per_output_kernels_and_oracle(i
     (96000, 48000, G.QualityVeryHigh, 8, 120000, "fir_f64_mma_s2"),    # /2 (path B maps VeryHigh to the 751-tap High filter)
     (48000, 16000, G.QualityHigh, 19, 90000, "fir_f64_mma_s3"),        # /3 with a ragged last group of streams
     (192000, 48000, G.QualityMedium, 9, 100000, "fir_f64_mma_s4"),     # /4
-    (44100, 48000, G.QualityHigh, 70, 16000, "fir_f64_mma_up2"),       # x2 stage in front of the polyphase stage (>= 64 rows: unfused)
+    (44100, 48000, G.QualityHigh, 70, 16000, "fir_f64_mma_up2"),       # x2 stage in front of the polyphase stage (>= 32 rows: unfused)
     # fewer than 8 rows: time segments of the rows are the MMA columns
     (96000, 48000, G.QualityVeryHigh, 2, 2100000, "fir_f64_mma_s2"),   # stereo, 2 rows x 4 segments
     (22050, 44100, G.QualityHigh, 1, 2050000, "fir_f64_mma_up2"),      # mono, 8 segments

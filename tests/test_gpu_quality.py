@@ -73,7 +73,7 @@ def test_thd_and_snr_floors_of_the_reference(ir, orr, q, rows):  # TestQualityRe
     # same figure as the oracle's output, not merely under the floor
     assert abs(thd_db(y[0], orr) - thd_db(want, orr)) <= 3.0 or thd_db(y[0], orr) <= -150.0
     if rows >= 8 and q != O.Q_QUICK:
-        # tensor-core kernels, or the fused register-tiled kernel rational ratios take below 64 rows
+        # tensor-core kernels, or the fused register-tiled kernel rational ratios take below 32 rows
         assert any("mma" in k or "fused_up2_rat" in k for k in kernels), kernels
 
 
