@@ -622,6 +622,9 @@ static bool launch_poly_rows_pipe_t(const PolyCall& c, cudaStream_t s) {
 
 // K3p variants: coefficient registers for K <= 80 or <= 112, 2 stages of 32 rows or (long spans) 3 stages of 16 rows
 static bool launch_poly_rows_pipe(const PolyCall& c, cudaStream_t s) {
+    static const int rb16_rows = [] { const char* e = std::getenv("GAR_K3P_RB16_ROWS"); return e ? std::atoi(e) : 0; }();
+    // fewer rows: 16-row stages keep the pipeline at least two stages deep
+    if (c.n_streams < rb16_rows && (launch_poly_rows_pipe_t<20, 16, 3>(c, s) || launch_poly_rows_pipe_t<28, 16, 3>(c, s))) return true;
     return launch_poly_rows_pipe_t<20, 32, 2>(c, s) || launch_poly_rows_pipe_t<20, 16, 3>(c, s) ||
            launch_poly_rows_pipe_t<28, 32, 2>(c, s) || launch_poly_rows_pipe_t<28, 16, 3>(c, s);
 }
@@ -669,7 +672,8 @@ static int launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
     if (!(r > 0.0) || r > 8.0) return 0;
     static const int ntask = [] { const char* e = std::getenv("GAR_K3M_NTASK"); return e ? std::atoi(e) : 8; }();
     static const bool pipe = [] { const char* e = std::getenv("GAR_K3M_PIPE"); return !e || e[0] != '0'; }();
-    static const int pipe_rows = [] { const char* e = std::getenv("GAR_K3M_PIPE_ROWS"); return e ? std::atoi(e) : 64; }();
+    static const int pipe_rows = [] { const char* e = std::getenv("GAR_K3M_PIPE_ROWS"); return e ? std::atoi(e) : 32; }();
+    // measured (44.1k->48k, 21 M samples): K3p against K3m 32 rows 20.9 / 19.9, 48 rows 21.8 / 20.4 TFLOP/s, equal below
     if (pipe && c.n_streams >= pipe_rows && launch_poly_rows_pipe(c, s)) return 2;
     if (ntask == 4) return (launch_poly_rows_mma_t<4>(c, s) || launch_poly_rows_mma_t<8>(c, s)) ? 1 : 0;
     return (launch_poly_rows_mma_t<8>(c, s) || launch_poly_rows_mma_t<4>(c, s)) ? 1 : 0;
