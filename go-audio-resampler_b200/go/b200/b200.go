@@ -376,3 +376,84 @@ func (b *Batch) Process(in []float32, nIn int, out []float32, outStride int) (in
 	runtime.KeepAlive(out)
 	return int(n), statusErr(st, b.h)
 }
+
+// Flush drains every stream of the batch (planar [Streams][outStride]); returns samples per row.
+func (b *Batch) Flush(out []float32, outStride int) (int, error) {
+	var n C.int64_t
+	st := C.gar_flush_batch(b.h, C.GAR_F32, unsafe.Pointer(&out[0]), C.int64_t(outStride), C.int64_t(outStride), &n)
+	runtime.KeepAlive(out)
+	return int(n), statusErr(st, b.h)
+}
+
+// Info mirrors resample.go:295-316; GetInfo: constant.go:452-485.
+type Info struct {
+	Algorithm    string
+	FilterLength int
+	Phases       int
+	Latency      int
+	MemoryUsage  int64
+	SIMDEnabled  bool
+	SIMDType     string
+}
+
+func (r *handle) GetInfo() Info {
+	var ci C.gar_info
+	C.gar_get_info(r.h, &ci)
+	return Info{
+		Algorithm:    C.GoString(&ci.algorithm[0]),
+		FilterLength: int(ci.filter_length),
+		Phases:       int(ci.phases),
+		Latency:      int(ci.latency),
+		MemoryUsage:  int64(ci.memory_usage),
+		SIMDEnabled:  ci.simd_enabled != 0,
+		SIMDType:     C.GoString(&ci.simd_type[0]),
+	}
+}
+
+// resampleAll: Process + Flush of one channel (convenience.go:206-229).
+func resampleAll(r *SimpleResampler, input []float64) ([]float64, error) {
+	out, err := r.Process(input)
+	if err != nil {
+		return nil, err
+	}
+	fl, err := r.Flush()
+	if err != nil {
+		return nil, err
+	}
+	return append(out, fl...), nil
+}
+
+// ResampleStereo: one engine for both channels, Reset() in between (convenience.go:233-257).
+func ResampleStereo(left, right []float64, inRate, outRate float64, q QualityPreset) (leftOut, rightOut []float64, err error) {
+	r, err := NewEngine(inRate, outRate, q)
+	if err != nil {
+		return nil, nil, err
+	}
+	if leftOut, err = resampleAll(r, left); err != nil {
+		return nil, nil, err
+	}
+	r.Reset()
+	if rightOut, err = resampleAll(r, right); err != nil {
+		return nil, nil, err
+	}
+	return leftOut, rightOut, nil
+}
+
+// ProcessInterleavedInt16 is one block of the resample-wav loop (cmd/resample-wav/helpers.go:77-334) for packed
+// int16 PCM: de-interleave + normalise, resample every channel, clamp + quantise + interleave on the device.
+// `r` must have been created with Channels = the number of interleaved channels.
+func (r *Resampler) ProcessInterleavedInt16(frames []int16, out []int16) (int, error) {
+	ch := r.channels
+	if ch <= 0 || len(frames)%ch != 0 {
+		return 0, fmt.Errorf("%w: interleaved length %d is not a multiple of %d channels", ErrInvalidConfig, len(frames), ch)
+	}
+	if len(frames) == 0 {
+		return 0, nil
+	}
+	var got C.int64_t
+	st := C.gar_process_interleaved(r.h, C.GAR_FMT_I16, 16, unsafe.Pointer(&frames[0]), C.int64_t(len(frames)/ch),
+		unsafe.Pointer(&out[0]), C.int64_t(len(out)/ch), &got)
+	runtime.KeepAlive(frames)
+	runtime.KeepAlive(out)
+	return int(got) * ch, statusErr(st, r.h)
+}
