@@ -1,6 +1,7 @@
 // kernels_poly.cu — arbitrary-ratio polyphase stage with cubic coefficient interpolation (polyphase_stage.go:186-312):
 // K3 (one thread per output), K3i (lanes = lock-step rows, coefficients interpolated once per batch), K3m (the same
-// contraction on the FP64 tensor cores), and launch_poly.
+// contraction on the FP64 tensor cores), K3p (K3m as a TMA producer / MMA consumer pipeline with the coefficient matrix in
+// registers), and launch_poly.
 #include "device_common.cuh"
 #include <type_traits>
 
