@@ -157,7 +157,7 @@ struct MmaGeom {
 };
 
 template <int M, int NF, int NW, int MT, bool KC>
-__global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : 1) fir_mma_f64_kernel(const FirCall c, const MmaGeom g) {
+__global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : (NW == 8 ? 2 : 1)) fir_mma_f64_kernel(const FirCall c, const MmaGeom g) {
     constexpr int JT = 8 / NF;                // positions per MMA tile
     static_assert(8 % NF == 0 && (JT * M) % 4 == 0, "tile shift must be a whole number of k-steps");
     constexpr int SH = JT * M / 4;            // k-steps between consecutive MMA tiles
