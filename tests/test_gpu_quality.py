@@ -6,46 +6,13 @@ import numpy as np
 import pytest
 
 from helpers import G, O
+from quality_metrics import snr_db, thd_db
 
 pytestmark = pytest.mark.gpu
 
-N, FFT = 65536, 16384
+N = 65536
 MAX_THD = {O.Q_QUICK: -80.0, O.Q_LOW: -130.0, O.Q_MEDIUM: -129.0, O.Q_HIGH: -140.0, O.Q_VERYHIGH: -140.0}
 MIN_SNR = 35.0
-
-
-def _spectrum(y):
-    w = 0.5 * (1.0 - np.cos(2.0 * np.pi * np.arange(FFT) / (FFT - 1)))
-    seg = np.zeros(FFT)
-    m = min(FFT, len(y))
-    seg[:m] = y[:m]
-    return np.abs(np.fft.fft(seg * w))
-
-
-def thd_db(y, out_rate, f0=1000.0):  # measureTHDInternal, quality_regression_test.go:292-342
-    mag = _spectrum(y)
-    fund = mag[int(f0 / out_rate * FFT)]
-    hp = 0.0
-    for h in range(2, 11):
-        if f0 * h >= out_rate / 2:
-            break
-        b = int(f0 * h / out_rate * FFT)
-        if b < FFT // 2:
-            hp += mag[b] ** 2
-    return 20 * np.log10(np.sqrt(hp) / (fund + 1e-20) + 1e-20)
-
-
-def snr_db(y, out_rate, f0=1000.0):  # measureSNRInternal, quality_regression_test.go:344-425
-    mag = _spectrum(y)
-    fb = int(f0 / out_rate * FFT)
-    sig = sum(mag[fb + b] ** 2 for b in range(-3, 4) if 0 < fb + b < FFT // 2)
-    hbins = [int(f0 * h / out_rate * FFT) for h in range(2, 11) if f0 * h < out_rate / 2]
-    noise = 0.0
-    for b in range(1, FFT // 2):
-        if fb - 3 <= b <= fb + 3 or any(hb - 2 <= b <= hb + 2 for hb in hbins):
-            continue
-        noise += mag[b] ** 2
-    return 10 * np.log10(sig + 1e-20) - 10 * np.log10(noise + 1e-20)
 
 
 def _run(ir, orr, q, rows):
