@@ -343,6 +343,7 @@ static int process_rows_host(gar_handle* h, int row0, int count, int io_dtype, c
     }
     cudaSetDevice(E.device());
     cudaStream_t s = E.stream();
+    E.begin_on(s);  // the scratch slots may still be read by work a batch call enqueued on a caller's stream
     const size_t iosz = dsize(io_dtype), csz = dsize(h->compute_dtype);
     const int64_t in_stride = (max_in + 3) & ~int64_t(3), out_stride = (max_out + 3) & ~int64_t(3);
     const bool cast = io_dtype != h->compute_dtype;
@@ -400,6 +401,7 @@ static int process_rows_host(gar_handle* h, int row0, int count, int io_dtype, c
             cudaMemcpyAsync(out[q], d_out_io + (size_t)q * (size_t)out_stride * iosz, (size_t)n_out[q] * iosz,
                             cudaMemcpyDeviceToHost, s);
     cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, GAR_CUDA_ERROR, std::string("stream sync: ") + cudaGetErrorString(e));
     return GAR_OK;
 }
@@ -488,6 +490,7 @@ static int batch_dev(gar_handle* h, int io_dtype, const void* d_in, int64_t in_s
     const size_t iosz = dsize(io_dtype), csz = dsize(h->compute_dtype);
     const bool cast = io_dtype != h->compute_dtype;
     cudaSetDevice(E.device());
+    if (cast) E.begin_on(s);  // cast scratch is shared handle state (Engine::run orders everything else itself)
     int r = 0;
     int64_t got_all = -1;
     while (r < count) {
@@ -522,6 +525,10 @@ static int batch_dev(gar_handle* h, int io_dtype, const void* d_in, int64_t in_s
         else if (got != got_all)
             return fail(h, GAR_NOT_SUPPORTED, "batch rows are not in lock step (mixed per-channel calls before a batch call)");
         r += run;
+    }
+    if (cast) {
+        E.end_on(s);
+        if (cudaGetLastError() != cudaSuccess) return fail(h, GAR_CUDA_ERROR, "cast kernel launch failed");
     }
     if (n_out) *n_out = got_all < 0 ? 0 : got_all;
     return GAR_OK;
@@ -582,22 +589,25 @@ static int batch_host(gar_handle* h, int io_dtype, const void* in, int64_t in_st
     // a handful of long rows stays together (their time segments fill the tensor-core kernels' columns) up to 1 GiB
     if (rows <= 2 || (rows <= 8 && rows * row_bytes <= (1ll << 30))) slice = rows;
     const size_t need_in = (size_t)slice * (size_t)is * iosz, need_out = (size_t)slice * (size_t)os * iosz;
-    if (need_in > h->slot_in_cap) {
+    auto grow = [&](void* (&slot)[2], size_t& cap, size_t need, const char* what) -> bool {
+        if (need <= cap) return true;
         cudaDeviceSynchronize();
+        cap = 0;  // nothing is published until both slots exist
         for (int i = 0; i < 2; ++i) {
-            if (h->slot_in[i]) cudaFree(h->slot_in[i]);
-            if (cudaMalloc(&h->slot_in[i], need_in) != cudaSuccess) return fail(h, GAR_CUDA_ERROR, "cudaMalloc(staging in)");
+            if (slot[i]) cudaFree(slot[i]);
+            slot[i] = nullptr;
         }
-        h->slot_in_cap = need_in;
-    }
-    if (need_out > h->slot_out_cap) {
-        cudaDeviceSynchronize();
-        for (int i = 0; i < 2; ++i) {
-            if (h->slot_out[i]) cudaFree(h->slot_out[i]);
-            if (cudaMalloc(&h->slot_out[i], need_out) != cudaSuccess) return fail(h, GAR_CUDA_ERROR, "cudaMalloc(staging out)");
-        }
-        h->slot_out_cap = need_out;
-    }
+        for (int i = 0; i < 2; ++i)
+            if (cudaMalloc(&slot[i], need) != cudaSuccess) {
+                slot[i] = nullptr;
+                fail(h, GAR_CUDA_ERROR, what);
+                return false;
+            }
+        cap = need;
+        return true;
+    };
+    if (!grow(h->slot_in, h->slot_in_cap, need_in, "cudaMalloc(staging in)")) return GAR_CUDA_ERROR;
+    if (!grow(h->slot_out, h->slot_out_cap, need_out, "cudaMalloc(staging out)")) return GAR_CUDA_ERROR;
     cudaStream_t sc = E.stream();
     int k = 0;
     for (int r0 = 0; r0 < rows; r0 += slice, ++k) {
@@ -685,6 +695,7 @@ static int interleaved_call(gar_handle* h, int fmt, int bit_depth, const void* i
     if (!flush && n_frames == 0) return GAR_OK;
     cudaSetDevice(E.device());
     cudaStream_t s = E.stream();
+    E.begin_on(s);
     const size_t isz = fmt_size(fmt), csz = dsize(h->compute_dtype);
     const bool is_int = fmt >= GAR_FMT_I16;
     const double maxv = is_int ? pcm_max(bit_depth) : 0.0;

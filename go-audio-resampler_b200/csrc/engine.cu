@@ -28,7 +28,21 @@ Engine::~Engine() {
     for (void* p : scratch_) if (p) cudaFree(p);
     if (d_cubic_idx_) cudaFree(d_cubic_idx_);
     if (d_cubic_phase_) cudaFree(d_cubic_phase_);
+    if (order_ev_) cudaEventDestroy(order_ev_);
     if (stream_) cudaStreamDestroy(stream_);
+}
+
+// All engine state on the device (tails, inter-stage buffers, scratch, coefficient-tile caches) is shared by every call on the
+// handle, whatever stream the caller enqueues on. Calls are ordered against each other with one event: recorded on the
+// stream of the last enqueue, waited for by the next enqueue when it uses a different stream.
+void Engine::order_before(cudaStream_t s) {
+    if (order_pending_ && last_stream_ != s) cudaStreamWaitEvent(s, order_ev_, 0);
+}
+void Engine::order_after(cudaStream_t s) {
+    if (!order_ev_) return;
+    cudaEventRecord(order_ev_, s);
+    last_stream_ = s;
+    order_pending_ = true;
 }
 
 int Engine::upload_bank(int stage, int which, const std::vector<double>& v, std::string& err) {
@@ -78,6 +92,7 @@ int Engine::init(const Chain& chain, int rows, int compute_dtype, int device, st
     }
     if (!cuda_ok(cudaSetDevice(device), err, "cudaSetDevice")) return 4;
     if (!cuda_ok(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), err, "cudaStreamCreate")) return 4;
+    if (!cuda_ok(cudaEventCreateWithFlags(&order_ev_, cudaEventDisableTiming), err, "cudaEventCreate")) return 4;
 
     const size_t S = chain_.stages.size();
     dev_.assign(S, StageDev{});
@@ -97,7 +112,7 @@ int Engine::init(const Chain& chain, int rows, int compute_dtype, int device, st
             case STAGE_CUBIC: cap = 4; break;
         }
         dev_[s].hist_cap = 0;
-        int rc = ensure_hist((int)s, cap, err);
+        int rc = ensure_hist((int)s, cap, stream_, err);
         if (rc) return rc;
     }
     name_kernels();
@@ -141,11 +156,13 @@ void Engine::reset_state() {
     }
     if (device_ < 0) return;
     cudaSetDevice(device_);
+    order_before(stream_);  // work enqueued on a caller's stream may still be reading the tails
     for (size_t s = 0; s < S; ++s)
         if (chain_.stages[s].kind == STAGE_CUBIC)
             for (auto& h : dev_[s].hist)
                 if (h) cudaMemsetAsync(h, 0, (size_t)rows_ * (size_t)dev_[s].hist_cap * esz_, stream_);
     if (stream_) cudaStreamSynchronize(stream_);
+    order_pending_ = false;  // everything enqueued so far has completed
 }
 
 int Engine::set_bank(int stage, int which, const double* coef, int64_t n, std::string& err) {
@@ -161,28 +178,36 @@ int Engine::set_bank(int stage, int which, const double* coef, int64_t n, std::s
     sd.bank[which].assign(coef, coef + n);
     if (device_ < 0) return 0;
     cudaSetDevice(device_);
-    cudaStreamSynchronize(stream_);
+    cudaDeviceSynchronize();  // the old bank and its coefficient tiles may be in use on any stream
+    order_pending_ = false;
     return upload_bank(stage, which, sd.bank[which], err);
 }
 
-int Engine::ensure_hist(int stage, int64_t need, std::string& err) {
+// Grows both ping-pong tail buffers of a stage. Everything (clear, copy of the old tails) is enqueued on `s`, the stream
+// the following kernels run on: the legacy default stream has no ordering with the engine's non-blocking streams.
+int Engine::ensure_hist(int stage, int64_t need, cudaStream_t s, std::string& err) {
     StageDev& d = dev_[(size_t)stage];
     if (need <= d.hist_cap) return 0;
     const int64_t ncap = std::max<int64_t>(need + need / 2, 16);
+    const size_t bytes = (size_t)rows_ * (size_t)ncap * esz_;
+    void* nb[2] = {nullptr, nullptr};
+    for (int p = 0; p < 2; ++p)
+        if (!cuda_ok(cudaMalloc(&nb[p], bytes), err, "cudaMalloc(hist)")) {
+            if (nb[0]) cudaFree(nb[0]);
+            return 4;  // nothing published: the old buffers and capacity stay valid
+        }
+    if (d.hist[0]) cudaDeviceSynchronize();  // the old tails may still be in use on any stream
     for (int p = 0; p < 2; ++p) {
-        void* nb = nullptr;
-        const size_t bytes = (size_t)rows_ * (size_t)ncap * esz_;
-        if (!cuda_ok(cudaMalloc(&nb, bytes), err, "cudaMalloc(hist)")) return 4;
-        cudaMemset(nb, 0, bytes);
+        cudaMemsetAsync(nb[p], 0, bytes, s);
         device_bytes_ += (int64_t)bytes;
         if (d.hist[p]) {
-            cudaDeviceSynchronize();
-            cudaMemcpy2D(nb, (size_t)ncap * esz_, d.hist[p], (size_t)d.hist_cap * esz_, (size_t)d.hist_cap * esz_,
-                         (size_t)rows_, cudaMemcpyDeviceToDevice);
+            cudaMemcpy2DAsync(nb[p], (size_t)ncap * esz_, d.hist[p], (size_t)d.hist_cap * esz_, (size_t)d.hist_cap * esz_,
+                              (size_t)rows_, cudaMemcpyDeviceToDevice, s);
+            cudaStreamSynchronize(s);
             cudaFree(d.hist[p]);
             device_bytes_ -= (int64_t)((size_t)rows_ * (size_t)d.hist_cap * esz_);
         }
-        d.hist[p] = nb;
+        d.hist[p] = nb[p];
     }
     d.hist_cap = ncap;
     return 0;
@@ -205,7 +230,7 @@ void* Engine::scratch(int slot, size_t bytes, std::string& err) {
     return scratch_[slot];
 }
 
-int Engine::ensure_internal(const Plan& p, std::string& err) {
+int Engine::ensure_internal(const Plan& p, cudaStream_t s, std::string& err) {
     for (size_t b = 0; b < p.buf_need.size(); ++b) {
         if (p.buf_need[b] <= ibuf_cap_[b]) continue;
         if (ibuf_[b]) {
@@ -213,6 +238,7 @@ int Engine::ensure_internal(const Plan& p, std::string& err) {
             cudaFree(ibuf_[b]);
             device_bytes_ -= (int64_t)((size_t)rows_ * (size_t)ibuf_cap_[b] * esz_);
             ibuf_[b] = nullptr;
+            ibuf_cap_[b] = 0;  // a failed allocation below must not leave a stale capacity behind
         }
         // rows padded to 16 bytes so that row starts stay TMA/vector aligned
         int64_t cap = p.buf_need[b] + p.buf_need[b] / 8 + 64;
@@ -229,20 +255,39 @@ int Engine::ensure_internal(const Plan& p, std::string& err) {
         if (zeros_) {
             cudaDeviceSynchronize();
             cudaFree(zeros_);
+            zeros_ = nullptr;
+            zeros_cap_ = 0;
         }
-        zeros_cap_ = zneed + 64;
-        if (!cuda_ok(cudaMalloc(&zeros_, (size_t)zeros_cap_ * 8), err, "cudaMalloc(zeros)")) return 4;
-        cudaMemset(zeros_, 0, (size_t)zeros_cap_ * 8);
+        const int64_t ncap = zneed + 64;
+        if (!cuda_ok(cudaMalloc(&zeros_, (size_t)ncap * 8), err, "cudaMalloc(zeros)")) {
+            zeros_ = nullptr;
+            return 4;
+        }
+        // cleared on the launch stream: the flush kernels that read the zero row are enqueued on `s` right after
+        cudaMemsetAsync(zeros_, 0, (size_t)ncap * 8, s);
+        zeros_cap_ = ncap;
     }
     if ((int64_t)p.cubic_idx.size() > cubic_cap_) {
-        if (d_cubic_idx_) {
+        if (d_cubic_idx_ || d_cubic_phase_) {
             cudaDeviceSynchronize();
-            cudaFree(d_cubic_idx_);
-            cudaFree(d_cubic_phase_);
+            if (d_cubic_idx_) cudaFree(d_cubic_idx_);
+            if (d_cubic_phase_) cudaFree(d_cubic_phase_);
+            d_cubic_idx_ = nullptr;
+            d_cubic_phase_ = nullptr;
+            cubic_cap_ = 0;
         }
-        cubic_cap_ = (int64_t)p.cubic_idx.size() * 2;
-        if (!cuda_ok(cudaMalloc(&d_cubic_idx_, (size_t)cubic_cap_ * 4), err, "cudaMalloc(cubic idx)")) return 4;
-        if (!cuda_ok(cudaMalloc(&d_cubic_phase_, (size_t)cubic_cap_ * 8), err, "cudaMalloc(cubic phase)")) return 4;
+        const int64_t ncap = (int64_t)p.cubic_idx.size() * 2;
+        if (!cuda_ok(cudaMalloc(&d_cubic_idx_, (size_t)ncap * 4), err, "cudaMalloc(cubic idx)")) {
+            d_cubic_idx_ = nullptr;
+            return 4;
+        }
+        if (!cuda_ok(cudaMalloc(&d_cubic_phase_, (size_t)ncap * 8), err, "cudaMalloc(cubic phase)")) {
+            cudaFree(d_cubic_idx_);
+            d_cubic_idx_ = nullptr;
+            d_cubic_phase_ = nullptr;
+            return 4;
+        }
+        cubic_cap_ = ncap;  // published only after both allocations succeeded
     }
     return 0;
 }
@@ -517,11 +562,12 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
         err = "output too long";
         return 1;
     }
-    int rc = ensure_internal(P, err);
+    order_before(s);
+    int rc = ensure_internal(P, s, err);
     if (rc) return rc;
     for (const Op& op : P.ops)
         if (op.stage >= 0) {
-            rc = ensure_hist(op.stage, op.new_hist_len, err);
+            rc = ensure_hist(op.stage, op.new_hist_len, s, err);
             if (rc) return rc;
         }
     if (!P.cubic_idx.empty()) {
@@ -649,6 +695,7 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
         }
         ++launches_;
     }
+    order_after(s);
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) {
         err = std::string("kernel launch failed: ") + cudaGetErrorString(le);

@@ -123,17 +123,25 @@ class Engine {
 
     // staging helpers (grow-only device scratch in bytes), slot 0..3
     void* scratch(int slot, size_t bytes, std::string& err);
+    // cross-stream ordering for callers that touch the scratch slots outside run() (capi.cu)
+    void begin_on(cudaStream_t s) { order_before(s); }
+    void end_on(cudaStream_t s) { order_after(s); }
 
   private:
     void name_kernels();
-    int ensure_internal(const Plan& p, std::string& err);
-    int ensure_hist(int stage, int64_t need, std::string& err);
+    int ensure_internal(const Plan& p, cudaStream_t s, std::string& err);
+    int ensure_hist(int stage, int64_t need, cudaStream_t s, std::string& err);
+    void order_before(cudaStream_t s);
+    void order_after(cudaStream_t s);
     int upload_bank(int stage, int which, const std::vector<double>& v, std::string& err);
 
     Chain chain_;
     int rows_ = 0, dtype_ = DT_F64, device_ = 0;
     size_t esz_ = 8;
     cudaStream_t stream_ = nullptr;
+    cudaEvent_t order_ev_ = nullptr;      // recorded after every enqueue (cross-stream ordering of the shared state)
+    cudaStream_t last_stream_ = nullptr;
+    bool order_pending_ = false;
     std::vector<StreamState> streams_;
     std::vector<StageDev> dev_;
     std::vector<void*> ibuf_;         // internal buffers [rows][cap]

@@ -804,7 +804,7 @@ static bool launch_rat_t(const FusedCall& c, cudaStream_t s, RatCache* cache) {
         const int key = (int)sizeof(T) * 1000003 + S * 100003 + RN * 10007 + g.tp * 131 + g.gpitch * 7 + L;
         if (!cache->dev || cache->tile_bytes != tile_bytes || cache->key != key || (int)cache->built.size() != L) {
             if (cache->dev) {
-                cudaStreamSynchronize(s);
+                cudaDeviceSynchronize();  // tiles may still be read by launches on any stream of this handle
                 cudaFree(cache->dev);
                 cache->dev = nullptr;
             }

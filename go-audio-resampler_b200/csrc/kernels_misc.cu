@@ -50,10 +50,11 @@ __global__ void carry_kernel(const T* hist, int64_t hist_stride, int hist_len, c
 }
 
 template <typename S, typename D>
-__global__ void cast_kernel(const S* src, int64_t src_stride, D* dst, int64_t dst_stride, int n) {
-    const int64_t row = blockIdx.y;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        dst[row * dst_stride + i] = (D)src[row * src_stride + i];
+__global__ void cast_kernel(const S* src, int64_t src_stride, D* dst, int64_t dst_stride, int n, int n_rows) {
+    // rows are strided over gridDim.y (limited to 65535) so any row count is covered
+    for (int64_t row = blockIdx.y; row < n_rows; row += gridDim.y)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            dst[row * dst_stride + i] = (D)src[row * src_stride + i];
 }
 
 
@@ -161,16 +162,16 @@ void launch_carry(const void* hist, int64_t hist_stride, int32_t hist_len, const
 void launch_cast(const void* src, int64_t src_stride, int src_dtype, void* dst, int64_t dst_stride, int dst_dtype,
                  int32_t n, int32_t n_rows, cudaStream_t s) {
     if (n <= 0 || n_rows <= 0) return;
-    dim3 grid((unsigned)((n + 1023) / 1024 < 4096 ? (n + 1023) / 1024 : 4096), (unsigned)n_rows);
+    dim3 grid((unsigned)((n + 1023) / 1024 < 4096 ? (n + 1023) / 1024 : 4096), (unsigned)(n_rows < 65535 ? n_rows : 65535));
     count_launch();
     if (src_dtype == DT_F32 && dst_dtype == DT_F64)
-        cast_kernel<float, double><<<grid, 256, 0, s>>>((const float*)src, src_stride, (double*)dst, dst_stride, n);
+        cast_kernel<float, double><<<grid, 256, 0, s>>>((const float*)src, src_stride, (double*)dst, dst_stride, n, n_rows);
     else if (src_dtype == DT_F64 && dst_dtype == DT_F32)
-        cast_kernel<double, float><<<grid, 256, 0, s>>>((const double*)src, src_stride, (float*)dst, dst_stride, n);
+        cast_kernel<double, float><<<grid, 256, 0, s>>>((const double*)src, src_stride, (float*)dst, dst_stride, n, n_rows);
     else if (src_dtype == DT_F32)
-        cast_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src, src_stride, (float*)dst, dst_stride, n);
+        cast_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src, src_stride, (float*)dst, dst_stride, n, n_rows);
     else
-        cast_kernel<double, double><<<grid, 256, 0, s>>>((const double*)src, src_stride, (double*)dst, dst_stride, n);
+        cast_kernel<double, double><<<grid, 256, 0, s>>>((const double*)src, src_stride, (double*)dst, dst_stride, n, n_rows);
 }
 
 namespace {

@@ -7,8 +7,9 @@
 //
 // so `resampler.New` can be pointed at the GPU engine without touching callers.
 // NOTE: this file cannot be compiled in the build image (no Go toolchain); it is the shim a
-// maintainer adds, see INTEGRATION.md. Build: CGO_CFLAGS=-I<repo>/include
-// CGO_LDFLAGS="-L<repo>/go-audio-resampler_b200/_build -lgar_b200" go build ./...
+// maintainer adds, see INTEGRATION.md. Build (go.mod beside this file; `make -C go-audio-resampler_b200/go check` does
+// vet + build + the parity dump on a machine that has Go and CUDA):
+//   CGO_CFLAGS=-I<repo>/include CGO_LDFLAGS="-L<repo>/go-audio-resampler_b200/_build -lgar_b200" go build ./...
 package b200
 
 /*
@@ -127,18 +128,46 @@ func New(config *Config) (*Resampler, error) {
 }
 
 // EstimateOutput: constant.go:117-119.
-func (r *handle) EstimateOutput(n int) int { return int(C.gar_estimate_output(r.h, C.int64_t(n))) }
-func (r *handle) GetRatio() float64        { return float64(C.gar_get_ratio(r.h)) }
-func (r *handle) GetLatency() int          { return int(C.gar_get_latency(r.h)) }
-func (r *handle) Reset()                   { C.gar_reset(r.h) }
+// Every method ends with runtime.KeepAlive(r): r.h is read before the cgo call, so without it the finalizer
+// (gar_destroy) could run while the C side still uses the handle.
+func (r *handle) EstimateOutput(n int) int {
+	v := int(C.gar_estimate_output(r.h, C.int64_t(n)))
+	runtime.KeepAlive(r)
+	return v
+}
+func (r *handle) GetRatio() float64 {
+	v := float64(C.gar_get_ratio(r.h))
+	runtime.KeepAlive(r)
+	return v
+}
+func (r *handle) GetLatency() int {
+	v := int(C.gar_get_latency(r.h))
+	runtime.KeepAlive(r)
+	return v
+}
+func (r *handle) Reset() {
+	C.gar_reset(r.h)
+	runtime.KeepAlive(r)
+}
+
+// nextOutputCount / nextFlushCount: exact sample counts of the next call (pure integer state machine).
+func (r *handle) nextOutputCount(ch, n int) int {
+	v := int(C.gar_next_output_count(r.h, C.int32_t(ch), C.int64_t(n)))
+	runtime.KeepAlive(r)
+	return v
+}
+func (r *handle) nextFlushCount(ch int) int {
+	v := int(C.gar_next_flush_count(r.h, C.int32_t(ch)))
+	runtime.KeepAlive(r)
+	return v
+}
 
 // Process returns an owned, exactly-sized slice (constant.go:88-96). The C side never retains `input`.
 func (r *Resampler) Process(input []float64) ([]float64, error) {
 	if len(input) == 0 {
 		return []float64{}, nil
 	}
-	want := int(C.gar_next_output_count(r.h, 0, C.int64_t(len(input))))
-	capN := max(want, r.EstimateOutput(len(input)))
+	capN := max(r.nextOutputCount(0, len(input)), r.EstimateOutput(len(input)))
 	out := make([]float64, capN)
 	n, err := r.ProcessInto(input, out)
 	if err != nil {
@@ -158,9 +187,11 @@ func (r *Resampler) ProcessInto(input, output []float64) (int, error) {
 		op = (*C.double)(unsafe.Pointer(&output[0]))
 	}
 	st := C.gar_process_f64(r.h, 0, ip, C.int64_t(len(input)), op, C.int64_t(len(output)), &n)
+	err := statusErr(st, r.h)
 	runtime.KeepAlive(input)
 	runtime.KeepAlive(output)
-	return int(n), statusErr(st, r.h)
+	runtime.KeepAlive(r)
+	return int(n), err
 }
 
 // ProcessFloat32Into: constant.go:161-199 (float64 pipeline between the casts, done on the device).
@@ -174,9 +205,11 @@ func (r *Resampler) ProcessFloat32Into(input, output []float32) (int, error) {
 		op = (*C.float)(unsafe.Pointer(&output[0]))
 	}
 	st := C.gar_process_f32(r.h, 0, ip, C.int64_t(len(input)), op, C.int64_t(len(output)), &n)
+	err := statusErr(st, r.h)
 	runtime.KeepAlive(input)
 	runtime.KeepAlive(output)
-	return int(n), statusErr(st, r.h)
+	runtime.KeepAlive(r)
+	return int(n), err
 }
 
 // ProcessFloat32: constant.go:128-147.
@@ -205,7 +238,7 @@ func (r *Resampler) ProcessMulti(input [][]float64) ([][]float64, error) {
 	capN := 1
 	for ch := range input {
 		nin[ch] = C.int64_t(len(input[ch]))
-		capN = max(capN, int(C.gar_next_output_count(r.h, C.int32_t(ch), nin[ch])))
+		capN = max(capN, r.nextOutputCount(ch, len(input[ch])))
 	}
 	output := make([][]float64, c)
 	var pin runtime.Pinner
@@ -221,7 +254,9 @@ func (r *Resampler) ProcessMulti(input [][]float64) ([][]float64, error) {
 	}
 	st := C.gar_process_multi_f64(r.h, (**C.double)(unsafe.Pointer(ins)), &nin[0],
 		(**C.double)(unsafe.Pointer(outs)), C.int64_t(capN), &nout[0])
-	if err := statusErr(st, r.h); err != nil {
+	err := statusErr(st, r.h)
+	runtime.KeepAlive(r)
+	if err != nil {
 		return nil, err
 	}
 	for ch := range output {
@@ -232,22 +267,24 @@ func (r *Resampler) ProcessMulti(input [][]float64) ([][]float64, error) {
 
 // Flush drains channel 0 only (constant.go:349-354); FlushMulti drains every channel (:390-404).
 func (r *Resampler) Flush() ([]float64, error) {
-	n := int(C.gar_next_flush_count(r.h, 0))
-	out := make([]float64, max(n, 1))
+	out := make([]float64, max(r.nextFlushCount(0), 1))
 	var got C.int64_t
 	st := C.gar_flush_f64(r.h, 0, (*C.double)(unsafe.Pointer(&out[0])), C.int64_t(len(out)), &got)
-	return out[:got:got], statusErr(st, r.h)
+	err := statusErr(st, r.h)
+	runtime.KeepAlive(r)
+	return out[:got:got], err
 }
 
 func (r *Resampler) FlushMulti() ([][]float64, error) {
 	out := make([][]float64, r.channels)
 	for ch := range out {
 		// per-channel calls keep the shim simple; gar_flush_multi_f64 does all channels in one pass
-		n := int(C.gar_next_flush_count(r.h, C.int32_t(ch)))
-		buf := make([]float64, max(n, 1))
+		buf := make([]float64, max(r.nextFlushCount(ch), 1))
 		var got C.int64_t
 		st := C.gar_flush_f64(r.h, C.int32_t(ch), (*C.double)(unsafe.Pointer(&buf[0])), C.int64_t(len(buf)), &got)
-		if err := statusErr(st, r.h); err != nil {
+		err := statusErr(st, r.h)
+		runtime.KeepAlive(r)
+		if err != nil {
 			return nil, err
 		}
 		out[ch] = buf[:got:got]
@@ -302,17 +339,19 @@ func (r *SimpleResamplerFloat32) Process(input []float32) ([]float32, error) {
 }
 
 func (r *SimpleResamplerFloat32) Flush() ([]float32, error) {
-	n := int(C.gar_next_flush_count(r.h, 0))
-	out := make([]float32, max(n, 1))
+	out := make([]float32, max(r.nextFlushCount(0), 1))
 	var got C.int64_t
 	st := C.gar_flush_f32(r.h, 0, (*C.float)(unsafe.Pointer(&out[0])), C.int64_t(len(out)), &got)
-	return out[:got:got], statusErr(st, r.h)
+	err := statusErr(st, r.h)
+	runtime.KeepAlive(r)
+	return out[:got:got], err
 }
 
 // GetStatistics: resampler.go:348-353.
 func (r *handle) GetStatistics() map[string]int64 {
 	var in, out C.int64_t
 	C.gar_get_stats(r.h, 0, 0, &in, &out)
+	runtime.KeepAlive(r)
 	return map[string]int64{"samplesIn": int64(in), "samplesOut": int64(out)}
 }
 
@@ -368,21 +407,46 @@ func NewBatchFloat32(in, out float64, q QualityPreset, streams, device int) (*Ba
 }
 
 // Process resamples planar [Streams][nIn] float32 (row stride nIn) into planar [Streams][outStride].
+// The C side reads Streams*nIn and writes up to Streams*outStride elements, so both slices are validated here:
+// nothing may be written past a Go slice.
 func (b *Batch) Process(in []float32, nIn int, out []float32, outStride int) (int, error) {
+	if nIn < 0 || outStride < 0 || b.Streams <= 0 {
+		return 0, fmt.Errorf("%w: negative length", ErrInvalidConfig)
+	}
+	if nIn == 0 {
+		return 0, nil
+	}
+	if len(in) < b.Streams*nIn {
+		return 0, fmt.Errorf("%w: input holds %d samples, %d streams x %d needed", ErrInvalidConfig, len(in), b.Streams, nIn)
+	}
+	if outStride < b.EstimateOutput(nIn) || len(out) < b.Streams*outStride {
+		return 0, ErrBufferTooSmall
+	}
 	var n C.int64_t
 	st := C.gar_process_batch(b.h, C.GAR_F32, unsafe.Pointer(&in[0]), C.int64_t(nIn), C.int64_t(nIn),
 		unsafe.Pointer(&out[0]), C.int64_t(outStride), C.int64_t(outStride), &n)
+	err := statusErr(st, b.h)
 	runtime.KeepAlive(in)
 	runtime.KeepAlive(out)
-	return int(n), statusErr(st, b.h)
+	runtime.KeepAlive(b)
+	return int(n), err
 }
 
 // Flush drains every stream of the batch (planar [Streams][outStride]); returns samples per row.
 func (b *Batch) Flush(out []float32, outStride int) (int, error) {
+	need := b.nextFlushCount(0)
+	if need == 0 {
+		return 0, nil
+	}
+	if outStride < need || len(out) < b.Streams*outStride {
+		return 0, ErrBufferTooSmall
+	}
 	var n C.int64_t
 	st := C.gar_flush_batch(b.h, C.GAR_F32, unsafe.Pointer(&out[0]), C.int64_t(outStride), C.int64_t(outStride), &n)
+	err := statusErr(st, b.h)
 	runtime.KeepAlive(out)
-	return int(n), statusErr(st, b.h)
+	runtime.KeepAlive(b)
+	return int(n), err
 }
 
 // Info mirrors resample.go:295-316; GetInfo: constant.go:452-485.
@@ -399,6 +463,7 @@ type Info struct {
 func (r *handle) GetInfo() Info {
 	var ci C.gar_info
 	C.gar_get_info(r.h, &ci)
+	runtime.KeepAlive(r)
 	return Info{
 		Algorithm:    C.GoString(&ci.algorithm[0]),
 		FilterLength: int(ci.filter_length),
@@ -450,10 +515,15 @@ func (r *Resampler) ProcessInterleavedInt16(frames []int16, out []int16) (int, e
 	if len(frames) == 0 {
 		return 0, nil
 	}
+	if len(out)/ch < r.EstimateOutput(len(frames)/ch) { // also rejects an empty `out` before &out[0]
+		return 0, ErrBufferTooSmall
+	}
 	var got C.int64_t
 	st := C.gar_process_interleaved(r.h, C.GAR_FMT_I16, 16, unsafe.Pointer(&frames[0]), C.int64_t(len(frames)/ch),
 		unsafe.Pointer(&out[0]), C.int64_t(len(out)/ch), &got)
+	err := statusErr(st, r.h)
 	runtime.KeepAlive(frames)
 	runtime.KeepAlive(out)
-	return int(got) * ch, statusErr(st, r.h)
+	runtime.KeepAlive(r)
+	return int(got) * ch, err
 }

@@ -329,7 +329,11 @@ class _Handle:
             _raise(st, self._h)
         return out2d[:, :n.value], n.value
 
-    # device-pointer variants (torch tensors or raw pointers); enqueue only
+    # device-pointer variants (torch tensors or raw pointers); enqueue only.
+    # `stream` is a raw cudaStream_t: pass the stream that produces d_in and consumes d_out (with torch:
+    # torch.cuda.current_stream().cuda_stream). stream=0 means the handle's own non-blocking stream, which is NOT ordered
+    # against the caller's streams: the caller must then synchronise d_in before and d_out after the call itself. Calls on
+    # one handle are ordered against each other whatever streams they use (Engine::order_before/after).
     def process_batch_dev(self, d_in, in_stride, n_in, d_out, out_stride, out_cap, stream=0, io_dtype=None):
         n = C.c_int64(0)
         st = lib().gar_process_batch_dev(self._h, self._io_code(io_dtype), C.c_void_p(d_in), in_stride, n_in, C.c_void_p(d_out),

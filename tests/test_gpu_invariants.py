@@ -429,3 +429,38 @@ def test_time_sliced_calls_are_bit_identical_to_unsliced(ir, orr, rows):
     np.testing.assert_array_equal(ya, yb)
     fa, fb = a.FlushBatch()[0], b.FlushBatch()[0]
     np.testing.assert_array_equal(fa, fb)
+
+
+def test_flush_right_after_the_first_process_on_a_busy_gpu_and_mixed_streams():
+    """the shared zero row and grown tail buffers are cleared on the launch stream, and calls on different streams
+    of one handle are ordered by the engine's event. A large matmul keeps the GPU busy on torch's stream while fresh handles
+    do Process -> Flush as their first device work; then device-batch calls alternate between a side stream, torch's stream
+    and the handle's own stream and must equal the one-stream result bit for bit."""
+    import torch
+    a = torch.randn(8192, 8192, device="cuda")
+    x = np.sin(2 * np.pi * 1000 * np.arange(6000) / 44100.0)
+    want = O.resample_mono(x, 44100, 48000, O.PRESET_HIGH)
+    for _ in range(12):
+        (a @ a).sum()  # asynchronous: stays in flight while the handle works
+        h = G.NewEngine(44100, 48000, G.QualityHigh)
+        got = np.concatenate([h.Process(x), h.Flush()])
+        assert len(got) == len(want) and np.max(np.abs(got - want)) <= 1e-12
+    torch.cuda.synchronize()
+    rows, n = 8, 20000
+    xb = np.random.default_rng(5).standard_normal((rows, 4 * n))
+    def run(streams):
+        hb = G.NewBatch(44100, 47999, G.QualityHigh, rows, np.float64)
+        dx = torch.from_numpy(xb).cuda()
+        ost = (hb.EstimateOutput(n) + 3) & ~3
+        dy = torch.zeros((5, rows, ost), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        counts = []
+        for k in range(4):
+            counts.append(hb.process_batch_dev(dx.data_ptr() + k * n * 8, 4 * n, n, dy[k].data_ptr(), ost, ost, streams[k % len(streams)], np.float64))
+        counts.append(hb.flush_batch_dev(dy[4].data_ptr(), ost, ost, streams[0], np.float64))
+        torch.cuda.synchronize()
+        return np.concatenate([dy[k, :, :c].cpu().numpy() for k, c in enumerate(counts)], axis=1)
+    side = torch.cuda.Stream()
+    one = run([side.cuda_stream])
+    mixed = run([side.cuda_stream, torch.cuda.current_stream().cuda_stream, 0])
+    np.testing.assert_array_equal(one, mixed)

@@ -200,9 +200,10 @@ def test_c1_c5b_full_length_batched_on_the_tensor_cores_equals_single_streams_an
     ostride = (h.EstimateOutput(n) + 3) & ~3
     dy = torch.zeros((rows, ostride), dtype=torch.float64, device="cuda")
     df = torch.zeros((rows, 1024), dtype=torch.float64, device="cuda")
-    c1 = h.process_batch_dev(dx.data_ptr(), n, n, dy.data_ptr(), ostride, ostride, 0, np.float64)
+    ts = torch.cuda.current_stream().cuda_stream  # the stream that produced dx/dy: the calls are ordered after it
+    c1 = h.process_batch_dev(dx.data_ptr(), n, n, dy.data_ptr(), ostride, ostride, ts, np.float64)
     used = set(h.last_kernels())
-    c2 = h.flush_batch_dev(df.data_ptr(), 1024, 1024, 0, np.float64)
+    c2 = h.flush_batch_dev(df.data_ptr(), 1024, 1024, ts, np.float64)
     torch.cuda.synchronize()
     assert (c1, c2) == counts
     assert "fir_f64_mma_up2" in used and any(k.startswith("poly_rows_mma_f64") and k.endswith("pipe") for k in used), used
