@@ -1,16 +1,86 @@
 // capi.cu — the C ABI declared in include/gar.h on top of gar::Engine.
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gar.h"
 #include "engine.hpp"
+#include "hostnuma.hpp"
 
 using namespace gar;
+
+// ---- multi-device handles ------------------------------------------------------------------------
+// The reference fans the channels of one call out over goroutines (constant.go:223-241). The GPU analogue: one handle
+// shards its rows (whole streams, or channels when there is a single stream) over K devices. Every shard is a complete
+// single-device handle driven by its own worker thread, which is bound to the cores of the device's NUMA node so that
+// staging, launches and the first touch of sharded pinned buffers all happen next to the device. Rows never migrate
+// between devices (carry state is per row), and there is no cross-device exchange: the host joins the workers.
+struct ShardWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, quit = false;
+    int node = -1;
+
+    void start(int device) {
+        th = std::thread([this, device] {
+            if (device >= 0) {
+                node = bind_thread_to_device(device);
+                cudaSetDevice(device);
+            }
+            std::unique_lock<std::mutex> lk(m);
+            for (;;) {
+                cv.wait(lk, [this] { return has_job || quit; });
+                if (quit) return;
+                lk.unlock();
+                job();
+                lk.lock();
+                has_job = false;
+                cv.notify_all();
+            }
+        });
+    }
+    void post(std::function<void()> f) {
+        std::unique_lock<std::mutex> lk(m);
+        job = std::move(f);
+        has_job = true;
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [this] { return !has_job; });
+    }
+    void stop() {
+        if (!th.joinable()) return;
+        {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [this] { return !has_job; });
+            quit = true;
+            cv.notify_all();
+        }
+        th.join();
+    }
+};
+
+struct Shard {
+    gar_handle* h = nullptr;  // complete single-device handle for rows [row0, row0 + rows)
+    int row0 = 0, rows = 0, device = 0;
+    int rc = 0;               // status of the last job
+    int64_t n_out = 0;
+    ShardWorker w;
+};
 
 struct gar_handle {
     gar_config cfg{};
@@ -29,7 +99,42 @@ struct gar_handle {
     void* slot_cin = nullptr;   // cast scratch (compute dtype) for I/O dtype != compute dtype
     void* slot_cout = nullptr;
     size_t slot_cin_cap = 0, slot_cout_cap = 0;
+    // multi-device handle: `eng` is geometry-only (chain, banks, static info); all streaming state lives in the shards
+    std::vector<std::unique_ptr<Shard>> shards;
+    bool multi() const { return !shards.empty(); }
 };
+
+namespace {
+// run f(shard) on every shard's worker thread and join; returns the first non-OK status (error text copied up)
+template <typename F>
+int for_shards(gar_handle* h, F f) {
+    for (auto& sp : h->shards) {
+        Shard* sh = sp.get();
+        sh->w.post([sh, f] { sh->rc = f(*sh); });
+    }
+    int rc = 0;
+    for (auto& sp : h->shards) {
+        sp->w.wait();
+        if (sp->rc && !rc) {
+            rc = sp->rc;
+            h->err = "device " + std::to_string(sp->device) + ": " + (sp->h ? sp->h->err : std::string("shard missing"));
+        }
+    }
+    return rc;
+}
+// shard owning `row`; *local = row index inside it
+Shard* shard_of(const gar_handle* h, int row, int* local) {
+    for (auto& sp : h->shards)
+        if (row >= sp->row0 && row < sp->row0 + sp->rows) {
+            if (local) *local = row - sp->row0;
+            return sp.get();
+        }
+    return nullptr;
+}
+// pinned buffers made by gar_host_alloc_rows (mmap + first touch + cudaHostRegister): base -> bytes
+std::mutex g_reg_mutex;
+std::map<void*, size_t> g_registered;
+}  // namespace
 
 static thread_local std::string g_create_err;
 
@@ -132,8 +237,112 @@ int32_t gar_create(const gar_config* cfg, gar_handle** out) {
     return GAR_OK;
 }
 
+int32_t gar_create_multi(const gar_config* cfg, const int32_t* devices, int32_t n_devices, gar_handle** out) {
+    if (out) *out = nullptr;
+    if (!cfg || !out || !devices || n_devices < 1 || n_devices > 64) {
+        g_create_err = "config or device list is nil / empty";
+        return GAR_INVALID_CONFIG;
+    }
+    // all ordinals -1: geometry-only shards (host logic of the sharding testable without a GPU, like device = -1 handles)
+    bool geometry_only = true;
+    for (int i = 0; i < n_devices; ++i) geometry_only = geometry_only && devices[i] == -1;
+    const int ndev = geometry_only ? 0 : gar_device_count();
+    if (!geometry_only && ndev <= 0) {
+        g_create_err = "no CUDA device available (this engine has no CPU fallback)";
+        return GAR_CUDA_ERROR;
+    }
+    for (int i = 0; i < n_devices && !geometry_only; ++i) {
+        if (devices[i] < 0 || devices[i] >= ndev) {
+            g_create_err = "CUDA device ordinal out of range";
+            return GAR_INVALID_CONFIG;
+        }
+        for (int j = 0; j < i; ++j)
+            if (devices[j] == devices[i]) {
+                g_create_err = "device listed twice";
+                return GAR_INVALID_CONFIG;
+            }
+    }
+    // the top handle validates the config, designs the filters once and answers every state-independent query
+    gar_config top = *cfg;
+    top.device = -1;
+    gar_handle* h = nullptr;
+    int32_t rc = gar_create(&top, &h);
+    if (rc) return rc;
+    h->cfg.device = devices[0];
+    // units that may be separated: whole streams (each with all its channels), or channels of the single stream
+    const bool by_stream = h->cfg.n_streams > 1;
+    const int units = by_stream ? h->cfg.n_streams : h->cfg.channels;
+    const int unit_rows = by_stream ? h->cfg.channels : 1;
+    const int K = std::min<int>(n_devices, units);
+    int unit0 = 0;
+    for (int d = 0; d < K; ++d) {
+        const int cnt = units / K + (d < units % K ? 1 : 0);
+        std::unique_ptr<Shard> sh(new Shard());
+        sh->device = devices[d];
+        sh->row0 = unit0 * unit_rows;
+        sh->rows = cnt * unit_rows;
+        sh->w.start(sh->device);
+        h->shards.push_back(std::move(sh));
+        unit0 += cnt;
+    }
+    const gar_config base = h->cfg;
+    rc = for_shards(h, [base, by_stream, unit_rows](Shard& sh) -> int {
+        gar_config c = base;
+        c.device = sh.device;
+        if (by_stream) c.n_streams = sh.rows / unit_rows;
+        else c.channels = sh.rows;
+        const int32_t r = gar_create(&c, &sh.h);
+        if (r) {  // gar_create's message is thread-local on the worker: keep it where for_shards can find it
+            sh.h = new gar_handle();
+            sh.h->err = g_create_err;
+            sh.h->eng.init(Chain{}, 0, DT_F64, -1, sh.h->err);
+        }
+        return r;
+    });
+    if (rc) {
+        g_create_err = h->err;
+        gar_destroy(h);
+        return rc;
+    }
+    h->gpu_name = h->shards[0]->h->gpu_name + " x" + std::to_string(K);
+    *out = h;
+    return GAR_OK;
+}
+
+int32_t gar_num_devices(const gar_handle* h) { return !h ? 0 : (h->multi() ? (int32_t)h->shards.size() : 1); }
+
+int32_t gar_shard_info(const gar_handle* h, int32_t shard, int32_t* device, int32_t* row0, int32_t* rows, int32_t* numa_node) {
+    if (!h) return GAR_INVALID_CONFIG;
+    if (!h->multi()) {
+        if (shard != 0) return GAR_INVALID_CONFIG;
+        if (device) *device = h->eng.device();
+        if (row0) *row0 = 0;
+        if (rows) *rows = h->rows;
+        if (numa_node) *numa_node = h->eng.device() >= 0 ? device_numa_node(h->eng.device()) : -1;
+        return GAR_OK;
+    }
+    if (shard < 0 || shard >= (int)h->shards.size()) return GAR_INVALID_CONFIG;
+    const Shard& sh = *h->shards[(size_t)shard];
+    if (device) *device = sh.device;
+    if (row0) *row0 = sh.row0;
+    if (rows) *rows = sh.rows;
+    if (numa_node) *numa_node = sh.device >= 0 ? device_numa_node(sh.device) : -1;
+    return GAR_OK;
+}
+
 void gar_destroy(gar_handle* h) {
     if (!h) return;
+    if (h->multi()) {
+        for (auto& sp : h->shards) {
+            Shard* sh = sp.get();
+            sh->w.post([sh] {
+                gar_destroy(sh->h);
+                sh->h = nullptr;
+            });
+        }
+        for (auto& sp : h->shards) sp->w.stop();
+        h->shards.clear();
+    }
     if (h->eng.device() < 0) {
         delete h;
         return;
@@ -161,6 +370,11 @@ int64_t gar_estimate_output(const gar_handle* h, int64_t n_in) {
 
 int64_t gar_next_output_count(const gar_handle* h, int32_t stream, int64_t n_in) {
     if (!h || stream < 0 || stream >= h->rows || n_in < 0) return -1;
+    if (h->multi()) {
+        int local = 0;
+        const Shard* sh = shard_of(h, stream, &local);
+        return gar_next_output_count(sh->h, local, n_in);
+    }
     StreamState st = h->eng.state(stream);
     Plan p;
     h->eng.plan(st, n_in, false, p);
@@ -169,6 +383,11 @@ int64_t gar_next_output_count(const gar_handle* h, int32_t stream, int64_t n_in)
 
 int64_t gar_next_flush_count(const gar_handle* h, int32_t stream) {
     if (!h || stream < 0 || stream >= h->rows) return -1;
+    if (h->multi()) {
+        int local = 0;
+        const Shard* sh = shard_of(h, stream, &local);
+        return gar_next_flush_count(sh->h, local);
+    }
     StreamState st = h->eng.state(stream);
     Plan p;
     h->eng.plan(st, 0, true, p);
@@ -201,6 +420,7 @@ int32_t gar_get_info(const gar_handle* h, gar_info* out) {  // constant.go:452-4
     std::snprintf(out->algorithm, sizeof(out->algorithm), "%s", "multi-stage");
     out->latency = gar_get_latency(h);
     out->memory_usage = h->eng.device_bytes();
+    for (const auto& sp : h->shards) out->memory_usage += sp->h->eng.device_bytes();
     const Chain& c = h->eng.chain();
     if (!c.engines.empty()) {
         const EngineDesign& e = c.engines[0];
@@ -225,6 +445,11 @@ int32_t gar_get_info(const gar_handle* h, gar_info* out) {  // constant.go:452-4
 
 int32_t gar_get_stats(const gar_handle* h, int32_t stream, int32_t e, int64_t* in, int64_t* outp) {
     if (!h || stream < 0 || stream >= h->rows) return GAR_INVALID_CONFIG;
+    if (h->multi()) {
+        int local = 0;
+        const Shard* sh = shard_of(h, stream, &local);
+        return gar_get_stats(sh->h, local, e, in, outp);
+    }
     const StreamState& st = h->eng.state(stream);
     if (e < 0 || e >= (int)st.samples_in.size()) return GAR_INVALID_CONFIG;
     if (in) *in = st.samples_in[(size_t)e];
@@ -237,6 +462,11 @@ int32_t gar_num_engines(const gar_handle* h) { return (int32_t)h->eng.chain().en
 
 int32_t gar_describe_stage(const gar_handle* h, int32_t stream, int32_t stage, gar_stage_desc* out) {
     if (!h || !out || stream < 0 || stream >= h->rows) return GAR_INVALID_CONFIG;
+    if (h->multi()) {
+        int local = 0;
+        const Shard* sh = shard_of(h, stream, &local);
+        return gar_describe_stage(sh->h, local, stage, out);
+    }
     const Chain& c = h->eng.chain();
     if (stage < 0 || stage >= (int)c.stages.size()) return GAR_INVALID_CONFIG;
     const StageDesign& s = c.stages[(size_t)stage];
@@ -273,18 +503,22 @@ int64_t gar_get_bank(const gar_handle* h, int32_t stage, int32_t which, double* 
 
 int32_t gar_upload_bank(gar_handle* h, int32_t stage, int32_t which, const double* coef, int64_t n) {
     if (!h || !coef) return GAR_INVALID_CONFIG;
-    return h->eng.set_bank(stage, which, coef, n, h->err);
+    const int rc = h->eng.set_bank(stage, which, coef, n, h->err);
+    if (rc || !h->multi()) return rc;
+    return for_shards(h, [=](Shard& sh) -> int { return gar_upload_bank(sh.h, stage, which, coef, n); });
 }
 
 int32_t gar_set_fusion(gar_handle* h, int32_t enabled) {
     if (!h) return GAR_INVALID_CONFIG;
     h->eng.set_fuse(enabled != 0);
+    for (auto& sp : h->shards) sp->h->eng.set_fuse(enabled != 0);
     return GAR_OK;
 }
 
 int32_t gar_set_slice_budget(gar_handle* h, int64_t bytes) {
     if (!h) return GAR_INVALID_CONFIG;
     h->eng.set_slice_budget(bytes < 0 ? 0 : bytes);
+    for (auto& sp : h->shards) sp->h->eng.set_slice_budget(bytes < 0 ? 0 : bytes);
     return GAR_OK;
 }
 
@@ -299,10 +533,15 @@ int64_t gar_kernel_launches(const gar_handle* h, int32_t reset) {
 int32_t gar_kernels_used(const gar_handle* h, char* buf, int32_t cap) {
     if (!h) return 0;
     std::string all;
-    for (const char* k : h->eng.kernels_used()) {
-        if (!all.empty()) all += ",";
-        all += k;
-    }
+    auto add = [&](const Engine& e) {
+        for (const char* k : e.kernels_used()) {
+            if (("," + all + ",").find(std::string(",") + k + ",") != std::string::npos) continue;
+            if (!all.empty()) all += ",";
+            all += k;
+        }
+    };
+    add(h->eng);
+    for (const auto& sp : h->shards) add(sp->h->eng);
     if (buf && cap > 0) {
         const size_t n = std::min<size_t>(all.size(), (size_t)cap - 1);
         std::memcpy(buf, all.data(), n);
@@ -313,6 +552,7 @@ int32_t gar_kernels_used(const gar_handle* h, char* buf, int32_t cap) {
 
 const char* gar_stage_kernel_name(const gar_handle* h, int32_t stage) {
     if (!h || stage < 0 || stage >= (int)h->eng.chain().stages.size()) return "";
+    if (h->multi()) return h->shards[0]->h->eng.stage_dev(stage).kernel;
     return h->eng.stage_dev(stage).kernel;
 }
 
@@ -324,6 +564,25 @@ static int process_rows_host(gar_handle* h, int row0, int count, int io_dtype, c
                              bool check_estimate) {
     Engine& E = h->eng;
     if (row0 < 0 || count < 1 || row0 + count > h->rows) return fail(h, GAR_INVALID_CONFIG, "channel out of range");
+    if (h->multi()) {
+        // every row range is served by the shard(s) that own it; ErrBufferTooSmall must come before ANY state change
+        // (constant.go:107-109), so the capacity check runs over all rows first
+        for (int r = 0; r < count; ++r) {
+            const int64_t n = flush ? 0 : n_in[r];
+            if (n < 0) return fail(h, GAR_INVALID_CONFIG, "negative input length");
+            if (!flush && check_estimate && out_cap < gar_estimate_output(h, n))
+                return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer smaller than EstimateOutput(len(input))");
+            const int64_t c = flush ? gar_next_flush_count(h, row0 + r) : gar_next_output_count(h, row0 + r, n);
+            if (c > out_cap) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
+        }
+        return for_shards(h, [=](Shard& sh) -> int {
+            const int a = std::max(row0, sh.row0), b = std::min(row0 + count, sh.row0 + sh.rows);
+            if (a >= b) return 0;
+            const int o = a - row0;
+            return process_rows_host(sh.h, a - sh.row0, b - a, io_dtype, in ? in + o : nullptr, n_in ? n_in + o : nullptr, out + o,
+                                     out_cap, n_out + o, flush, check_estimate);
+        });
+    }
     if (E.device() < 0) return fail(h, GAR_CUDA_ERROR, "geometry-only handle (device = -1) cannot process samples");
     int64_t max_in = 0;
     for (int r = 0; r < count; ++r) {
@@ -470,6 +729,11 @@ int32_t gar_flush_multi_f64(gar_handle* h, double* const* out, int64_t out_cap, 
 
 int32_t gar_advance_geometry(gar_handle* h, int32_t stream, int64_t n_in, int32_t flush, int64_t* n_out) {
     if (!h || stream < 0 || stream >= h->rows || n_in < 0) return GAR_INVALID_CONFIG;
+    if (h->multi()) {
+        int local = 0;
+        Shard* sh = shard_of(h, stream, &local);
+        return gar_advance_geometry(sh->h, local, n_in, flush, n_out);
+    }
     const int64_t n = h->eng.advance(stream, flush ? 0 : n_in, flush != 0);
     if (n_out) *n_out = n;
     return GAR_OK;
@@ -478,6 +742,7 @@ int32_t gar_advance_geometry(gar_handle* h, int32_t stream, int64_t n_in, int32_
 int32_t gar_reset(gar_handle* h) {
     if (!h) return GAR_INVALID_CONFIG;
     h->eng.reset_state();
+    if (h->multi()) return for_shards(h, [](Shard& sh) -> int { return gar_reset(sh.h); });
     return GAR_OK;
 }
 
@@ -537,6 +802,7 @@ static int batch_dev(gar_handle* h, int io_dtype, const void* d_in, int64_t in_s
 int32_t gar_process_batch_dev(gar_handle* h, int32_t io_dtype, const void* d_in, int64_t in_stride, int64_t n_in,
                               void* d_out, int64_t out_stride, int64_t out_cap, int64_t* n_out, void* cuda_stream) {
     if (!h) return GAR_INVALID_CONFIG;
+    if (h->multi()) return fail(h, GAR_NOT_SUPPORTED, "device-pointer calls need a single-device handle (one per device)");
     if (n_in < 0) return fail(h, GAR_INVALID_CONFIG, "negative input length");
     if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->compute_dtype)
         return fail(h, GAR_NOT_SUPPORTED, "engine handles take their own dtype");
@@ -551,6 +817,7 @@ int32_t gar_process_batch_dev(gar_handle* h, int32_t io_dtype, const void* d_in,
 int32_t gar_flush_batch_dev(gar_handle* h, int32_t io_dtype, void* d_out, int64_t out_stride, int64_t out_cap,
                             int64_t* n_out, void* cuda_stream) {
     if (!h) return GAR_INVALID_CONFIG;
+    if (h->multi()) return fail(h, GAR_NOT_SUPPORTED, "device-pointer calls need a single-device handle (one per device)");
     if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->compute_dtype)
         return fail(h, GAR_NOT_SUPPORTED, "engine handles take their own dtype");
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->eng.stream();
@@ -562,6 +829,25 @@ int32_t gar_flush_batch_dev(gar_handle* h, int32_t io_dtype, void* d_out, int64_
 static int batch_host(gar_handle* h, int io_dtype, const void* in, int64_t in_stride, int64_t n_in, void* out,
                       int64_t out_stride, int64_t out_cap, int64_t* n_out, bool flush) {
     Engine& E = h->eng;
+    if (h->multi()) {
+        // shard the rows over the devices: every worker runs the single-device pipeline (sliced H2D / kernels / D2H overlap)
+        // on its own row block of the caller's buffers; all shards must agree on the count (lock step)
+        const size_t isz = dsize(io_dtype);
+        const int64_t want = flush ? gar_next_flush_count(h, 0) : gar_next_output_count(h, 0, n_in);
+        for (auto& sp : h->shards) {
+            const int64_t w = flush ? gar_next_flush_count(sp->h, 0) : gar_next_output_count(sp->h, 0, n_in);
+            if (w != want || sp->h->eng.lockstep_run(0, sp->rows) != sp->rows)
+                return fail(h, GAR_NOT_SUPPORTED, "batch rows are not in lock step (mixed per-channel calls before a batch call)");
+        }
+        if (want > out_cap) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
+        if (n_out) *n_out = want;
+        if (!flush && n_in == 0) return GAR_OK;
+        return for_shards(h, [=](Shard& sh) -> int {
+            const char* ip = in ? (const char*)in + (size_t)sh.row0 * (size_t)in_stride * isz : nullptr;
+            char* op = out ? (char*)out + (size_t)sh.row0 * (size_t)out_stride * isz : nullptr;
+            return batch_host(sh.h, io_dtype, ip, in_stride, n_in, op, out_stride, out_cap, &sh.n_out, flush);
+        });
+    }
     if (E.device() < 0) return fail(h, GAR_CUDA_ERROR, "geometry-only handle (device = -1) cannot process samples");
     cudaSetDevice(E.device());
     const size_t iosz = dsize(io_dtype);
@@ -685,6 +971,7 @@ static int interleaved_call(gar_handle* h, int fmt, int bit_depth, const void* i
                             int64_t out_cap, int64_t* n_frames_out, bool flush) {
     Engine& E = h->eng;
     if (fmt < GAR_FMT_F64 || fmt > GAR_FMT_I64) return fail(h, GAR_INVALID_CONFIG, "unknown sample format");
+    if (h->multi()) return fail(h, GAR_NOT_SUPPORTED, "interleaved calls need a single-device handle");
     if (E.device() < 0) return fail(h, GAR_CUDA_ERROR, "geometry-only handle (device = -1) cannot process samples");
     const int C = h->rows;
     if (E.lockstep_run(0, C) != C) return fail(h, GAR_NOT_SUPPORTED, "channels are not in lock step");
@@ -746,8 +1033,57 @@ void* gar_host_alloc(size_t bytes) {
     return p;
 }
 void gar_host_free(void* p) {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_reg_mutex);
+        auto it = g_registered.find(p);
+        if (it != g_registered.end()) {
+            bytes = it->second;
+            g_registered.erase(it);
+        }
+    }
+    if (bytes) {
+        cudaHostUnregister(p);
+        munmap(p, bytes);
+        return;
+    }
+    cudaFreeHost(p);
 }
+
+void* gar_host_alloc_rows(gar_handle* h, size_t row_bytes) {
+    if (!h || row_bytes == 0 || h->rows <= 0) return nullptr;
+    const size_t page = 4096;
+    const size_t total = (((size_t)h->rows * row_bytes) + page - 1) / page * page;
+    void* base = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == MAP_FAILED) return nullptr;
+    // first touch decides the NUMA node of a page: every shard's rows are touched by a thread bound to its device's node
+    if (h->multi()) {
+        for_shards(h, [=](Shard& sh) -> int {
+            std::memset((char*)base + (size_t)sh.row0 * row_bytes, 0, (size_t)sh.rows * row_bytes);
+            return 0;
+        });
+    } else {
+        const int dev = h->eng.device();
+        std::thread t([=] {
+            if (dev >= 0) bind_thread_to_device(dev);
+            std::memset(base, 0, total);
+        });
+        t.join();
+    }
+    if (h->eng.device() >= 0 || h->multi()) cudaSetDevice(h->multi() ? h->shards[0]->device : h->eng.device());
+    if (cudaHostRegister(base, total, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        munmap(base, total);
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(g_reg_mutex);
+    g_registered[base] = total;
+    return base;
+}
+
+int32_t gar_bind_thread_to_device(int32_t device) { return bind_thread_to_device(device); }
+int32_t gar_device_numa_node(int32_t device) { return device_numa_node(device); }
 
 int32_t gar_measure_fma_peak(int32_t device, int32_t dtype, double* tflops) {
     if (!tflops) return GAR_INVALID_CONFIG;

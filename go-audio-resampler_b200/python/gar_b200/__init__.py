@@ -87,6 +87,9 @@ _vp, _i32, _i64, _d = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 _pi64 = C.POINTER(C.c_int64)
 SYMBOLS = {
     "gar_create": (_i32, [C.POINTER(_Config), C.POINTER(_vp)]),
+    "gar_create_multi": (_i32, [C.POINTER(_Config), C.POINTER(C.c_int32), _i32, C.POINTER(_vp)]),
+    "gar_num_devices": (_i32, [_vp]),
+    "gar_shard_info": (_i32, [_vp, _i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "gar_destroy": (None, [_vp]),
     "gar_last_error": (C.c_char_p, [_vp]),
     "gar_status_string": (C.c_char_p, [_i32]),
@@ -119,6 +122,9 @@ SYMBOLS = {
     "gar_flush_interleaved": (_i32, [_vp, _i32, _i32, _vp, _i64, _pi64]),
     "gar_host_alloc": (_vp, [C.c_size_t]),
     "gar_host_free": (None, [_vp]),
+    "gar_host_alloc_rows": (_vp, [_vp, C.c_size_t]),
+    "gar_bind_thread_to_device": (_i32, [_i32]),
+    "gar_device_numa_node": (_i32, [_i32]),
     "gar_device_count": (_i32, []),
     "gar_set_fusion": (_i32, [_vp, _i32]),
     "gar_kernel_launches": (_i64, [_vp, _i32]),
@@ -195,13 +201,35 @@ class Config:  # resample.go:46-73
 
 
 class _Handle:
-    def __init__(self, cfg: _Config):
+    def __init__(self, cfg: _Config, devices=None):
         h = C.c_void_p()
-        st = lib().gar_create(C.byref(cfg), C.byref(h))
+        if devices is None:
+            st = lib().gar_create(C.byref(cfg), C.byref(h))
+        else:  # one handle, rows sharded over several devices (gar_create_multi)
+            devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+            st = lib().gar_create_multi(C.byref(cfg), devs, len(devices), C.byref(h))
         if st != OK:
             _raise(st, None)
         self._h = h
         self.rows = max(1, cfg.channels) * max(1, cfg.n_streams)
+
+    def shards(self):
+        """[(device, row0, rows, numa_node)] — one entry per device behind this handle."""
+        out = []
+        for k in range(lib().gar_num_devices(self._h)):
+            d, r0, n, node = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+            lib().gar_shard_info(self._h, k, C.byref(d), C.byref(r0), C.byref(n), C.byref(node))
+            out.append((d.value, r0.value, n.value, node.value))
+        return out
+
+    def host_alloc_rows(self, n_cols, dtype):
+        """Pinned [rows, n_cols] host array whose row blocks sit on the NUMA node of the device that copies them."""
+        dt = np.dtype(dtype)
+        p = lib().gar_host_alloc_rows(self._h, int(n_cols) * dt.itemsize)
+        if not p:
+            raise CudaError("gar_host_alloc_rows failed")
+        buf = (C.c_char * (self.rows * int(n_cols) * dt.itemsize)).from_address(p)
+        return np.frombuffer(buf, dtype=dt, count=self.rows * int(n_cols)).reshape(self.rows, int(n_cols)), p
 
     def close(self):
         if getattr(self, "_h", None):
@@ -404,7 +432,7 @@ class _Handle:
 class Resampler(_Handle):
     """constantRateResampler behind New(Config) (constant.go:16-485)."""
 
-    def __init__(self, config: Config, n_streams: int = 0, io_dtype=np.float64):
+    def __init__(self, config: Config, n_streams: int = 0, io_dtype=np.float64, devices=None):
         if config is None:
             raise ErrInvalidConfig("config is nil")
         q = config.Quality
@@ -412,7 +440,7 @@ class Resampler(_Handle):
                       int(q.Preset), int(q.Precision), float(q.PhaseResponse), float(q.PassbandEnd),
                       float(q.StopbandBegin), F64, -1, int(n_streams), int(config.Device),
                       int(config.MaxInputSize), int(q.Flags) | (int(config.EnableParallel) << 16))
-        super().__init__(cfg)
+        super().__init__(cfg, devices)
         self.channels = int(config.Channels)
 
     def Process(self, x):  # constant.go:88-96 (channel 0)
@@ -466,11 +494,12 @@ def New(config: Config) -> Resampler:  # resample.go:272-292
 class SimpleResampler(_Handle):
     """SimpleResampler / SimpleResamplerFloat32 (convenience.go:118-186, 315-395)."""
 
-    def __init__(self, input_rate, output_rate, quality, dtype=np.float64, engine_quality=-1, device=0, n_streams=0):
+    def __init__(self, input_rate, output_rate, quality, dtype=np.float64, engine_quality=-1, device=0, n_streams=0,
+                 devices=None):
         self.dtype = np.dtype(dtype).type
         cfg = _Config(float(input_rate), float(output_rate), 1, PATH_ENGINE, int(quality), 0, 0.0, 0.0, 0.0,
                       F32 if self.dtype == np.float32 else F64, int(engine_quality), int(n_streams), int(device), 0, 0)
-        super().__init__(cfg)
+        super().__init__(cfg, devices)
 
     def Process(self, x):
         return self._process(0, x, self.dtype)
@@ -539,8 +568,9 @@ class BatchResampler(SimpleResampler):
     (SURVEY.md CS4); one device pass per chunk.
     """
 
-    def __init__(self, input_rate, output_rate, quality, n_streams, dtype=np.float32, device=0, engine_quality=-1):
-        super().__init__(input_rate, output_rate, quality, dtype, engine_quality, device, n_streams)
+    def __init__(self, input_rate, output_rate, quality, n_streams, dtype=np.float32, device=0, engine_quality=-1,
+                 devices=None):
+        super().__init__(input_rate, output_rate, quality, dtype, engine_quality, device, n_streams, devices)
         self.n_streams = int(n_streams)
 
 
@@ -567,6 +597,15 @@ def host_free(p):
 
 def device_count():
     return lib().gar_device_count()
+
+
+def bind_thread_to_device(device: int) -> int:
+    """Restrict the calling thread to the cores of the device's NUMA node (-1: nothing changed)."""
+    return int(lib().gar_bind_thread_to_device(int(device)))
+
+
+def device_numa_node(device: int) -> int:
+    return int(lib().gar_device_numa_node(int(device)))
 
 
 def set_tiled_polyphase(enabled: bool):

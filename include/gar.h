@@ -125,6 +125,17 @@ typedef struct gar_info {
  * Validates like Config.Validate (resample.go:168-214) and engine.NewResampler (resampler.go:51-70),
  * designs the Kaiser banks on the host once per config (shared by all channels), uploads them. */
 int32_t gar_create(const gar_config* cfg, gar_handle** out);
+/* Multi-device handle — the GPU analogue of the channel fan-out inside one call (constant.go:223-241, ProcessMulti's
+ * goroutines): ONE handle shards its rows over `n_devices` CUDA devices (whole streams when n_streams > 1, else channels),
+ * each shard with its own device state, streams, pinned staging and a worker thread bound to the device's NUMA node; calls
+ * fan out to the shards and join on the host. Rows never migrate and nothing is exchanged between devices. cfg->device
+ * is ignored. Supported: every host-buffer call (gar_process_* / gar_flush_* / *_multi / *_batch), Reset, queries.
+ * Not supported (GAR_NOT_SUPPORTED): the *_dev and *_interleaved calls (their buffers belong to one device). */
+int32_t gar_create_multi(const gar_config* cfg, const int32_t* devices, int32_t n_devices, gar_handle** out);
+/* Number of shards behind a handle (1 for gar_create handles) and the device / row block of shard k. A device list of
+ * all -1 makes geometry-only shards (host logic only, like device = -1). */
+int32_t gar_num_devices(const gar_handle* h);
+int32_t gar_shard_info(const gar_handle* h, int32_t shard, int32_t* device, int32_t* row0, int32_t* rows, int32_t* numa_node);
 void gar_destroy(gar_handle* h);
 /* Last error text of this handle (or of the last failed gar_create when h == NULL). */
 const char* gar_last_error(const gar_handle* h);
@@ -218,6 +229,14 @@ int32_t gar_flush_interleaved(gar_handle* h, int32_t fmt, int32_t bit_depth, voi
 /* Pinned host memory for callers that want full PCIe rate (Go slices are pageable). */
 void* gar_host_alloc(size_t bytes);
 void gar_host_free(void* p);
+/* Pinned planar buffer of rows(h) x row_bytes for the batch calls whose pages are placed shard by shard on the NUMA node of
+ * the device that will copy them (first touch by the shard's bound worker thread, then cudaHostRegister). Free with
+ * gar_host_free. On single-socket machines it is simply a pinned buffer. */
+void* gar_host_alloc_rows(gar_handle* h, size_t row_bytes);
+/* Restrict the calling thread to the cores of `device`'s NUMA node (sysfs numa_node of its PCI function). One-process-
+ * per-GPU callers (torchrun ranks) call it once before allocating pinned memory. Returns the node, -1 if nothing changed. */
+int32_t gar_bind_thread_to_device(int32_t device);
+int32_t gar_device_numa_node(int32_t device);
 int32_t gar_device_count(void);
 /* Enable (default) / disable the fused x2 -> polyphase launch (K4); results agree to rounding, used for A/B tests. */
 int32_t gar_set_fusion(gar_handle* h, int32_t enabled);
