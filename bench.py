@@ -68,6 +68,9 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the float64 side measurements (BASELINE configs 1 and 3)")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="target wall time of the CPU baseline sample")
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node (A/B)")
+    ap.add_argument("--no-ceiling", action="store_true", help="skip the in-job copy-ceiling measurement")
+    ap.add_argument("--parity-rows", type=int, default=16, help="rows of the timed run checked against the oracle")
     return ap.parse_args()
 
 
@@ -184,7 +187,9 @@ def run_reference(a, rank):
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "step": f"bounded sample: {ns} streams per step on {cores} host threads"},
+            "config": {"workload": workload_name(a), "step": f"bounded sample: {ns} streams per step on {cores} host threads",
+                       "reference_sample_streams": ns, "workload_streams": a.streams,
+                       "note": "throughput metric: the bounded sample runs the same per-stream work as the full workload"},
             "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{ns} streams x {n} samples per step; C++ restatement of the Go path "
                                        "(oracle/, AVX2+FMA) — the Go reference cannot be built in this image"},
@@ -194,57 +199,161 @@ def run_reference(a, rank):
 
 
 def extra_f64(dev, local, tstream):
-    """Side measurements, not the headline: the float64 kernels of BASELINE configs 1 and 3 on this GPU (CUDA events,
-    inputs resident in HBM, Process + Flush), against the fp64 dependent-FMA probe. Config 1's chain batched over 256
-    streams runs the x2 stage and the polyphase stage on the FP64 tensor cores (K1m + K3m); config 3 is the 8-channel
-    1223-tap /2 decimator (K2m)."""
+    """Side measurements, not the headline: the other BASELINE configs on this GPU, so that their numbers are driver-observed.
+    Per config: device time of one Process+Flush pass (CUDA events on the launching stream, inputs resident in HBM, Reset
+    between passes), the host-facing call (numpy host buffers through the C ABI, wall clock), the CPU oracle on ONE host
+    thread on the same input, and the achieved FMA rate against BOTH float64 probes of this job: vector DFMA and the FP64
+    tensor cores (DMMA.8x8x4) — kernels that run on the tensor cores are quoted against the DMMA probe."""
     import torch
 
     import gar_b200 as G
+    from oracle import oracle as O
 
     peak64 = G.measure_fma_peak(np.float64, local)
-    out = {"fp64_fma_peak_tflops": round(peak64, 2)}
+    peak_dmma = G.measure_fma_peak(np.float64, local, tensor=True)
+    out = {"fp64_fma_peak_tflops": round(peak64, 2), "fp64_dmma_peak_tflops": round(peak_dmma, 2)}
 
-    def timed(h, x, flops_per_out, reps=5):
+    def timed(h, x, flops_per_out, reps=5, io=np.float64, host=True):
         rows, n_in = x.shape
+        tdt, esz = (torch.float32, 4) if io == np.float32 else (torch.float64, 8)
         est = h.EstimateOutput(n_in)
         ostride = (est + 8192 + 3) & ~3
-        dx = torch.from_numpy(x).to(dev)
-        dy = torch.zeros((rows, ostride), dtype=torch.float64, device=dev)
+        dx = torch.from_numpy(np.ascontiguousarray(x, dtype=io)).to(dev)
+        dy = torch.zeros((rows, ostride), dtype=tdt, device=dev)
 
         def one():
             h.Reset()
-            n1 = h.process_batch_dev(dx.data_ptr(), n_in, n_in, dy.data_ptr(), ostride, ostride, tstream.cuda_stream, np.float64)
-            n2 = h.flush_batch_dev(dy.data_ptr() + n1 * 8, ostride, ostride - n1, tstream.cuda_stream, np.float64)
+            n1 = h.process_batch_dev(dx.data_ptr(), n_in, n_in, dy.data_ptr(), ostride, ostride, tstream.cuda_stream, io)
+            n2 = h.flush_batch_dev(dy.data_ptr() + n1 * esz, ostride, ostride - n1, tstream.cuda_stream, io)
             return n1 + n2
 
         for _ in range(3):
             n = one()
         torch.cuda.synchronize()
+        G.kernel_launches(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(tstream)
         for _ in range(reps):
             one()
         e1.record(tstream)
         torch.cuda.synchronize()
+        launches = G.kernel_launches() / reps
         ms = e0.elapsed_time(e1) / reps
         tf = rows * n * flops_per_out / (ms * 1e-3) / 1e12
-        return {"ms": round(ms, 4), "msamples_per_s": round(rows * n / ms / 1e3, 1), "tflops": round(tf, 2),
-                "frac_of_fp64_fma_peak": round(tf / peak64, 4), "kernels": h.last_kernels()}
+        kernels = h.last_kernels()
+        tensor = any("mma" in k for k in kernels)
+        r = {"device_us": round(ms * 1e3, 2), "launches_per_pass": launches, "msamples_per_s": round(rows * n / ms / 1e3, 1),
+             "tflops": round(tf, 2), "frac_of_fp64_fma_peak": round(tf / peak64, 4),
+             "frac_of_fp64_dmma_peak": round(tf / peak_dmma, 4), "frac": round(tf / (peak_dmma if tensor else peak64), 4),
+             "frac_denominator": "dmma probe" if tensor else "vector dfma probe", "kernels": kernels}
+        if host:
+            xh = np.ascontiguousarray(x, dtype=io)
+            yh = np.empty((rows, ostride), dtype=io)
+            for _ in range(2):
+                h.Reset()
+                _, m1 = h.ProcessBatch(xh, yh)
+                h.FlushBatch(yh[:, m1:])
+            t0 = time.perf_counter()
+            for _ in range(5):
+                h.Reset()
+                _, m1 = h.ProcessBatch(xh, yh)
+                h.FlushBatch(yh[:, m1:])
+            r["host_call_us"] = round((time.perf_counter() - t0) / 5 * 1e6, 1)
+        return r
 
-    t = np.arange(441000) / 44100.0
-    x1 = np.tile(np.sin(2 * np.pi * 1000.0 * t)[None, :], (256, 1))
+    def cpu_ms(fn):
+        t0 = time.perf_counter()
+        fn()
+        return round((time.perf_counter() - t0) * 1e3, 1)
+
+    def cfg(ir, orr, ch, preset):
+        return G.Config(InputRate=ir, OutputRate=orr, Channels=ch, Quality=G.QualitySpec(Preset=preset))
+
+    t1 = np.arange(441000) / 44100.0
+    x1 = np.sin(2 * np.pi * 1000.0 * t1)
+    # C1: ResampleMono 44.1k -> 48k QualityHigh float64, one stream
+    out["c1_single_stream"] = dict(
+        timed(G.NewEngine(44100, 48000, G.QualityHigh), x1[None, :], 738.0, reps=20),
+        cpu_1thread_ms=cpu_ms(lambda: O.resample_mono(x1, 44100, 48000, O.PRESET_HIGH)),
+        workload="BASELINE config 1: ResampleMono 44.1k->48k QualityHigh float64, 441000 samples")
+    # C5b: 44.1k -> 47.999k (cubic coefficient interpolation), one stream
+    out["c5b_single_stream"] = dict(
+        timed(G.NewEngine(44100, 47999, G.QualityHigh), x1[None, :], 692.0, reps=20),
+        cpu_1thread_ms=cpu_ms(lambda: O.resample_mono(x1, 44100, 47999, O.PRESET_HIGH)),
+        workload="BASELINE config 5b: 44.1k->47.999k QualityHigh float64, 441000 samples")
+    # C5a: 8k -> 192k multistage, one stream
+    x5 = np.sin(2 * np.pi * 1000.0 * np.arange(80000) / 8000.0)
+
+    def c5a_cpu():
+        p = O.Pipeline(8000, 192000, 1, O.PRESET_HIGH)
+        p.process(x5)
+        p.flush()
+    out["c5a_single_stream"] = dict(
+        timed(G.New(cfg(8000, 192000, 1, G.QualityHigh)), x5[None, :], 1233.3, reps=20), cpu_1thread_ms=cpu_ms(c5a_cpu),
+        workload="BASELINE config 5a: 8k->192k QualityHigh float64 (five x2 stages + polyphase), 80000 samples")
+    # C2: stereo 48k -> 44.1k High, float32 I/O, 4096-frame chunks + Flush: two mono instances (constant.go), per chunk
+    tc = np.arange(480000) / 48000.0
+    left = (np.sin(2 * np.pi * 440 * tc) + 0.1 * np.sin(2 * np.pi * 1320 * tc)).astype(np.float32)
+    h2 = G.New(cfg(48000, 44100, 1, G.QualityHigh))
+    chunks = [left[i:i + 4096] for i in range(0, len(left), 4096)]
+    obuf = np.empty(h2.EstimateOutput(4096), dtype=np.float32)
+    for c in chunks[:8]:
+        h2.ProcessFloat32Into(c, obuf)
+    h2.Reset()
+    t0 = time.perf_counter()
+    for c in chunks:
+        h2.ProcessFloat32Into(c, obuf)
+    host_chunk_us = (time.perf_counter() - t0) / len(chunks) * 1e6
+    h2.Flush()
+    dl = torch.from_numpy(left).to(dev)
+    dob = torch.zeros(8192, dtype=torch.float32, device=dev)
+    h2.Reset()
+    for k in range(8):
+        h2.process_batch_dev(dl.data_ptr() + k * 4096 * 4, 4096, 4096, dob.data_ptr(), 8192, 8192, tstream.cuda_stream, np.float32)
+    torch.cuda.synchronize()
+    h2.Reset()
+    G.kernel_launches(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(tstream)
+    nfull = len(left) // 4096
+    for k in range(nfull):
+        h2.process_batch_dev(dl.data_ptr() + k * 4096 * 4, 4096, 4096, dob.data_ptr(), 8192, 8192, tstream.cuda_stream, np.float32)
+    e1.record(tstream)
+    torch.cuda.synchronize()
+
+    def c2_cpu():
+        p = O.Pipeline(48000, 44100, 1, O.PRESET_HIGH)
+        ob = np.empty(p.estimate_output(4096), dtype=np.float32)
+        for c in chunks:
+            p.process_f32_into(c, ob)
+        p.flush()
+    c2cpu = cpu_ms(c2_cpu)
+    out["c2_streaming_chunk"] = {
+        "device_us_per_chunk": round(e0.elapsed_time(e1) / nfull * 1e3, 2), "launches_per_chunk": G.kernel_launches() / nfull,
+        "host_call_us_per_chunk": round(host_chunk_us, 1), "cpu_1thread_us_per_chunk": round(c2cpu * 1e3 / len(chunks), 1),
+        "kernels": h2.last_kernels(),
+        "workload": "BASELINE config 2, one channel (the reference runs two mono instances): 48k->44.1k QualityHigh, float32 "
+                    "I/O through ProcessFloat32Into in 4096-frame chunks (117 chunks + tail), float64 inside"}
+    del h2, dl, dob
+    # C1 chain batched over 256 lock-step streams (tensor-core kernels)
+    x256 = np.tile(x1[None, :], (256, 1))
     out["c1_chain_x256_streams_10s_f64"] = dict(
-        timed(G.NewBatch(44100, 48000, G.QualityHigh, 256, np.float64), x1, 738.0),
+        timed(G.NewBatch(44100, 48000, G.QualityHigh, 256, np.float64), x256, 738.0, host=False),
         workload="BASELINE config 1's chain (44.1k->48k QualityHigh float64) x 256 lock-step streams x 10 s")
-    del x1
+    del x256
+    # C3: 8 channels 96k -> 48k VeryHigh (1223-tap /2)
     rng = np.random.default_rng(4242)
     t3 = np.arange(960000) / 96000.0
     x3 = np.stack([0.7 * np.sin(2 * np.pi * 440 * t3 + c) + 0.2 * np.sin(2 * np.pi * 1750 * t3) + 0.1 * (rng.random(t3.size) - 0.5)
                    for c in range(8)])
-    cfg = G.Config(InputRate=96000, OutputRate=48000, Channels=8, Quality=G.QualitySpec(Preset=G.QualityVeryHigh))
+
+    def c3_cpu():
+        p = O.Pipeline(96000, 48000, 1, O.PRESET_VERYHIGH)
+        p.process(x3[0])
+        p.flush()
     out["c3_8ch_96k_to_48k_veryhigh_f64"] = dict(
-        timed(G.New(cfg), x3, 2446.0, reps=10),
+        timed(G.New(cfg(96000, 48000, 8, G.QualityVeryHigh)), x3, 2446.0, reps=10),
+        cpu_1thread_ms_per_channel=cpu_ms(c3_cpu),
         workload="BASELINE config 3: 8 channels x 960000 samples, 96k->48k QualityVeryHigh float64 (1223-tap /2)")
     return out
 
@@ -259,9 +368,16 @@ def main():
         run_reference(a, rank)
         return
 
+    import gar_b200 as G
+
+    affinity0 = os.sched_getaffinity(0)
+    # One process per GPU: bind this rank to the cores of its GPU's NUMA node BEFORE torch spawns its threads and before any
+    # pinned host memory is allocated (first touch places the pages). SCALE_r01's e2e numbers were taken unbound.
+    numa = {"bound_node": None if a.no_bind else G.bind_thread_to_device(local), "device_node": G.device_numa_node(local),
+            "cpus_allowed": len(os.sched_getaffinity(0))}
+
     import torch
     import torch.distributed as dist
-    import gar_b200 as G
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -382,8 +498,9 @@ def main():
     e2e = None
     xh = None
     if not a.no_e2e:
-        xh, px = G.host_alloc((rows, n_in), np.float32)
-        yh, py = G.host_alloc((rows, ostride), np.float32)
+        # pinned caller buffers, first-touched by a thread bound to this GPU's NUMA node (gar_host_alloc_rows)
+        xh, px = b.host_alloc_rows(n_in, np.float32)
+        yh, py = b.host_alloc_rows(ostride, np.float32)
         for r0 in range(0, rows, 256):
             xh[r0:r0 + 256] = x[r0:r0 + 256].cpu().numpy()
 
@@ -415,6 +532,60 @@ def main():
         chk = torch.from_numpy(yh[:2, :n1 + n2].copy()).to(dev)
         assert torch.equal(chk, y[:2, :n1 + n2]), "host and device paths disagree"
 
+        # ---- in-job copy ceiling: the same bytes as one e2e step, plain cudaMemcpyAsync, one call per ~64 MiB slice, H2D and
+        # D2H concurrently on two streams, all ranks at once (barrier on both sides, max over ranks) ----
+        if not a.no_ceiling:
+            L = G.lib()
+            s_h2d, s_d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            slice_rows = max(1, (64 << 20) // (n_in * 4))
+            out_cols = n1 + n2
+
+            def copy_pass():
+                for r0 in range(0, rows, slice_rows):
+                    cnt = min(slice_rows, rows - r0)
+                    L.gar_memcpy_async(x.data_ptr() + r0 * n_in * 4, xh.ctypes.data + r0 * n_in * 4, cnt * n_in * 4, 1,
+                                       s_h2d.cuda_stream)
+                    L.gar_memcpy_async(yh.ctypes.data + r0 * ostride * 4, y.data_ptr() + r0 * ostride * 4,
+                                       cnt * ostride * 4, 2, s_d2h.cuda_stream)
+            copy_pass()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                copy_pass()
+            torch.cuda.synchronize()
+            ct = torch.tensor([(time.perf_counter() - t0) / 3], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+            cs = float(ct.item())
+            e2e["copy_ceiling"] = {
+                "ms_per_step": round(cs * 1e3, 3),
+                "h2d_gbs_per_gpu": round(rows * n_in * 4 / cs / 1e9, 2),
+                "d2h_gbs_per_gpu": round(rows * ostride * 4 / cs / 1e9, 2),
+                "value_at_ceiling": round(out_per_rank * world / cs / 1e6, 1),
+                "e2e_over_ceiling": round(cs / float(tt.item()), 4),
+                "how": "same H2D + D2H bytes as one e2e step per rank, plain cudaMemcpyAsync per 64 MiB slice on two "
+                       "streams, all ranks concurrently, wall clock, max over ranks (out_cols=%d padded to %d)" % (out_cols, ostride)}
+        e2e["numa"] = numa
+
+    # ---- parity spot check of THIS run's output (outside every timed region): random rows of the device result against the
+    # CPU oracle on the very same input rows ----
+    parity_spot = None
+    os.sched_setaffinity(0, affinity0)  # the CPU legs use every host core again
+    if rank == 0 and a.parity_rows > 0:
+        from oracle import oracle as O
+        step_device()
+        torch.cuda.synchronize()
+        pick = sorted(np.random.default_rng(2026).choice(rows, size=min(a.parity_rows, rows), replace=False).tolist())
+        xr = x[pick].cpu().numpy()
+        got = y[pick, :n1 + n2].cpu().numpy().astype(np.float64)
+        want, cnts = O.batch_resample(xr, IN_RATE, OUT_RATE, O.preset_to_engine_quality(PRESETS[a.preset]),
+                                      n_threads=min(len(pick), os.cpu_count() or 1))
+        err = float(np.max(np.abs(got - want[:, :n1 + n2].astype(np.float64))))
+        parity_spot = {"rows": len(pick), "row_ids": pick, "samples_per_row": int(n1 + n2), "counts_equal": bool(np.all(cnts == n1 + n2)),
+                       "max_abs_err": err, "tolerance": 1e-6, "ok": bool(err <= 1e-6 and np.all(cnts == n1 + n2)),
+                       "referee": "oracle/ (C++ restatement of the Go path) on the same input rows, full length"}
+        assert parity_spot["ok"], parity_spot
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
         xc = xh if xh is not None else x[:min(rows, 512)].cpu().numpy()
@@ -437,7 +608,7 @@ def main():
                            "l2": "inputs larger than L2 (%.1f GB per GPU per step)" % (rows * n_in * 4 / 1e9),
                            "timer": "CUDA events on the launching stream, max over ranks"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "extra_f64": extra}
+                "clocks": clocks, "parity_spot": parity_spot, "extra_f64": extra}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -1082,6 +1082,11 @@ void* gar_host_alloc_rows(gar_handle* h, size_t row_bytes) {
     return base;
 }
 
+int32_t gar_memcpy_async(void* dst, const void* src, size_t bytes, int32_t kind, void* cuda_stream) {
+    const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : (kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDefault);
+    return cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)cuda_stream) == cudaSuccess ? GAR_OK : GAR_CUDA_ERROR;
+}
+
 int32_t gar_bind_thread_to_device(int32_t device) { return bind_thread_to_device(device); }
 int32_t gar_device_numa_node(int32_t device) { return device_numa_node(device); }
 
@@ -1091,8 +1096,9 @@ int32_t gar_measure_fma_peak(int32_t device, int32_t dtype, double* tflops) {
     double best = 0;
     for (int rep = 0; rep < 3; ++rep) {
         double flops = 0;
-        // dtype 2 = packed fp32x2 (FFMA2) probe
-        const float ms = run_fma_probe(dtype == 2 ? 2 : (dtype == GAR_F32 ? DT_F32 : DT_F64), dtype == GAR_F64 ? 2048 : 4096, &flops, 0);
+        // dtype 2 = packed fp32x2 (FFMA2) probe, 3 = FP64 tensor cores (DMMA.8x8x4)
+        const float ms = run_fma_probe(dtype == 2 || dtype == 3 ? dtype : (dtype == GAR_F32 ? DT_F32 : DT_F64),
+                                       dtype == 3 ? 512 : (dtype == GAR_F64 ? 2048 : 4096), &flops, 0);
         if (ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
     if (cudaGetLastError() != cudaSuccess || best <= 0) return GAR_CUDA_ERROR;

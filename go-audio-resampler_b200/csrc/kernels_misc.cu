@@ -225,6 +225,26 @@ long long launch_count(bool reset) {
     return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
+// FP64 tensor-core probe: 8 independent accumulator tiles per warp, mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) back to back.
+// One instruction = 8x8x4 = 256 FMAs per warp = 8 per thread; 8 tiles x 8 reps = 64 instructions per iteration.
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters, double a0, double b0) {
+    double acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = threadIdx.x * 1e-3 + i;
+    const double a = a0 + threadIdx.x * 1e-9, b = b0;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc[i][0]), "+d"(acc[i][1]) : "d"(a), "d"(b));
+    double sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += acc[i][0] + acc[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
 float run_fma_probe(int dtype, int iters, double* flops, cudaStream_t s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -236,7 +256,8 @@ float run_fma_probe(int dtype, int iters, double* flops, cudaStream_t s) {
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     auto run = [&](int n) {
-        if (dtype == 2)  // packed f32x2: 4 reps x 8 chains x 2 lanes = 64 FMA per iteration, same as the others
+        if (dtype == 3) dmma_probe_kernel<<<blocks, threads, 0, s>>>((double*)buf, n, 0.999999, 1e-7);
+        else if (dtype == 2)  // packed f32x2: 4 reps x 8 chains x 2 lanes = 64 FMA per iteration, same as the others
             ffma2_probe_kernel<<<blocks, threads, 0, s>>>((float2*)buf, n, make_float2(0.999999f, 0.999998f),
                                                           make_float2(1e-7f, 2e-7f));
         else if (dtype == DT_F32) fma_probe_kernel<float><<<blocks, threads, 0, s>>>((float*)buf, n, 0.999999f, 1e-7f);
@@ -252,7 +273,8 @@ float run_fma_probe(int dtype, int iters, double* flops, cudaStream_t s) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(buf);
-    *flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    // per thread and iteration: 64 scalar FMAs, or 64 DMMA instructions x 8 FMAs per thread
+    *flops = 2.0 * 64.0 * (dtype == 3 ? 8.0 : 1.0) * (double)iters * (double)blocks * (double)threads;
     return ms;
 }
 

@@ -123,6 +123,7 @@ SYMBOLS = {
     "gar_host_alloc": (_vp, [C.c_size_t]),
     "gar_host_free": (None, [_vp]),
     "gar_host_alloc_rows": (_vp, [_vp, C.c_size_t]),
+    "gar_memcpy_async": (_i32, [_vp, _vp, C.c_size_t, _i32, _vp]),
     "gar_bind_thread_to_device": (_i32, [_i32]),
     "gar_device_numa_node": (_i32, [_i32]),
     "gar_device_count": (_i32, []),
@@ -622,10 +623,10 @@ def kernel_launches(reset=False):
     return int(lib().gar_kernel_launches(None, 1 if reset else 0))
 
 
-def measure_fma_peak(dtype=np.float32, device=0, packed=False):
-    """Dependent-FMA probe (TFLOP/s). packed=True uses fma.rn.f32x2 (FFMA2)."""
+def measure_fma_peak(dtype=np.float32, device=0, packed=False, tensor=False):
+    """Dependent-FMA probe (TFLOP/s). packed=True: fma.rn.f32x2 (FFMA2); tensor=True: FP64 tensor cores (DMMA.8x8x4)."""
     v = C.c_double(0)
-    code = 2 if packed else (F32 if np.dtype(dtype) == np.float32 else F64)
+    code = 3 if tensor else 2 if packed else (F32 if np.dtype(dtype) == np.float32 else F64)
     st = lib().gar_measure_fma_peak(device, code, C.byref(v))
     if st != OK:
         _raise(st, None)

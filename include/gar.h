@@ -258,7 +258,11 @@ const char* gar_stage_kernel_name(const gar_handle* h, int32_t stage);
 /* Comma-separated names of the distinct kernel variants the handle has launched so far (fused launches appear
  * under their own names), written to buf (NUL-terminated, truncated to cap). Returns the untruncated length. */
 int32_t gar_kernels_used(const gar_handle* h, char* buf, int32_t cap);
-/* Dependent-FMA micro-benchmark on `device`: achieved FMA TFLOP/s for dtype (roofline denominator). */
+/* Plain cudaMemcpyAsync (kind 1 = host to device, 2 = device to host, else default) on `cuda_stream` of the current
+ * device: lets ctypes / cgo callers measure the box's copy ceiling next to the batch calls (bench.py `copy_ceiling`). */
+int32_t gar_memcpy_async(void* dst, const void* src, size_t bytes, int32_t kind, void* cuda_stream);
+/* Dependent-FMA micro-benchmark on `device`: achieved TFLOP/s (roofline denominators). dtype: GAR_F64 / GAR_F32 vector FMA,
+ * 2 = packed fma.rn.f32x2 (FFMA2), 3 = FP64 tensor cores (mma.sync.m8n8k4.f64, DMMA.8x8x4). */
 int32_t gar_measure_fma_peak(int32_t device, int32_t dtype, double* tflops);
 const char* gar_version(void);
 
