@@ -20,6 +20,7 @@ Engine::~Engine() {
     if (device_ >= 0 && (stream_ || !dev_.empty())) cudaSetDevice(device_);
     for (auto& d : dev_) {
         for (auto& b : d.bank) if (b) cudaFree(b);
+        if (d.bank_il) cudaFree(d.bank_il);
         for (auto& h : d.hist) if (h) cudaFree(h);
         if (d.rat_cache.dev) cudaFree(d.rat_cache.dev);
     }
@@ -66,6 +67,31 @@ int Engine::upload_bank(int stage, int which, const std::vector<double>& v, std:
     return 0;
 }
 
+// a,b,c,d of a polyphase stage interleaved per tap (float64 engines, fractional step only): the phase-sorted kernel copies a
+// phase's four rows into shared memory with 16-byte asynchronous copies
+int Engine::upload_interleaved(int stage, std::string& err) {
+    StageDev& d = dev_[(size_t)stage];
+    const StageDesign& sd = chain_.stages[(size_t)stage];
+    if (d.bank_il) {
+        cudaFree(d.bank_il);
+        d.bank_il = nullptr;
+    }
+    if (sd.kind != STAGE_POLY || dtype_ != DT_F64 || !sd.interp) return 0;
+    const size_t n = sd.bank[0].size();
+    for (int w = 1; w < 4; ++w)
+        if (sd.bank[w].size() != n) return 0;
+    std::vector<double> il(n * 4);
+    for (size_t i = 0; i < n; ++i)
+        for (int w = 0; w < 4; ++w) il[i * 4 + (size_t)w] = sd.bank[w][i];
+    if (!cuda_ok(cudaMalloc(&d.bank_il, il.size() * 8), err, "cudaMalloc(interleaved bank)")) {
+        d.bank_il = nullptr;
+        return 4;
+    }
+    device_bytes_ += (int64_t)(il.size() * 8);
+    if (!cuda_ok(cudaMemcpy(d.bank_il, il.data(), il.size() * 8, cudaMemcpyHostToDevice), err, "bank upload")) return 4;
+    return 0;
+}
+
 int Engine::init(const Chain& chain, int rows, int compute_dtype, int device, std::string& err) {
     chain_ = chain;
     rows_ = rows;
@@ -104,6 +130,10 @@ int Engine::init(const Chain& chain, int rows, int compute_dtype, int device, st
                 if (rc) return rc;
             }
         }
+        {
+            int rc = upload_interleaved((int)s, err);
+            if (rc) return rc;
+        }
         int64_t cap = 8;
         switch (sd.kind) {
             case STAGE_UP: cap = sd.taps + 8; break;
@@ -121,6 +151,7 @@ int Engine::init(const Chain& chain, int rows, int compute_dtype, int device, st
     streams_.assign((size_t)rows, StreamState{});
     if (const char* e = std::getenv("GAR_NO_FUSE")) fuse_ = !(e[0] && e[0] != '0');
     if (const char* e = std::getenv("GAR_L2_SLICE_MB")) slice_budget_ = (int64_t)std::atoll(e) << 20;
+    order_after(stream_);  // the tail clears above were enqueued on stream_: later calls on other streams wait for them
     reset_state();
     return 0;
 }
@@ -155,14 +186,22 @@ void Engine::reset_state() {
             if (chain_.stages[s].kind == STAGE_CUBIC) st.st[s].hist_len = 3;  // cubic.go:18: zero-initialised 4-point window
     }
     if (device_ < 0) return;
-    cudaSetDevice(device_);
-    order_before(stream_);  // work enqueued on a caller's stream may still be reading the tails
+    // Only the cubic stage keeps device state that Reset must clear (its zero-initialised 4-point window); everything else
+    // is defined by the integer state above. The clear is enqueued on the handle's stream and ordered against the calls
+    // before and after it by the engine's event — Reset never blocks the host.
+    bool any = false;
     for (size_t s = 0; s < S; ++s)
         if (chain_.stages[s].kind == STAGE_CUBIC)
             for (auto& h : dev_[s].hist)
-                if (h) cudaMemsetAsync(h, 0, (size_t)rows_ * (size_t)dev_[s].hist_cap * esz_, stream_);
-    if (stream_) cudaStreamSynchronize(stream_);
-    order_pending_ = false;  // everything enqueued so far has completed
+                if (h) {
+                    if (!any) {
+                        cudaSetDevice(device_);
+                        order_before(stream_);
+                        any = true;
+                    }
+                    cudaMemsetAsync(h, 0, (size_t)rows_ * (size_t)dev_[s].hist_cap * esz_, stream_);
+                }
+    if (any) order_after(stream_);
 }
 
 int Engine::set_bank(int stage, int which, const double* coef, int64_t n, std::string& err) {
@@ -180,7 +219,8 @@ int Engine::set_bank(int stage, int which, const double* coef, int64_t n, std::s
     cudaSetDevice(device_);
     cudaDeviceSynchronize();  // the old bank and its coefficient tiles may be in use on any stream
     order_pending_ = false;
-    return upload_bank(stage, which, sd.bank[which], err);
+    const int rc = upload_bank(stage, which, sd.bank[which], err);
+    return rc ? rc : upload_interleaved(stage, err);
 }
 
 // Grows both ping-pong tail buffers of a stage. Everything (clear, copy of the old tails) is enqueued on `s`, the stream
@@ -627,6 +667,7 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                 f.hist_p_out = (char*)dpv.hist[nx.parity_in ^ 1] + (size_t)row0 * (size_t)dpv.hist_cap * esz_;
                 f.hist_p_out_stride = dpv.hist_cap; f.drop_p = (int32_t)nx.drop; f.new_hp = (int32_t)nx.new_hist_len;
                 f.bank_a = dpv.bank[0]; f.bank_b = dpv.bank[1]; f.bank_c = dpv.bank[2]; f.bank_d = dpv.bank[3];
+                f.bank_il = dpv.bank_il;
                 f.t2 = spd.taps; f.L = spd.factor; f.at0 = nx.first; f.step = spd.step;
                 f.n_out = (int32_t)nx.n_out; f.interp = nx.interp ? 1 : 0;
                 f.out = optr; f.out_stride = ostride; f.n_streams = count;

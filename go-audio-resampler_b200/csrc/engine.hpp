@@ -66,6 +66,7 @@ struct Plan {
 
 struct StageDev {
     void* bank[4] = {nullptr, nullptr, nullptr, nullptr};
+    void* bank_il = nullptr;  // POLY stages with a fractional step: a,b,c,d interleaved per tap [L][taps][4] (K4s)
     void* hist[2] = {nullptr, nullptr};
     int64_t hist_cap = 0;
     const char* kernel = "";
@@ -134,6 +135,7 @@ class Engine {
     void order_before(cudaStream_t s);
     void order_after(cudaStream_t s);
     int upload_bank(int stage, int which, const std::vector<double>& v, std::string& err);
+    int upload_interleaved(int stage, std::string& err);
 
     Chain chain_;
     int rows_ = 0, dtype_ = DT_F64, device_ = 0;

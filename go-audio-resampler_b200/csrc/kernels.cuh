@@ -60,6 +60,7 @@ struct FusedCall {
     void* hist_p_out;     int64_t hist_p_out_stride;
     int32_t drop_p;       int32_t new_hp;
     const void* bank_a;   const void* bank_b;      const void* bank_c;   const void* bank_d;
+    const void* bank_il;  // optional: the four banks interleaved per tap, [L][t2][4] = a,b,c,d (K4s); null if absent
     int32_t t2;           int32_t L;
     int64_t at0;          int64_t step;
     int32_t n_out;        int32_t interp;

@@ -216,6 +216,206 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
 }
 
 // =============================================================================================
+// K4s — fused x2 up-sampler + polyphase stage for IRRATIONAL ratios on one / a few rows (BASELINE config 5b as a single
+// stream; polyphase_stage.go:260-288 with cubic coefficient interpolation).
+//
+// With a fractional phase step no two outputs of a stream share their coefficients, and a thread-per-output kernel reads
+// four bank rows per output through L1/L2 (4 scattered loads per FMA-tap: K4 measured 3.5 % of the FMA peak on config 5b).
+// But outputs that share the INTEGER phase share the four rows a/b/c/d[phase] and differ only in the fraction x. So a
+// block takes a large tile (about 15.5 outputs per phase), sorts its outputs by phase in shared memory (counting sort:
+// histogram, scan, scatter), and a HALF-WARP processes one phase at a time: the phase's rows, interleaved as [tap]{a,b,c,d},
+// are copied into the half-warp's shared-memory slot with 16-byte cp.async (from a pre-interleaved copy of the banks), the
+// lanes are the outputs of that phase, and per tap every lane does 2 broadcast LDS.128 (coefficients) + 1 LDS.64 (sample)
+// for 4 DFMAs: three Horner steps and the dot-product step, in exactly K4's operation order (bit-identical results).
+// The x2 stage runs as in K4 (register-tiled core into a shared-memory tile), in NPASS passes per tile because the tile
+// is several times larger than one pass of NT*R positions; the coefficient slots alias the x2 stage's dead input window.
+// =============================================================================================
+struct SortGeom {
+    int32_t n_tiles, ms, cp, xlen, hpf, npass, ocap;
+    const void* bank_il;  // [L][t2][4] = a,b,c,d per tap
+};
+
+template <int R, int NT>
+__global__ void __launch_bounds__(NT, 1) fused_up2_poly_sorted_kernel(const FusedCall c, const SortGeom g) {
+    using T = double;
+    using V = double2;
+    constexpr int VEC = 2, NF = 2;
+    constexpr int TP = NT * R;    // positions per pass
+    constexpr int MT = TP * NF;   // intermediate samples per pass
+    constexpr int NHW = NT / 16;  // half-warps per block
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    T* cs = reinterpret_cast<T*>(smem_raw + 16);  // [2][cp]
+    T* xs = cs + NF * g.cp;                       // [xlen]
+    T* vp = xs + g.xlen;                          // [hpf + npass*MT]
+    T* slots = vp + g.hpf + g.npass * MT;         // [NHW][2][t2*4]: the rows of two adjacent phases per half-warp
+    int* hist = reinterpret_cast<int*>(slots + (size_t)NHW * 2 * c.t2 * 4);  // [L]
+    int* start = hist + c.L;                                                 // [L + 1]
+    int* cursor = start + c.L + 1;                                           // [L]
+    unsigned short* key = reinterpret_cast<unsigned short*>(cursor + c.L);   // [ocap] phase of output i (unsorted)
+    unsigned short* s_ph = key + g.ocap;                                     // sorted: phase,
+    unsigned short* s_n = s_ph + g.ocap;                                     //   output index - n_lo,
+    unsigned short* s_div = s_n + g.ocap;                                    //   window start - vbase,
+    unsigned short* s_x = s_div + g.ocap;                                    //   fraction bits
+
+    const int n_tiles = g.n_tiles, ms = g.ms, hpf = g.hpf;
+    const int tile = blockIdx.x % (n_tiles + 1);
+    const int64_t row = blockIdx.x / (n_tiles + 1);
+    const int tid = threadIdx.x;
+    const T* __restrict__ hist_u = static_cast<const T*>(c.hist_u) + row * c.hist_u_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    const T* __restrict__ hist_p = static_cast<const T*>(c.hist_p) + row * c.hist_p_stride;
+    const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
+
+    if (tile == n_tiles) {  // ---- carried tails ----
+        fused_carry_tails_rt<T>(c, row, xs, g.xlen + hpf + g.npass * MT);
+        return;
+    }
+
+    // ---- 1. stage the x2 stage's input window of the whole tile ----
+    const int n_mid = c.np * NF;
+    const int m0 = tile * ms;                             // first intermediate sample of the tile (even)
+    const int need_mid = min(ms + c.t2 - 1, n_mid - m0);  // intermediate samples the tile's outputs read
+    const int p0 = m0 >> 1;
+    const int need_pos = (need_mid + 1) >> 1;
+    const int npass = (need_pos + TP - 1) / TP;
+    const int need = need_pos > 0 ? need_pos - 1 + c.t1 : 0;
+    int a = 0;
+    bool bulk = false;
+    {
+        const int gi = p0 - c.hu;
+        if (gi >= 0 && need > 0) {
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(in + gi);
+            const int mis = (int)((addr & 15u) / sizeof(T));
+            const int words = ((need + mis + VEC - 1) / VEC) * VEC;
+            if (gi - mis >= 0 && gi - mis + words <= c.n_in && words <= g.xlen) {
+                bulk = true;
+                a = mis;
+            }
+        }
+    }
+    if (bulk) {
+        const int gi = p0 - c.hu - a;
+        const int words = ((need + a + VEC - 1) / VEC) * VEC;
+        if (tid == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)(words * sizeof(T)));
+            bulk_g2s(xs, in + gi, (uint32_t)(words * sizeof(T)), bar);
+        }
+        for (int i = words + tid; i < g.xlen; i += NT) xs[i] = T(0);
+    } else {
+        for (int i = tid; i < g.xlen; i += NT) xs[i] = i < need ? vload(hist_u, c.hu, in, c.n_in, p0 + i) : T(0);
+    }
+    for (int i = tid; i < NF * g.cp; i += NT) {
+        const int p = i / g.cp, k = i % g.cp - a;
+        cs[i] = (k >= 0 && k < c.t1) ? bank_u[p * c.t1 + k] : T(0);
+    }
+    const int front = tile == 0 ? hpf : 0;
+    if (tile == 0)
+        for (int i = tid; i < c.hp; i += NT) vp[hpf - c.hp + i] = hist_p[i];
+
+    // ---- 2. phase histogram of the tile's outputs (independent of the samples: overlaps the bulk copy) ----
+    const int64_t Lq = (int64_t)c.L << 16;
+    const int64_t lo = tile == 0 ? 0 : (int64_t)c.hp + (int64_t)tile * ms;
+    const int64_t hi = (int64_t)c.hp + (int64_t)(tile + 1) * ms;
+    auto first_n = [&](const int64_t d) -> int64_t {  // smallest n with div_n >= d
+        const int64_t need_at = d * Lq - c.at0;
+        return need_at <= 0 ? 0 : (need_at + c.step - 1) / c.step;
+    };
+    const int64_t n_lo = min((int64_t)c.n_out, first_n(lo));
+    const int64_t n_hi = tile == n_tiles - 1 ? (int64_t)c.n_out : min((int64_t)c.n_out, first_n(hi));
+    const int cnt = (int)(n_hi - n_lo);  // <= ocap by construction (launcher)
+    const int64_t vbase = tile == 0 ? (int64_t)c.hp - hpf : lo;
+    for (int i = tid; i < c.L; i += NT) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < cnt; i += NT) {
+        const int64_t full = (c.at0 + (n_lo + i) * c.step) >> 16;
+        const int ph = (int)(full % c.L);
+        key[i] = (unsigned short)ph;
+        atomicAdd(&hist[ph], 1);
+    }
+    if (bulk) {
+        while (!mbar_try_wait(bar, 0)) {
+        }
+    }
+
+    // ---- 3. x2 FIR core -> intermediate tile in shared memory ----
+    for (int q = 0; q < npass; ++q) {
+        T res[R][NF];
+        fir_tile_accumulate<T, 1, NF, R>(xs + R * (q * NT + tid), cs, g.cp, c.t1, a, res);
+        T* mp = vp + front + (size_t)R * NF * (q * NT + tid);
+#pragma unroll
+        for (int w = 0; w < R * NF / VEC; ++w) reinterpret_cast<V*>(mp)[w] = vec_pack(&res[0][0] + w * VEC);
+    }
+    __syncthreads();  // tile complete, histogram complete
+
+    // ---- 4. counting sort by phase: sorted position -> (phase, output, window start, fraction) ----
+    for (int p = tid; p <= c.L; p += NT) {
+        int sum = 0;
+        for (int j = 0; j < p; ++j) sum += hist[j];
+        start[p] = sum;
+        if (p < c.L) cursor[p] = sum;
+    }
+    __syncthreads();
+    for (int i = tid; i < cnt; i += NT) {
+        const int ph = key[i];
+        const int64_t at = c.at0 + (n_lo + i) * c.step;
+        const int64_t div = ((at >> 16) - ph) / c.L;  // exact: (full - phase) is a multiple of L
+        const int pos = atomicAdd(&cursor[ph], 1);
+        s_ph[pos] = (unsigned short)ph;
+        s_n[pos] = (unsigned short)i;
+        s_div[pos] = (unsigned short)(div - vbase);
+        s_x[pos] = (unsigned short)(at & 0xFFFF);
+    }
+    __syncthreads();
+
+    // ---- 5. groups of 16 phase-sorted outputs per half-warp; the rows of two adjacent phases per slot load ----
+    const int hw = tid >> 4, l16 = tid & 15;
+    const unsigned hmask = 0xFFFFu << (tid & 16);
+    T* slot = slots + (size_t)hw * 2 * c.t2 * 4;
+    const T* __restrict__ il = static_cast<const T*>(g.bank_il);
+    T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+    const int n_groups = (cnt + 15) >> 4;
+    for (int gi = hw; gi < n_groups; gi += NHW) {
+        const int j = gi * 16 + l16;
+        const bool active = j < cnt;
+        const int my_ph = active ? (int)s_ph[j] : -1;
+        const int pf = s_ph[gi * 16], pl = s_ph[min(cnt, gi * 16 + 16) - 1];
+        T x = 0;
+        const T* h = vp;
+        int64_t n = 0;
+        if (active) {
+            x = (T)(int)s_x[j] * (T)(1.0 / 65536.0);
+            h = vp + s_div[j];
+            n = n_lo + s_n[j];
+        }
+        for (int pw = pf; pw <= pl; pw += 2) {
+            const int chunks16 = min(2, pl - pw + 1) * c.t2 * 2;  // 16-byte pieces: rows pw (and pw + 1) are contiguous
+            const T* src = il + (size_t)pw * c.t2 * 4;
+            for (int ch = l16; ch < chunks16; ch += 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(slot + ch * 2)), "l"(src + ch * 2) : "memory");
+            cp_async_wait_all();
+            __syncwarp(hmask);
+            if (my_ph == pw || my_ph == pw + 1) {
+                const T* sl = slot + (size_t)(my_ph - pw) * c.t2 * 4;
+                double acc = 0;
+#pragma unroll 4
+                for (int k = 0; k < c.t2; ++k) {
+                    const V ab = *reinterpret_cast<const V*>(sl + 4 * k);
+                    const V cd = *reinterpret_cast<const V*>(sl + 4 * k + 2);
+                    const T coef = fma(x, fma(x, fma(x, cd.y, cd.x), ab.y), ab.x);
+                    acc = fma(h[k], coef, acc);
+                }
+                out[n] = acc;
+            }
+            __syncwarp(hmask);  // every lane is done with the slot before it is overwritten
+        }
+    }
+}
+
+// =============================================================================================
 // K4r — fused x2 up-sampler + polyphase stage for RATIONAL ratios (step and phase accumulator have no
 // fractional bits: 44.1k<->48k, 8k->12k, ... every ratio whose L/M is exact), register-tiled.
 //
@@ -701,6 +901,76 @@ static bool launch_fused_r(const FusedCall& c, cudaStream_t s) {
     return true;
 }
 
+// K4s launcher: float64, interpolated coefficients, fewer rows than the tensor-core batch kernels take.
+template <int NT>
+static bool launch_fused_sorted_nt(const FusedCall& c, const void* bank_il, cudaStream_t s) {
+    constexpr int R = 6, VEC = 2;
+    constexpr int NCH = (R - 1 + VEC - 1) / VEC + 1;
+    constexpr int MT = NT * R * 2;
+    const double r = (double)c.step / ((double)c.L * 65536.0);  // intermediate samples per output
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_mid = c.np * 2;
+    const int hpf = (c.hp + VEC - 1) / VEC * VEC;
+    const int cp = ((c.t1 + VEC - 1 + VEC - 1) / VEC) * VEC;
+    auto geom = [&](int ms, SortGeom& g) -> size_t {
+        g.ms = ms;
+        g.npass = ((ms + c.t2) / 2 + NT * R - 1) / (NT * R);
+        g.xlen = R * (g.npass * NT - 1) + (cp / VEC + NCH + 1) * VEC;
+        g.ocap = ((int)((double)(ms + c.hp + 2) / r) + 4 + 7) & ~7;  // tile 0 also covers the carried tail
+        g.n_tiles = (n_mid + ms - 1) / ms;
+        return 16 + ((size_t)2 * cp + g.xlen + hpf + (size_t)g.npass * MT + (size_t)(NT / 16) * 2 * c.t2 * 4) * sizeof(double) +
+               ((size_t)3 * c.L + 1) * sizeof(int) + (size_t)5 * g.ocap * sizeof(unsigned short) + 16;
+    };
+    // One block per SM (the block is 16 or 8 warps wide). Tile = an even share of the row per SM, so that one wave of
+    // blocks covers the call; at least ~4 outputs per phase (fewer leave the half-warp groups spread over many phases),
+    // at most what fits shared memory — then several balanced waves.
+    SortGeom g{};
+    g.cp = cp; g.hpf = hpf; g.bank_il = bank_il;
+    const int64_t total_mid = (int64_t)n_mid * c.n_streams;
+    const int slots = std::max(1, sms - c.n_streams);  // every row adds one carry block to the wave
+    int ms = (int)((total_mid + slots - 1) / slots);
+    ms = std::max(ms, (int)(4.0 * c.L * r));
+    ms = std::max((ms + 1) & ~1, 8 * c.t2);
+    size_t smem = geom(ms, g);
+    if (smem > 227 * 1024) {
+        int lo = 8 * c.t2, hi = ms;  // largest tile that fits
+        if (geom(lo, g) > 227 * 1024) return false;
+        while (hi - lo > 2) {
+            const int mid = ((lo + hi) / 2) & ~1;
+            if (geom(mid, g) <= 227 * 1024) lo = mid; else hi = mid;
+        }
+        // balanced waves: the tile count of every row rounded up to a whole number of waves
+        int tiles = (n_mid + lo - 1) / lo;
+        const int64_t waves = ((int64_t)(tiles + 1) * c.n_streams + sms - 1) / sms;
+        tiles = (int)std::max<int64_t>(tiles, waves * sms / c.n_streams - 1);
+        ms = std::max(((n_mid + tiles - 1) / tiles + 1) & ~1, 8 * c.t2);
+        if (ms > lo) ms = lo;
+        smem = geom(ms, g);
+    }
+    if (g.ocap > 65535 || smem > 227 * 1024 || hpf + g.npass * MT + c.hp > 65535) return false;
+    auto k = fused_up2_poly_sorted_kernel<R, NT>;
+    static size_t configured[64] = {0};
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)(g.n_tiles + 1) * c.n_streams;
+    k<<<(unsigned)blocks, NT, smem, s>>>(c, g);
+    count_launch();
+    return true;
+}
+
+static bool launch_fused_sorted(const FusedCall& c, const void* bank_il, cudaStream_t s) {
+    if (!bank_il || c.np <= 0 || c.n_out <= 0 || c.hp > 1024 || c.L > 512 || c.t2 > 200 || c.t2 < 2) return false;
+    const double r = (double)c.step / ((double)c.L * 65536.0);
+    if (!(r > 0.05) || r > 16.0) return false;
+    // 16 warps per block when the coefficient slots of 32 half-warps leave room for a useful tile, else 8 warps
+    if ((size_t)32 * 2 * c.t2 * 32 <= 100 * 1024 && launch_fused_sorted_nt<512>(c, bank_il, s)) return true;
+    return launch_fused_sorted_nt<256>(c, bank_il, s);
+}
+
 // Tile size by call size: big tiles (R = 6 / 12 positions per thread) keep the FIR core FMA-bound; a streaming-size call
 // has only a handful of them, so its critical path is one tile long — small tiles (R = 2 / 4) spread it over more SMs.
 template <typename T, bool INTERP>
@@ -888,6 +1158,10 @@ const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s,
             c.L <= 4096 && c.t2 <= 1024)
             return nullptr;
     }
+    // irrational ratio on one / a few rows: phase-sorted tiles (K4s) once the call is large enough to fill them
+    if (c.interp && g_fused_rat && c.bank_il && (int64_t)c.n_out >= 16 * (int64_t)c.L &&
+        launch_fused_sorted(c, c.bank_il, s))
+        return "fused_up2_poly_sorted_f64";
     if (c.interp) return launch_fused_t<double, true>(c, s) ? "fused_up2_poly_f64_interp" : nullptr;
     return launch_fused_t<double, false>(c, s) ? "fused_up2_poly_f64" : nullptr;
 }

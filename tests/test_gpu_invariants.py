@@ -464,3 +464,35 @@ def test_flush_right_after_the_first_process_on_a_busy_gpu_and_mixed_streams():
     one = run([side.cuda_stream])
     mixed = run([side.cuda_stream, torch.cuda.current_stream().cuda_stream, 0])
     np.testing.assert_array_equal(one, mixed)
+
+
+@pytest.mark.parametrize("ir,orr,rows,n", [(44100, 47999, 1, 200000), (48000, 44101, 1, 150000), (44100, 32001, 3, 90000),
+                                            (32000, 47999, 7, 50000), (96000, 44101, 2, 120000), (22050, 47999, 1, 60000)])
+def test_phase_sorted_fused_kernel_irrational_ratios_vs_thread_per_output_kernel_and_oracle(ir, orr, rows, n):
+    """K4s (fused x2 -> polyphase with cubic coefficient interpolation, outputs sorted by phase inside a tile, a half-warp per
+    phase): same operation order as the thread-per-output kernel => bit-identical, in one shot and in chunks; <= 1e-12 vs the
+    oracle; counts exact (polyphase_stage.go:186-312)."""
+    rng = np.random.default_rng(ir + orr + rows)
+    x = 0.5 * rng.standard_normal((rows, n))
+    cuts = [0, n // 3 + 17, n]
+
+    def run(fast):
+        G.set_tiled_polyphase(fast)
+        try:
+            h = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float64)
+            ys = [h.ProcessBatch(np.ascontiguousarray(x[:, a:b]))[0].copy() for a, b in zip(cuts[:-1], cuts[1:])]
+            ys.append(h.FlushBatch()[0].copy())
+            return np.concatenate(ys, axis=1), h.last_kernels()
+        finally:
+            G.set_tiled_polyphase(True)
+
+    fast, kf = run(True)
+    slow, ks = run(False)
+    assert "fused_up2_poly_sorted_f64" in kf and "fused_up2_poly_sorted_f64" not in ks, (kf, ks)
+    np.testing.assert_array_equal(fast, slow)
+    h1 = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float64)
+    one = np.concatenate([h1.ProcessBatch(x)[0], h1.FlushBatch()[0]], axis=1)
+    np.testing.assert_array_equal(one, fast)  # chunked == one shot, bit for bit
+    want, counts = O.batch_resample(x, ir, orr, O.Q_HIGH, n_threads=min(rows, 4))
+    assert np.all(counts == fast.shape[1])
+    assert np.max(np.abs(fast - want[:, :fast.shape[1]])) <= 1e-12
