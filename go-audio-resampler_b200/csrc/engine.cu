@@ -149,8 +149,8 @@ int Engine::init(const Chain& chain, int rows, int compute_dtype, int device, st
     ibuf_.assign(chain_.engines.size() * 2, nullptr);
     ibuf_cap_.assign(chain_.engines.size() * 2, 0);
     streams_.assign((size_t)rows, StreamState{});
-    if (const char* e = std::getenv("GAR_NO_FUSE")) fuse_ = !(e[0] && e[0] != '0');
-    if (const char* e = std::getenv("GAR_L2_SLICE_MB")) slice_budget_ = (int64_t)std::atoll(e) << 20;
+    if (const char* e = gar::tune_env("GAR_NO_FUSE")) fuse_ = !(e[0] && e[0] != '0');
+    if (const char* e = gar::tune_env("GAR_L2_SLICE_MB")) slice_budget_ = (int64_t)std::atoll(e) << 20;
     order_after(stream_);  // the tail clears above were enqueued on stream_: later calls on other streams wait for them
     reset_state();
     return 0;

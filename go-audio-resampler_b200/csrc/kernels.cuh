@@ -91,6 +91,12 @@ struct CubicCall {
 
 enum Dtype : int { DT_F64 = 0, DT_F32 = 1 };
 
+// Every tuning / A-B environment variable of the kernels (GAR_MMA_*, GAR_K3M_*, GAR_RAT_*, GAR_NO_*, GAR_TENSOR_MIN_ROWS,
+// GAR_L2_SLICE_MB ...) is read through this one switch: they are ignored unless GAR_DEBUG_TUNING=1 is set, so a stray
+// variable in a production environment cannot change kernel selection. The supported A/B switches are the API calls
+// (gar_set_fusion, gar_set_tiled_polyphase, gar_set_tensor_fir, gar_set_slice_budget).
+const char* tune_env(const char* name);
+
 // launchers (kernels_fir.cu, kernels_poly.cu, kernels_fused.cu, kernels_misc.cu). Return the name of the kernel variant used.
 const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s);
 const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* cache);

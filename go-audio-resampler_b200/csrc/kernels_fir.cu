@@ -403,7 +403,7 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
     // the same offset of BOTH filters; 8 doubles apart modulo the 16 eight-byte banks (length = 8 mod 16) the two groups do
     // not collide (ncu: the A loads took 4 wavefronts instead of 2 with the unpadded length)
     g.blen = (4 * g.nk + (JT - 1) * M + 5) & ~1;
-    static const bool pad_bank = [] { const char* e = std::getenv("GAR_MMA_BANKPAD"); return !e || e[0] != '0'; }();
+    static const bool pad_bank = [] { const char* e = gar::tune_env("GAR_MMA_BANKPAD"); return !e || e[0] != '0'; }();
     if (NF == 2 && pad_bank) g.blen = ((g.blen + 7) & ~15) + 8;
     const size_t bank_bytes = 16 + (size_t)NF * g.blen * sizeof(double);
     // nkc > 1: tap-chunked staging (KC kernels); max_smem: give up when a block needs more (0: whatever fits an SM)
@@ -419,7 +419,7 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
         g.pitch = ((g.xlen + 15) / 16) * 16 + 4;  // rows 32 bytes apart modulo 128: the 8 x 32-byte B fragment reads tile two wavefronts
         const size_t xbytes = (size_t)8 * g.pitch * sizeof(double);
         // two window buffers (the next tile is prefetched under the MMAs) when at least two such blocks fit an SM
-        static const int force_nbuf = [] { const char* e = std::getenv("GAR_MMA_NBUF"); return e ? std::atoi(e) : 0; }();
+        static const int force_nbuf = [] { const char* e = gar::tune_env("GAR_MMA_NBUF"); return e ? std::atoi(e) : 0; }();
         g.nbuf = bank_bytes + 2 * xbytes <= 110 * 1024 ? 2 : 1;
         if (force_nbuf == 1) g.nbuf = 1;
         if (force_nbuf == 2 && bank_bytes + 2 * xbytes <= 227 * 1024) g.nbuf = 2;
@@ -451,8 +451,8 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
     // 8-warp block is staged in 2-4 chunks along the taps until TWO blocks fit an SM (C3: 0.398 -> 0.374 ms against one
     // 16-warp block per SM with the whole window; chunking that 16-warp block or double-buffering the chunks was slower).
     // GAR_MMA_CFG = 1 / 3 forces 16 / 8 warps with the whole window, GAR_MMA_NKC = n the chunk count.
-    static const int forced = [] { const char* e = std::getenv("GAR_MMA_CFG"); return e ? std::atoi(e) : -1; }();
-    static const int nkc_env = [] { const char* e = std::getenv("GAR_MMA_NKC"); return e ? std::atoi(e) : 0; }();
+    static const int forced = [] { const char* e = gar::tune_env("GAR_MMA_CFG"); return e ? std::atoi(e) : -1; }();
+    static const int nkc_env = [] { const char* e = gar::tune_env("GAR_MMA_NKC"); return e ? std::atoi(e) : 0; }();
     if (forced == 1) return run(fir_mma_f64_kernel<M, NF, 16, 4, false>, 16, 4, 1, 1, 0);
     if (forced == 3) return run(fir_mma_f64_kernel<M, NF, 8, 4, false>, 8, 4, 3, 1, 0);
     if (c.taps > 600) {
@@ -467,7 +467,7 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
 }
 
 static bool g_fir_mma = [] {
-    const char* e = std::getenv("GAR_NO_MMA");
+    const char* e = gar::tune_env("GAR_NO_MMA");
     return !(e && e[0] && e[0] != '0');
 }();
 // float64 FIR on the FP64 tensor cores: x2 up-sampler and /2 /3 /4 decimators, any number of lock-step rows (fewer than 8:

@@ -854,7 +854,7 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
 
 // A/B toggle (GAR_NO_RAT=1 or set_tiled_polyphase(false)): fall back to the one-thread-per-output kernels (no K4r / K3r / K3i)
 static bool g_fused_rat = [] {
-    const char* e = std::getenv("GAR_NO_RAT");
+    const char* e = gar::tune_env("GAR_NO_RAT");
     return !(e && e[0] && e[0] != '0');
 }();
 void set_tiled_polyphase(bool on) { g_fused_rat = on; }
@@ -1019,7 +1019,7 @@ static bool launch_rat_t(const FusedCall& c, cudaStream_t s, RatCache* cache) {
     }
     static const int* forced = [] {  // tuning override: GAR_RAT_OPT="P,threads,xbufs,nv"
         static int v[4];
-        const char* e = std::getenv("GAR_RAT_OPT");
+        const char* e = gar::tune_env("GAR_RAT_OPT");
         return (e && std::sscanf(e, "%d,%d,%d,%d", v, v + 1, v + 2, v + 3) == 4) ? v : (const int*)nullptr;
     }();
     if (forced) opts[0] = Opt{forced[0], forced[1], FUSED ? forced[2] : 0, forced[3], 227 * 1024};
@@ -1062,7 +1062,7 @@ static bool launch_rat_t(const FusedCall& c, cudaStream_t s, RatCache* cache) {
         g.tiles_per_block = (int32_t)tpb;
         g.n_groups = (g.n_tiles + g.tiles_per_block - 1) / g.tiles_per_block;
     }
-    if (const char* e = std::getenv("GAR_RAT_TPB")) {  // tuning override
+    if (const char* e = gar::tune_env("GAR_RAT_TPB")) {  // tuning override
         const int v = std::atoi(e);
         if (v >= 1 && v <= RAT_MAXT) {
             g.tiles_per_block = v < g.n_tiles ? v : g.n_tiles;
@@ -1144,7 +1144,7 @@ const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s,
     //    one-thread-per-output kernel is 10x slower there).
     {
         const bool rational = !c.interp && ((c.step | c.at0) & 0xFFFF) == 0;
-        static const int rational_min_rows = [] { const char* e = std::getenv("GAR_TENSOR_MIN_ROWS"); return e ? std::atoi(e) : 32; }();
+        static const int rational_min_rows = [] { const char* e = gar::tune_env("GAR_TENSOR_MIN_ROWS"); return e ? std::atoi(e) : 32; }();
         if (tensor_fir_enabled() && g_fused_rat && (int64_t)c.np * c.n_streams >= 32768 &&
             c.n_streams >= (rational ? rational_min_rows : 8))
             return nullptr;

@@ -9,6 +9,14 @@ std::atomic<long long> g_launches{0};
 }  // namespace
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+const char* tune_env(const char* name) {
+    static const bool on = [] {
+        const char* e = std::getenv("GAR_DEBUG_TUNING");
+        return e && e[0] && e[0] != '0';
+    }();
+    return on ? std::getenv(name) : nullptr;
+}
+
 namespace {
 
 // =============================================================================================

@@ -623,7 +623,7 @@ static bool launch_poly_rows_pipe_t(const PolyCall& c, cudaStream_t s) {
 
 // K3p variants: coefficient registers for K <= 80 or <= 112, 2 stages of 32 rows or (long spans) 3 stages of 16 rows
 static bool launch_poly_rows_pipe(const PolyCall& c, cudaStream_t s) {
-    static const int rb16_rows = [] { const char* e = std::getenv("GAR_K3P_RB16_ROWS"); return e ? std::atoi(e) : 0; }();
+    static const int rb16_rows = [] { const char* e = gar::tune_env("GAR_K3P_RB16_ROWS"); return e ? std::atoi(e) : 0; }();
     // fewer rows: 16-row stages keep the pipeline at least two stages deep
     if (c.n_streams < rb16_rows && (launch_poly_rows_pipe_t<20, 16, 3>(c, s) || launch_poly_rows_pipe_t<28, 16, 3>(c, s))) return true;
     return launch_poly_rows_pipe_t<20, 32, 2>(c, s) || launch_poly_rows_pipe_t<20, 16, 3>(c, s) ||
@@ -645,9 +645,9 @@ static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s) {
     g.nrb = 1;
     // measured on the batched 44.1k->48k chain (256 rows): 1 / 2 / 4 / 8 row blocks per coefficient evaluation -> 1.93 / 1.45 /
     // 1.19 / 1.10 ms for the polyphase stage
-    static const int max_nrb = [] { const char* e = std::getenv("GAR_K3M_NRB"); return e ? std::atoi(e) : 8; }();
+    static const int max_nrb = [] { const char* e = gar::tune_env("GAR_K3M_NRB"); return e ? std::atoi(e) : 8; }();
     while (g.nrb < max_nrb && g.nrb * 2 <= n_rb && (int64_t)g.n_tiles * ((n_rb + g.nrb * 2 - 1) / (g.nrb * 2)) >= 4 * 148) g.nrb *= 2;
-    static const int force_nbuf = [] { const char* e = std::getenv("GAR_K3M_NBUF"); return e ? std::atoi(e) : 0; }();
+    static const int force_nbuf = [] { const char* e = gar::tune_env("GAR_K3M_NBUF"); return e ? std::atoi(e) : 0; }();
     const size_t fixed = 16 + (size_t)NTASK * g.kp * 8 * sizeof(double) + (size_t)NTASK * 8 * 4 * sizeof(int);
     const size_t xbytes = (size_t)32 * g.pitch * sizeof(double);
     g.nbuf = force_nbuf ? force_nbuf : 1;
@@ -671,9 +671,9 @@ static int launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
     if (!tensor_fir_enabled() || c.n_streams < 8 || (int64_t)c.n_out * c.n_streams < 16384 || c.L > 4096 || c.taps > 1024) return 0;
     const double r = (double)c.step / ((double)c.L * 65536.0);
     if (!(r > 0.0) || r > 8.0) return 0;
-    static const int ntask = [] { const char* e = std::getenv("GAR_K3M_NTASK"); return e ? std::atoi(e) : 8; }();
-    static const bool pipe = [] { const char* e = std::getenv("GAR_K3M_PIPE"); return !e || e[0] != '0'; }();
-    static const int pipe_rows = [] { const char* e = std::getenv("GAR_K3M_PIPE_ROWS"); return e ? std::atoi(e) : 32; }();
+    static const int ntask = [] { const char* e = gar::tune_env("GAR_K3M_NTASK"); return e ? std::atoi(e) : 8; }();
+    static const bool pipe = [] { const char* e = gar::tune_env("GAR_K3M_PIPE"); return !e || e[0] != '0'; }();
+    static const int pipe_rows = [] { const char* e = gar::tune_env("GAR_K3M_PIPE_ROWS"); return e ? std::atoi(e) : 32; }();
     // measured (44.1k->48k, 21 M samples): K3p against K3m 32 rows 20.9 / 19.9, 48 rows 21.8 / 20.4 TFLOP/s, equal below
     if (pipe && c.n_streams >= pipe_rows && launch_poly_rows_pipe(c, s)) return 2;
     if (ntask == 4) return (launch_poly_rows_mma_t<4>(c, s) || launch_poly_rows_mma_t<8>(c, s)) ? 1 : 0;
