@@ -88,6 +88,10 @@ struct gar_handle {
     double ratio = 1.0;
     int rows = 1;
     int compute_dtype = DT_F64;
+    // float32 ENGINE handle whose batches run on the float64 tensor-core kernels: samples and coefficients are float32 values
+    // (I/O, banks rounded to float32), arithmetic and carried state are float64 — at least as accurate as float32 arithmetic
+    // and 1.6x (rational) to 7x (irrational ratios) faster than the float32 one-thread-per-output kernels for >= 8-32 rows.
+    bool wide_f32 = false;
     std::string err;
     std::string gpu_name;
     // batch pipelining
@@ -219,6 +223,16 @@ int32_t gar_create(const gar_config* cfg, gar_handle** out) {
         compute = cfg->dtype == GAR_F32 ? DT_F32 : DT_F64;
     }
     chain.ratio = ratio;
+    // wide mode: a float32 batch at a non-integer ratio (x2 stage + polyphase stage) large enough for the FP64 tensor-core
+    // kernels (K1m + K3m/K3p: irrational ratios from 8 rows, rational ones from 32 — below that the fused kernels win)
+    bool wide = false;
+    if (path == GAR_PATH_ENGINE && compute == DT_F32) {
+        const int rows_total = channels * (cfg->n_streams > 1 ? cfg->n_streams : 1);
+        for (const StageDesign& sd : chain.stages)
+            if (sd.kind == STAGE_POLY && rows_total >= (sd.interp ? 8 : 32)) wide = true;
+        if (const char* e = gar::tune_env("GAR_NO_WIDE_F32")) wide = wide && !(e[0] && e[0] != '0');
+        if (wide) compute = DT_F64;
+    }
 
     std::unique_ptr<gar_handle> h(new gar_handle());
     h->cfg = *cfg;
@@ -226,7 +240,8 @@ int32_t gar_create(const gar_config* cfg, gar_handle** out) {
     h->ratio = ratio;
     h->rows = channels * (cfg->n_streams > 1 ? cfg->n_streams : 1);
     h->compute_dtype = compute;
-    int rc = h->eng.init(chain, h->rows, compute, cfg->device, err);
+    h->wide_f32 = wide;
+    int rc = h->eng.init(chain, h->rows, compute, cfg->device, err, wide);
     if (rc) {
         g_create_err = err;
         return rc;
@@ -496,7 +511,7 @@ int64_t gar_get_bank(const gar_handle* h, int32_t stage, int32_t which, double* 
     if (stage < 0 || stage >= (int)c.stages.size() || which < 0 || which > 3) return -1;
     const std::vector<double>& b = c.stages[(size_t)stage].bank[which];
     if ((int64_t)b.size() > cap) return -(int64_t)b.size();
-    const bool f32 = h->compute_dtype == DT_F32;
+    const bool f32 = h->compute_dtype == DT_F32 || h->wide_f32;
     for (size_t i = 0; i < b.size(); ++i) out[i] = f32 ? (double)(float)b[i] : b[i];
     return (int64_t)b.size();
 }
@@ -669,7 +684,7 @@ int32_t gar_process_f64(gar_handle* h, int32_t ch, const double* in, int64_t n_i
                         int64_t* n_out) {
     if (!h || !n_out) return GAR_INVALID_CONFIG;
     *n_out = 0;
-    if (h->compute_dtype != DT_F64) return fail(h, GAR_NOT_SUPPORTED, "float32 engine: use gar_process_f32");
+    if (h->compute_dtype != DT_F64 || h->wide_f32) return fail(h, GAR_NOT_SUPPORTED, "float32 engine: use gar_process_f32");
     if (n_in < 0) return fail(h, GAR_INVALID_CONFIG, "negative input length");
     if (out_cap < gar_estimate_output(h, n_in)) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
     if (n_in == 0) return GAR_OK;
@@ -682,7 +697,7 @@ int32_t gar_process_f32(gar_handle* h, int32_t ch, const float* in, int64_t n_in
                         int64_t* n_out) {
     if (!h || !n_out) return GAR_INVALID_CONFIG;
     *n_out = 0;
-    if (h->cfg.path == GAR_PATH_ENGINE && h->compute_dtype != DT_F32)
+    if (h->cfg.path == GAR_PATH_ENGINE && h->compute_dtype != DT_F32 && !h->wide_f32)
         return fail(h, GAR_NOT_SUPPORTED, "float64 engine: use gar_process_f64");
     if (n_in < 0) return fail(h, GAR_INVALID_CONFIG, "negative input length");
     if (out_cap < gar_estimate_output(h, n_in)) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
@@ -695,7 +710,7 @@ int32_t gar_process_f32(gar_handle* h, int32_t ch, const float* in, int64_t n_in
 int32_t gar_process_multi_f64(gar_handle* h, const double* const* in, const int64_t* n_in, double* const* out,
                               int64_t out_cap, int64_t* n_out) {
     if (!h || !in || !n_in || !out || !n_out) return GAR_INVALID_CONFIG;
-    if (h->compute_dtype != DT_F64) return fail(h, GAR_NOT_SUPPORTED, "float32 engine has no ProcessMulti");
+    if (h->compute_dtype != DT_F64 || h->wide_f32) return fail(h, GAR_NOT_SUPPORTED, "float32 engine has no ProcessMulti");
     const int C = h->cfg.channels;
     for (int c = 0; c < C; ++c) n_out[c] = 0;
     return process_rows_host(h, 0, C, GAR_F64, (const void* const*)in, n_in, (void* const*)out, out_cap, n_out, false,
@@ -705,7 +720,7 @@ int32_t gar_process_multi_f64(gar_handle* h, const double* const* in, const int6
 int32_t gar_flush_f64(gar_handle* h, int32_t ch, double* out, int64_t out_cap, int64_t* n_out) {
     if (!h || !n_out) return GAR_INVALID_CONFIG;
     *n_out = 0;
-    if (h->compute_dtype != DT_F64) return fail(h, GAR_NOT_SUPPORTED, "float32 engine: use gar_flush_f32");
+    if (h->compute_dtype != DT_F64 || h->wide_f32) return fail(h, GAR_NOT_SUPPORTED, "float32 engine: use gar_flush_f32");
     void* op = out;
     return process_rows_host(h, ch, 1, GAR_F64, nullptr, nullptr, &op, out_cap, n_out, true, false);
 }
@@ -713,7 +728,7 @@ int32_t gar_flush_f64(gar_handle* h, int32_t ch, double* out, int64_t out_cap, i
 int32_t gar_flush_f32(gar_handle* h, int32_t ch, float* out, int64_t out_cap, int64_t* n_out) {
     if (!h || !n_out) return GAR_INVALID_CONFIG;
     *n_out = 0;
-    if (h->cfg.path == GAR_PATH_ENGINE && h->compute_dtype != DT_F32)
+    if (h->cfg.path == GAR_PATH_ENGINE && h->compute_dtype != DT_F32 && !h->wide_f32)
         return fail(h, GAR_NOT_SUPPORTED, "float64 engine: use gar_flush_f64");
     void* op = out;
     return process_rows_host(h, ch, 1, GAR_F32, nullptr, nullptr, &op, out_cap, n_out, true, false);
@@ -721,7 +736,7 @@ int32_t gar_flush_f32(gar_handle* h, int32_t ch, float* out, int64_t out_cap, in
 
 int32_t gar_flush_multi_f64(gar_handle* h, double* const* out, int64_t out_cap, int64_t* n_out) {
     if (!h || !out || !n_out) return GAR_INVALID_CONFIG;
-    if (h->compute_dtype != DT_F64) return fail(h, GAR_NOT_SUPPORTED, "float32 engine has no FlushMulti");
+    if (h->compute_dtype != DT_F64 || h->wide_f32) return fail(h, GAR_NOT_SUPPORTED, "float32 engine has no FlushMulti");
     const int C = h->cfg.channels;
     for (int c = 0; c < C; ++c) n_out[c] = 0;
     return process_rows_host(h, 0, C, GAR_F64, nullptr, nullptr, (void* const*)out, out_cap, n_out, true, false);
@@ -804,7 +819,7 @@ int32_t gar_process_batch_dev(gar_handle* h, int32_t io_dtype, const void* d_in,
     if (!h) return GAR_INVALID_CONFIG;
     if (h->multi()) return fail(h, GAR_NOT_SUPPORTED, "device-pointer calls need a single-device handle (one per device)");
     if (n_in < 0) return fail(h, GAR_INVALID_CONFIG, "negative input length");
-    if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->compute_dtype)
+    if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->cfg.dtype)
         return fail(h, GAR_NOT_SUPPORTED, "engine handles take their own dtype");
     if (n_in == 0) {
         if (n_out) *n_out = 0;
@@ -818,7 +833,7 @@ int32_t gar_flush_batch_dev(gar_handle* h, int32_t io_dtype, void* d_out, int64_
                             int64_t* n_out, void* cuda_stream) {
     if (!h) return GAR_INVALID_CONFIG;
     if (h->multi()) return fail(h, GAR_NOT_SUPPORTED, "device-pointer calls need a single-device handle (one per device)");
-    if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->compute_dtype)
+    if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->cfg.dtype)
         return fail(h, GAR_NOT_SUPPORTED, "engine handles take their own dtype");
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->eng.stream();
     return batch_dev(h, io_dtype, nullptr, 0, 0, d_out, out_stride, out_cap, n_out, true, s, 0, h->rows);
@@ -936,7 +951,7 @@ int32_t gar_process_batch(gar_handle* h, int32_t io_dtype, const void* in, int64
                           int64_t out_stride, int64_t out_cap, int64_t* n_out) {
     if (!h) return GAR_INVALID_CONFIG;
     if (n_in < 0) return fail(h, GAR_INVALID_CONFIG, "negative input length");
-    if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->compute_dtype)
+    if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->cfg.dtype)
         return fail(h, GAR_NOT_SUPPORTED, "engine handles take their own dtype");
     if (out_cap < gar_estimate_output(h, n_in)) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
     return batch_host(h, io_dtype, in, in_stride, n_in, out, out_stride, out_cap, n_out, false);
@@ -945,7 +960,7 @@ int32_t gar_process_batch(gar_handle* h, int32_t io_dtype, const void* in, int64
 int32_t gar_flush_batch(gar_handle* h, int32_t io_dtype, void* out, int64_t out_stride, int64_t out_cap,
                         int64_t* n_out) {
     if (!h) return GAR_INVALID_CONFIG;
-    if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->compute_dtype)
+    if (h->cfg.path == GAR_PATH_ENGINE && io_dtype != h->cfg.dtype)
         return fail(h, GAR_NOT_SUPPORTED, "engine handles take their own dtype");
     return batch_host(h, io_dtype, nullptr, 0, 0, out, out_stride, out_cap, n_out, true);
 }
@@ -993,7 +1008,7 @@ static int interleaved_call(gar_handle* h, int fmt, int bit_depth, const void* i
         d_pl_in = (char*)E.scratch(1, (size_t)C * (size_t)is * csz, h->err);
         if (!d_il_in || !d_pl_in) return GAR_CUDA_ERROR;
         cudaMemcpyAsync(d_il_in, in, (size_t)C * (size_t)n_frames * isz, cudaMemcpyHostToDevice, s);
-        launch_deinterleave(d_il_in, fmt, C, n_frames, d_pl_in, is, h->compute_dtype, is_int ? 1.0 / maxv : 0.0, s);
+        launch_deinterleave(d_il_in, fmt, C, n_frames, d_pl_in, is, h->compute_dtype, is_int ? 1.0 / maxv : 0.0, h->wide_f32 ? 1 : 0, s);
     }
     if (want > 0) {
         d_pl_out = (char*)E.scratch(2, (size_t)C * (size_t)os * csz, h->err);
@@ -1004,7 +1019,7 @@ static int interleaved_call(gar_handle* h, int fmt, int bit_depth, const void* i
     int rc = E.run(0, C, d_pl_in, is, flush ? 0 : n_frames, d_pl_out, os, os, flush, s, &got, h->err);
     if (rc) return rc;
     if (got > 0) {
-        launch_interleave(d_pl_out, os, h->compute_dtype, C, got, d_il_out, fmt, maxv, s);
+        launch_interleave(d_pl_out, os, h->compute_dtype, C, got, d_il_out, fmt, maxv, h->wide_f32 ? 1 : 0, s);
         cudaMemcpyAsync(out, d_il_out, (size_t)C * (size_t)got * isz, cudaMemcpyDeviceToHost, s);
     }
     cudaError_t e = cudaStreamSynchronize(s);

@@ -92,8 +92,13 @@ int Engine::upload_interleaved(int stage, std::string& err) {
     return 0;
 }
 
-int Engine::init(const Chain& chain, int rows, int compute_dtype, int device, std::string& err) {
+int Engine::init(const Chain& chain, int rows, int compute_dtype, int device, std::string& err, bool round_banks_f32) {
     chain_ = chain;
+    round_banks_f32_ = round_banks_f32 && compute_dtype == DT_F64;
+    if (round_banks_f32_)  // the coefficients a float32 engine uses (polyphase_stage.go:149-152, dft_stage.go:98,464), widened
+        for (StageDesign& sd : chain_.stages)
+            for (auto& b : sd.bank)
+                for (double& v : b) v = (double)(float)v;
     rows_ = rows;
     dtype_ = compute_dtype;
     esz_ = compute_dtype == DT_F32 ? 4 : 8;

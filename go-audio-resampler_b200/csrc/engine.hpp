@@ -81,7 +81,8 @@ class Engine {
     Engine& operator=(const Engine&) = delete;
 
     // returns gar_status
-    int init(const Chain& chain, int rows, int compute_dtype, int device, std::string& err);
+    // round_banks_f32: float64 compute on float32-rounded coefficients (float32 engines in wide mode)
+    int init(const Chain& chain, int rows, int compute_dtype, int device, std::string& err, bool round_banks_f32 = false);
 
     const Chain& chain() const { return chain_; }
     int rows() const { return rows_; }
@@ -155,6 +156,7 @@ class Engine {
     int32_t* d_cubic_idx_ = nullptr;
     double* d_cubic_phase_ = nullptr;
     int64_t cubic_cap_ = 0;
+    bool round_banks_f32_ = false;
     bool fuse_ = true;  // K4 fused x2 -> polyphase launches (GAR_NO_FUSE=1 disables, for A/B tests)
     int64_t launches_ = 0;
     // bytes of the largest inter-stage buffer per slice. Default 2 GiB: a memory-footprint guard only. L2-sized slices

@@ -114,10 +114,11 @@ void launch_cast(const void* src, int64_t src_stride, int src_dtype, void* dst, 
 //   deinterleave: planar[ch][i] = T(double(interleaved[i*C+ch]) * inv_max)   (inv_max == 0: plain cast, float I/O)
 //   interleave:   interleaved[i*C+ch] = int(clamp(double(planar[ch][i]), -1, 1) * max_val)  (truncating; max_val == 0: cast)
 // fmt: 0 f64, 1 f32, 2 int16, 3 int32, 4 int64 containers
+// round_f32: values pass through float32 on the way (float32 engines that compute in float64, see gar_handle::wide_f32)
 void launch_deinterleave(const void* in, int fmt, int channels, int64_t n_frames, void* planar, int64_t stride,
-                         int dtype, double inv_max, cudaStream_t s);
+                         int dtype, double inv_max, int round_f32, cudaStream_t s);
 void launch_interleave(const void* planar, int64_t stride, int dtype, int channels, int64_t n_frames, void* out, int fmt,
-                       double max_val, cudaStream_t s);
+                       double max_val, int round_f32, cudaStream_t s);
 // dependent-FMA probe; returns elapsed ms for `iters` iterations, flops in *flops
 float run_fma_probe(int dtype, int iters, double* flops, cudaStream_t s);
 // kernels launched by this library in this process (optionally resetting the counter)

@@ -69,23 +69,26 @@ __global__ void cast_kernel(const S* src, int64_t src_stride, D* dst, int64_t ds
 // ---- N1: interleaved / integer-PCM boundary -------------------------------------------------------
 template <typename TI, typename T>
 __global__ void deinterleave_kernel(const TI* __restrict__ in, int channels, int64_t n_frames, T* __restrict__ planar,
-                                    int64_t stride, double inv_max) {
+                                    int64_t stride, double inv_max, int round_f32) {
     const int64_t total = n_frames * channels;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = idx / channels;
         const int ch = (int)(idx - i * channels);
         const double v = (double)in[idx];
-        planar[ch * stride + i] = inv_max != 0.0 ? (T)__dmul_rn(v, inv_max) : (T)v;  // main.go:444-470 deinterleaveInto
+        double y = inv_max != 0.0 ? __dmul_rn(v, inv_max) : v;  // main.go:444-470 deinterleaveInto: F(float64(v) * invMaxVal)
+        if (round_f32) y = (double)(float)y;                    // float32 engine computing in float64: F = float32 first
+        planar[ch * stride + i] = (T)y;
     }
 }
 template <typename T, typename TO>
 __global__ void interleave_kernel(const T* __restrict__ planar, int64_t stride, int channels, int64_t n_frames,
-                                  TO* __restrict__ out, double max_val) {
+                                  TO* __restrict__ out, double max_val, int round_f32) {
     const int64_t total = n_frames * channels;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = idx / channels;
         const int ch = (int)(idx - i * channels);
         double v = (double)planar[ch * stride + i];
+        if (round_f32) v = (double)(float)v;  // the float32 engine hands float32 samples to interleaveInto
         if (max_val != 0.0) {  // main.go:474-520 interleaveInto: clamp, scale, truncate
             v = v > 1.0 ? 1.0 : (v < -1.0 ? -1.0 : v);
             out[idx] = (TO)__double2ll_rz(__dmul_rn(v, max_val));
@@ -189,43 +192,43 @@ inline unsigned grid_for(int64_t total) {
 }
 template <typename TI>
 void deint_dispatch(const void* in, int channels, int64_t n, void* planar, int64_t stride, int dtype, double inv,
-                    cudaStream_t s) {
+                    int round_f32, cudaStream_t s) {
     const unsigned g = grid_for(n * channels);
-    if (dtype == DT_F32) deinterleave_kernel<TI, float><<<g, 256, 0, s>>>((const TI*)in, channels, n, (float*)planar, stride, inv);
-    else deinterleave_kernel<TI, double><<<g, 256, 0, s>>>((const TI*)in, channels, n, (double*)planar, stride, inv);
+    if (dtype == DT_F32) deinterleave_kernel<TI, float><<<g, 256, 0, s>>>((const TI*)in, channels, n, (float*)planar, stride, inv, round_f32);
+    else deinterleave_kernel<TI, double><<<g, 256, 0, s>>>((const TI*)in, channels, n, (double*)planar, stride, inv, round_f32);
 }
 template <typename TO>
 void int_dispatch(const void* planar, int64_t stride, int dtype, int channels, int64_t n, void* out, double maxv,
-                  cudaStream_t s) {
+                  int round_f32, cudaStream_t s) {
     const unsigned g = grid_for(n * channels);
-    if (dtype == DT_F32) interleave_kernel<float, TO><<<g, 256, 0, s>>>((const float*)planar, stride, channels, n, (TO*)out, maxv);
-    else interleave_kernel<double, TO><<<g, 256, 0, s>>>((const double*)planar, stride, channels, n, (TO*)out, maxv);
+    if (dtype == DT_F32) interleave_kernel<float, TO><<<g, 256, 0, s>>>((const float*)planar, stride, channels, n, (TO*)out, maxv, round_f32);
+    else interleave_kernel<double, TO><<<g, 256, 0, s>>>((const double*)planar, stride, channels, n, (TO*)out, maxv, round_f32);
 }
 }  // namespace
 
 void launch_deinterleave(const void* in, int fmt, int channels, int64_t n_frames, void* planar, int64_t stride,
-                         int dtype, double inv_max, cudaStream_t s) {
+                         int dtype, double inv_max, int round_f32, cudaStream_t s) {
     if (n_frames <= 0 || channels <= 0) return;
     count_launch();
     switch (fmt) {
-        case 0: deint_dispatch<double>(in, channels, n_frames, planar, stride, dtype, 0.0, s); break;
-        case 1: deint_dispatch<float>(in, channels, n_frames, planar, stride, dtype, 0.0, s); break;
-        case 2: deint_dispatch<int16_t>(in, channels, n_frames, planar, stride, dtype, inv_max, s); break;
-        case 3: deint_dispatch<int32_t>(in, channels, n_frames, planar, stride, dtype, inv_max, s); break;
-        default: deint_dispatch<long long>(in, channels, n_frames, planar, stride, dtype, inv_max, s); break;
+        case 0: deint_dispatch<double>(in, channels, n_frames, planar, stride, dtype, 0.0, round_f32, s); break;
+        case 1: deint_dispatch<float>(in, channels, n_frames, planar, stride, dtype, 0.0, round_f32, s); break;
+        case 2: deint_dispatch<int16_t>(in, channels, n_frames, planar, stride, dtype, inv_max, round_f32, s); break;
+        case 3: deint_dispatch<int32_t>(in, channels, n_frames, planar, stride, dtype, inv_max, round_f32, s); break;
+        default: deint_dispatch<long long>(in, channels, n_frames, planar, stride, dtype, inv_max, round_f32, s); break;
     }
 }
 
 void launch_interleave(const void* planar, int64_t stride, int dtype, int channels, int64_t n_frames, void* out, int fmt,
-                       double max_val, cudaStream_t s) {
+                       double max_val, int round_f32, cudaStream_t s) {
     if (n_frames <= 0 || channels <= 0) return;
     count_launch();
     switch (fmt) {
-        case 0: int_dispatch<double>(planar, stride, dtype, channels, n_frames, out, 0.0, s); break;
-        case 1: int_dispatch<float>(planar, stride, dtype, channels, n_frames, out, 0.0, s); break;
-        case 2: int_dispatch<int16_t>(planar, stride, dtype, channels, n_frames, out, max_val, s); break;
-        case 3: int_dispatch<int32_t>(planar, stride, dtype, channels, n_frames, out, max_val, s); break;
-        default: int_dispatch<long long>(planar, stride, dtype, channels, n_frames, out, max_val, s); break;
+        case 0: int_dispatch<double>(planar, stride, dtype, channels, n_frames, out, 0.0, round_f32, s); break;
+        case 1: int_dispatch<float>(planar, stride, dtype, channels, n_frames, out, 0.0, round_f32, s); break;
+        case 2: int_dispatch<int16_t>(planar, stride, dtype, channels, n_frames, out, max_val, round_f32, s); break;
+        case 3: int_dispatch<int32_t>(planar, stride, dtype, channels, n_frames, out, max_val, round_f32, s); break;
+        default: int_dispatch<long long>(planar, stride, dtype, channels, n_frames, out, max_val, round_f32, s); break;
     }
 }
 

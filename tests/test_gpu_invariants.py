@@ -496,3 +496,30 @@ def test_phase_sorted_fused_kernel_irrational_ratios_vs_thread_per_output_kernel
     want, counts = O.batch_resample(x, ir, orr, O.Q_HIGH, n_threads=min(rows, 4))
     assert np.all(counts == fast.shape[1])
     assert np.max(np.abs(fast - want[:, :fast.shape[1]])) <= 1e-12
+
+
+@pytest.mark.parametrize("ir,orr,rows,n", [(44100, 48000, 40, 60000), (48000, 44100, 33, 50000), (44100, 47999, 8, 80000),
+                                            (32000, 44101, 12, 40000)])
+def test_float32_engine_batches_run_wide_on_the_tensor_cores_within_1e6_of_the_float32_oracle(ir, orr, rows, n):
+    """NewEngineFloat32 batches at non-integer ratios (convenience.go:329-366; polyphase_stage.go / dft_stage.go are generic
+    over F): float32 samples and float32-rounded coefficients, float64 arithmetic on the FP64 tensor-core kernels
+    (gar_handle::wide_f32). Counts exact, <= 1e-6 against the oracle's float32 path, chunked == one shot to 1e-6,
+    and the handle still behaves as a float32 engine at the API."""
+    rng = np.random.default_rng(rows)
+    x = (0.5 * rng.standard_normal((rows, n))).astype(np.float32)
+    h = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float32)
+    y = np.concatenate([h.ProcessBatch(x)[0], h.FlushBatch()[0]], axis=1)
+    assert y.dtype == np.float32
+    assert any("mma" in k for k in h.last_kernels()), h.last_kernels()
+    want, counts = O.batch_resample(x[:3], ir, orr, O.Q_HIGH, n_threads=3)
+    assert np.all(counts == y.shape[1])
+    assert np.max(np.abs(y[:3].astype(np.float64) - want[:, :y.shape[1]].astype(np.float64))) <= 1e-6
+    h.Reset()
+    parts = [h.ProcessBatch(np.ascontiguousarray(c))[0].copy() for c in np.array_split(x, 3, axis=1)]
+    y2 = np.concatenate(parts + [h.FlushBatch()[0]], axis=1)
+    assert y2.shape == y.shape and np.max(np.abs(y2.astype(np.float64) - y)) <= 1e-6
+    with pytest.raises(G.ErrNotSupported):  # still a float32 engine
+        G.lib()  # noqa: B018
+        h._process(0, x[0].astype(np.float64), np.float64)
+    bank = h.bank(0)
+    assert np.array_equal(bank, bank.astype(np.float32).astype(np.float64))  # coefficients are float32 values
