@@ -103,6 +103,8 @@ struct gar_handle {
     void* slot_cin = nullptr;   // cast scratch (compute dtype) for I/O dtype != compute dtype
     void* slot_cout = nullptr;
     size_t slot_cin_cap = 0, slot_cout_cap = 0;
+    void* pin = nullptr;  // pinned, device-mapped staging of streaming-size per-channel calls (zero-copy over PCIe)
+    size_t pin_cap = 0;
     // multi-device handle: `eng` is geometry-only (chain, banks, static info); all streaming state lives in the shards
     std::vector<std::unique_ptr<Shard>> shards;
     bool multi() const { return !shards.empty(); }
@@ -371,6 +373,7 @@ void gar_destroy(gar_handle* h) {
         if (h->slot_in[i]) cudaFree(h->slot_in[i]);
         if (h->slot_out[i]) cudaFree(h->slot_out[i]);
     }
+    if (h->pin) cudaFreeHost(h->pin);
     if (h->slot_cin) cudaFree(h->slot_cin);
     if (h->slot_cout) cudaFree(h->slot_cout);
     if (h->s_in) cudaStreamDestroy(h->s_in);
@@ -620,11 +623,49 @@ static int process_rows_host(gar_handle* h, int row0, int count, int io_dtype, c
     E.begin_on(s);  // the scratch slots may still be read by work a batch call enqueued on a caller's stream
     const size_t iosz = dsize(io_dtype), csz = dsize(h->compute_dtype);
     const int64_t in_stride = (max_in + 3) & ~int64_t(3), out_stride = (max_out + 3) & ~int64_t(3);
-    const bool cast = io_dtype != h->compute_dtype;
+    bool cast = io_dtype != h->compute_dtype;
+    // lock-step groups: consecutive rows with identical state and identical chunk length share launches
+    struct Group { int r, run; };
+    std::vector<Group> groups;
+    for (int r = 0; r < count;) {
+        int run = E.lockstep_run(row0 + r, row0 + count);
+        if (!flush) {
+            int k = 1;
+            while (k < run && n_in[r + k] == n_in[r]) ++k;
+            run = k;
+        }
+        groups.push_back({r, run});
+        r += run;
+    }
+    // float32 I/O on a float64 engine (ProcessFloat32Into, constant.go:161-199): when every group is one streaming-size fused
+    // launch, the kernel converts on load / store and the two cast launches disappear
+    bool fold = cast && io_dtype == GAR_F32 && !flush;
+    for (const Group& g : groups) fold = fold && E.io32_foldable(row0 + g.r, n_in[g.r], flush);
+    if (fold) cast = false;
+    // Streaming-size calls skip the copy engines: the chunk is placed in pinned, device-mapped staging that the kernels read
+    // and write directly over PCIe (two cudaMemcpyAsync calls and their DMA start-up cost more than the 16 KB they move).
+    const size_t in_bytes = (size_t)count * (size_t)in_stride * iosz, out_bytes = (size_t)count * (size_t)out_stride * iosz;
+    const bool zero_copy = in_bytes + out_bytes <= (512u << 10);
+    if (zero_copy && in_bytes + out_bytes > h->pin_cap) {
+        if (h->pin) {
+            cudaStreamSynchronize(s);
+            cudaFreeHost(h->pin);
+            h->pin = nullptr;
+            h->pin_cap = 0;
+        }
+        const size_t want = std::max<size_t>(2 * (in_bytes + out_bytes), 128u << 10);
+        if (cudaHostAlloc(&h->pin, want, cudaHostAllocMapped) != cudaSuccess) {
+            h->pin = nullptr;
+            cudaGetLastError();
+        } else {
+            h->pin_cap = want;
+        }
+    }
+    const bool zc = zero_copy && h->pin != nullptr;
     char* d_in_io = nullptr;
     char* d_in_c = nullptr;
     if (max_in > 0) {
-        d_in_io = (char*)E.scratch(0, (size_t)count * (size_t)in_stride * iosz, h->err);
+        d_in_io = zc ? (char*)h->pin : (char*)E.scratch(0, in_bytes, h->err);
         if (!d_in_io) return GAR_CUDA_ERROR;
         d_in_c = d_in_io;
         if (cast) {
@@ -635,48 +676,47 @@ static int process_rows_host(gar_handle* h, int row0, int count, int io_dtype, c
     char* d_out_c = nullptr;
     char* d_out_io = nullptr;
     if (max_out > 0) {
-        d_out_c = (char*)E.scratch(2, (size_t)count * (size_t)out_stride * csz, h->err);
-        if (!d_out_c) return GAR_CUDA_ERROR;
-        d_out_io = d_out_c;
+        char* io_buf = zc ? (char*)h->pin + ((in_bytes + 255) & ~(size_t)255) : nullptr;
         if (cast) {
-            d_out_io = (char*)E.scratch(3, (size_t)count * (size_t)out_stride * iosz, h->err);
-            if (!d_out_io) return GAR_CUDA_ERROR;
+            d_out_c = (char*)E.scratch(2, (size_t)count * (size_t)out_stride * csz, h->err);
+            d_out_io = zc ? io_buf : (char*)E.scratch(3, out_bytes, h->err);
+        } else {
+            d_out_c = d_out_io = zc ? io_buf : (char*)E.scratch(2, out_bytes, h->err);
         }
+        if (!d_out_c || !d_out_io) return GAR_CUDA_ERROR;
     }
     if (!flush)
         for (int r = 0; r < count; ++r)
-            if (n_in[r] > 0)
-                cudaMemcpyAsync(d_in_io + (size_t)r * (size_t)in_stride * iosz, in[r], (size_t)n_in[r] * iosz,
-                                cudaMemcpyHostToDevice, s);
+            if (n_in[r] > 0) {
+                if (zc) std::memcpy(d_in_io + (size_t)r * (size_t)in_stride * iosz, in[r], (size_t)n_in[r] * iosz);
+                else cudaMemcpyAsync(d_in_io + (size_t)r * (size_t)in_stride * iosz, in[r], (size_t)n_in[r] * iosz,
+                                     cudaMemcpyHostToDevice, s);
+            }
     if (cast && max_in > 0) {
         launch_cast(d_in_io, in_stride, io_dtype, d_in_c, in_stride, h->compute_dtype, (int32_t)max_in, count, s);
     }
-    // lock-step groups: consecutive rows with identical state and identical chunk length share launches
-    int r = 0;
-    while (r < count) {
-        int run = E.lockstep_run(row0 + r, row0 + count);
-        if (!flush) {
-            int k = 1;
-            while (k < run && n_in[r + k] == n_in[r]) ++k;
-            run = k;
-        }
+    const size_t esz_run = fold ? iosz : csz;  // element size of the buffers Engine::run sees
+    for (const Group& g : groups) {
         int64_t got = 0;
-        int rc = E.run(row0 + r, run, d_in_c ? d_in_c + (size_t)r * (size_t)in_stride * csz : nullptr, in_stride,
-                       flush ? 0 : n_in[r], d_out_c ? d_out_c + (size_t)r * (size_t)out_stride * csz : nullptr,
-                       out_stride, out_stride, flush, s, &got, h->err);
+        int rc = E.run(row0 + g.r, g.run, d_in_c ? d_in_c + (size_t)g.r * (size_t)in_stride * esz_run : nullptr, in_stride,
+                       flush ? 0 : n_in[g.r], d_out_c ? d_out_c + (size_t)g.r * (size_t)out_stride * esz_run : nullptr,
+                       out_stride, out_stride, flush, s, &got, h->err, fold);
         if (rc) return rc;
-        for (int k = 0; k < run; ++k) n_out[r + k] = got;
-        r += run;
+        for (int k = 0; k < g.run; ++k) n_out[g.r + k] = got;
     }
     if (cast && max_out > 0)
         launch_cast(d_out_c, out_stride, h->compute_dtype, d_out_io, out_stride, io_dtype, (int32_t)max_out, count, s);
-    for (int q = 0; q < count; ++q)
-        if (n_out[q] > 0)
-            cudaMemcpyAsync(out[q], d_out_io + (size_t)q * (size_t)out_stride * iosz, (size_t)n_out[q] * iosz,
-                            cudaMemcpyDeviceToHost, s);
+    if (!zc)
+        for (int q = 0; q < count; ++q)
+            if (n_out[q] > 0)
+                cudaMemcpyAsync(out[q], d_out_io + (size_t)q * (size_t)out_stride * iosz, (size_t)n_out[q] * iosz,
+                                cudaMemcpyDeviceToHost, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, GAR_CUDA_ERROR, std::string("stream sync: ") + cudaGetErrorString(e));
+    if (zc)
+        for (int q = 0; q < count; ++q)
+            if (n_out[q] > 0) std::memcpy(out[q], d_out_io + (size_t)q * (size_t)out_stride * iosz, (size_t)n_out[q] * iosz);
     return GAR_OK;
 }
 
@@ -781,6 +821,9 @@ static int batch_dev(gar_handle* h, int io_dtype, const void* d_in, int64_t in_s
         int rc;
         if (!cast) {
             rc = E.run(row0 + r, run, ip, in_stride, flush ? 0 : n_in, op, out_stride, out_cap, flush, s, &got, h->err);
+        } else if (io_dtype == GAR_F32 && !flush && E.io32_foldable(row0 + r, n_in, flush)) {
+            // streaming-size fused launch: float32 samples converted on load / store, no cast launches
+            rc = E.run(row0 + r, run, ip, in_stride, n_in, op, out_stride, out_cap, flush, s, &got, h->err, true);
         } else {
             // I/O dtype differs from the compute dtype (path A with float32 I/O): cast through scratch
             const int64_t want = flush ? gar_next_flush_count(h, row0 + r) : gar_next_output_count(h, row0 + r, n_in);

@@ -553,8 +553,24 @@ int64_t Engine::slice_length(int row0, int count, int64_t n_in) const {
     return len < n_in ? len : 0;
 }
 
+bool Engine::io32_foldable(int row0, int64_t n_in, bool flush) const {
+    if (device_ < 0 || dtype_ != DT_F64 || !fuse_ || flush || n_in <= 0 || n_in > 32768) return false;
+    StreamState st = streams_[(size_t)row0];
+    Plan P;
+    plan(st, n_in, false, P);
+    if (P.ops.size() != 2) return false;
+    const Op &a = P.ops[0], &b = P.ops[1];
+    if (a.stage < 0 || b.stage != a.stage + 1 || a.src_buf != BUF_EXT_IN || b.dst_buf != BUF_OUT || b.src_buf != a.dst_buf ||
+        a.dst_buf < 0 || a.n_out <= 0 || b.n_out <= 0 || b.n_in != a.n_out || b.dst_off != 0)
+        return false;
+    const StageDesign &su = chain_.stages[(size_t)a.stage], &sp = chain_.stages[(size_t)b.stage];
+    return su.kind == STAGE_UP && su.factor == 2 && sp.kind == STAGE_POLY && sp.engine_index == su.engine_index &&
+           sp.taps <= 200 && b.hist_len <= 1024;
+}
+
 int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
-                int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err) {
+                int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, bool io32) {
+    if (io32) return run_once(row0, count, d_in, in_stride, n_in, d_out, out_stride, out_cap, flush, s, n_out, err, true);
     // the slice length is derived from ALL rows of the handle, not from this call's row range: row groups of one batch call
     // must advance through the same sequence of stage calls to stay in lock step (same tail ping-pong parity)
     const int64_t slice = flush || device_ < 0 ? 0 : slice_length(row0, rows_, n_in);
@@ -583,7 +599,7 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
 }
 
 int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
-                     int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err) {
+                     int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, bool io32) {
     if (count <= 0) return 0;
     if (device_ < 0) {
         err = "geometry-only handle (device = -1) cannot process samples; there is no CPU fallback";
@@ -676,13 +692,22 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                 f.t2 = spd.taps; f.L = spd.factor; f.at0 = nx.first; f.step = spd.step;
                 f.n_out = (int32_t)nx.n_out; f.interp = nx.interp ? 1 : 0;
                 f.out = optr; f.out_stride = ostride; f.n_streams = count;
+                f.in_f32 = f.out_f32 = io32 ? 1 : 0;
                 if (const char* kn = launch_fused_up2_poly(f, dtype_, s, &dpv.rat_cache)) {
                     note_kernel(kn);
                     ++launches_;
                     ++oi;  // the polyphase op is done too
                     continue;
                 }
+                if (io32) {
+                    err = "internal: float32 I/O was folded into a call the fused kernel did not take";
+                    return 5;
+                }
             }
+        }
+        if (io32) {
+            err = "internal: float32 I/O folding needs the fused x2 -> polyphase launch";
+            return 5;
         }
         if (op.stage < 0) {
             launch_cast(sp, sstride, dtype_, dp, dstride, dtype_, (int32_t)op.n_in, count, s);

@@ -104,8 +104,13 @@ class Engine {
 
     // Execute on rows [row0,row0+count) which must share identical state. d_in/d_out point at row row0,
     // compute dtype. Enqueues on `s`; commits the state. Returns status; *n_out per row.
+    // io32: d_in / d_out hold float32 samples although the engine computes in float64 (strides in float32 elements); only
+    // valid when io32_foldable() said so — the single fused launch converts on load / store (no cast launches).
     int run(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
-            int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err);
+            int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, bool io32 = false);
+    // A Process call of n_in samples on rows in row0's state is ONE fused x2 -> polyphase launch of streaming size, which can
+    // take float32 input / output directly (constant.go:161-199 ProcessFloat32Into without the two cast passes).
+    bool io32_foldable(int row0, int64_t n_in, bool flush) const;
     // Time slicing of multi-stage calls: a Process call whose inter-stage buffers would exceed `bytes` is run as a
     // sequence of shorter Process calls (identical samples and counts: every stage is greedy), so that the intermediate-rate
     // buffers stay small (and, with an L2-sized budget, the intermediate-rate streams stay L2-resident). 0 disables.
@@ -164,7 +169,7 @@ class Engine {
     // instead of 5: every slice pays a launch ramp and tail), and those chains are FMA-bound, not HBM-bound.
     int64_t slice_budget_ = 2ll << 30;
     int run_once(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
-                 int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err);
+                 int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, bool io32 = false);
     std::vector<const char*> kernels_used_;
     void note_kernel(const char* name);
     int64_t device_bytes_ = 0;

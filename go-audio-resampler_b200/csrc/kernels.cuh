@@ -66,6 +66,9 @@ struct FusedCall {
     int32_t n_out;        int32_t interp;
     void* out;            int64_t out_stride;
     int32_t n_streams;
+    // float64 engines behind a float32 API (ProcessFloat32Into, constant.go:161-199): `in` / `out` hold float32 samples and the
+    // kernel converts on load / store instead of two cast launches (streaming-size calls; strides are in float32 elements)
+    int32_t in_f32;       int32_t out_f32;
 };
 
 // Per polyphase stage, device-resident cache of the K4r kernel's coefficient tiles: for every start phase

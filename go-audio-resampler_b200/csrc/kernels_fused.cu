@@ -9,14 +9,27 @@ namespace {
 // Carried tails of a fused x2 -> polyphase call (one block per row): the x2 stage's new tail is a plain copy,
 // the polyphase stage's new tail needs the last few intermediate samples, recomputed here with the same
 // strictly sequential chain as the tile core (bit-identical in float64).
+// v[g] of the x2 stage's virtual input hist_u ++ in, where `in` may hold float32 samples (FusedCall::in_f32)
+template <typename T>
+__device__ __forceinline__ T fused_vin(const FusedCall& c, const T* __restrict__ hist_u, const int64_t row, const int g) {
+    if (g < 0) return T(0);
+    if (g < c.hu) return hist_u[g];
+    const int i = g - c.hu;
+    if (i >= c.n_in) return T(0);
+    if (sizeof(T) == 8 && c.in_f32) return (T)(static_cast<const float*>(c.in) + row * c.in_stride)[i];
+    return (static_cast<const T*>(c.in) + row * c.in_stride)[i];
+}
+
 template <typename T>
 __device__ __forceinline__ void fused_carry_tails_rt(const FusedCall& c, const int64_t row, T* scratch, const int scratch_cap) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const T* __restrict__ hist_u = static_cast<const T*>(c.hist_u) + row * c.hist_u_stride;
-    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
     const T* __restrict__ hist_p = static_cast<const T*>(c.hist_p) + row * c.hist_p_stride;
     const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
-    carry_row(hist_u, c.hu, in, c.n_in, static_cast<T*>(c.hist_u_out) + row * c.hist_u_out_stride, c.drop_u, c.new_hu);
+    {
+        T* hu_out = static_cast<T*>(c.hist_u_out) + row * c.hist_u_out_stride;
+        for (int i = tid; i < c.new_hu; i += NT) hu_out[i] = fused_vin<T>(c, hist_u, row, c.drop_u + i);
+    }
     T* hp_out = static_cast<T*>(c.hist_p_out) + row * c.hist_p_out_stride;
     // intermediate samples [j_lo, j_hi) are needed: stage their input span and the x2 bank in shared memory first, so the
     // strictly sequential chains below run on shared-memory latency instead of one global round trip per tap (this block
@@ -28,7 +41,7 @@ __device__ __forceinline__ void fused_carry_tails_rt(const FusedCall& c, const i
     T* xb = scratch;
     T* bk = scratch + span;
     if (staged) {
-        for (int i = tid; i < span; i += NT) xb[i] = vload(hist_u, c.hu, in, c.n_in, p_lo + i);
+        for (int i = tid; i < span; i += NT) xb[i] = fused_vin<T>(c, hist_u, row, p_lo + i);
         for (int i = tid; i < 2 * c.t1; i += NT) bk[i] = bank_u[i];
         __syncthreads();
     }
@@ -55,12 +68,12 @@ __device__ __forceinline__ void fused_carry_tails_rt(const FusedCall& c, const i
                 const T* __restrict__ bkg = bank_u + (j & 1) * c.t1;
                 if (sizeof(T) == 8) {
                     T acc = 0;
-                    for (int t = 0; t < c.t1; ++t) acc = fma(vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), bkg[t], acc);
+                    for (int t = 0; t < c.t1; ++t) acc = fma(fused_vin<T>(c, hist_u, row, (j >> 1) + t), bkg[t], acc);
                     v = acc;
                 } else {
                     double acc = 0;
                     for (int t = 0; t < c.t1; ++t)
-                        acc = fma((double)vload(hist_u, c.hu, in, c.n_in, (j >> 1) + t), (double)bkg[t], acc);
+                        acc = fma((double)fused_vin<T>(c, hist_u, row, (j >> 1) + t), (double)bkg[t], acc);
                     v = (T)acc;
                 }
             }
@@ -118,7 +131,7 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
     bool bulk = false;
     {
         const int gi = p0 - c.hu;
-        if (gi >= 0 && need > 0) {
+        if (gi >= 0 && need > 0 && !(sizeof(T) == 8 && c.in_f32)) {  // float32 samples are converted by guarded loads
             const uintptr_t addr = reinterpret_cast<uintptr_t>(in + gi);
             const int mis = (int)((addr & 15u) / sizeof(T));
             const int words = ((need + mis + VEC - 1) / VEC) * VEC;
@@ -139,7 +152,7 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
         }
         for (int i = words + tid; i < xlen; i += NT) xs[i] = T(0);
     } else {
-        for (int i = tid; i < xlen; i += NT) xs[i] = i < need ? vload(hist_u, c.hu, in, c.n_in, p0 + i) : T(0);
+        for (int i = tid; i < xlen; i += NT) xs[i] = i < need ? fused_vin<T>(c, hist_u, row, p0 + i) : T(0);
     }
     for (int i = tid; i < NF * cp; i += NT) {
         const int p = i / cp, k = i % cp - a;
@@ -184,6 +197,8 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
     // virtual vp index d lives at shared-memory element d - vbase
     const int64_t vbase = tile == 0 ? (int64_t)c.hp - hpf : lo;
     T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+    float* __restrict__ out32 = static_cast<float*>(c.out) + row * c.out_stride;  // FusedCall::out_f32
+    const bool o32 = sizeof(T) == 8 && c.out_f32;
     const T* __restrict__ ga = static_cast<const T*>(c.bank_a);
     const T* __restrict__ gb = static_cast<const T*>(c.bank_b);
     const T* __restrict__ gc = static_cast<const T*>(c.bank_c);
@@ -211,7 +226,8 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
                 else acc0 = fma((double)h[k], (double)ca[k], acc0);
             }
         }
-        out[n] = (T)(acc0 + acc1);
+        if (o32) out32[n] = (float)(acc0 + acc1);  // float32(v): constant.go:195-197
+        else out[n] = (T)(acc0 + acc1);
     }
 }
 
@@ -1131,6 +1147,10 @@ bool launch_rat_poly_only_f64(const FusedCall& c, cudaStream_t s, RatCache* cach
 
 const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s, RatCache* cache) {
     if (c.n_streams <= 0) return "none";
+    if (dtype == DT_F64 && (c.in_f32 || c.out_f32)) {  // float32 I/O folded into the kernel: the generic K4 only
+        if (c.interp) return launch_fused_t<double, true>(c, s) ? "fused_up2_poly_f64_interp_io32" : nullptr;
+        return launch_fused_t<double, false>(c, s) ? "fused_up2_poly_f64_io32" : nullptr;
+    }
     if (dtype == DT_F32) {
         if (c.interp) return launch_fused_t<float, true>(c, s) ? "fused_up2_poly_f32_interp" : nullptr;
         return launch_fused_t<float, false>(c, s) ? "fused_up2_poly_f32" : nullptr;
