@@ -40,10 +40,36 @@ __device__ __forceinline__ T vload(const T* __restrict__ hist, int hist_len, con
     return g < n_in ? in[g] : T(0);
 }
 
+// Pull the 128-byte lines of row[0 .. n) into L1 (streaming-size launches: the per-tap coefficient loads of the polyphase
+// loops otherwise pay one L2 round trip per unrolled group; issued before the staging / FIR phases they land in time)
+template <typename T>
+__device__ __forceinline__ void prefetch_row_l1(const T* row, const int n) {
+    const uintptr_t b = reinterpret_cast<uintptr_t>(row) & ~(uintptr_t)127, e = reinterpret_cast<uintptr_t>(row + n);
+    for (uintptr_t q = b; q < e; q += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+}
+
+// dst(i) = src(i) for i in [0, n), block-wide, FOUR loads in flight per thread before the first store: a plain
+// `for (i = tid; ...) dst[i] = load(i)` issues load, waits, stores, loads again — one full memory round trip per
+// iteration, which is what a streaming-size launch (a few hundred elements per block) spends most of its time on.
+template <class Load, class Store>
+__device__ __forceinline__ void block_copy4(const int n, Load load, Store store) {
+    const int nt = blockDim.x;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * nt) {
+        decltype(load(0)) v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j * nt < n) v[j] = load(i0 + j * nt);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j * nt < n) store(i0 + j * nt, v[j]);
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ void carry_row(const T* hist, int hist_len, const T* in, int n_in, T* hist_out, int drop,
                                           int new_len) {
-    for (int i = threadIdx.x; i < new_len; i += blockDim.x) hist_out[i] = vload(hist, hist_len, in, n_in, drop + i);
+    block_copy4(new_len, [&](int i) { return vload(hist, hist_len, in, n_in, drop + i); },
+                [&](int i, T v) { hist_out[i] = v; });
 }
 
 // calls f(integral_constant<N>) for the N in [LO, HI] equal to n, f(integral_constant<0>) when n is outside the range

@@ -77,12 +77,10 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before async-proxy (TMA) writes
     {  // filter bank, shifted by the pad, zero elsewhere
         const T* __restrict__ bank = static_cast<const T*>(c.bank);
-#pragma unroll
-        for (int p = 0; p < NF; ++p)
-            for (int kk = tid; kk < cp; kk += NT) {
-                const int k = kk - a;
-                cs[p * cp + kk] = (k >= 0 && k < c.taps) ? bank[p * c.taps + k] : T(0);
-            }
+        block_copy4(NF * cp, [&](int i) {
+            const int p = i / cp, k = i % cp - a;
+            return (k >= 0 && k < c.taps) ? bank[p * c.taps + k] : T(0);
+        }, [&](int i, T v) { cs[i] = v; });
     }
     __syncthreads();
     if (tid == 0) issue_bulk(t_first, 0);
@@ -104,8 +102,8 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
             if (buf) phase1 ^= 1u;
             else phase0 ^= 1u;
         } else {  // edge tile (touches the carried tail or the end of the row): guarded loads
-            for (int i = tid; i < xlen; i += NT)
-                xs[i] = i < words ? vload(hist, c.hist_len, in, c.n_in, g0a + i) : T(0);
+            block_copy4(xlen, [&](int i) { return i < words ? vload(hist, c.hist_len, in, c.n_in, g0a + i) : T(0); },
+                        [&](int i, T v) { xs[i] = v; });
             __syncthreads();
         }
 
@@ -832,6 +830,14 @@ bool tensor_fir_enabled() { return g_fir_mma; }
     X(double, DT_F64, 1, 3, 2, "fir_f64_up3_r2")  \
     X(double, DT_F64, 1, 4, 2, "fir_f64_up4_r2")
 
+// float64 streaming-size / flush calls (a handful of tiles at most): 2-3 positions per thread instead of 6-7, so the one
+// tile that is the whole critical path is three times shorter and the positions spread over more threads; same tap order
+// per output, bit-identical to the large-tile variants
+#define GAR_FIR_SMALL_VARIANTS(X)                 \
+    X(double, DT_F64, 1, 2, 2, "fir_f64_up2_r2")  \
+    X(double, DT_F64, 2, 1, 3, "fir_f64_s2_r3")   \
+    X(double, DT_F64, 3, 1, 2, "fir_f64_s3_r2")
+
 void set_tensor_fir(bool on) { g_fir_mma = on; }
 
 const char* fir_variant_name(int dtype, int stride, int nf, int taps, int64_t n_pos, int n_streams) {
@@ -863,6 +869,15 @@ const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s) {
     }
     GAR_FIR_X2_VARIANTS(X)
 #undef X
+    if ((int64_t)c.n_pos * c.n_streams <= 4096) {
+#define X(T, DT, M, NF, R, NAME)                           \
+    if (dtype == DT && c.stride == M && c.nf == NF) {      \
+        launch_fir_tiled<T, M, NF, R>(c, s);               \
+        return NAME;                                       \
+    }
+        GAR_FIR_SMALL_VARIANTS(X)
+#undef X
+    }
 #define X(T, DT, M, NF, R, NAME)                           \
     if (dtype == DT && c.stride == M && c.nf == NF) {      \
         launch_fir_tiled<T, M, NF, R>(c, s);               \

@@ -28,7 +28,7 @@ __device__ __forceinline__ void fused_carry_tails_rt(const FusedCall& c, const i
     const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
     {
         T* hu_out = static_cast<T*>(c.hist_u_out) + row * c.hist_u_out_stride;
-        for (int i = tid; i < c.new_hu; i += NT) hu_out[i] = fused_vin<T>(c, hist_u, row, c.drop_u + i);
+        block_copy4(c.new_hu, [&](int i) { return fused_vin<T>(c, hist_u, row, c.drop_u + i); }, [&](int i, T v) { hu_out[i] = v; });
     }
     T* hp_out = static_cast<T*>(c.hist_p_out) + row * c.hist_p_out_stride;
     // intermediate samples [j_lo, j_hi) are needed: stage their input span and the x2 bank in shared memory first, so the
@@ -41,8 +41,8 @@ __device__ __forceinline__ void fused_carry_tails_rt(const FusedCall& c, const i
     T* xb = scratch;
     T* bk = scratch + span;
     if (staged) {
-        for (int i = tid; i < span; i += NT) xb[i] = fused_vin<T>(c, hist_u, row, p_lo + i);
-        for (int i = tid; i < 2 * c.t1; i += NT) bk[i] = bank_u[i];
+        block_copy4(span, [&](int i) { return fused_vin<T>(c, hist_u, row, p_lo + i); }, [&](int i, T v) { xb[i] = v; });
+        block_copy4(2 * c.t1, [&](int i) { return bank_u[i]; }, [&](int i, T v) { bk[i] = v; });
         __syncthreads();
     }
     for (int i = tid; i < c.new_hp; i += NT) {
@@ -123,6 +123,31 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
         return;
     }
 
+    // ---- 0. this thread's outputs are known from the geometry alone: pull their coefficient rows into L1 now, so the
+    // polyphase loop at the end does not pay an L2 round trip per unrolled tap group (a streaming-size launch spends
+    // 40 % of its time there otherwise) ----
+    const int64_t Lq = (int64_t)c.L << 16;
+    const int64_t lo = tile == 0 ? 0 : (int64_t)c.hp + (int64_t)tile * ms;
+    const int64_t hi = (int64_t)c.hp + (int64_t)(tile + 1) * ms;
+    auto first_n = [&](const int64_t d) -> int64_t {  // smallest n with div_n >= d
+        const int64_t need_at = d * Lq - c.at0;
+        return need_at <= 0 ? 0 : (need_at + c.step - 1) / c.step;
+    };
+    const int64_t n_lo = min((int64_t)c.n_out, first_n(lo));
+    const int64_t n_hi = tile == n_tiles - 1 ? (int64_t)c.n_out : min((int64_t)c.n_out, first_n(hi));
+    if (bank_pitch == 0 && n_hi - n_lo <= 4 * NT) {
+        for (int64_t n = n_lo + tid; n < n_hi; n += NT) {
+            const int64_t full = (c.at0 + n * c.step) >> 16;
+            const int64_t co = (full % c.L) * c.t2;
+            prefetch_row_l1(static_cast<const T*>(c.bank_a) + co, c.t2);
+            if (INTERP) {
+                prefetch_row_l1(static_cast<const T*>(c.bank_b) + co, c.t2);
+                prefetch_row_l1(static_cast<const T*>(c.bank_c) + co, c.t2);
+                prefetch_row_l1(static_cast<const T*>(c.bank_d) + co, c.t2);
+            }
+        }
+    }
+
     // ---- 1. stage the x2 stage's input window ----
     const int p0 = (tile * ms) >> 1;  // first position of the tile (ms is even)
     const int tp = min(TP, c.np - p0);
@@ -152,17 +177,16 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
         }
         for (int i = words + tid; i < xlen; i += NT) xs[i] = T(0);
     } else {
-        for (int i = tid; i < xlen; i += NT) xs[i] = i < need ? fused_vin<T>(c, hist_u, row, p0 + i) : T(0);
+        block_copy4(xlen, [&](int i) { return i < need ? fused_vin<T>(c, hist_u, row, p0 + i) : T(0); }, [&](int i, T v) { xs[i] = v; });
     }
-    for (int i = tid; i < NF * cp; i += NT) {
+    block_copy4(NF * cp, [&](int i) {
         const int p = i / cp, k = i % cp - a;
-        cs[i] = (k >= 0 && k < c.t1) ? bank_u[p * c.t1 + k] : T(0);
-    }
+        return (k >= 0 && k < c.t1) ? bank_u[p * c.t1 + k] : T(0);
+    }, [&](int i, T v) { cs[i] = v; });
     // polyphase side: carried tail right-aligned in front of tile 0 (the tile itself starts 16-byte aligned),
     // optional a-bank copy (odd pitch: conflict-free rows)
     const int front = tile == 0 ? hpf : 0;
-    if (tile == 0)
-        for (int i = tid; i < c.hp; i += NT) vp[hpf - c.hp + i] = hist_p[i];
+    if (tile == 0) block_copy4(c.hp, [&](int i) { return hist_p[i]; }, [&](int i, T v) { vp[hpf - c.hp + i] = v; });
     if (bank_pitch > 0) {
         const T* __restrict__ ba = static_cast<const T*>(c.bank_a);
 #pragma unroll 8
@@ -185,15 +209,6 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
     __syncthreads();
 
     // ---- 3. polyphase outputs whose window starts in [lo, hi) of vp = hist_p ++ mid ----
-    const int64_t Lq = (int64_t)c.L << 16;
-    const int64_t lo = tile == 0 ? 0 : (int64_t)c.hp + (int64_t)tile * ms;
-    const int64_t hi = (int64_t)c.hp + (int64_t)(tile + 1) * ms;
-    auto first_n = [&](const int64_t d) -> int64_t {  // smallest n with div_n >= d
-        const int64_t need_at = d * Lq - c.at0;
-        return need_at <= 0 ? 0 : (need_at + c.step - 1) / c.step;
-    };
-    const int64_t n_lo = min((int64_t)c.n_out, first_n(lo));
-    const int64_t n_hi = tile == n_tiles - 1 ? (int64_t)c.n_out : min((int64_t)c.n_out, first_n(hi));
     // virtual vp index d lives at shared-memory element d - vbase
     const int64_t vbase = tile == 0 ? (int64_t)c.hp - hpf : lo;
     T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;

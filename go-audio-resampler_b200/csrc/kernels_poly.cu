@@ -717,17 +717,10 @@ __global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_
     const int n0 = tile * TO;
     const int n1 = min(n0 + TO, c.n_out) - 1;
     const int64_t L = c.L;
-    const int div0 = (int)(((c.at0 + (int64_t)n0 * c.step) >> 16) / L);
-    const int div1 = (int)(((c.at0 + (int64_t)n1 * c.step) >> 16) / L);
-    const int span = div1 - div0 + c.taps;
-    const bool staged = span <= xcap;
-    if (staged) {
-        for (int i = threadIdx.x; i < span; i += TO) xs[i] = vload(hist, c.hist_len, in, c.n_in, div0 + i);
-        __syncthreads();
-    }
+    // this thread's output and its coefficient rows first: their lines are prefetched into L1 while the samples are staged
     const int n = n0 + threadIdx.x;
-    if (n >= c.n_out) return;
-    const int64_t at = c.at0 + (int64_t)n * c.step;
+    const bool live = n < c.n_out;
+    const int64_t at = c.at0 + (int64_t)(live ? n : n0) * c.step;
     const int64_t full = at >> 16;
     const int div = (int)(full / L);
     const int phase = (int)(full - (int64_t)div * L);
@@ -737,6 +730,23 @@ __global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_
     const T* __restrict__ cb = static_cast<const T*>(c.bank_b) + co;
     const T* __restrict__ cc = static_cast<const T*>(c.bank_c) + co;
     const T* __restrict__ cd = static_cast<const T*>(c.bank_d) + co;
+    if (live) {
+        prefetch_row_l1(ca, c.taps);
+        if (INTERP) {
+            prefetch_row_l1(cb, c.taps);
+            prefetch_row_l1(cc, c.taps);
+            prefetch_row_l1(cd, c.taps);
+        }
+    }
+    const int div0 = (int)(((c.at0 + (int64_t)n0 * c.step) >> 16) / L);
+    const int div1 = (int)(((c.at0 + (int64_t)n1 * c.step) >> 16) / L);
+    const int span = div1 - div0 + c.taps;
+    const bool staged = span <= xcap;
+    if (staged) {
+        block_copy4(span, [&](int i) { return vload(hist, c.hist_len, in, c.n_in, div0 + i); }, [&](int i, T v) { xs[i] = v; });
+        __syncthreads();
+    }
+    if (!live) return;
     // products of two float32 are exact in float64, so the float32 path only rounds once, at the store (two
     // interleaved chains); float64 sums strictly in tap order, like every other float64 kernel here, so the
     // fused kernels reproduce the stand-alone launches bit for bit
