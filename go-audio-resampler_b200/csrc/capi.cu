@@ -1090,6 +1090,11 @@ void* gar_host_alloc(size_t bytes) {
     if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
     return p;
 }
+void* gar_host_alloc_wc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
 void gar_host_free(void* p) {
     if (!p) return;
     size_t bytes = 0;

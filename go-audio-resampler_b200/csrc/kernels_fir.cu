@@ -474,7 +474,8 @@ static const char* launch_fir_mma(const FirCall& c, cudaStream_t s) {
     if (!g_fir_mma || c.n_streams < 1 || (int64_t)c.n_pos * c.n_streams < 32768 || c.taps < 16) return nullptr;
     // fewer than 8 rows (time-segment columns): only long calls — measured +5 % on 60 s of stereo 96k->48k, but a loss on the
     // sub-millisecond stages of a single 10 s stream (C5a), which are launch-latency-bound
-    if (c.n_streams < 8 && (int64_t)c.n_pos * c.n_streams < 2000000) return nullptr;
+    static const int64_t seg_min = [] { const char* e = gar::tune_env("GAR_MMA_SEG_MIN"); return e ? std::atoll(e) : 2000000ll; }();
+    if (c.n_streams < 8 && (int64_t)c.n_pos * c.n_streams < seg_min) return nullptr;
     if (c.stride == 1 && c.nf == 2) return launch_fir_mma_t<1, 2>(c, s) ? "fir_f64_mma_up2" : nullptr;
     if (c.nf == 1 && c.stride == 2) return launch_fir_mma_t<2, 1>(c, s) ? "fir_f64_mma_s2" : nullptr;
     if (c.nf == 1 && c.stride == 3) return launch_fir_mma_t<3, 1>(c, s) ? "fir_f64_mma_s3" : nullptr;

@@ -122,6 +122,7 @@ SYMBOLS = {
     "gar_flush_interleaved": (_i32, [_vp, _i32, _i32, _vp, _i64, _pi64]),
     "gar_host_alloc": (_vp, [C.c_size_t]),
     "gar_host_free": (None, [_vp]),
+    "gar_host_alloc_wc": (_vp, [C.c_size_t]),
     "gar_host_alloc_rows": (_vp, [_vp, C.c_size_t]),
     "gar_memcpy_async": (_i32, [_vp, _vp, C.c_size_t, _i32, _vp]),
     "gar_bind_thread_to_device": (_i32, [_i32]),
@@ -590,6 +591,17 @@ def host_alloc(shape, dtype):
     buf = (C.c_char * max(n, 1)).from_address(p)
     arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
     return arr, p
+
+
+def host_alloc_wc(shape, dtype):
+    """Write-combined pinned host ndarray for input buffers the host only writes."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = lib().gar_host_alloc_wc(max(n, 1))
+    if not p:
+        raise CudaError("cudaHostAlloc(write-combined) failed")
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape), p
 
 
 def host_free(p):

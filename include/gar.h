@@ -229,6 +229,9 @@ int32_t gar_flush_interleaved(gar_handle* h, int32_t fmt, int32_t bit_depth, voi
 /* Pinned host memory for callers that want full PCIe rate (Go slices are pageable). */
 void* gar_host_alloc(size_t bytes);
 void gar_host_free(void* p);
+/* Write-combined pinned memory (cudaHostAllocWriteCombined): for INPUT buffers the host only writes — not snooped during the
+ * DMA read, which helps on platforms whose host-to-device path is the ceiling; never read it back on the CPU (slow). */
+void* gar_host_alloc_wc(size_t bytes);
 /* Pinned planar buffer of rows(h) x row_bytes for the batch calls whose pages are placed shard by shard on the NUMA node of
  * the device that will copy them (first touch by the shard's bound worker thread, then cudaHostRegister). Free with
  * gar_host_free. On single-socket machines it is simply a pinned buffer. */
