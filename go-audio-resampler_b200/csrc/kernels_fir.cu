@@ -620,22 +620,41 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
                     cv[p][sh][0] = v.x;
                     cv[p][sh][1] = v.y;
                 }
+            auto fma2 = [&](const int q, const int r, const u64 cf) {
+                const int sh = (M * r) & 1;
+                const int eh = (M * r - sh) / 2;
+                const u64 xv = xw[(u * 2 + q + eh) % (NCH * 2)];
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int sh = (M * r) & 1;
-                    const int eh = (M * r - sh) / 2;
-                    const u64 xv = xw[(u * 2 + q + eh) % (NCH * 2)];
-#pragma unroll
-                    for (int p = 0; p < NF; ++p) {
-                        u64 d;
-                        asm("fma.rn.f32x2 %0, %1, %2, %3;"
-                            : "=l"(d)
-                            : "l"(xv), "l"(cv[p][NS == 2 ? sh : 0][q]), "l"(acc[r][p]));
-                        acc[r][p] = d;
-                    }
+                for (int p = 0; p < NF; ++p) {
+                    u64 d;
+                    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(xv), "l"(cf), "l"(acc[r][p]));
+                    acc[r][p] = d;
                 }
+            };
+            if constexpr (NS == 2 && R == 12 && NF == 1) {
+                // Two register copies of the step's four coefficient pairs, the second loaded again through an opaque
+                // ld.shared so that ptxas cannot merge them: positions 0..5 read one copy, 6..11 the other. With ONE copy
+                // ptxas chains 5-6 FFMA2s on the same coefficient register (.reuse) and the loop runs at the rate
+                // tools/probe_fma_patterns3.cu measures for that operand pattern (50-63 TFLOP/s depending on the order it
+                // picks); with two copies the kernel gains 2.4 % (a third copy loses it again: register pressure).
+                u64 cw[NS][2];
+#pragma unroll
+                for (int sh = 0; sh < NS; ++sh) {
+                    ulonglong2 v;
+                    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(smem_u32(cs + sh * cp + it * 4)));
+                    cw[sh][0] = v.x;
+                    cw[sh][1] = v.y;
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) fma2(q, r, r < R / 2 ? cv[0][r & 1][q] : cw[r & 1][q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) fma2(q, r, cv[0][NS == 2 ? ((M * r) & 1) : 0][q]);
+            }
             const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xt + (it + NCH) * 4);
             xw[(u % NCH) * 2] = v.x;
             xw[(u % NCH) * 2 + 1] = v.y;
