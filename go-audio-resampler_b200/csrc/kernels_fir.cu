@@ -889,7 +889,8 @@ const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s) {
     }
     GAR_FIR_X2_VARIANTS(X)
 #undef X
-    if ((int64_t)c.n_pos * c.n_streams <= 4096) {
+    static const int64_t small_max = [] { const char* e = gar::tune_env("GAR_FIR_SMALL_MAX"); return e ? std::atoll(e) : 4096ll; }();
+    if ((int64_t)c.n_pos * c.n_streams <= small_max) {
 #define X(T, DT, M, NF, R, NAME)                           \
     if (dtype == DT && c.stride == M && c.nf == NF) {      \
         launch_fir_tiled<T, M, NF, R>(c, s);               \

@@ -1090,6 +1090,23 @@ static bool launch_rat_t(const FusedCall& c, cudaStream_t s, RatCache* cache) {
         tpb = std::max<int64_t>(tpb, FUSED ? 3 : 6);
         tpb = std::min<int64_t>(tpb, std::max<int64_t>(1, total_tiles / slots));
         tpb = std::min<int64_t>(std::min<int64_t>(tpb, RAT_MAXT), g.n_tiles);
+        // A call of only a few blocks per SM (one long row: 8k->192k's last stage is 1810 tiles) is governed by quantisation:
+        // its time is the number of tiles the busiest SM gets = ceil(blocks / SMs) x tiles per block (two blocks share an
+        // SM; a lone block hides latency worse: +15 %). 604 three-tile blocks: 5 x 3 = 15 tile times; 259 seven-tile
+        // blocks: 2 x 7 = 14. (44.1k->48k as one 10 s row, 375 tiles, stays at one tile per block: 3 x 1.)
+        if (total_tiles <= slots * 24) {
+            const int64_t nsm = slots / 2;
+            double best = 1e30;
+            for (int64_t t = 1; t <= std::min<int64_t>(RAT_MAXT, g.n_tiles); ++t) {
+                const int64_t groups = ((g.n_tiles + t - 1) / t + 1) * c.n_streams;  // + the carry block of every row
+                const int64_t per_sm = (groups + nsm - 1) / nsm;
+                const double cost = (double)per_sm * (double)t * (per_sm < 2 ? 1.15 : 1.0);
+                if (cost < best - 1e-9) {
+                    best = cost;
+                    tpb = t;
+                }
+            }
+        }
         g.tiles_per_block = (int32_t)tpb;
         g.n_groups = (g.n_tiles + g.tiles_per_block - 1) / g.tiles_per_block;
     }

@@ -406,6 +406,48 @@ func NewBatchFloat32(in, out float64, q QualityPreset, streams, device int) (*Ba
 	return &Batch{h, streams}, nil
 }
 
+// NewBatchFloat32Multi is NewBatchFloat32 over several GPUs inside ONE handle (gar_create_multi): the streams are sharded
+// by contiguous blocks over `devices`, each shard with its own device state and a worker thread bound to the device's NUMA
+// node; Process / Flush fan out and join inside the call — the GPU analogue of the per-channel goroutines of
+// constant.go:223-241. A single-process Go caller reaches the multi-GPU numbers without running one process per GPU.
+func NewBatchFloat32Multi(in, out float64, q QualityPreset, streams int, devices []int) (*Batch, error) {
+	if len(devices) == 0 {
+		return nil, fmt.Errorf("%w: empty device list", ErrInvalidConfig)
+	}
+	cfg := C.gar_config{input_rate: C.double(in), output_rate: C.double(out), channels: 1,
+		path: C.GAR_PATH_ENGINE, preset: C.int32_t(q), dtype: C.GAR_F32, engine_quality: -1,
+		n_streams: C.int32_t(streams)}
+	devs := make([]C.int32_t, len(devices))
+	for i, d := range devices {
+		devs[i] = C.int32_t(d)
+	}
+	var h *C.gar_handle
+	if st := C.gar_create_multi(&cfg, &devs[0], C.int32_t(len(devs)), &h); st != C.GAR_OK {
+		return nil, statusErr(st, nil)
+	}
+	r := &handle{h: h}
+	runtime.SetFinalizer(r, func(r *handle) { C.gar_destroy(r.h) })
+	return &Batch{r, streams}, nil
+}
+
+// HostAllocRows returns a pinned planar [Streams][cols] float32 buffer whose row blocks live on the NUMA node of the
+// device that copies them (gar_host_alloc_rows); pass it to Process / Flush for full PCIe rate. Release with HostFree.
+func (b *Batch) HostAllocRows(cols int) []float32 {
+	p := C.gar_host_alloc_rows(b.h, C.size_t(cols)*4)
+	runtime.KeepAlive(b)
+	if p == nil {
+		return nil
+	}
+	return unsafe.Slice((*float32)(p), b.Streams*cols)
+}
+
+// HostFree releases a buffer made by HostAllocRows.
+func HostFree(buf []float32) {
+	if len(buf) > 0 {
+		C.gar_host_free(unsafe.Pointer(&buf[0]))
+	}
+}
+
 // Process resamples planar [Streams][nIn] float32 (row stride nIn) into planar [Streams][outStride].
 // The C side reads Streams*nIn and writes up to Streams*outStride elements, so both slices are validated here:
 // nothing may be written past a Go slice.
