@@ -78,6 +78,7 @@ struct Shard {
     gar_handle* h = nullptr;  // complete single-device handle for rows [row0, row0 + rows)
     int row0 = 0, rows = 0, device = 0;
     int rc = 0;               // status of the last job
+    std::string err;          // message of a failed job that has no handle to carry it (shard creation)
     int64_t n_out = 0;
     ShardWorker w;
 };
@@ -123,7 +124,7 @@ int for_shards(gar_handle* h, F f) {
         sp->w.wait();
         if (sp->rc && !rc) {
             rc = sp->rc;
-            h->err = "device " + std::to_string(sp->device) + ": " + (sp->h ? sp->h->err : std::string("shard missing"));
+            h->err = "device " + std::to_string(sp->device) + ": " + (sp->h ? sp->h->err : sp->err);
         }
     }
     return rc;
@@ -309,11 +310,7 @@ int32_t gar_create_multi(const gar_config* cfg, const int32_t* devices, int32_t 
         if (by_stream) c.n_streams = sh.rows / unit_rows;
         else c.channels = sh.rows;
         const int32_t r = gar_create(&c, &sh.h);
-        if (r) {  // gar_create's message is thread-local on the worker: keep it where for_shards can find it
-            sh.h = new gar_handle();
-            sh.h->err = g_create_err;
-            sh.h->eng.init(Chain{}, 0, DT_F64, -1, sh.h->err);
-        }
+        if (r) sh.err = g_create_err;  // gar_create's message is thread-local on the worker: keep it for for_shards
         return r;
     });
     if (rc) {
