@@ -95,7 +95,9 @@ __device__ __forceinline__ void fused_carry_tails_rt(const FusedCall& c, const i
 template <typename T, bool INTERP, int R, int NT>
 __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, const int n_tiles, const int ms,
                                                             const int cp, const int xlen, const int hpf,
-                                                            const int bank_pitch /*0: read banks through L1*/) {
+                                                            const int bank_pitch /*0: read banks through L1*/,
+                                                            const int rowcap /*> 0: gather the outputs' rows by TMA*/,
+                                                            const int cpitch) {
     using V = typename VecOf<T>::type;
     constexpr int VEC = VecOf<T>::N;
     constexpr int NF = 2;
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
     T* xs = cs + NF * cp;                         // [xlen]
     T* vp = xs + xlen;                            // [hpf + MT] polyphase input: (tail |) intermediate tile
     T* pbank = vp + hpf + MT;                     // [L][bank_pitch] a-bank copy (optional)
+    T* crow = pbank;                              // [rowcap][cpitch] the coefficient row of every output (optional)
 
     const int tile = blockIdx.x % (n_tiles + 1);
     const int64_t row = blockIdx.x / (n_tiles + 1);
@@ -123,9 +126,16 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
         return;
     }
 
-    // ---- 0. this thread's outputs are known from the geometry alone: pull their coefficient rows into L1 now, so the
-    // polyphase loop at the end does not pay an L2 round trip per unrolled tap group (a streaming-size launch spends
-    // 40 % of its time there otherwise) ----
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+    }
+    __syncthreads();
+
+    // ---- 0. this block's outputs are known from the geometry alone. Streaming-size launches (rowcap > 0): warp 0 gathers the
+    // coefficient row of EVERY output into shared memory with one TMA bulk copy per row, all in flight at once, while the
+    // block stages its samples and runs the x2 core — the per-tap loads of the polyphase loop otherwise pay an L2 round trip
+    // per unrolled group (the source view put 40 % of a chunk launch there). Otherwise the rows are prefetched into L1. ----
     const int64_t Lq = (int64_t)c.L << 16;
     const int64_t lo = tile == 0 ? 0 : (int64_t)c.hp + (int64_t)tile * ms;
     const int64_t hi = (int64_t)c.hp + (int64_t)(tile + 1) * ms;
@@ -135,7 +145,25 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
     };
     const int64_t n_lo = min((int64_t)c.n_out, first_n(lo));
     const int64_t n_hi = tile == n_tiles - 1 ? (int64_t)c.n_out : min((int64_t)c.n_out, first_n(hi));
-    if (bank_pitch == 0 && n_hi - n_lo <= 4 * NT) {
+    const bool gather = !INTERP && rowcap > 0 && n_hi - n_lo <= rowcap;
+    auto row_pad = [&](const T* rowp) -> int {  // elements between the 16-byte aligned address below the row and the row
+        return (int)((reinterpret_cast<uintptr_t>(rowp) & 15u) / sizeof(T));
+    };
+    if (gather) {  // every thread issues the copies of its own outputs; each warp adds its byte count to the barrier
+        uint32_t bytes = 0;
+        for (int64_t n = n_lo + tid; n < n_hi; n += NT) {
+            const int64_t full = (c.at0 + n * c.step) >> 16;
+            const T* rowp = static_cast<const T*>(c.bank_a) + (full % c.L) * c.t2;
+            const int pad = row_pad(rowp);
+            const uint32_t nb = (uint32_t)(((c.t2 + pad) * sizeof(T) + 15) & ~(size_t)15);
+            bulk_g2s(crow + (size_t)(n - n_lo) * cpitch, rowp - pad, nb, bar + 1);
+            bytes += nb;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+        if ((tid & 31) == 0 && bytes)
+            asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar + 1)), "r"(bytes) : "memory");
+    } else if (bank_pitch == 0 && n_hi - n_lo <= 4 * NT) {
         for (int64_t n = n_lo + tid; n < n_hi; n += NT) {
             const int64_t full = (c.at0 + n * c.step) >> 16;
             const int64_t co = (full % c.L) * c.t2;
@@ -169,8 +197,6 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
     if (bulk) {
         const int gi = p0 - c.hu - a;
         const int words = ((need + a + VEC - 1) / VEC) * VEC;
-        if (tid == 0) mbar_init(bar, 1);
-        __syncthreads();
         if (tid == 0) {
             mbar_expect_tx(bar, (uint32_t)(words * sizeof(T)));
             bulk_g2s(xs, in + gi, (uint32_t)(words * sizeof(T)), bar);
@@ -193,6 +219,8 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
         for (int i = tid; i < c.L * c.t2; i += NT) pbank[(i / c.t2) * bank_pitch + (i % c.t2)] = ba[i];  // 8 loads in flight
     }
     __syncthreads();
+    if (gather && tid == 0)  // the single arrival: every warp's expect_tx above is ordered before it by the barrier
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar + 1)) : "memory");
     if (bulk) {
         while (!mbar_try_wait(bar, 0)) {
         }
@@ -219,6 +247,10 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
     const T* __restrict__ gc = static_cast<const T*>(c.bank_c);
     const T* __restrict__ gd = static_cast<const T*>(c.bank_d);
     (void)n_mid;
+    if (gather) {
+        while (!mbar_try_wait(bar + 1, 0)) {
+        }
+    }
     for (int64_t n = n_lo + tid; n < n_hi; n += NT) {
         const int64_t at = c.at0 + n * c.step;
         const int64_t full = at >> 16;
@@ -236,6 +268,7 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
             }
         } else {
             const T* __restrict__ ca = bank_pitch > 0 ? pbank + phase * bank_pitch : ga + (int64_t)phase * c.t2;
+            if (gather) ca = crow + (size_t)(n - n_lo) * cpitch + row_pad(ca);
             for (int k = 0; k < c.t2; ++k) {
                 if ((k & 1) && sizeof(T) == 4) acc1 = fma((double)h[k], (double)ca[k], acc1);
                 else acc0 = fma((double)h[k], (double)ca[k], acc0);
@@ -917,6 +950,22 @@ static bool launch_fused_r(const FusedCall& c, cudaStream_t s) {
             words += (size_t)c.L * pitch;
         }
     }
+    // streaming-size launches: one TMA bulk copy per output gathers its coefficient row (rows padded to 16-byte multiples,
+    // pitch = 2 elements of 8 bytes mod 16 so that the lanes' rows start in different banks)
+    int rowcap = 0, cpitch = 0;
+    // (measured, warm caches: a Flush launch of one tile 14.3 -> 12.0 us; a 4096-frame chunk of 18 tiles is better off with the
+    //  L1 prefetch, 12.2 against 13.3 us, so the gather is for launches of a few tiles only)
+    if (!INTERP && bank_pitch == 0 && (int64_t)n_tiles * c.n_streams <= 4) {
+        const double r = (double)c.step / ((double)c.L * 65536.0);
+        const int cap = (int)((double)(MT + c.hp + 2) / r) + 4;
+        int pitch = ((c.t2 + VEC + VEC - 1) / VEC) * VEC;  // room for the alignment pad
+        while ((pitch * (int)sizeof(T)) % 128 != 16) pitch += VEC;
+        if ((words + (size_t)cap * pitch) * sizeof(T) + 16 <= 200 * 1024) {
+            rowcap = cap;
+            cpitch = pitch;
+            words += (size_t)cap * pitch;
+        }
+    }
     const size_t smem = 16 + words * sizeof(T);
     auto k = fused_up2_poly_kernel<T, INTERP, R, NT>;
     static size_t configured[64] = {0};
@@ -927,7 +976,7 @@ static bool launch_fused_r(const FusedCall& c, cudaStream_t s) {
         configured[dev & 63] = smem;
     }
     const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
-    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, ms, cp, xlen, hpf, bank_pitch);
+    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, ms, cp, xlen, hpf, bank_pitch, rowcap, cpitch);
     count_launch();
     return true;
 }

@@ -702,9 +702,12 @@ static bool launch_poly_rows(const PolyCall& c, cudaStream_t s) {
 // Polyphase stage. One thread per output; the block's input span sits in shared memory.
 // =============================================================================================
 template <typename T, bool INTERP, int TO>
-__global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_tiles, const int xcap) {
+__global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_tiles, const int xcap,
+                                                  const int cpitch /*> 0: gather every output's coefficient row by TMA*/) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* xs = reinterpret_cast<T*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    T* xs = reinterpret_cast<T*>(smem_raw + 16);
+    T* crow = xs + ((xcap + 3) & ~3);  // [TO][cpitch]
     const int tile = blockIdx.x % (n_tiles + 1);
     const int64_t row = blockIdx.x / (n_tiles + 1);
     const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
@@ -730,7 +733,24 @@ __global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_
     const T* __restrict__ cb = static_cast<const T*>(c.bank_b) + co;
     const T* __restrict__ cc = static_cast<const T*>(c.bank_c) + co;
     const T* __restrict__ cd = static_cast<const T*>(c.bank_d) + co;
-    if (live) {
+    // streaming-size launches: one TMA bulk copy per output fetches its coefficient row (all in flight at once) while the
+    // samples are staged; larger launches prefetch the rows into L1
+    const bool gather = !INTERP && cpitch > 0;
+    const int cpad = (int)((reinterpret_cast<uintptr_t>(ca) & 15u) / sizeof(T));
+    if (gather) {
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        const uint32_t nb = live ? (uint32_t)(((c.taps + cpad) * sizeof(T) + 15) & ~(size_t)15) : 0u;
+        if (live) bulk_g2s(crow + (size_t)threadIdx.x * cpitch, ca - cpad, nb, bar);
+        uint32_t bytes = nb;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+        // every warp adds its bytes without arriving; thread 0 alone arrives (init count 1) after its own warp's share
+        if ((threadIdx.x & 31) == 0 && threadIdx.x != 0 && bytes)
+            asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) mbar_expect_tx(bar, bytes);
+    } else if (live) {
         prefetch_row_l1(ca, c.taps);
         if (INTERP) {
             prefetch_row_l1(cb, c.taps);
@@ -746,14 +766,19 @@ __global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_
         block_copy4(span, [&](int i) { return vload(hist, c.hist_len, in, c.n_in, div0 + i); }, [&](int i, T v) { xs[i] = v; });
         __syncthreads();
     }
+    if (gather) {
+        while (!mbar_try_wait(bar, 0)) {
+        }
+    }
     if (!live) return;
+    const T* __restrict__ cg = gather ? crow + (size_t)threadIdx.x * cpitch + cpad : ca;
     // products of two float32 are exact in float64, so the float32 path only rounds once, at the store (two
     // interleaved chains); float64 sums strictly in tap order, like every other float64 kernel here, so the
     // fused kernels reproduce the stand-alone launches bit for bit
     double acc0 = 0, acc1 = 0;
     const int base = div - div0;
     for (int k = 0; k < c.taps; ++k) {
-        T coef = ca[k];
+        T coef = cg[k];
         if (INTERP) coef = fma(x, fma(x, fma(x, cd[k], cc[k]), cb[k]), coef);
         const T h = staged ? xs[base + k] : vload(hist, c.hist_len, in, c.n_in, div + k);
         if ((k & 1) && sizeof(T) == 4) acc1 = fma((double)h, (double)coef, acc1);
@@ -801,12 +826,20 @@ const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* 
     int64_t span = (((int64_t)(TO - 1) * c.step) >> 16) / c.L + 2 + c.taps;
     const int64_t cap_words = (96 * 1024) / (int64_t)esz;
     int xcap = (int)(span < cap_words ? span : 0);  // 0 => read straight from global
-    size_t smem = (size_t)xcap * esz;
+    // streaming-size launches gather the outputs' coefficient rows by TMA (pitch: 16 bytes mod 128, room for the alignment pad)
+    int cpitch = 0;
+    if (!c.interp && blocks <= 2 * 148) {
+        const int vec = 16 / (int)esz;
+        int pitch = ((c.taps + vec + vec - 1) / vec) * vec;
+        while ((pitch * (int)esz) % 128 != 16) pitch += vec;
+        if ((size_t)(xcap + 4 + TO * pitch) * esz + 16 <= 160 * 1024) cpitch = pitch;
+    }
+    size_t smem = 16 + (size_t)((xcap + 3) & ~3) * esz + (size_t)TO * cpitch * esz;
 #define LAUNCH(T, I)                                                                                          \
     {                                                                                                         \
         auto k = poly_kernel<T, I, TO>;                                                                       \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
-        k<<<(unsigned)blocks, TO, smem, s>>>(c, n_tiles, xcap);                                               \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024); \
+        k<<<(unsigned)blocks, TO, smem, s>>>(c, n_tiles, xcap, cpitch);                                       \
         count_launch();                                                                                       \
     }
     if (dtype == DT_F32) {
