@@ -20,7 +20,33 @@ int pick_tiles_per_block(int n_tiles, int n_streams, int* n_groups);
 // K3r: the rational-ratio kernel without the x2 stage (kernels_fused.cu), used by launch_poly
 bool launch_rat_poly_only_f64(const FusedCall& c, cudaStream_t s, RatCache* cache);
 
+// Programmatic dependent launch (sm_90+): a kernel launched with this attribute may start its blocks while the previous
+// kernel of the stream is still running (as soon as that kernel's blocks have called pdl_trigger() or exited); it must call
+// pdl_wait() before it touches anything the previous kernel reads or writes. The streaming-size kernels use it to overlap
+// their prologue (barrier set-up, geometry, TMA gather / prefetch of the constant coefficient banks, instruction fetch)
+// with the tail of the launch before them: a Flush of the 8k->192k pipeline is ten dependent launches of a few microseconds.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 namespace {
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// only small grids let their successor in early: its waiting blocks would otherwise take slots from this kernel's own blocks
+__device__ __forceinline__ void pdl_trigger_if_small() {
+    if (gridDim.x <= 296) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 template <typename T> struct VecOf;
 template <> struct VecOf<float> { using type = float4; static constexpr int N = 4; };

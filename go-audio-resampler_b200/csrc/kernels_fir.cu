@@ -40,7 +40,9 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
     const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
     const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
 
+    pdl_trigger_if_small();
     if (group == n_groups) {  // carry block
+        pdl_wait();
         carry_row(hist, c.hist_len, in, c.n_in, static_cast<T*>(c.hist_out) + row * c.hist_out_stride, c.drop,
                   c.new_hist_len);
         return;
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
             return (k >= 0 && k < c.taps) ? bank[p * c.taps + k] : T(0);
         }, [&](int i, T v) { cs[i] = v; });
     }
+    pdl_wait();  // everything above touched shared memory and the constant bank only
     __syncthreads();
     if (tid == 0) issue_bulk(t_first, 0);
     uint32_t phase0 = 0u, phase1 = 0u;
@@ -779,7 +782,7 @@ void launch_fir_tiled(const FirCall& c, cudaStream_t s) {
         configured[dev & 63] = smem;
     }
     const int64_t blocks = (int64_t)(n_groups + 1) * c.n_streams;
-    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, tpb, n_groups, cp, xlen);
+    launch_pdl(k, (unsigned)blocks, (unsigned)NT, smem, s, c, n_tiles, tpb, n_groups, cp, xlen);
     count_launch();
 }
 

@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
     const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
     const int n_mid = c.np * NF;
 
+    pdl_trigger_if_small();
     if (tile == n_tiles) {  // ---- carried tails ----
+        pdl_wait();
         fused_carry_tails_rt<T>(c, row, xs, xlen + hpf + MT);
         return;
     }
@@ -175,6 +177,8 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
             }
         }
     }
+
+    pdl_wait();  // up to here: shared memory, geometry and the constant banks only
 
     // ---- 1. stage the x2 stage's input window ----
     const int p0 = (tile * ms) >> 1;  // first position of the tile (ms is even)
@@ -976,7 +980,7 @@ static bool launch_fused_r(const FusedCall& c, cudaStream_t s) {
         configured[dev & 63] = smem;
     }
     const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;
-    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, ms, cp, xlen, hpf, bank_pitch, rowcap, cpitch);
+    launch_pdl(k, (unsigned)blocks, (unsigned)NT, smem, s, c, n_tiles, ms, cp, xlen, hpf, bank_pitch, rowcap, cpitch);
     count_launch();
     return true;
 }

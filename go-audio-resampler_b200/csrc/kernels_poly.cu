@@ -712,7 +712,9 @@ __global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_
     const int64_t row = blockIdx.x / (n_tiles + 1);
     const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
     const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    pdl_trigger_if_small();
     if (tile == n_tiles) {
+        pdl_wait();
         carry_row(hist, c.hist_len, in, c.n_in, static_cast<T*>(c.hist_out) + row * c.hist_out_stride, c.drop,
                   c.new_hist_len);
         return;
@@ -762,6 +764,7 @@ __global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_
     const int div1 = (int)(((c.at0 + (int64_t)n1 * c.step) >> 16) / L);
     const int span = div1 - div0 + c.taps;
     const bool staged = span <= xcap;
+    pdl_wait();  // up to here: geometry and the constant banks only
     if (staged) {
         block_copy4(span, [&](int i) { return vload(hist, c.hist_len, in, c.n_in, div0 + i); }, [&](int i, T v) { xs[i] = v; });
         __syncthreads();
@@ -839,7 +842,7 @@ const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* 
     {                                                                                                         \
         auto k = poly_kernel<T, I, TO>;                                                                       \
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024); \
-        k<<<(unsigned)blocks, TO, smem, s>>>(c, n_tiles, xcap, cpitch);                                       \
+        launch_pdl(k, (unsigned)blocks, (unsigned)TO, smem, s, c, n_tiles, xcap, cpitch);                     \
         count_launch();                                                                                       \
     }
     if (dtype == DT_F32) {
