@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(NT, 1) fused_up2_poly_sorted_kernel(const Fuse
     const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
     const T* __restrict__ hist_p = static_cast<const T*>(c.hist_p) + row * c.hist_p_stride;
     const T* __restrict__ bank_u = static_cast<const T*>(c.bank_u);
+    pdl_wait();  // launched as a programmatic dependent: its blocks may be resident before the previous launch has drained
 
     if (tile == n_tiles) {  // ---- carried tails ----
         fused_carry_tails_rt<T>(c, row, xs, g.xlen + hpf + g.npass * MT);
@@ -573,6 +574,7 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
     constexpr int R = sizeof(T) == 8 ? 6 : 12;  // x2 core: positions per thread task
     constexpr int WN = (RN - 1) * S + 1;        // register window of the polyphase phase
     const int NT = blockDim.x;
+    pdl_wait();  // launched as a programmatic dependent (its coefficient tile may come from the launch just before it)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // [4] one mbarrier per input window buffer, [4]: the tile
@@ -1041,7 +1043,7 @@ static bool launch_fused_sorted_nt(const FusedCall& c, const void* bank_il, cuda
         configured[dev & 63] = smem;
     }
     const int64_t blocks = (int64_t)(g.n_tiles + 1) * c.n_streams;
-    k<<<(unsigned)blocks, NT, smem, s>>>(c, g);
+    launch_pdl(k, (unsigned)blocks, (unsigned)NT, smem, s, c, g);
     count_launch();
     return true;
 }
@@ -1205,7 +1207,7 @@ static bool launch_rat_t(const FusedCall& c, cudaStream_t s, RatCache* cache) {
         configured[dev & 63] = smem;
     }
     const int64_t blocks = (int64_t)(g.n_groups + 1) * c.n_streams;
-    k<<<(unsigned)blocks, nthreads, smem, s>>>(c, g);
+    launch_pdl(k, (unsigned)blocks, (unsigned)nthreads, smem, s, c, g);
     count_launch();
     return true;
 }
