@@ -61,6 +61,7 @@ int Engine::upload_bank(int stage, int which, const std::vector<double>& v, std:
         std::vector<float> f(v.size());
         for (size_t i = 0; i < v.size(); ++i) f[i] = (float)v[i];
         if (!cuda_ok(cudaMemcpy(d.bank[which], f.data(), bytes, cudaMemcpyHostToDevice), err, "bank upload")) return 4;
+        if (which == 0 && chain_.stages[(size_t)stage].kind != STAGE_POLY) d.bank_h32 = std::move(f);
     } else {
         if (!cuda_ok(cudaMemcpy(d.bank[which], v.data(), bytes, cudaMemcpyHostToDevice), err, "bank upload")) return 4;
     }
@@ -728,6 +729,7 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                 c.hist_out = hout; c.hist_out_stride = dv.hist_cap;
                 c.drop = (int32_t)op.drop; c.new_hist_len = (int32_t)op.new_hist_len;
                 c.bank = dv.bank[0];
+                c.bank_host_f32 = dv.bank_h32.empty() ? nullptr : dv.bank_h32.data();
                 c.taps = sd.taps;
                 if (sd.kind == STAGE_UP) {
                     c.stride = 1; c.nf = sd.factor; c.first = 0; c.n_pos = (int32_t)(op.n_out / sd.factor);

@@ -24,6 +24,8 @@ struct FirCall {
     void* hist_out;       int64_t hist_out_stride;                     // new tail = v[drop .. hist_len+n_in)
     int32_t drop;         int32_t new_hist_len;
     const void* bank;     // device, [nf][taps]
+    const float* bank_host_f32;  // optional host copy of a float32 bank: float32 decimators pass their taps as KERNEL
+                                 // PARAMETERS (constant bank) so that the FMAs take them from uniform registers
     int32_t taps;         int32_t stride;       int32_t nf;
     int32_t first;        int32_t n_pos;
     int32_t n_streams;    // rows processed by this launch (row r of every pointer = base + r*stride)

@@ -731,6 +731,237 @@ __global__ void __launch_bounds__(NT) fir_f32x2_kernel(const FirCall c, const in
 
 
 
+// ---- the same kernel with the taps in the CONSTANT bank (round 2) -----------------------------------------------------
+// An FFMA2 whose three 64-bit operands all come from the register file runs at ~2/3 rate (tools/probe_fma_patterns3.cu);
+// ptxas hides part of that with .reuse chains on the coefficient operand, which is what capped the kernel above at 77 % of
+// the FMA probe. Here the filter travels as a KERNEL PARAMETER (two copies, shifted by 0 and 1 tap, zero-padded): every lane
+// of a warp uses the same tap pair, so ptxas loads it into a UNIFORM register (LDCU.64 c[0x0][UR+imm]) and issues
+// FFMA2 R, R, UR, R — two register-file operands, no coefficient LDS, no coefficient registers
+// (tools/probe_fma_const.cu: 68.7 against 56.2 TFLOP/s for this loop's operand pattern). CPF = floats per copy.
+template <int CPF>
+struct FirTapsParam {
+    unsigned long long pair[2][CPF / 2];  // pair[s][i] = (tap[2i - 4 - s], tap[2i + 1 - 4 - s]), zero outside the filter
+};
+
+template <int M, int NF, int R, int NT, int CPF>
+__global__ void __launch_bounds__(NT) fir_f32x2c_kernel(const FirCall c, const int n_tiles, const int tiles_per_block,
+                                                        const int n_groups, const int xlen, const int a_param,
+                                                        const __grid_constant__ FirTapsParam<CPF> P) {
+    static_assert(NF == 1, "decimators only");
+    typedef unsigned long long u64;
+    constexpr int MAXE = M * (R - 1) - ((M * (R - 1)) & 1);
+    constexpr int NCH = (MAXE + 4 + 3) / 4;
+    constexpr int NS = ((M & 1) && R > 1) ? 2 : 1;  // filter copies: shift 0 (even offsets), shift 1 (odd offsets)
+    constexpr int TJ = NT * R;
+    static_assert((TJ * M) % 4 == 0, "tile stride must keep the 16-byte alignment of the window");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // two mbarriers, one per window buffer
+    float* xs0 = reinterpret_cast<float*>(smem_raw + 16);   // [2][xlen] double-buffered sample window
+
+    // grid.x = rows * (n_groups + 1): a block owns `tiles_per_block` consecutive tiles of one row; the extra
+    // block of every row writes the carried tail.
+    const int group = blockIdx.x % (n_groups + 1);
+    const int64_t row = blockIdx.x / (n_groups + 1);
+    const int tid = threadIdx.x;
+    const float* __restrict__ hist = static_cast<const float*>(c.hist) + row * c.hist_stride;
+    const float* __restrict__ in = static_cast<const float*>(c.in) + row * c.in_stride;
+    if (group == n_groups) {
+        carry_row(hist, c.hist_len, in, c.n_in, static_cast<float*>(c.hist_out) + row * c.hist_out_stride, c.drop,
+                  c.new_hist_len);
+        return;
+    }
+    const int t_first = group * tiles_per_block;
+    const int nt = min(tiles_per_block, n_tiles - t_first);
+
+    // Leading pad `a` (same for every tile of the row because the tile stride is a multiple of 16 bytes): the
+    // window of a tile starts `a` samples early so that its global address is 16-byte aligned for the TMA
+    // bulk copy; the filter is shifted by `a` zero taps to compensate.
+    // the pad is the same for every row (row stride a multiple of 16 bytes: checked by the launcher) and comes in as a
+    // kernel parameter, so everything that indexes the constant bank is provably warp-uniform for ptxas
+    const int a = a_param;
+    auto tile_geom = [&](const int t, int& g0a, int& words, bool& bulk) {
+        const int j0 = t * TJ;
+        const int tj = min(TJ, c.n_pos - j0);
+        g0a = c.first + j0 * M - a;                       // virtual index of xs[0]
+        words = (((tj - 1) * M + c.taps + a + 3) / 4) * 4;  // samples the tile reads, rounded to 16 bytes
+        const int gi = g0a - c.hist_len;                  // index into `in`
+        bulk = gi >= 0 && gi + words <= c.n_in && words <= xlen;
+    };
+    auto issue_bulk = [&](const int t, const int buf) {  // one thread
+        int g0a, words;
+        bool bulk;
+        tile_geom(t, g0a, words, bulk);
+        if (bulk) {
+            mbar_expect_tx(bar + buf, (uint32_t)(words * sizeof(float)));
+            bulk_g2s(xs0 + buf * xlen, in + (g0a - c.hist_len), (uint32_t)(words * sizeof(float)), bar + buf);
+        }
+    };
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+    }
+    // both window buffers start as zeros: whatever a later, shorter tile leaves behind is finite
+    for (int i = tid; i < 2 * xlen; i += NT) xs0[i] = 0.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros before async-proxy (TMA) writes
+    // tap pair (t, t+1) with t = 4*it + 2*q - a - sh lives in copy s = (a + sh) & 1 at pair index (t + 4 + s) / 2
+    int csel[NS], cbase[NS];
+#pragma unroll
+    for (int sh = 0; sh < NS; ++sh) {
+        csel[sh] = (a + sh) & 1;
+        cbase[sh] = (4 + csel[sh] - a - sh) >> 1;
+    }
+    __syncthreads();
+    if (tid == 0) issue_bulk(t_first, 0);
+    uint32_t phase0 = 0u, phase1 = 0u;
+
+    const int n_iter = (c.taps + a + (NS - 1) + 3) / 4;
+    const int itf0 = ((c.taps - 1) / 2 + a) / 4, itf1 = itf0 + 2;  // centre-of-main-lobe folds (see fir_tiled_kernel)
+    float* __restrict__ out = static_cast<float*>(c.out) + row * c.out_stride;
+
+    for (int k = 0; k < nt; ++k) {
+        const int t = t_first + k;
+        const int buf = k & 1;
+        float* xs = xs0 + buf * xlen;
+        int g0a, words;
+        bool bulk;
+        tile_geom(t, g0a, words, bulk);
+        // prefetch the next tile into the other buffer (free since the __syncthreads that ended tile k-1)
+        if (tid == 0 && k + 1 < nt) issue_bulk(t + 1, buf ^ 1);
+        if (bulk) {
+            const uint32_t ph = buf ? phase1 : phase0;
+            while (!mbar_try_wait(bar + buf, ph)) {
+            }
+            if (buf) phase1 ^= 1u;
+            else phase0 ^= 1u;
+        } else {  // edge tile (touches the carried tail or the end of the row): guarded loads
+            for (int i = tid; i < xlen; i += NT)
+                xs[i] = i < words ? vload(hist, c.hist_len, in, c.n_in, g0a + i) : 0.f;
+            __syncthreads();
+        }
+
+        // ---- register-tiled sliding window on packed FMAs ----
+        const float* xt = xs + M * R * tid;
+        u64 xw[NCH * 2];
+        u64 acc[R][NF];
+        double tot[R][NF];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int p = 0; p < NF; ++p) {
+                acc[r][p] = 0ull;
+                tot[r][p] = 0.0;
+            }
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xt + ch * 4);
+            xw[ch * 2] = v.x;
+            xw[ch * 2 + 1] = v.y;
+        }
+        // tap-pair cursors into the parameter bank: advanced by the steps themselves (which run in order it = 0, 1, 2, ...), so
+        // their address arithmetic never mixes with the per-thread shared-memory addressing and stays in uniform registers
+        const u64* cq[NS];
+#pragma unroll
+        for (int sh = 0; sh < NS; ++sh) cq[sh] = &P.pair[csel[sh]][cbase[sh]];
+        auto step = [&](const int u, const int it) {
+            // (tools/probe_fma_patterns2.cu: FFMA2 loses ~15 % when one coefficient pair feeds 6 FMAs in a row;
+            //  duplicating the pair with a second, unmergeable ld.shared cost more than it gained — measured)
+            u64 cv[NF][NS][2];
+#pragma unroll
+            for (int sh = 0; sh < NS; ++sh) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) cv[0][sh][q] = cq[sh][q];  // warp-uniform address chain of its own: LDCU.64
+                cq[sh] += 2;
+            }
+            auto fma2 = [&](const int q, const int r, const u64 cf) {
+                const int sh = (M * r) & 1;
+                const int eh = (M * r - sh) / 2;
+                const u64 xv = xw[(u * 2 + q + eh) % (NCH * 2)];
+#pragma unroll
+                for (int p = 0; p < NF; ++p) {
+                    u64 d;
+                    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(xv), "l"(cf), "l"(acc[r][p]));
+                    acc[r][p] = d;
+                }
+            };
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int r = 0; r < R; ++r) fma2(q, r, cv[0][NS == 2 ? ((M * r) & 1) : 0][q]);
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xt + (it + NCH) * 4);
+            xw[(u % NCH) * 2] = v.x;
+            xw[(u % NCH) * 2 + 1] = v.y;
+        };
+        auto fold = [&]() {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int p = 0; p < NF; ++p) {
+                    const float lo = __uint_as_float((unsigned)(acc[r][p] & 0xffffffffull));
+                    const float hi = __uint_as_float((unsigned)(acc[r][p] >> 32));
+                    tot[r][p] += (double)lo + (double)hi;
+                    acc[r][p] = 0ull;
+                }
+        };
+        // three straight loops (plain bodies, the one or two bodies holding the centre, plain bodies): no
+        // per-body bookkeeping; float32 partial sums are folded into float64 only around the centre of the
+        // main lobe and at the loop boundaries (the tails stay small, see fir_tile_accumulate)
+        const int nb = n_iter / NCH;
+        const int bs0 = min(nb, itf0 / NCH), bs1 = min(nb, itf1 / NCH + 1);
+        int b = 0;
+        for (; b < bs0; ++b) {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) step(u, b * NCH + u);
+        }
+        fold();
+        for (; b < bs1; ++b) {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) {
+                step(u, b * NCH + u);
+                if (b * NCH + u >= itf0 && b * NCH + u <= itf1) fold();
+            }
+        }
+        for (; b < nb; ++b) {
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) step(u, b * NCH + u);
+        }
+        const int it0 = nb * NCH;
+#pragma unroll
+        for (int u = 0; u < NCH; ++u)
+            if (it0 + u < n_iter) {
+                step(u, it0 + u);
+                if (it0 + u >= itf0 && it0 + u <= itf1) fold();
+            }
+        fold();
+
+        // ---- vectorised store ----
+        const int jb = t * TJ + R * tid;
+        float* op = out + (int64_t)jb * NF;
+        if (jb + R <= c.n_pos && (R * NF) % 4 == 0 && (reinterpret_cast<uintptr_t>(op) & 15u) == 0) {
+#pragma unroll
+            for (int q = 0; q < R * NF / 4; ++q) {
+                float4 v;
+                v.x = (float)tot[(q * 4 + 0) / NF][(q * 4 + 0) % NF];
+                v.y = (float)tot[(q * 4 + 1) / NF][(q * 4 + 1) % NF];
+                v.z = (float)tot[(q * 4 + 2) / NF][(q * 4 + 2) % NF];
+                v.w = (float)tot[(q * 4 + 3) / NF][(q * 4 + 3) % NF];
+                reinterpret_cast<float4*>(op)[q] = v;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (jb + r < c.n_pos) {
+#pragma unroll
+                    for (int p = 0; p < NF; ++p) op[r * NF + p] = (float)tot[r][p];
+                }
+        }
+        __syncthreads();  // every thread is done with xs[buf] before the next prefetch overwrites it
+    }
+}
+
+
+
 // Fallback: one thread per output element, operands straight from global/L1.
 template <typename T>
 __global__ void __launch_bounds__(256) fir_generic_kernel(const FirCall c, const int n_tiles) {
@@ -786,9 +1017,54 @@ void launch_fir_tiled(const FirCall& c, cudaStream_t s) {
     count_launch();
 }
 
+template <int M, int NF, int R, int CPF>
+bool launch_fir_f32x2c(const FirCall& c, cudaStream_t s) {
+    constexpr int NT = 128;
+    constexpr int MAXE = M * (R - 1) - ((M * (R - 1)) & 1);
+    constexpr int NCH = (MAXE + 4 + 3) / 4;
+    constexpr int NS = ((M & 1) && R > 1) ? 2 : 1;
+    constexpr int TJ = NT * R;
+    const int cp = ((c.taps + 3 + (NS - 1) + 3) / 4) * 4;
+    // pair indices reach (4*n_iter + 4) / 2 with n_iter = (taps + 3 + (NS-1) + 3) / 4: keep a safety margin of 8 floats
+    if (!c.bank_host_f32 || cp + 16 > CPF) return false;
+    if (c.in_stride != 0 && (c.in_stride & 3) != 0) return false;  // rows must share the 16-byte alignment pad
+    const int a_param = (int)(((reinterpret_cast<uintptr_t>(c.in) >> 2) + (uintptr_t)(int64_t)(c.first - c.hist_len)) & 3u);
+    static_assert(sizeof(FirTapsParam<CPF>) + 256 <= 32764, "kernel parameters are limited to 32 KB");
+    FirTapsParam<CPF> P;
+    float* flat = reinterpret_cast<float*>(&P);
+    for (int sc = 0; sc < 2; ++sc)
+        for (int i = 0; i < CPF; ++i) {
+            const int k = i - 4 - sc;
+            flat[sc * CPF + i] = (k >= 0 && k < c.taps) ? c.bank_host_f32[k] : 0.f;
+        }
+    const int xlen = M * R * (NT - 1) + (cp / 4 + NCH + 1) * 4;
+    const size_t smem = 16 + (size_t)(2 * xlen) * sizeof(float);
+    const int n_tiles = (c.n_pos + TJ - 1) / TJ;
+    int n_groups = 1;
+    const int tpb = pick_tiles_per_block(n_tiles, c.n_streams, &n_groups);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto k = fir_f32x2c_kernel<M, NF, R, NT, CPF>;
+    static size_t configured[64] = {0};
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)(n_groups + 1) * c.n_streams;
+    k<<<(unsigned)blocks, NT, smem, s>>>(c, n_tiles, tpb, n_groups, xlen, a_param, P);
+    count_launch();
+    return true;
+}
+
 template <int M, int NF, int R>
 void launch_fir_f32x2(const FirCall& c, cudaStream_t s) {
     constexpr int NT = 128;
+    if constexpr (NF == 1) {  // taps as kernel parameters (uniform-register FFMA2 operands) when they fit 8 / 24 KB
+        static const bool no_const = [] { const char* e = gar::tune_env("GAR_NO_CONST_TAPS"); return e && e[0] && e[0] != '0'; }();
+        if (!no_const && c.n_pos * (int64_t)c.n_streams >= 4096 &&
+            (launch_fir_f32x2c<M, NF, R, 1024>(c, s) || launch_fir_f32x2c<M, NF, R, 3072>(c, s)))
+            return;
+    }
     constexpr int MAXE = M * (R - 1) - ((M * (R - 1)) & 1);
     constexpr int NCH = (MAXE + 4 + 3) / 4;
     constexpr int NS = ((M & 1) && R > 1) ? 2 : 1;
