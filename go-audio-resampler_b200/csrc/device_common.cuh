@@ -229,6 +229,81 @@ __device__ __forceinline__ void fir_tile_accumulate(const T* __restrict__ xt, co
 }
 
 
+// ---- float64 FIR core with the taps in the CONSTANT bank (kernel parameters) --------------------------------------------
+// Every lane of a warp multiplies by the same tap, so when the filter travels as a kernel parameter ptxas loads each tap into a
+// UNIFORM register (LDCU.64 c[0x0][UR+imm]) and issues DFMA R, R, UR, R: two register-file operands instead of three, and no
+// coefficient LDS at all. tools/probe_dfma_const.cu: 35.6 against 29.7 TFLOP/s for this core's operand pattern.
+// Layout: c[p][i] = bank[p][i - 2] (two leading zeros absorb the alignment pad a in {0, 1}), zero after the last tap.
+template <int NFM, int CPD>
+struct FirTapsD {
+    double c[NFM][CPD];
+};
+constexpr int FIR_TAPS_CPD = 288;  // taps per phase + 6 must fit (the quality presets need at most 267 + pad)
+
+// host side: fill the parameter block from a host copy of the bank ([nf][taps] doubles); false when it does not fit
+template <int NFM, int CPD>
+inline bool fill_fir_taps(FirTapsD<NFM, CPD>& P, const double* bank, int nf, int taps) {
+    if (!bank || nf > NFM || taps + 6 > CPD) return false;
+    for (int p = 0; p < NFM; ++p)
+        for (int i = 0; i < CPD; ++i) {
+            const int k = i - 2;
+            P.c[p][i] = (p < nf && k >= 0 && k < taps) ? bank[(size_t)p * taps + k] : 0.0;
+        }
+    return true;
+}
+
+// Same arithmetic and the same summation order as fir_tile_accumulate<double, M, NF, R> (bit-identical results). The tap
+// cursors cur[p] walk the parameter bank on their own so that their address arithmetic stays in uniform registers.
+template <int M, int NF, int R, int NFM, int CPD>
+__device__ __forceinline__ void fir_tile_accumulate_uc(const double* __restrict__ xt, const FirTapsD<NFM, CPD>& P,
+                                                       const int taps, const int a, double (&res)[R][NF]) {
+    constexpr int VEC = 2;
+    constexpr int NCH = (M * (R - 1) + VEC - 1) / VEC + 1;
+    constexpr int WREG = NCH * VEC;
+    const int n_iter = (taps + a + VEC - 1) / VEC;
+    double xr[WREG];
+    double acc[R][NF];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < NF; ++p) acc[r][p] = 0.0;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) vec_unpack(*reinterpret_cast<const double2*>(xt + ch * VEC), xr + ch * VEC);
+    const double* cur[NF];
+#pragma unroll
+    for (int p = 0; p < NF; ++p) cur[p] = &P.c[p][2 - a];
+    auto step = [&](const int u, const int it) {
+        double cv[NF][VEC];
+#pragma unroll
+        for (int p = 0; p < NF; ++p) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) cv[p][i] = cur[p][i];
+            cur[p] += VEC;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const double xv = xr[(u * VEC + i + M * r) % WREG];
+#pragma unroll
+                for (int p = 0; p < NF; ++p) acc[r][p] = fma(xv, cv[p][i], acc[r][p]);
+            }
+        vec_unpack(*reinterpret_cast<const double2*>(xt + (it + NCH) * VEC), xr + (u % NCH) * VEC);
+    };
+    int it0 = 0;
+    for (; it0 + NCH <= n_iter; it0 += NCH) {
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) step(u, it0 + u);
+    }
+#pragma unroll
+    for (int u = 0; u < NCH; ++u)
+        if (it0 + u < n_iter) step(u, it0 + u);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < NF; ++p) res[r][p] = acc[r][p];
+}
+
 __device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, const double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1)

@@ -64,6 +64,7 @@ int Engine::upload_bank(int stage, int which, const std::vector<double>& v, std:
         if (which == 0 && chain_.stages[(size_t)stage].kind != STAGE_POLY) d.bank_h32 = std::move(f);
     } else {
         if (!cuda_ok(cudaMemcpy(d.bank[which], v.data(), bytes, cudaMemcpyHostToDevice), err, "bank upload")) return 4;
+        if (which == 0 && chain_.stages[(size_t)stage].kind != STAGE_POLY) d.bank_h64 = v;
     }
     return 0;
 }
@@ -684,6 +685,7 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                 f.hist_u_out = (char*)du.hist[op.parity_in ^ 1] + (size_t)row0 * (size_t)du.hist_cap * esz_;
                 f.hist_u_out_stride = du.hist_cap; f.drop_u = (int32_t)op.drop; f.new_hu = (int32_t)op.new_hist_len;
                 f.bank_u = du.bank[0]; f.t1 = su.taps; f.np = (int32_t)(op.n_out / 2);
+                f.bank_u_host = du.bank_h64.empty() ? nullptr : du.bank_h64.data();
                 f.hist_p = (const char*)dpv.hist[nx.parity_in] + (size_t)row0 * (size_t)dpv.hist_cap * esz_;
                 f.hist_p_stride = dpv.hist_cap; f.hp = (int32_t)nx.hist_len;
                 f.hist_p_out = (char*)dpv.hist[nx.parity_in ^ 1] + (size_t)row0 * (size_t)dpv.hist_cap * esz_;
@@ -730,6 +732,7 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                 c.drop = (int32_t)op.drop; c.new_hist_len = (int32_t)op.new_hist_len;
                 c.bank = dv.bank[0];
                 c.bank_host_f32 = dv.bank_h32.empty() ? nullptr : dv.bank_h32.data();
+                c.bank_host_f64 = dv.bank_h64.empty() ? nullptr : dv.bank_h64.data();
                 c.taps = sd.taps;
                 if (sd.kind == STAGE_UP) {
                     c.stride = 1; c.nf = sd.factor; c.first = 0; c.n_pos = (int32_t)(op.n_out / sd.factor);

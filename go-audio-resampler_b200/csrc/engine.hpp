@@ -66,6 +66,7 @@ struct Plan {
 
 struct StageDev {
     void* bank[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<double> bank_h64;  // float64 engines, FIR stages: host copy of bank[0] as uploaded (kernel-parameter taps)
     std::vector<float> bank_h32;  // float32 engines, FIR stages: host copy of bank[0] as uploaded (kernel-parameter taps)
     void* bank_il = nullptr;  // POLY stages with a fractional step: a,b,c,d interleaved per tap [L][taps][4] (K4s)
     void* hist[2] = {nullptr, nullptr};

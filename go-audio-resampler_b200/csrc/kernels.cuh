@@ -26,6 +26,7 @@ struct FirCall {
     const void* bank;     // device, [nf][taps]
     const float* bank_host_f32;  // optional host copy of a float32 bank: float32 decimators pass their taps as KERNEL
                                  // PARAMETERS (constant bank) so that the FMAs take them from uniform registers
+    const double* bank_host_f64; // the same for float64 banks (vector-FMA FIR stages)
     int32_t taps;         int32_t stride;       int32_t nf;
     int32_t first;        int32_t n_pos;
     int32_t n_streams;    // rows processed by this launch (row r of every pointer = base + r*stride)
@@ -57,6 +58,7 @@ struct FusedCall {
     void* hist_u_out;     int64_t hist_u_out_stride;
     int32_t drop_u;       int32_t new_hu;
     const void* bank_u;   int32_t t1;              int32_t np;       // positions; 2*np intermediate samples
+    const double* bank_u_host;  // optional host copy of a float64 x2 bank: passed as kernel parameters (uniform-register taps)
     // polyphase stage
     const void* hist_p;   int64_t hist_p_stride;   int32_t hp;
     void* hist_p_out;     int64_t hist_p_out_stride;

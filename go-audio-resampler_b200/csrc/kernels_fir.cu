@@ -20,7 +20,8 @@ namespace {
 template <typename T, int M, int NF, int R, int NT>
 __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const int n_tiles, const int tiles_per_block,
                                                        const int n_groups, const int cp /*padded taps*/,
-                                                       const int xlen) {
+                                                       const int xlen, const int uc_a /*>= 0: taps from PU, pad = uc_a*/,
+                                                       const __grid_constant__ FirTapsD<(sizeof(T) == 8 ? NF : 1), (sizeof(T) == 8 ? FIR_TAPS_CPD : 2)> PU) {
     using V = typename VecOf<T>::type;
     constexpr int VEC = VecOf<T>::N;
     constexpr int TJ = NT * R;
@@ -51,8 +52,11 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
     const int nt = min(tiles_per_block, n_tiles - t_first);
 
     // leading pad so that every tile's bulk source address is 16-byte aligned (constant along the row)
-    const int a = (int)(((reinterpret_cast<uintptr_t>(in) / sizeof(T)) + (uintptr_t)(int64_t)(c.first - c.hist_len)) &
-                        (uintptr_t)(VEC - 1));
+    // (uc_a >= 0: the pad is the same for every row and comes in as a kernel parameter, which keeps the constant-bank tap
+    //  addressing of fir_tile_accumulate_uc provably warp-uniform)
+    const int a = uc_a >= 0 ? uc_a
+                            : (int)(((reinterpret_cast<uintptr_t>(in) / sizeof(T)) + (uintptr_t)(int64_t)(c.first - c.hist_len)) &
+                                    (uintptr_t)(VEC - 1));
     auto tile_geom = [&](const int t, int& g0a, int& words, bool& bulk) {
         const int j0 = t * TJ;
         const int tj = min(TJ, c.n_pos - j0);
@@ -112,7 +116,12 @@ __global__ void __launch_bounds__(NT) fir_tiled_kernel(const FirCall c, const in
 
         // ---- register-tiled sliding-window FIR ----
         T res[R][NF];
-        fir_tile_accumulate<T, M, NF, R>(xs + M * R * tid, cs, cp, c.taps, a, res);
+        if constexpr (sizeof(T) == 8) {
+            if (uc_a >= 0) fir_tile_accumulate_uc<M, NF, R>(xs + M * R * tid, PU, c.taps, a, res);
+            else fir_tile_accumulate<T, M, NF, R>(xs + M * R * tid, cs, cp, c.taps, a, res);
+        } else {
+            fir_tile_accumulate<T, M, NF, R>(xs + M * R * tid, cs, cp, c.taps, a, res);
+        }
 
         // ---- interleaved, vectorised store: out[(j*NF + p)] ----
         const int jb = t * TJ + R * tid;
@@ -1013,7 +1022,16 @@ void launch_fir_tiled(const FirCall& c, cudaStream_t s) {
         configured[dev & 63] = smem;
     }
     const int64_t blocks = (int64_t)(n_groups + 1) * c.n_streams;
-    launch_pdl(k, (unsigned)blocks, (unsigned)NT, smem, s, c, n_tiles, tpb, n_groups, cp, xlen);
+    // float64: taps as kernel parameters (uniform-register DFMA operands) when they fit and every row has the same pad
+    FirTapsD<(sizeof(T) == 8 ? NF : 1), (sizeof(T) == 8 ? FIR_TAPS_CPD : 2)> PU;
+    int uc_a = -1;
+    if constexpr (sizeof(T) == 8) {
+        if ((c.in_stride & 1) == 0 && fill_fir_taps(PU, c.bank_host_f64, NF, c.taps))
+            uc_a = (int)(((reinterpret_cast<uintptr_t>(c.in) / sizeof(T)) + (uintptr_t)(int64_t)(c.first - c.hist_len)) & 1u);
+    } else {
+        PU.c[0][0] = PU.c[0][1] = 0.0;
+    }
+    launch_pdl(k, (unsigned)blocks, (unsigned)NT, smem, s, c, n_tiles, tpb, n_groups, cp, xlen, uc_a, PU);
     count_launch();
 }
 

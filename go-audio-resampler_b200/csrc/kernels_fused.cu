@@ -899,6 +899,8 @@ __global__ void __launch_bounds__(512, 1) fused_up2_rat_kernel(const FusedCall c
         if (task < n_tasks) {
             const int woff = tg_woff[k];  // w of the first sample of the tile's first position
             T res[R][NF];
+            // (the constant-bank / uniform-register form of the core, fir_tile_accumulate_uc, needs warp-convergent code:
+            //  inside this work-queue loop ptxas keeps the taps in vector registers and nothing is gained — measured)
             fir_tile_accumulate<T, 1, NF, R>(xs + R * task, cs, g.cp, c.t1, 0, res);
             int w = woff + 2 * R * task;
             int j = (w + Mi) / Mi - 1, r = w - j * Mi;  // floor division (w >= -Mi)

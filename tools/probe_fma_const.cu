@@ -60,13 +60,13 @@ int main() {
 #define RUN(KERN, FL, label) { KERN<<<blocks, 128>>>((decltype(KERN == nullptr, (u64*)0))out, iters / 4, (const u64*)in, P); }
     k<0><<<blocks, 128>>>((u64*)out, iters / 4, (const u64*)in, P); cudaDeviceSynchronize();
     cudaEventRecord(a); k<0><<<blocks, 128>>>((u64*)out, iters, (const u64*)in, P); cudaEventRecord(b); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
-    printf("  FFMA2, coefficients via shared memory -> registers     %6.1f TFLOP/s\n", 2.0 * 96.0 * iters * blocks * 128.0 / (ms * 1e-3) / 1e12);
+    printf("  FFMA2, coefficients via shared memory -> registers     %6.1f TFLOP/s\n", 96.0 * iters * blocks * 128.0 / (ms * 1e-3) / 1e12);
     k<1><<<blocks, 128>>>((u64*)out, iters / 4, (const u64*)in, P); cudaDeviceSynchronize();
     cudaEventRecord(a); k<1><<<blocks, 128>>>((u64*)out, iters, (const u64*)in, P); cudaEventRecord(b); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
-    printf("  FFMA2, coefficients from the parameter (constant) bank %6.1f TFLOP/s\n", 2.0 * 96.0 * iters * blocks * 128.0 / (ms * 1e-3) / 1e12);
+    printf("  FFMA2, coefficients from the parameter (constant) bank %6.1f TFLOP/s\n", 96.0 * iters * blocks * 128.0 / (ms * 1e-3) / 1e12);
     ks<0><<<blocks, 128>>>((float*)out, iters / 4, (const float*)in, P); cudaDeviceSynchronize();
     cudaEventRecord(a); ks<0><<<blocks, 128>>>((float*)out, iters, (const float*)in, P); cudaEventRecord(b); cudaEventSynchronize(b); cudaEventElapsedTime(&ms, a, b);
-    printf("  scalar FFMA, coefficients from the constant bank        %6.1f TFLOP/s\n", 2.0 * 96.0 * iters * blocks * 128.0 / (ms * 1e-3) / 1e12);
+    printf("  scalar FFMA, coefficients from the constant bank        %6.1f TFLOP/s\n", 96.0 * iters * blocks * 128.0 / (ms * 1e-3) / 1e12);
     printf("status: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
