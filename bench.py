@@ -471,10 +471,10 @@ def main():
     value = out_per_rank * world / (ms_step_max * 1e-3) / 1e6
 
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this very workload
-    # (profiles/r1_traffic.json); null when the launch shape differs (other --streams/--seconds/--gpus)
+    # (profiles/r2_traffic.json); null when the launch shape differs (other --streams/--seconds/--gpus)
     traffic = None
     try:
-        tj = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+        tj = json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())
         if tj.get("algorithmic_bytes_per_launch") == rows * (n_in + n1) * 4 and tj.get("kernel") == kname:
             traffic = {"bytes_per_launch": tj["traffic_bytes_per_launch"],
                        "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"],
