@@ -23,6 +23,7 @@ Engine::~Engine() {
         if (d.bank_il) cudaFree(d.bank_il);
         for (auto& h : d.hist) if (h) cudaFree(h);
         if (d.rat_cache.dev) cudaFree(d.rat_cache.dev);
+        if (d.chain_ws.dev) cudaFree(d.chain_ws.dev);
     }
     for (void* b : ibuf_) if (b) cudaFree(b);
     if (zeros_) cudaFree(zeros_);
@@ -696,6 +697,12 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                 f.n_out = (int32_t)nx.n_out; f.interp = nx.interp ? 1 : 0;
                 f.out = optr; f.out_stride = ostride; f.n_streams = count;
                 f.in_f32 = f.out_f32 = io32 ? 1 : 0;
+                if (dtype_ == DT_F64 && !io32 && launch_chain_up2_poly(f, s, &dpv.chain_ws)) {
+                    note_kernel("chain_up2_poly_f64_mma");
+                    ++launches_;
+                    ++oi;
+                    continue;
+                }
                 if (const char* kn = launch_fused_up2_poly(f, dtype_, s, &dpv.rat_cache)) {
                     note_kernel(kn);
                     ++launches_;

@@ -73,6 +73,7 @@ struct StageDev {
     int64_t hist_cap = 0;
     const char* kernel = "";
     RatCache rat_cache;  // POLY stages: coefficient tiles of the fused rational-ratio kernel
+    ChainWs chain_ws;    // POLY stages: ring + counters of the persistent x2 -> polyphase chain kernel (K5)
 };
 
 class Engine {

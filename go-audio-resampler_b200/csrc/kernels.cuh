@@ -86,6 +86,13 @@ struct RatCache {
     std::vector<uint8_t> built; // [L]
 };
 
+// Per polyphase stage, device workspace of the persistent chain kernel K5 (kernels_chain.cu): the L2-resident ring of
+// intermediate-rate samples and the work-queue / completion counters. Owned by the engine, grown on demand.
+struct ChainWs {
+    void* dev = nullptr;
+    size_t bytes = 0;
+};
+
 // cubic.go:33-90 — indices/phases precomputed on the host by the exact float64 recurrence
 struct CubicCall {
     const void* hist;     int64_t hist_stride;                         // 3 previous samples (zeros at start)
@@ -110,6 +117,12 @@ const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* 
 const char* launch_cubic(const CubicCall& c, int dtype, cudaStream_t s);
 // returns nullptr when the pair cannot be fused (caller falls back to the two stand-alone launches)
 const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s, RatCache* cache);
+// K5: the x2 stage and the polyphase stage of a large lock-step batch as ONE persistent launch (intermediate samples in an
+// L2-resident ring); false when the call is outside its domain (the caller runs the two stand-alone launches)
+bool launch_chain_up2_poly(const FusedCall& c, cudaStream_t s, ChainWs* ws);
+// process-wide A/B switch for K5; on by default
+void set_chain_kernel(bool on);
+bool chain_kernel_enabled();
 // carry only (a call that produced no output but appended to the tail)
 void launch_carry(const void* hist, int64_t hist_stride, int32_t hist_len, const void* in, int64_t in_stride,
                   int32_t n_in, void* hist_out, int64_t hist_out_stride, int32_t drop, int32_t new_len,

@@ -135,6 +135,7 @@ SYMBOLS = {
     "gar_set_tiled_polyphase": (None, [_i32]),
     "gar_set_slice_budget": (_i32, [_vp, _i64]),
     "gar_set_tensor_fir": (None, [_i32]),
+    "gar_set_chain_kernel": (None, [_i32]),
     "gar_measure_fma_peak": (_i32, [_i32, _i32, C.POINTER(C.c_double)]),
     "gar_version": (C.c_char_p, []),
 }
@@ -629,6 +630,11 @@ def set_tiled_polyphase(enabled: bool):
 def set_tensor_fir(enabled: bool):
     """Process-wide A/B switch for the FP64 tensor-core (DMMA) FIR kernels."""
     lib().gar_set_tensor_fir(1 if enabled else 0)
+
+
+def set_chain_kernel(enabled: bool):
+    """Process-wide A/B switch for the persistent x2 -> polyphase chain kernel (K5) of large float64 batches."""
+    lib().gar_set_chain_kernel(1 if enabled else 0)
 
 
 def kernel_launches(reset=False):

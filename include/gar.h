@@ -254,6 +254,10 @@ void gar_set_tiled_polyphase(int32_t enabled);
 /* Process-wide A/B switch: 0 routes the float64 integer-factor FIR stages of >= 8-row batches through the vector-FMA
  * kernels instead of the FP64 tensor-core (DMMA) kernels. The two differ in the last bits (taps grouped in fours). Default 1. */
 void gar_set_tensor_fir(int32_t enabled);
+/* Process-wide A/B switch: 0 runs the x2 -> polyphase chain of large float64 batches (>= 32 lock-step rows) as the two
+ * stand-alone tensor-core launches with a full-size intermediate buffer instead of the persistent chain kernel (one launch per
+ * Process, intermediate-rate samples in an L2-resident ring; resampler.go:182-227). Results are bit-identical. Default 1. */
+void gar_set_chain_kernel(int32_t enabled);
 /* Number of this library's kernels launched through the handle since creation / last reset of the counter. */
 int64_t gar_kernel_launches(const gar_handle* h, int32_t reset);
 /* Name of the dominant kernel variant chosen for stage `stage` (for bench/ncu filters). */
