@@ -24,7 +24,7 @@ def _run(ir, orr, x, cuts, chain):
 
 
 @pytest.mark.parametrize("ir,orr,rows,n,cuts", [
-    (44100, 48000, 256, 60000, None),               # rational 147/80, 16-row stages, ring wraps ~3 times
+    (44100, 48000, 256, 100000, None),              # rational 147/80, 16-row stages, ring wraps ~3 times
     (44100, 47999, 40, 150000, None),               # cubic coefficient interpolation live
     (48000, 44100, 70, 120000, None),               # 2.18 samples per output; ragged last groups (70 = 8*8 + 6 = 2*32 + 6)
     (44100, 48000, 64, 200001, [0, 90001, 200001]), # two large calls: the second starts from carried tails and a non-zero phase
