@@ -539,7 +539,7 @@ int32_t gar_set_slice_budget(gar_handle* h, int64_t bytes) {
 
 void gar_set_tiled_polyphase(int32_t enabled) { gar::set_tiled_polyphase(enabled != 0); }
 void gar_set_tensor_fir(int32_t enabled) { gar::set_tensor_fir(enabled != 0); }
-void gar_set_chain_kernel(int32_t enabled) { gar::set_chain_kernel(enabled != 0); }
+void gar_set_chain_kernel(int32_t mode) { gar::set_chain_kernel(mode); }
 
 int64_t gar_kernel_launches(const gar_handle* h, int32_t reset) {
     (void)h;  // process-wide counter: every <<<>>> of this library

@@ -578,6 +578,13 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
     // must advance through the same sequence of stage calls to stay in lock step (same tail ping-pong parity)
     const int64_t slice = flush || device_ < 0 ? 0 : slice_length(row0, rows_, n_in);
     if (slice <= 0) return run_once(row0, count, d_in, in_stride, n_in, d_out, out_stride, out_cap, flush, s, n_out, err);
+    // The call exceeds the inter-stage memory budget. A call over ALL rows of the handle whose x2 -> polyphase pair the
+    // persistent chain kernel (K5) takes needs no full-size intermediate buffer at all: one launch instead of time slices.
+    // (Row groups of a batch must make the same number of stage calls to stay in lock step, hence all rows or none.)
+    if (chain_kernel_mode() != 0 && fuse_ && count == rows_ && dtype_ == DT_F64) {
+        const int rc = run_once(row0, count, d_in, in_stride, n_in, d_out, out_stride, out_cap, false, s, n_out, err, false, true);
+        if (rc != -1) return rc;  // -1: K5 does not take it, nothing was touched
+    }
     {   // ErrBufferTooSmall is decided for the whole call, before any state changes (constant.go:107-109)
         StreamState st = streams_[(size_t)row0];
         Plan P;
@@ -602,7 +609,7 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
 }
 
 int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
-                     int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, bool io32) {
+                     int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, bool io32, bool chain_required) {
     if (count <= 0) return 0;
     if (device_ < 0) {
         err = "geometry-only handle (device = -1) cannot process samples; there is no CPU fallback";
@@ -626,6 +633,41 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
         err = "output too long";
         return 1;
     }
+    // x2 -> polyphase pairs of one engine that the persistent chain kernel (K5) takes: decided on the geometry alone, before the
+    // inter-stage buffers are sized — the pair's intermediate buffer is not needed then
+    auto up2_poly_pair = [&](size_t oi) -> bool {
+        if (!fuse_ || oi + 1 >= P.ops.size()) return false;
+        const Op &op = P.ops[oi], &nx = P.ops[oi + 1];
+        if (op.stage < 0 || nx.stage != op.stage + 1) return false;
+        const StageDesign& su = chain_.stages[(size_t)op.stage];
+        return su.kind == STAGE_UP && su.factor == 2 && op.n_out > 0 && chain_.stages[(size_t)nx.stage].kind == STAGE_POLY &&
+               nx.src_buf == op.dst_buf && op.dst_buf >= 0 && nx.n_in == op.n_out &&
+               chain_.stages[(size_t)nx.stage].engine_index == su.engine_index;
+    };
+    std::vector<char> use_chain(P.ops.size(), 0);
+    bool any_chain = false;
+    if (dtype_ == DT_F64 && !io32 && !flush && (chain_required || chain_kernel_mode() == 1)) {
+        for (size_t oi = 0; oi < P.ops.size(); ++oi) {
+            if (!up2_poly_pair(oi)) continue;
+            const Op &op = P.ops[oi], &nx = P.ops[oi + 1];
+            const StageDesign &su = chain_.stages[(size_t)op.stage], &spd = chain_.stages[(size_t)nx.stage];
+            FusedCall f{};
+            f.hu = (int32_t)op.hist_len; f.n_in = (int32_t)op.n_in; f.new_hu = (int32_t)op.new_hist_len;
+            f.t1 = su.taps; f.np = (int32_t)(op.n_out / 2);
+            f.hp = (int32_t)nx.hist_len; f.new_hp = (int32_t)nx.new_hist_len;
+            f.t2 = spd.taps; f.L = spd.factor; f.at0 = nx.first; f.step = spd.step;
+            f.n_out = (int32_t)nx.n_out; f.interp = nx.interp ? 1 : 0; f.n_streams = count;
+            if (launch_chain_up2_poly(f, s, nullptr, true)) {
+                use_chain[oi] = 1;
+                any_chain = true;
+                bool shared = false;  // (the buffer between the two stages has no other user inside a Process call)
+                for (size_t k = 0; k < P.ops.size(); ++k)
+                    if (k != oi && k != oi + 1 && (P.ops[k].dst_buf == op.dst_buf || P.ops[k].src_buf == op.dst_buf)) shared = true;
+                if (!shared) P.buf_need[(size_t)op.dst_buf] = 0;
+            }
+        }
+    }
+    if (chain_required && !any_chain) return -1;  // the caller falls back to time slices; nothing has been touched
     order_before(s);
     int rc = ensure_internal(P, s, err);
     if (rc) return rc;
@@ -697,7 +739,14 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                 f.n_out = (int32_t)nx.n_out; f.interp = nx.interp ? 1 : 0;
                 f.out = optr; f.out_stride = ostride; f.n_streams = count;
                 f.in_f32 = f.out_f32 = io32 ? 1 : 0;
-                if (dtype_ == DT_F64 && !io32 && launch_chain_up2_poly(f, s, &dpv.chain_ws)) {
+                if (use_chain[oi]) {
+                    const size_t ws_before = dpv.chain_ws.bytes;
+                    const bool ok = launch_chain_up2_poly(f, s, &dpv.chain_ws);
+                    device_bytes_ += (int64_t)dpv.chain_ws.bytes - (int64_t)ws_before;
+                    if (!ok) {
+                        err = "chain kernel: workspace allocation failed";
+                        return 4;
+                    }
                     note_kernel("chain_up2_poly_f64_mma");
                     ++launches_;
                     ++oi;

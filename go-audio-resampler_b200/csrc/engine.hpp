@@ -172,7 +172,8 @@ class Engine {
     // instead of 5: every slice pays a launch ramp and tail), and those chains are FMA-bound, not HBM-bound.
     int64_t slice_budget_ = 2ll << 30;
     int run_once(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
-                 int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, bool io32 = false);
+                 int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, bool io32 = false,
+                 bool chain_required = false);  // chain_required: K5 or nothing (-1: not taken, nothing touched)
     std::vector<const char*> kernels_used_;
     void note_kernel(const char* name);
     int64_t device_bytes_ = 0;

@@ -119,10 +119,12 @@ const char* launch_cubic(const CubicCall& c, int dtype, cudaStream_t s);
 const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s, RatCache* cache);
 // K5: the x2 stage and the polyphase stage of a large lock-step batch as ONE persistent launch (intermediate samples in an
 // L2-resident ring); false when the call is outside its domain (the caller runs the two stand-alone launches)
-bool launch_chain_up2_poly(const FusedCall& c, cudaStream_t s, ChainWs* ws);
-// process-wide A/B switch for K5; on by default
-void set_chain_kernel(bool on);
-bool chain_kernel_enabled();
+// dry: eligibility only (geometry; no allocation, no launch)
+bool launch_chain_up2_poly(const FusedCall& c, cudaStream_t s, ChainWs* ws, bool dry = false);
+// process-wide policy for K5: 0 never, 1 every eligible call, 2 (default) eligible calls whose full-size intermediate buffer
+// would exceed the engine's inter-stage memory budget
+void set_chain_kernel(int mode);
+int chain_kernel_mode();
 // carry only (a call that produced no output but appended to the tail)
 void launch_carry(const void* hist, int64_t hist_stride, int32_t hist_len, const void* in, int64_t in_stride,
                   int32_t n_in, void* hist_out, int64_t hist_out_stride, int32_t drop, int32_t new_len,

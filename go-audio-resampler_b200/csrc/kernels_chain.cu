@@ -72,6 +72,13 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
     return v;
 }
 __device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// TMA bulk copy with an L2 evict-first policy: the input rows stream through L2 once, the ring should stay
+__device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void red_release_gpu(int* p, const int v) {
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -101,6 +108,7 @@ __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu
     uint64_t* dfull = sempty + 4;                                   // [CH_ND] descriptor published
     uint64_t* dempty = dfull + CH_ND;                               // [CH_ND] descriptor read (8 MMA warps)
     ChainDesc* desc = reinterpret_cast<ChainDesc*>(smem_raw + 128); // [CH_ND]
+    int* icnt = &desc[0].pad[0];                                    // desc[ds].pad[0]: MMA warps that have finished items of slot ds
     double* Bs = reinterpret_cast<double*>(smem_raw + 256);         // [2][blen] zero-padded x2 bank, staged once per block
     double* stg = Bs + 2 * g.blen;                                  // [NST][stage_elems]: x2 windows [8][pitch_u] | polyphase [RB][pitch_p]
 
@@ -125,6 +133,7 @@ __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu
         for (int b = 0; b < CH_ND; ++b) {
             mbar_init(dfull + b, 1);
             mbar_init(dempty + b, NTASK);
+            desc[b].pad[0] = 0;
         }
     }
     __syncthreads();
@@ -174,6 +183,8 @@ __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu
     if (warp == NTASK) {
         // =========================================== scheduler / producer warp ===========================================
         uint32_t st = 0u, dk = 0u;
+        uint64_t pol_stream;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
         int u_ok = -1, p_ok = -1;  // every x2 / polyphase chunk up to here is known to be finished
         const int n_u_items = g.n_carry_items + g.NC * g.items_u_chunk;  // x2 queue: carried tails, then the chunks in order
         const int n_p_items = g.NC * g.items_p_chunk + g.n_carry_items;  // polyphase queue: the chunks in order, then the tails
@@ -299,9 +310,9 @@ __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu
                         }
                         __syncwarp();
                         if (lane < 8)
-                            bulk_g2s(xs + lane * g.pitch_u,
-                                     static_cast<const double*>(cu.in) + (int64_t)(sbase + lane) * cu.in_stride + ((int64_t)jb0 - cu.hist_len - a),
-                                     (uint32_t)(wlen * sizeof(double)), sfull + buf);
+                            bulk_g2s_stream(xs + lane * g.pitch_u,
+                                            static_cast<const double*>(cu.in) + (int64_t)(sbase + lane) * cu.in_stride + ((int64_t)jb0 - cu.hist_len - a),
+                                            (uint32_t)(wlen * sizeof(double)), sfull + buf, pol_stream);
                     } else {  // edge tile (the carried tail, the end of the rows, a ragged last row group): element copies
                         for (int r = 0; r < 8; ++r) {
                             double* __restrict__ dst = xs + r * g.pitch_u;
@@ -394,9 +405,17 @@ __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu
     // =================================================== MMA warps ===================================================
     uint32_t st = 0u;
     const int ctid = tid;  // 0 .. 255
-    auto item_done = [&](int* counter) {  // this warp's stores of the item are visible before the count
+    // The item is counted once, by the LAST of the 8 MMA warps to finish it: the others synchronise with it at block scope
+    // (acq_rel shared-memory atomic), its red.release at gpu scope is cumulative over their stores. One MEMBAR.GPU per item
+    // instead of eight (they had the MMA warps stalled ~5 % of the time). The slot counters are never reset: use m of a slot
+    // (descriptor number dk = m * CH_ND + slot) ends when its counter reaches 8 * (m + 1).
+    auto item_done = [&](int* counter, const int ds, const uint32_t dk) {
         __syncwarp();
-        if (lane == 0) red_release_gpu(counter, 1);  // release at gpu scope, cumulative over the warp's stores
+        if (lane == 0) {
+            int prev;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], 1;" : "=r"(prev) : "r"(smem_u32(icnt + ds * (int)(sizeof(ChainDesc) / 4))) : "memory");
+            if (prev == (int)(NTASK * (dk / CH_ND + 1u)) - 1 && counter) red_release_gpu(counter, NTASK);
+        }
     };
     for (uint32_t dk = 0u;; ++dk) {
         const int ds = (int)(dk % CH_ND);
@@ -414,6 +433,7 @@ __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu
                 double* __restrict__ ho = static_cast<double*>(cu.hist_out) + (int64_t)r * cu.hist_out_stride;
                 for (int i = ctid; i < cu.new_hist_len; i += 256) ho[i] = vload(hist, cu.hist_len, in, cu.n_in, cu.drop + i);
             }
+            item_done(nullptr, ds, dk);
             continue;
         }
         if (kind == 4) {
@@ -430,6 +450,7 @@ __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu
                     ho[i] = x;
                 }
             }
+            item_done(nullptr, ds, dk);
             continue;
         }
         if (kind == 1) {
@@ -480,7 +501,7 @@ __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu
                     }
                 }
             }
-            item_done(udone + c);  // (the generic -> async proxy fence for the TMA reads of the ring sits on the reader's side)
+            item_done(udone + c, ds, dk);  // (the generic -> async proxy fence for the TMA reads of the ring sits on the reader's side)
             continue;
         }
         // =============================== polyphase item: task = 8 outputs nf .. nf+7 ===============================
@@ -527,21 +548,22 @@ __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu
 #pragma unroll
                         for (int t = 0; t < NT8; ++t) {
                             const int64_t s0 = (int64_t)row0 + t * 8 + 2 * (lane & 3);
-                            if (s0 < cp.n_streams) (static_cast<double*>(cp.out) + s0 * cp.out_stride)[nf + i] = acc[t][0];
-                            if (s0 + 1 < cp.n_streams) (static_cast<double*>(cp.out) + (s0 + 1) * cp.out_stride)[nf + i] = acc[t][1];
+                            // streaming stores: the outputs should not push the ring out of L2
+                            if (s0 < cp.n_streams) __stcs(static_cast<double*>(cp.out) + s0 * cp.out_stride + (nf + i), acc[t][0]);
+                            if (s0 + 1 < cp.n_streams) __stcs(static_cast<double*>(cp.out) + (s0 + 1) * cp.out_stride + (nf + i), acc[t][1]);
                         }
                     }
                 } else {
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sempty + buf)) : "memory");
                 }
             }
-            item_done(pdone + c);  // the stages of this item have been read: its ring samples may be overwritten
+            item_done(pdone + c, ds, dk);  // the stages of this item have been read: its ring samples may be overwritten
         }
     }
 }
 
 template <int NK, int RB, int NST>
-bool launch_chain_t(const FusedCall& c, cudaStream_t s, ChainWs* wsp, const int variant) {
+bool launch_chain_t(const FusedCall& c, cudaStream_t s, ChainWs* wsp, const int variant, const bool dry) {
     const double r = (double)c.step / ((double)c.L * 65536.0);
     ChainGeom g{};
     // ---- polyphase geometry: K3p's (launch_poly_rows_pipe_t) ----
@@ -622,6 +644,7 @@ bool launch_chain_t(const FusedCall& c, cudaStream_t s, ChainWs* wsp, const int 
     g.carry_rows = 8;
     g.n_carry_items = (c.n_streams + g.carry_rows - 1) / g.carry_rows;
 
+    if (dry) return true;  // geometry only: the engine asks before it sizes its inter-stage buffers
     // ---- workspace: counters + ring (rows 16-byte aligned) ----
     const size_t cnt_bytes = (((size_t)(WS_HDR + 2 * g.NC) * 4) + 255) & ~(size_t)255;
     const int64_t ring_stride = ((int64_t)g.RS + g.H + 1) & ~int64_t(1);
@@ -678,24 +701,26 @@ bool launch_chain_t(const FusedCall& c, cudaStream_t s, ChainWs* wsp, const int 
 
 }  // namespace
 
-static bool g_chain = [] {
-    const char* e = gar::tune_env("GAR_NO_CHAIN");
-    return !(e && e[0] && e[0] != '0');
+// 0: never, 1: every eligible call, 2 (default): eligible calls whose full-size intermediate buffer would exceed the engine's
+// inter-stage memory budget (the engine decides; see Engine::run)
+static int g_chain_mode = [] {
+    const char* e = gar::tune_env("GAR_CHAIN_MODE");
+    return e ? std::atoi(e) : 2;
 }();
-void set_chain_kernel(bool on) { g_chain = on; }
-bool chain_kernel_enabled() { return g_chain; }
+void set_chain_kernel(int mode) { g_chain_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
+int chain_kernel_mode() { return g_chain_mode; }
 
 // K5 dispatch: float64 batches of at least 32 lock-step rows whose x2 and polyphase stages both run on the tensor cores
-// (the K1m / K3p domain), calls long enough for a few ring cycles
-bool launch_chain_up2_poly(const FusedCall& c, cudaStream_t s, ChainWs* ws) {
-    if (!g_chain || !ws || !tensor_fir_enabled() || !tiled_polyphase_enabled()) return false;
+// (the K1m / K3p domain), calls long enough for a few ring cycles. dry: eligibility only (no allocation, no launch).
+bool launch_chain_up2_poly(const FusedCall& c, cudaStream_t s, ChainWs* ws, bool dry) {
+    if (g_chain_mode == 0 || (!ws && !dry) || !tensor_fir_enabled() || !tiled_polyphase_enabled()) return false;
     if (c.in_f32 || c.out_f32 || c.n_streams < 32 || c.t1 < 16 || c.np <= 0 || c.n_out <= 0) return false;
     if ((int64_t)c.np * c.n_streams < (1 << 21) || c.L > 4096 || c.t2 > 1024) return false;
     if (2 * (int64_t)c.np > 0x7ffffff0LL) return false;
     const double r = (double)c.step / ((double)c.L * 65536.0);
     if (!(r > 0.0) || r > 8.0) return false;
     // coefficient registers for K <= 80 or <= 112; three stages of 16 rows (one stage also holds an 8-row x2 window)
-    return launch_chain_t<20, 16, 3>(c, s, ws, 0) || launch_chain_t<28, 16, 3>(c, s, ws, 1);
+    return launch_chain_t<20, 16, 3>(c, s, ws, 0, dry) || launch_chain_t<28, 16, 3>(c, s, ws, 1, dry);
 }
 
 }  // namespace gar

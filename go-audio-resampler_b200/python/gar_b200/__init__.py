@@ -632,9 +632,10 @@ def set_tensor_fir(enabled: bool):
     lib().gar_set_tensor_fir(1 if enabled else 0)
 
 
-def set_chain_kernel(enabled: bool):
-    """Process-wide A/B switch for the persistent x2 -> polyphase chain kernel (K5) of large float64 batches."""
-    lib().gar_set_chain_kernel(1 if enabled else 0)
+def set_chain_kernel(mode):
+    """Process-wide policy for the persistent x2 -> polyphase chain kernel (K5) of large float64 batches:
+    0 / False never, 1 / True every eligible call, 2 (default) calls that exceed the inter-stage memory budget."""
+    lib().gar_set_chain_kernel(int(mode))
 
 
 def kernel_launches(reset=False):

@@ -1,32 +1,45 @@
 """K5 — the persistent x2 -> polyphase chain kernel (kernels_chain.cu): one launch per Process for large float64 batches, the
-intermediate-rate samples in an L2-resident ring. Same MMA cores as the two stand-alone launches (K1m + K3p): every sample
-must be bit-identical to them, and within 1e-12 of the oracle's restatement of resampler.go:182-227 / polyphase_stage.go:186-312."""
+intermediate-rate samples in an L2-resident ring instead of a full-size device buffer. Same MMA cores as the two stand-alone
+launches (K1m + K3p): every sample must be bit-identical to them, and within 1e-12 of the oracle's restatement of
+resampler.go:182-227 / polyphase_stage.go:186-312. Calls go through the C ABI's device entry points (gar_process_batch_dev)."""
 import numpy as np
 import pytest
+import torch
 
 from helpers import G, O
 
 pytestmark = pytest.mark.gpu
 
 
-def _run(ir, orr, x, cuts, chain):
-    G.set_chain_kernel(chain)
+def _run(ir, orr, x, cuts, mode, budget=None):
+    """Process the column ranges `cuts` of x as successive batch calls on device buffers, then Flush."""
+    G.set_chain_kernel(mode)
     try:
-        h = G.NewBatch(ir, orr, G.QualityHigh, x.shape[0], np.float64)
-        ys, ks = [], []
+        dev = torch.device("cuda", 0)
+        rows = x.shape[0]
+        h = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float64)
+        if budget is not None:
+            h.set_slice_budget(budget)
+        G.kernel_launches(reset=True)
+        ys = []
         for lo, hi in zip(cuts[:-1], cuts[1:]):
-            ys.append(h.ProcessBatch(np.ascontiguousarray(x[:, lo:hi]))[0].copy())
-            ks.append(h.last_kernels())
+            dx = torch.from_numpy(np.ascontiguousarray(x[:, lo:hi])).to(dev)
+            n = hi - lo
+            cap = (h.EstimateOutput(n) + 64 + 3) & ~3
+            dy = torch.zeros((rows, cap), dtype=torch.float64, device=dev)
+            k = h.process_batch_dev(dx.data_ptr(), n, n, dy.data_ptr(), cap, cap, 0, np.float64)
+            torch.cuda.synchronize()
+            ys.append(dy[:, :k].cpu().numpy())
         ys.append(h.FlushBatch()[0].copy())
-        return np.concatenate(ys, axis=1), h.last_kernels(), G.kernel_launches()
+        return np.concatenate(ys, axis=1), h.last_kernels(), G.kernel_launches(), h
     finally:
-        G.set_chain_kernel(True)
+        G.set_chain_kernel(2)
 
 
 @pytest.mark.parametrize("ir,orr,rows,n,cuts", [
-    (44100, 48000, 256, 100000, None),              # rational 147/80, 16-row stages, ring wraps ~3 times
-    (44100, 47999, 40, 150000, None),               # cubic coefficient interpolation live
-    (48000, 44100, 70, 120000, None),               # 2.18 samples per output; ragged last groups (70 = 8*8 + 6 = 2*32 + 6)
+    (44100, 48000, 256, 60000, None),               # rational 147/80; the ring wraps several times
+    (44100, 47999, 40, 150000, None),               # cubic coefficient interpolation live; 40 rows = 2 full 16-row stages + 8
+    (48000, 44100, 70, 120000, None),               # 2.18 samples per output; ragged last groups (70 = 8*8 + 6 = 4*16 + 6)
     (44100, 48000, 64, 200001, [0, 90001, 200001]), # two large calls: the second starts from carried tails and a non-zero phase
     (44100, 48000, 33, 260000, [0, 1000, 260000]),  # a small call (stand-alone kernels) in front of a chain call
 ])
@@ -34,10 +47,8 @@ def test_chain_kernel_bit_identical_to_stand_alone_launches_and_oracle(ir, orr, 
     rng = np.random.default_rng(5)
     x = 0.5 * rng.standard_normal((rows, n))
     cuts = cuts or [0, n]
-    G.kernel_launches(reset=True)
-    ya, ka, la = _run(ir, orr, x, cuts, True)
-    G.kernel_launches(reset=True)
-    yb, kb, lb = _run(ir, orr, x, cuts, False)
+    ya, ka, la, _ = _run(ir, orr, x, cuts, 1)
+    yb, kb, lb, _ = _run(ir, orr, x, cuts, 0)
     assert "chain_up2_poly_f64_mma" in ka, ka
     assert "chain_up2_poly_f64_mma" not in kb and "fir_f64_mma_up2" in kb, kb
     assert la < lb, (la, lb)  # one launch instead of two per large Process call
@@ -56,7 +67,27 @@ def test_chain_kernel_keeps_streaming_state():
     rows, n = 48, 140000
     x = 0.5 * rng.standard_normal((rows, n))
     cuts = [0, 120000, 120300, 125000, n]
-    ya, ka, _ = _run(44100, 48000, x, cuts, True)
-    yb, _, _ = _run(44100, 48000, x, cuts, False)
+    ya, ka, _, _ = _run(44100, 48000, x, cuts, 1)
+    yb, _, _, _ = _run(44100, 48000, x, cuts, 0)
     assert "chain_up2_poly_f64_mma" in ka, ka
     assert np.array_equal(ya, yb)
+
+
+def test_chain_kernel_replaces_time_slices_above_the_memory_budget():
+    """Default policy (mode 2): a call over all rows whose intermediate buffer would exceed the inter-stage budget runs as ONE
+    chain launch without that buffer instead of a sequence of time slices; below the budget the two stand-alone launches
+    stay. Identical samples either way."""
+    rng = np.random.default_rng(7)
+    rows, n = 64, 200000
+    x = 0.5 * rng.standard_normal((rows, n))
+    budget = 64 << 20                                  # the intermediate buffer would be 64 x 400k x 8 = 205 MB
+    ya, ka, la, ha = _run(44100, 48000, x, [0, n], 2, budget)
+    yb, kb, lb, hb = _run(44100, 48000, x, [0, n], 0, budget)   # time slices
+    yc, kc, _, hc = _run(44100, 48000, x, [0, n], 2)            # default budget (2 GiB): not exceeded
+    assert "chain_up2_poly_f64_mma" in ka, ka
+    assert "chain_up2_poly_f64_mma" not in kb and "chain_up2_poly_f64_mma" not in kc, (kb, kc)
+    assert la < lb, (la, lb)
+    assert np.array_equal(ya, yb) and np.array_equal(ya, yc)
+    # no full-size intermediate buffer (205 MB here): the ring and its counters instead (<= 45 MB)
+    ma, mc = ha.GetInfo()["MemoryUsage"], hc.GetInfo()["MemoryUsage"]
+    assert ma + (150 << 20) < mc, (ma, mc)
