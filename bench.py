@@ -339,7 +339,19 @@ def extra_f64(dev, local, tstream):
     x256 = np.tile(x1[None, :], (256, 1))
     out["c1_chain_x256_streams_10s_f64"] = dict(
         timed(G.NewBatch(44100, 48000, G.QualityHigh, 256, np.float64), x256, 738.0, host=False),
-        workload="BASELINE config 1's chain (44.1k->48k QualityHigh float64) x 256 lock-step streams x 10 s")
+        workload="BASELINE config 1's chain (44.1k->48k QualityHigh float64) x 256 lock-step streams x 10 s; default path: "
+                 "two tensor-core launches (K1m + K3p), full-size intermediate buffer")
+    # the same call through the persistent chain kernel K5: one launch per Process, intermediate samples in an L2-resident
+    # ring (no 1.8 GB buffer); DRAM traffic of both paths measured with ncu: profiles/r2_chain_traffic.txt
+    G.set_chain_kernel(1)
+    try:
+        k5 = timed(G.NewBatch(44100, 48000, G.QualityHigh, 256, np.float64), x256, 738.0, host=False)
+    finally:
+        G.set_chain_kernel(2)
+    out["c1_chain_x256_streams_10s_f64_k5"] = dict(
+        k5, workload="the same call with gar_set_chain_kernel(1): ONE persistent launch per Process (chain_up2_poly_f64_mma)",
+        dram_bytes_per_pass_ncu={"k5": 2.17e9, "two_launches": 5.53e9, "algorithmic": 1.886e9,
+                                 "source": "profiles/r2_chain_traffic.txt"})
     del x256
     # C3: 8 channels 96k -> 48k VeryHigh (1223-tap /2)
     rng = np.random.default_rng(4242)
