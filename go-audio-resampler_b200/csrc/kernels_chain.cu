@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu
                 }
                 // nothing is ready: other blocks are working on the items this one waits for
                 __nanosleep(100);
-                if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a scheduling bug must not hang the device
+                if (clock64() - t0 > 20000000000ll) __trap();  // ~10 s: a scheduling bug must not hang the device
             }
             if (kind == 0) {
                 publish(0, 0, 0, 0, 0);
