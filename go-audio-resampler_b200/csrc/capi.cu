@@ -843,7 +843,13 @@ static int batch_dev(gar_handle* h, int io_dtype, const void* d_in, int64_t in_s
             rc = E.run(row0 + r, run, ip, in_stride, flush ? 0 : n_in, op, out_stride, out_cap, flush, s, &got, h->err);
         } else if (io_dtype == GAR_F32 && !flush && E.io32_foldable(row0 + r, n_in, flush)) {
             // streaming-size fused launch: float32 samples converted on load / store, no cast launches
-            rc = E.run(row0 + r, run, ip, in_stride, n_in, op, out_stride, out_cap, flush, s, &got, h->err, true);
+            rc = E.run(row0 + r, run, ip, in_stride, n_in, op, out_stride, out_cap, flush, s, &got, h->err, 1);
+        } else if (io_dtype == GAR_F32 && !flush && E.pair32_foldable(row0 + r, run, n_in, in_stride)) {
+            // large batched x2 -> polyphase call on the tensor cores: K1m widens the float32 windows in shared memory, K3p narrows
+            // on the store — no cast launches, no float64 copies of the input and the output in HBM
+            const int64_t want = gar_next_output_count(h, row0 + r, n_in);
+            if (want > out_cap) return fail(h, GAR_BUFFER_TOO_SMALL, "output buffer too small");
+            rc = E.run(row0 + r, run, ip, in_stride, n_in, op, out_stride, out_cap, flush, s, &got, h->err, 2);
         } else {
             // I/O dtype differs from the compute dtype (path A with float32 I/O): cast through scratch
             const int64_t want = flush ? gar_next_flush_count(h, row0 + r) : gar_next_output_count(h, row0 + r, n_in);

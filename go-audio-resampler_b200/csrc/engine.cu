@@ -571,9 +571,30 @@ bool Engine::io32_foldable(int row0, int64_t n_in, bool flush) const {
            sp.taps <= 200 && b.hist_len <= 1024;
 }
 
+bool Engine::pair32_foldable(int row0, int count, int64_t n_in, int64_t in_stride) const {
+    if (device_ < 0 || dtype_ != DT_F64 || !fuse_ || n_in <= 32768 || count < 32 || (in_stride & 3) != 0) return false;
+    if (slice_length(row0, rows_, n_in) > 0) return false;  // time-sliced calls keep the cast launches
+    StreamState st = streams_[(size_t)row0];
+    Plan P;
+    plan(st, n_in, false, P);
+    if (P.ops.size() != 2) return false;
+    const Op &a = P.ops[0], &b = P.ops[1];
+    if (a.stage < 0 || b.stage != a.stage + 1 || a.src_buf != BUF_EXT_IN || b.dst_buf != BUF_OUT || b.src_buf != a.dst_buf ||
+        a.dst_buf < 0 || a.n_out <= 0 || b.n_out <= 0 || b.n_in != a.n_out || b.dst_off != 0)
+        return false;
+    const StageDesign &su = chain_.stages[(size_t)a.stage], &sp = chain_.stages[(size_t)b.stage];
+    if (!(su.kind == STAGE_UP && su.factor == 2 && sp.kind == STAGE_POLY && sp.engine_index == su.engine_index)) return false;
+    FirCall fc{};
+    fc.taps = su.taps; fc.stride = 1; fc.nf = 2; fc.n_pos = (int32_t)(a.n_out / 2); fc.n_streams = count; fc.in_stride = in_stride;
+    PolyCall pc{};
+    pc.taps = sp.taps; pc.L = sp.factor; pc.at0 = b.first; pc.step = sp.step; pc.n_out = (int32_t)b.n_out;
+    pc.interp = b.interp ? 1 : 0; pc.n_streams = count;
+    return fir_mma_up2_in32_takes(fc) && poly_rows_pipe_out32_takes(pc);
+}
+
 int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
-                int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, bool io32) {
-    if (io32) return run_once(row0, count, d_in, in_stride, n_in, d_out, out_stride, out_cap, flush, s, n_out, err, true);
+                int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, int io32) {
+    if (io32) return run_once(row0, count, d_in, in_stride, n_in, d_out, out_stride, out_cap, flush, s, n_out, err, io32);
     // the slice length is derived from ALL rows of the handle, not from this call's row range: row groups of one batch call
     // must advance through the same sequence of stage calls to stay in lock step (same tail ping-pong parity)
     const int64_t slice = flush || device_ < 0 ? 0 : slice_length(row0, rows_, n_in);
@@ -609,7 +630,7 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
 }
 
 int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
-                     int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, bool io32, bool chain_required) {
+                     int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, int io32, bool chain_required) {
     if (count <= 0) return 0;
     if (device_ < 0) {
         err = "geometry-only handle (device = -1) cannot process samples; there is no CPU fallback";
@@ -710,7 +731,7 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
         void* dp = dst_ptr(op, dstride);
         // K4: an x2 stage whose whole output is consumed by the polyphase stage of the same engine runs as
         // ONE fused launch; the intermediate-rate samples never reach HBM.
-        if (fuse_ && op.stage >= 0 && oi + 1 < P.ops.size()) {
+        if (fuse_ && io32 != 2 && op.stage >= 0 && oi + 1 < P.ops.size()) {
             const Op& nx = P.ops[oi + 1];
             const StageDesign& su = chain_.stages[(size_t)op.stage];
             if (nx.stage == op.stage + 1 && su.kind == STAGE_UP && su.factor == 2 && op.n_out > 0 &&
@@ -738,7 +759,7 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                 f.t2 = spd.taps; f.L = spd.factor; f.at0 = nx.first; f.step = spd.step;
                 f.n_out = (int32_t)nx.n_out; f.interp = nx.interp ? 1 : 0;
                 f.out = optr; f.out_stride = ostride; f.n_streams = count;
-                f.in_f32 = f.out_f32 = io32 ? 1 : 0;
+                f.in_f32 = f.out_f32 = io32 == 1 ? 1 : 0;
                 if (use_chain[oi]) {
                     const size_t ws_before = dpv.chain_ws.bytes;
                     const bool ok = launch_chain_up2_poly(f, s, &dpv.chain_ws);
@@ -764,7 +785,7 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                 }
             }
         }
-        if (io32) {
+        if (io32 == 1) {
             err = "internal: float32 I/O folding needs the fused x2 -> polyphase launch";
             return 5;
         }
@@ -796,7 +817,13 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                     c.stride = sd.factor; c.nf = 1; c.first = (int32_t)op.first; c.n_pos = (int32_t)op.n_out;
                 }
                 c.n_streams = count;
-                note_kernel(launch_fir(c, dtype_, s));
+                c.in_f32 = io32 == 2 && op.src_buf == BUF_EXT_IN ? 1 : 0;
+                const char* kn = launch_fir(c, dtype_, s);
+                if (!kn) {
+                    err = "internal: float32 input was folded into a call the x2 tensor-core kernel did not take";
+                    return 5;
+                }
+                note_kernel(kn);
                 break;
             }
             case STAGE_POLY: {
@@ -810,7 +837,13 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                 c.taps = sd.taps; c.L = sd.factor; c.at0 = op.first; c.step = sd.step;
                 c.n_out = (int32_t)op.n_out; c.interp = op.interp ? 1 : 0;
                 c.n_streams = count;
-                note_kernel(launch_poly(c, dtype_, s, &dv.rat_cache));
+                c.out_f32 = io32 == 2 && op.dst_buf == BUF_OUT ? 1 : 0;
+                const char* kn = launch_poly(c, dtype_, s, &dv.rat_cache);
+                if (!kn) {
+                    err = "internal: float32 output was folded into a call the pipelined polyphase kernel did not take";
+                    return 5;
+                }
+                note_kernel(kn);
                 break;
             }
             case STAGE_CUBIC: {

@@ -110,10 +110,13 @@ class Engine {
     // io32: d_in / d_out hold float32 samples although the engine computes in float64 (strides in float32 elements); only
     // valid when io32_foldable() said so — the single fused launch converts on load / store (no cast launches).
     int run(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
-            int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, bool io32 = false);
+            int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, int io32 = 0);
     // A Process call of n_in samples on rows in row0's state is ONE fused x2 -> polyphase launch of streaming size, which can
     // take float32 input / output directly (constant.go:161-199 ProcessFloat32Into without the two cast passes).
     bool io32_foldable(int row0, int64_t n_in, bool flush) const;
+    // io32 = 2: a large batched call that runs as the two tensor-core launches K1m (x2 stage) + K3p (polyphase stage) can take
+    // float32 input / output as well: K1m widens its sample windows in shared memory, K3p narrows on the store
+    bool pair32_foldable(int row0, int count, int64_t n_in, int64_t in_stride) const;
     // Time slicing of multi-stage calls: a Process call whose inter-stage buffers would exceed `bytes` is run as a
     // sequence of shorter Process calls (identical samples and counts: every stage is greedy), so that the intermediate-rate
     // buffers stay small (and, with an L2-sized budget, the intermediate-rate streams stay L2-resident). 0 disables.
@@ -172,7 +175,7 @@ class Engine {
     // instead of 5: every slice pays a launch ramp and tail), and those chains are FMA-bound, not HBM-bound.
     int64_t slice_budget_ = 2ll << 30;
     int run_once(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
-                 int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, bool io32 = false,
+                 int64_t out_cap, bool flush, cudaStream_t s, int64_t* n_out, std::string& err, int io32 = 0,
                  bool chain_required = false);  // chain_required: K5 or nothing (-1: not taken, nothing touched)
     std::vector<const char*> kernels_used_;
     void note_kernel(const char* name);

@@ -30,6 +30,7 @@ struct FirCall {
     int32_t taps;         int32_t stride;       int32_t nf;
     int32_t first;        int32_t n_pos;
     int32_t n_streams;    // rows processed by this launch (row r of every pointer = base + r*stride)
+    int32_t in_f32;       // `in` holds float32 samples (in_stride in float32 elements); only the x2 tensor-core kernel (K1m) takes it
 };
 
 // out[n] = sum_k v[div_n + k] * (a + x(b + x(c + x d)))[phase_n][k]   (polyphase_stage.go:186-312)
@@ -45,6 +46,7 @@ struct PolyCall {
     int64_t at0;          int64_t step;
     int32_t n_out;        int32_t interp;       // interp: (step & 0xFFFF) != 0 || (at0 & 0xFFFF) != 0
     int32_t n_streams;
+    int32_t out_f32;      // `out` holds float32 samples (out_stride in float32 elements); only the pipelined tensor-core kernel (K3p) takes it
 };
 
 // K4: x2 up-sampler fused with the polyphase stage that follows it inside one engine.Resampler
@@ -125,6 +127,10 @@ bool launch_chain_up2_poly(const FusedCall& c, cudaStream_t s, ChainWs* ws, bool
 // would exceed the engine's inter-stage memory budget
 void set_chain_kernel(int mode);
 int chain_kernel_mode();
+// float32 I/O folded into the two tensor-core launches of a batched x2 -> polyphase chain: will launch_fir / launch_poly take the
+// call with in_f32 / out_f32 set? (the engine asks before it decides against the cast launches)
+bool fir_mma_up2_in32_takes(const FirCall& c);
+bool poly_rows_pipe_out32_takes(const PolyCall& c);
 // carry only (a call that produced no output but appended to the tail)
 void launch_carry(const void* hist, int64_t hist_stride, int32_t hist_len, const void* in, int64_t in_stride,
                   int32_t n_in, void* hist_out, int64_t hist_out_stride, int32_t drop, int32_t new_len,

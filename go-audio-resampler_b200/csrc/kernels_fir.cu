@@ -166,7 +166,10 @@ struct MmaGeom {
     int32_t nkc, nqc;       // window chunks per tile along the taps (long filters), k-steps per chunk (multiple of the A window)
 };
 
-template <int M, int NF, int NW, int MT, bool KC>
+// IN32: `in` holds float32 samples (float64 pipelines behind the float32 API, constant.go:161-199; float32 engines computing in
+// float64): the window is bulk-copied as float32 into the upper half of its row buffer and widened in place by all threads
+// (read - barrier - write), so the stand-alone cast launch and its 12 bytes per sample of HBM traffic disappear.
+template <int M, int NF, int NW, int MT, bool KC, bool IN32 = false>
 __global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : (NW == 8 ? 2 : 1)) fir_mma_f64_kernel(const FirCall c, const MmaGeom g) {
     constexpr int JT = 8 / NF;                // positions per MMA tile
     static_assert(8 % NF == 0 && (JT * M) % 4 == 0, "tile shift must be a whole number of k-steps");
@@ -188,6 +191,18 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : (NW 
     const int n_work = g.n_sg * g.n_groups;
     if ((int)blockIdx.x >= n_work) {  // carried tail of one row
         const int64_t row = (int)blockIdx.x - n_work;
+        if (IN32) {
+            const double* __restrict__ hist = static_cast<const double*>(c.hist) + row * c.hist_stride;
+            const float* __restrict__ in32 = static_cast<const float*>(c.in) + row * c.in_stride;
+            double* __restrict__ ho = static_cast<double*>(c.hist_out) + row * c.hist_out_stride;
+            block_copy4(c.new_hist_len,
+                        [&](int i) {
+                            const int v = c.drop + i;
+                            return v < c.hist_len ? hist[v] : (v - c.hist_len < c.n_in ? (double)in32[v - c.hist_len] : 0.0);
+                        },
+                        [&](int i, double v) { ho[i] = v; });
+            return;
+        }
         carry_row(static_cast<const double*>(c.hist) + row * c.hist_stride, c.hist_len,
                   static_cast<const double*>(c.in) + row * c.in_stride, c.n_in,
                   static_cast<double*>(c.hist_out) + row * c.hist_out_stride, c.drop, c.new_hist_len);
@@ -214,7 +229,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : (NW 
     uint32_t ph0 = 0u, ph1 = 0u;
     // TMA bulk copies need 16-byte aligned sources: all 8 columns share the alignment when the row stride and the segment
     // length in samples are even
-    const bool rows_bulk = (c.in_stride & 1) == 0 && (((int64_t)g.ps * M) & 1) == 0 && sbase + 8 <= g.nvs;
+    constexpr int AL = IN32 ? 4 : 2;  // samples per 16 bytes of the source
+    const bool rows_bulk = (c.in_stride & (AL - 1)) == 0 && (((int64_t)g.ps * M) & (AL - 1)) == 0 && sbase + 8 <= g.nvs;
     const int xbuf = 8 * g.pitch;
     // column r of the block: row, first position of its segment — fixed for the block, tabulated once (no divisions per tile)
     __shared__ int s_col_row[8], s_col_pos0[8];
@@ -230,7 +246,8 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : (NW 
         pos0_min = min(pos0_min, s_col_pos0[r]);
         pos0_max = max(pos0_max, s_col_pos0[r]);
     }
-    const double* __restrict__ col0_in = static_cast<const double*>(c.in) + col_row(0) * c.in_stride + col_pos0(0) * M;
+    const size_t isz = IN32 ? sizeof(float) : sizeof(double);
+    const char* __restrict__ col0_in = static_cast<const char*>(c.in) + (col_row(0) * c.in_stride + col_pos0(0) * M) * isz;
 
     // geometry of iteration `it` = (local tile kt, tap chunk kc): segment-local first position jb0, first k-step qa of the
     // chunk, staged length (from window sample 4*qa on), bulk-copy parameters
@@ -249,9 +266,9 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : (NW 
         const int64_t g0 = (int64_t)c.first + (int64_t)jb0 * M - c.hist_len + 4 * qa;
         const int64_t gmin = g0 + (int64_t)pos0_min * M, gmax = g0 + (int64_t)pos0_max * M;
         if (gmin < 0) return false;
-        const double* src0 = col0_in + g0;
-        a = (int)((reinterpret_cast<uintptr_t>(src0) & 15u) >> 3);  // start `a` samples early: aligned sources
-        wlen = (len + a + 1) & ~1;
+        const char* src0 = col0_in + g0 * (int64_t)isz;
+        a = (int)((reinterpret_cast<uintptr_t>(src0) & 15u) / isz);  // start `a` samples early: aligned sources
+        wlen = (len + a + AL - 1) & ~(AL - 1);
         if (gmin - a >= 0 && gmax - a + wlen <= c.n_in && wlen <= g.pitch) return true;
         a = 0;  // element copies start exactly at the window
         return false;
@@ -260,11 +277,13 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : (NW 
         int jb0, qa, len, a, wlen;
         if (!tile_geom(it, jb0, qa, len, a, wlen)) return;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar + buf, (uint32_t)(8 * wlen * sizeof(double)));
+        mbar_expect_tx(bar + buf, (uint32_t)(8 * wlen * isz));
         for (int r = 0; r < 8; ++r) {
             const int64_t gi = (int64_t)c.first + (col_pos0(r) + jb0) * M - c.hist_len + 4 * qa - a;
-            bulk_g2s(Xs0 + buf * xbuf + r * g.pitch, static_cast<const double*>(c.in) + col_row(r) * c.in_stride + gi,
-                     (uint32_t)(wlen * sizeof(double)), bar + buf);
+            // float32 windows land in the upper half of the row buffer (float index pitch ..), widened in place after the wait
+            void* dst = IN32 ? static_cast<void*>(reinterpret_cast<float*>(Xs0 + buf * xbuf + r * g.pitch) + g.pitch)
+                             : static_cast<void*>(Xs0 + buf * xbuf + r * g.pitch);
+            bulk_g2s(dst, static_cast<const char*>(c.in) + (col_row(r) * c.in_stride + gi) * (int64_t)isz, (uint32_t)(wlen * isz), bar + buf);
         }
     };
 
@@ -292,6 +311,31 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : (NW 
             }
             if (buf) ph1 ^= 1u;
             else ph0 ^= 1u;
+            if (IN32) {  // widen the 8 float32 windows in place: every thread reads its share, barrier, writes
+                constexpr int PER = 16;  // elements per thread and round (8 * wlen <= 8 * pitch; two rounds cover any window)
+                const int tot = 8 * wlen;
+                for (int base = 0; base < tot; base += NT * PER) {
+                    float v[PER];
+#pragma unroll
+                    for (int u = 0; u < PER; ++u) {
+                        const int e = base + u * NT + tid;
+                        if (e < tot) {
+                            const int r = e / wlen, i = e - r * wlen;
+                            v[u] = reinterpret_cast<const float*>(Xs + r * g.pitch)[g.pitch + i];
+                        }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int u = 0; u < PER; ++u) {
+                        const int e = base + u * NT + tid;
+                        if (e < tot) {
+                            const int r = e / wlen, i = e - r * wlen;
+                            Xs[r * g.pitch + i] = (double)v[u];
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
         } else {  // edge tile (a column touches the carried tail or the end of its row): element copies
             for (int r = warp; r < 8; r += NW) {
                 double* __restrict__ dst = Xs + r * g.pitch;
@@ -304,10 +348,16 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : (NW 
                 const int i1 = (int)min((int64_t)len, max((int64_t)0, (int64_t)c.hist_len - v0));
                 const int i2 = (int)min((int64_t)len, max((int64_t)i1, total - v0));
                 const double* __restrict__ hsrc = static_cast<const double*>(c.hist) + row * c.hist_stride + v0;
-                const double* __restrict__ isrc = static_cast<const double*>(c.in) + row * c.in_stride + (v0 - c.hist_len);
                 for (int i = lane; i < i1; i += 32) dst[i] = hsrc[i];
+                if (IN32) {
+                    const float* __restrict__ isrc32 = static_cast<const float*>(c.in) + row * c.in_stride + (v0 - c.hist_len);
 #pragma unroll 4
-                for (int i = i1 + lane; i < i2; i += 32) cp_async_elem(dst + i, isrc + i);
+                    for (int i = i1 + lane; i < i2; i += 32) dst[i] = (double)isrc32[i];
+                } else {
+                    const double* __restrict__ isrc = static_cast<const double*>(c.in) + row * c.in_stride + (v0 - c.hist_len);
+#pragma unroll 4
+                    for (int i = i1 + lane; i < i2; i += 32) cp_async_elem(dst + i, isrc + i);
+                }
                 for (int i = i2 + lane; i < len; i += 32) dst[i] = 0.0;
             }
             cp_async_wait_all();
@@ -445,7 +495,7 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
         tpb = std::max<int64_t>(1, std::min<int64_t>(tpb, 8));
         g.tiles_per_block = (int32_t)std::min<int64_t>(tpb, g.n_tiles);
         g.n_groups = (g.n_tiles + g.tiles_per_block - 1) / g.tiles_per_block;
-        static size_t configured[64][4] = {{0}};
+        static size_t configured[64][6] = {{0}};
         size_t& conf = configured[dev & 63][slot];
         if (smem > conf) {
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -463,6 +513,11 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
     // GAR_MMA_CFG = 1 / 3 forces 16 / 8 warps with the whole window, GAR_MMA_NKC = n the chunk count.
     static const int forced = [] { const char* e = gar::tune_env("GAR_MMA_CFG"); return e ? std::atoi(e) : -1; }();
     static const int nkc_env = [] { const char* e = gar::tune_env("GAR_MMA_NKC"); return e ? std::atoi(e) : 0; }();
+    if constexpr (M == 1 && NF == 2) {
+        if (c.in_f32) return c.taps <= 600 && run(fir_mma_f64_kernel<M, NF, 8, 4, false, true>, 8, 4, 4, 1, 0);
+    } else {
+        if (c.in_f32) return false;
+    }
     if (forced == 1) return run(fir_mma_f64_kernel<M, NF, 16, 4, false>, 16, 4, 1, 1, 0);
     if (forced == 3) return run(fir_mma_f64_kernel<M, NF, 8, 4, false>, 8, 4, 3, 1, 0);
     if (c.taps > 600) {
@@ -1170,6 +1225,12 @@ const char* fir_variant_name(int dtype, int stride, int nf, int taps, int64_t n_
     return dtype == DT_F32 ? "fir_f32_generic" : "fir_f64_generic";
 }
 
+// float32 input folded into the x2 tensor-core kernel: the conditions under which launch_fir takes it (those of launch_fir_mma)
+bool fir_mma_up2_in32_takes(const FirCall& c) {
+    return g_fir_mma && c.n_streams >= 8 && (int64_t)c.n_pos * c.n_streams >= 32768 && c.taps >= 16 && c.taps <= 600 &&
+           c.stride == 1 && c.nf == 2 && (c.in_stride & 3) == 0;
+}
+
 const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s) {
     if (c.n_streams <= 0) return "none";
     if (c.n_pos <= 0) {
@@ -1179,6 +1240,7 @@ const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s) {
     }
     if (dtype == DT_F64)
         if (const char* nm = launch_fir_mma(c, s)) return nm;
+    if (c.in_f32) return nullptr;  // only the x2 tensor-core kernel widens float32 input (the engine asked fir_mma_up2_in32_takes first)
 #define X(M, NF, R, NAME)                                       \
     if (dtype == DT_F32 && c.stride == M && c.nf == NF) {       \
         launch_fir_f32x2<M, NF, R>(c, s);                       \

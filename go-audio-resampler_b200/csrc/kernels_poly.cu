@@ -576,11 +576,20 @@ __global__ void __launch_bounds__(288, 2) poly_rows_pipe_kernel(const PolyCall c
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + buf)) : "memory");
             if (live) {
+                if (c.out_f32) {  // float32(v) on the way out (constant.go:195-197): no cast launch behind this one
 #pragma unroll
-                for (int t = 0; t < NT8; ++t) {
-                    const int64_t s0 = (int64_t)row0 + t * 8 + 2 * (lane & 3);
-                    if (s0 < c.n_streams) (static_cast<double*>(c.out) + s0 * c.out_stride)[nf + i] = acc[t][0];
-                    if (s0 + 1 < c.n_streams) (static_cast<double*>(c.out) + (s0 + 1) * c.out_stride)[nf + i] = acc[t][1];
+                    for (int t = 0; t < NT8; ++t) {
+                        const int64_t s0 = (int64_t)row0 + t * 8 + 2 * (lane & 3);
+                        if (s0 < c.n_streams) (static_cast<float*>(c.out) + s0 * c.out_stride)[nf + i] = (float)acc[t][0];
+                        if (s0 + 1 < c.n_streams) (static_cast<float*>(c.out) + (s0 + 1) * c.out_stride)[nf + i] = (float)acc[t][1];
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < NT8; ++t) {
+                        const int64_t s0 = (int64_t)row0 + t * 8 + 2 * (lane & 3);
+                        if (s0 < c.n_streams) (static_cast<double*>(c.out) + s0 * c.out_stride)[nf + i] = acc[t][0];
+                        if (s0 + 1 < c.n_streams) (static_cast<double*>(c.out) + (s0 + 1) * c.out_stride)[nf + i] = acc[t][1];
+                    }
                 }
             }
         } else {
@@ -590,7 +599,7 @@ __global__ void __launch_bounds__(288, 2) poly_rows_pipe_kernel(const PolyCall c
 }
 
 template <int NK, int RB, int NST>
-static bool launch_poly_rows_pipe_t(const PolyCall& c, cudaStream_t s) {
+static bool launch_poly_rows_pipe_t(const PolyCall& c, cudaStream_t s, const bool dry = false) {
     constexpr int TO = 64;
     const double r = (double)c.step / ((double)c.L * 65536.0);
     RowsMmaGeom g{};
@@ -608,6 +617,7 @@ static bool launch_poly_rows_pipe_t(const PolyCall& c, cudaStream_t s) {
     g.nbuf = NST;
     const size_t smem = 64 + (size_t)NST * RB * g.pitch * sizeof(double);
     if (smem > 113 * 1024) return false;  // two blocks per SM
+    if (dry) return true;
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -622,12 +632,12 @@ static bool launch_poly_rows_pipe_t(const PolyCall& c, cudaStream_t s) {
 }
 
 // K3p variants: coefficient registers for K <= 80 or <= 112, 2 stages of 32 rows or (long spans) 3 stages of 16 rows
-static bool launch_poly_rows_pipe(const PolyCall& c, cudaStream_t s) {
+static bool launch_poly_rows_pipe(const PolyCall& c, cudaStream_t s, const bool dry = false) {
     static const int rb16_rows = [] { const char* e = gar::tune_env("GAR_K3P_RB16_ROWS"); return e ? std::atoi(e) : 0; }();
     // fewer rows: 16-row stages keep the pipeline at least two stages deep
-    if (c.n_streams < rb16_rows && (launch_poly_rows_pipe_t<20, 16, 3>(c, s) || launch_poly_rows_pipe_t<28, 16, 3>(c, s))) return true;
-    return launch_poly_rows_pipe_t<20, 32, 2>(c, s) || launch_poly_rows_pipe_t<20, 16, 3>(c, s) ||
-           launch_poly_rows_pipe_t<28, 32, 2>(c, s) || launch_poly_rows_pipe_t<28, 16, 3>(c, s);
+    if (c.n_streams < rb16_rows && (launch_poly_rows_pipe_t<20, 16, 3>(c, s, dry) || launch_poly_rows_pipe_t<28, 16, 3>(c, s, dry))) return true;
+    return launch_poly_rows_pipe_t<20, 32, 2>(c, s, dry) || launch_poly_rows_pipe_t<20, 16, 3>(c, s, dry) ||
+           launch_poly_rows_pipe_t<28, 32, 2>(c, s, dry) || launch_poly_rows_pipe_t<28, 16, 3>(c, s, dry);
 }
 
 template <int NTASK>
@@ -666,8 +676,8 @@ static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s) {
     return true;
 }
 
-// 0: not taken, 1: K3m, 2: K3p
-static int launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
+// 0: not taken, 1: K3m, 2: K3p. dry: eligibility only (no launch); K3m is then reported as not taken.
+static int launch_poly_rows_mma(const PolyCall& c, cudaStream_t s, const bool dry = false) {
     if (!tensor_fir_enabled() || c.n_streams < 8 || (int64_t)c.n_out * c.n_streams < 16384 || c.L > 4096 || c.taps > 1024) return 0;
     const double r = (double)c.step / ((double)c.L * 65536.0);
     if (!(r > 0.0) || r > 8.0) return 0;
@@ -675,7 +685,8 @@ static int launch_poly_rows_mma(const PolyCall& c, cudaStream_t s) {
     static const bool pipe = [] { const char* e = gar::tune_env("GAR_K3M_PIPE"); return !e || e[0] != '0'; }();
     static const int pipe_rows = [] { const char* e = gar::tune_env("GAR_K3M_PIPE_ROWS"); return e ? std::atoi(e) : 32; }();
     // measured (44.1k->48k, 21 M samples): K3p against K3m 32 rows 20.9 / 19.9, 48 rows 21.8 / 20.4 TFLOP/s, equal below
-    if (pipe && c.n_streams >= pipe_rows && launch_poly_rows_pipe(c, s)) return 2;
+    if (pipe && c.n_streams >= pipe_rows && launch_poly_rows_pipe(c, s, dry)) return 2;
+    if (dry || c.out_f32) return 0;  // only K3p narrows to float32 on the way out
     if (ntask == 4) return (launch_poly_rows_mma_t<4>(c, s) || launch_poly_rows_mma_t<8>(c, s)) ? 1 : 0;
     return (launch_poly_rows_mma_t<8>(c, s) || launch_poly_rows_mma_t<4>(c, s)) ? 1 : 0;
 }
@@ -792,6 +803,10 @@ __global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_
 
 }  // namespace
 
+bool poly_rows_pipe_out32_takes(const PolyCall& c) {
+    return c.n_out > 0 && tiled_polyphase_enabled() && launch_poly_rows_mma(c, nullptr, true) == 2;
+}
+
 const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* cache) {
     if (c.n_streams <= 0) return "none";
     if (c.n_out <= 0) {
@@ -805,6 +820,7 @@ const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* 
         if (k == 2) return c.interp ? "poly_rows_mma_f64_interp_pipe" : "poly_rows_mma_f64_pipe";
         if (k == 1) return c.interp ? "poly_rows_mma_f64_interp" : "poly_rows_mma_f64";
     }
+    if (c.out_f32) return nullptr;  // (the engine asked poly_rows_pipe_out32_takes first)
     // Batches of >= 8 rows with an even period length run K3i rather than K3r: K3r then stages its padded periods with
     // element copies from one warp (measured on the batched 48k->44.1k chain: 0.63 ms against 0.78 ms)
     if (dtype == DT_F64 && tiled_polyphase_enabled() && !c.interp && c.n_streams >= 8 && ((c.step >> 16) & 1) == 0 &&

@@ -91,3 +91,52 @@ def test_chain_kernel_replaces_time_slices_above_the_memory_budget():
     # no full-size intermediate buffer (205 MB here): the ring and its counters instead (<= 45 MB)
     ma, mc = ha.GetInfo()["MemoryUsage"], hc.GetInfo()["MemoryUsage"]
     assert ma + (150 << 20) < mc, (ma, mc)
+
+
+@pytest.mark.parametrize("ir,orr,rows,n,make", [
+    (48000, 44100, 64, 90000, "pipeline"),    # BASELINE config 2's shape: float64 pipeline behind the float32 API
+    (44100, 48000, 40, 120001, "engine32"),   # NewEngineFloat32 at a non-integer ratio (float64 tensor-core arithmetic inside)
+    (44100, 47999, 33, 100000, "pipeline"),   # interpolated coefficients, ragged row groups
+])
+def test_float32_io_folded_into_the_tensor_core_pair_equals_the_cast_launches(ir, orr, rows, n, make):
+    """Large float32-I/O batches on float64 arithmetic: K1m widens its float32 sample windows in shared memory and K3p narrows on
+    the store (no cast launches, no float64 copies of input and output in HBM). Same samples as casting through scratch buffers
+    (gar_set_fusion(h, 0) keeps the casts), and within 1e-6 of the oracle."""
+    rng = np.random.default_rng(8)
+    x = (0.5 * rng.standard_normal((rows, n))).astype(np.float32)
+    dev = torch.device("cuda", 0)
+
+    def run(fold):
+        if make == "pipeline":
+            h = G.Resampler(G.Config(InputRate=ir, OutputRate=orr, Channels=1, Quality=G.QualitySpec(Preset=G.QualityHigh)),
+                            n_streams=rows)
+        else:
+            h = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float32)
+        h.set_fusion(fold)
+        ys = []
+        for lo, hi in [(0, n // 2 + 3), (n // 2 + 3, n)]:
+            dx = torch.from_numpy(np.ascontiguousarray(x[:, lo:hi])).to(dev)
+            m = hi - lo
+            istride = (m + 3) & ~3
+            dxp = torch.zeros((rows, istride), dtype=torch.float32, device=dev)
+            dxp[:, :m] = dx
+            cap = (h.EstimateOutput(m) + 64 + 3) & ~3
+            dy = torch.zeros((rows, cap), dtype=torch.float32, device=dev)
+            G.kernel_launches(reset=True)
+            k = h.process_batch_dev(dxp.data_ptr(), istride, m, dy.data_ptr(), cap, cap, 0, np.float32)
+            torch.cuda.synchronize()
+            ys.append(dy[:, :k].cpu().numpy())
+        launches = G.kernel_launches()
+        ys.append(h.FlushBatch(io_dtype=np.float32)[0].copy() if make == "pipeline" else h.FlushBatch()[0].copy())
+        return np.concatenate(ys, axis=1), launches, h.last_kernels()
+
+    ya, la, ka = run(True)
+    yb, lb, kb = run(False)
+    assert la == 2 and lb == 4, (la, lb, ka, kb)  # x2 + polyphase against cast + x2 + polyphase + cast
+    assert ya.dtype == np.float32 and ya.shape == yb.shape
+    assert np.array_equal(ya, yb), float(np.max(np.abs(ya.astype(np.float64) - yb)))
+    if make == "pipeline":
+        p = O.Pipeline(ir, orr, 1, O.PRESET_HIGH)
+        want = np.concatenate([p.process(x[0].astype(np.float64)), p.flush()])
+        assert len(want) == ya.shape[1]
+        assert np.max(np.abs(ya[0].astype(np.float64) - want)) <= 1e-6
