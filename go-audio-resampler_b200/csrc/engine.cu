@@ -577,13 +577,17 @@ bool Engine::pair32_foldable(int row0, int count, int64_t n_in, int64_t in_strid
     StreamState st = streams_[(size_t)row0];
     Plan P;
     plan(st, n_in, false, P);
-    if (P.ops.size() != 2) return false;
-    const Op &a = P.ops[0], &b = P.ops[1];
-    if (a.stage < 0 || b.stage != a.stage + 1 || a.src_buf != BUF_EXT_IN || b.dst_buf != BUF_OUT || b.src_buf != a.dst_buf ||
-        a.dst_buf < 0 || a.n_out <= 0 || b.n_out <= 0 || b.n_in != a.n_out || b.dst_off != 0)
+    // the op that reads the caller's input is an x2 stage (K1m), the op that writes the caller's output a polyphase stage (K3p);
+    // whatever lies between (the further x2 stages of an 8k -> 192k pipeline) runs on float64 inter-stage buffers as ever
+    if (P.ops.size() < 2) return false;
+    const Op &a = P.ops.front(), &b = P.ops.back();
+    if (a.stage < 0 || b.stage < 0 || a.src_buf != BUF_EXT_IN || b.dst_buf != BUF_OUT || a.dst_buf < 0 || b.src_buf < 0 ||
+        a.n_out <= 0 || b.n_out <= 0 || b.dst_off != 0)
         return false;
+    for (size_t k = 1; k + 1 < P.ops.size(); ++k)
+        if (P.ops[k].stage < 0 || P.ops[k].src_buf == BUF_EXT_IN || P.ops[k].dst_buf == BUF_OUT || P.ops[k].n_out <= 0) return false;
     const StageDesign &su = chain_.stages[(size_t)a.stage], &sp = chain_.stages[(size_t)b.stage];
-    if (!(su.kind == STAGE_UP && su.factor == 2 && sp.kind == STAGE_POLY && sp.engine_index == su.engine_index)) return false;
+    if (!(su.kind == STAGE_UP && su.factor == 2 && sp.kind == STAGE_POLY)) return false;
     FirCall fc{};
     fc.taps = su.taps; fc.stride = 1; fc.nf = 2; fc.n_pos = (int32_t)(a.n_out / 2); fc.n_streams = count; fc.in_stride = in_stride;
     PolyCall pc{};
