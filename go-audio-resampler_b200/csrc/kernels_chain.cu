@@ -3,20 +3,25 @@
 // no full-size intermediate buffer exists: they live in a ring of R chunks per row (a few tens of MB for the whole batch)
 // that stays resident in the 126 MB L2.
 //
-//   * Work items of the two stages come from one ordered queue (an atomic counter):  slot s = the x2 items of chunk s
-//     (8 rows x a few 128-position MMA tiles each, the arithmetic of K1m), then the polyphase items of chunk s - D
-//     (64 outputs x up to 256 rows each, the arithmetic of K3p: register-resident coefficient matrices, TMA producer warp).
-//     Chunk c of the x2 stage = intermediate samples [c*S, (c+1)*S); chunk c of the polyphase stage = the 64-output tiles
-//     whose sample windows END inside chunk c.
-//   * A polyphase item waits until the x2 items of every chunk <= c have finished (per-chunk completion counters,
-//     red.release / ld.acquire at gpu scope); an x2 item of chunk c waits until the polyphase chunks that read the ring slot
-//     it overwrites (<= c-R+2) have finished. An item only ever waits for items EARLIER in the queue, and items are claimed in
-//     order by running blocks, so the schedule cannot deadlock whatever the number of co-resident blocks. The lag D and the
-//     ring depth R = 2D + 2 are sized so that a dependency is two waves of items old when it is checked: the waits are
-//     almost never taken.
+//   * Work items. x2 item = 8 rows x 1-2 MMA tiles of 128 positions (the arithmetic of K1m); polyphase item = one 64-output
+//     tile x up to 128 rows (the arithmetic of K3p: register-resident coefficient matrices). Chunk c of the x2 stage =
+//     intermediate samples [c*S, (c+1)*S); chunk c of the polyphase stage = the 64-output tiles whose sample windows END inside
+//     chunk c.
+//   * Dataflow schedule. A polyphase item is READY when the x2 items of every chunk <= c have finished; an x2 item may
+//     overwrite its ring slot when the polyphase chunks <= c-R+2 (the readers of that slot and of the mirror) have finished.
+//     Completion is counted per chunk in global memory: red.release.gpu by the last of the 8 MMA warps to finish an item,
+//     relaxed polls + one acquire fence on the reader's side. x2 items are claimed in order by fetch-and-add and stay
+//     PENDING in their block until their slot is free; polyphase items are owned statically (item i belongs to block
+//     i mod grid) and a block serves its own ready polyphase items first — they are what frees the ring — so the schedule
+//     cannot deadlock whatever the number of co-resident blocks (induction over the chunk index, R > 2). A bounded spin turns
+//     a scheduling bug into a launch error instead of a hung device.
 //   * A block is 8 MMA warps + 1 scheduler / producer warp that claims items, checks their dependencies and streams their
 //     sample windows into shared-memory stages by TMA ahead of the MMA warps, across item boundaries; two blocks share an
-//     SM, so the polyphase items' coefficient gathers hide under the other block's MMAs.
+//     SM. The scheduler claims LATE (at most one issued stage unread): whatever queues inside a block lengthens the life of
+//     its samples in the ring, and the ring has to hold (bytes per microsecond) x (microseconds from the x2 store to the last
+//     polyphase read) — Little's law is what bounds this kernel (profiles/r2_chain_k5.md).
+//   * Input windows are loaded with an L2 evict-first policy and outputs stored with streaming stores: what stays in L2 is
+//     the ring.
 //   * The first H samples of the ring are mirrored behind its end, so that a window that starts near the end of the ring is
 //     contiguous for the TMA bulk copy.
 // Results are bit-identical to the two stand-alone launches (same cores, mma_cores.cuh).
@@ -34,12 +39,11 @@ struct ChainGeom {
     int32_t S, R, RS, H;                  // chunk length, chunks in the ring, ring length R*S, mirrored head (samples)
     // polyphase stage: 8 warp tasks x 8 outputs = 64 outputs per tile, stages of RB rows
     int32_t span, pitch_p, kp, n_tiles_p, nrb, n_rg_p;
-    int32_t items_p_chunk;                // polyphase items reserved per slot (max over the chunks)
+    int32_t items_p_chunk;                // polyphase queue entries per chunk (max over the chunks; the rest are no-ops)
     int32_t NC;                           // chunks
     int32_t carry_rows;                   // rows per carry item
     int32_t n_carry_items;                // per stage
     int32_t ahead;                        // stages the scheduler may be ahead of the MMA warps when it claims an item
-    int32_t p_every;                      // every p_every-th block owns polyphase items
     int32_t stage_elems;                  // doubles per shared-memory stage: max(8 * pitch_u, RB * pitch_p)
 };
 
@@ -89,12 +93,12 @@ struct ChainDesc {
 constexpr int CH_ND = 4;
 
 // Block = 8 MMA warps + 1 scheduler / producer warp, no block-wide barrier after the set-up:
-//   scheduler warp: claims the next item from the queue, waits for its dependencies, publishes its descriptor and streams its
+//   scheduler warp: takes the next ready item (see the file header), publishes its descriptor and streams its
 //     sample windows into a ring of NST shared-memory stages by TMA bulk copies (x2 item: one 8-row window per 128-position
 //     tile; polyphase item: one RB-row window block per stage) — it runs ahead of the MMA warps across item boundaries, so
 //     the queue atomics, the dependency checks and the copy latencies hide under the MMAs of the items before;
 //   MMA warps: take the descriptors in order, wait for each stage (mbarrier full), run the K1m / K3p core on it, release
-//     it (mbarrier empty), store, and count the item as finished (one release-increment per warp).
+//     it (mbarrier empty), store, and count the item as finished (one release-increment per item, by the last warp).
 template <int NK, int RB, int NST>
 __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu, const PolyCall cp, const ChainGeom g,
                                                                 int* __restrict__ ws) {
@@ -231,9 +235,7 @@ __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu
         // becomes ready, and equal shares of these equal-cost items); x2 items are claimed by fetch-and-add. A claimed x2 item
         // whose ring slot is still being read stays pending while the block keeps serving its own polyphase items — the items
         // that free the ring — so the scheme cannot deadlock (induction over the chunk index, R > 2).
-        // only every g.p_every-th block owns polyphase items: its pipeline then holds few x2 items in front of them
-        const int n_p_cta = ((int)gridDim.x + g.p_every - 1) / g.p_every;
-        int my_p = (int)blockIdx.x % g.p_every == g.p_every - 1 || g.p_every == 1 ? (int)blockIdx.x / g.p_every : 0x7fffffff;
+        int my_p = (int)blockIdx.x;  // next polyphase-queue item of this block
         int pending_u = -1;          // claimed x2 item waiting for its ring slot
         bool u_exhausted = false;
         for (;;) {
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(288, 2) chain_up2_poly_kernel(const FirCall cu
                     if (u_done_upto(c_need)) {
                         kind = 2;
                         item = my_p;
-                        my_p += n_p_cta;
+                        my_p += (int)gridDim.x;
                         break;
                     }
                 }
@@ -637,8 +639,6 @@ bool launch_chain_t(const FusedCall& c, cudaStream_t s, ChainWs* wsp, const int 
         }
     }
     g.items_p_chunk = pmax * g.n_rg_p;
-    static const int pevery_env = [] { const char* e = gar::tune_env("GAR_CHAIN_PEVERY"); return e ? std::atoi(e) : 1; }();
-    g.p_every = std::max(1, pevery_env);
     static const int ahead_env = [] { const char* e = gar::tune_env("GAR_CHAIN_AHEAD"); return e ? std::atoi(e) : 1; }();
     g.ahead = std::max(0, std::min(NST - 1, ahead_env));
     g.carry_rows = 8;

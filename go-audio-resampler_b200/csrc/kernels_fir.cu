@@ -1,7 +1,7 @@
 // kernels_fir.cu — integer-factor FIR stages (dft_stage.go): K1/K2 register-tiled vector kernels (fir_tiled_kernel,
 // fir_f32x2_kernel with packed fma.rn.f32x2), K1m/K2m on the FP64 tensor cores (fir_mma_f64_kernel, DMMA), the generic
 // fallback, and launch_fir.
-#include "device_common.cuh"
+#include "mma_cores.cuh"
 #include <type_traits>
 
 namespace gar {
@@ -376,52 +376,9 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : (NW 
             const double* __restrict__ xw = Xs + (lane >> 2) * g.pitch + (lane & 3) + a + 4 * (warp * MT * SH) - 4 * qa;
             // A fragment: lane l holds A[row = l/4][w = 4*kk + l%4] = bank[p][4*kk + l%4 - jj*M], row = jj*NF + p
             const double* __restrict__ aw = Bs + ((lane >> 2) % NF) * blen + BOFF + (lane & 3) - ((lane >> 2) / NF) * M;
-            // WA steps; CK = false: every step has all MT tiles inside the filter (no predicates, no re-convergence code
-            // around the MMAs) — the steady state between the ramp-up of the first and the ramp-down of the last tiles
-            // MODE 0: every step has all MT tiles inside the filter; MODE 2: the first group (q0 = 0), where which tiles have
-            // started is known at compile time; MODE 1: run-time checks (ramp-down, short filters)
-            auto steps = [&](const int q0, auto mode) {
-                constexpr int MODE = decltype(mode)::value;
-#pragma unroll
-                for (int u = 0; u < WA; ++u) {
-                    const int q = MODE == 2 ? u : q0 + u;
-                    if (MODE != 1 || q < qb) {
-                        Areg[u] = (MODE != 1 || q < g.nk) ? aw[4 * q] : 0.0;
-                        const double bf = xw[4 * q];
-#pragma unroll
-                        for (int b = 0; b < MT; ++b) {
-                            const int kk = q - b * SH;
-                            const bool on = MODE == 0 ? true : MODE == 2 ? u - b * SH >= 0 : (kk >= 0 && kk < g.nk);
-                            if (on) dmma884(acc[b][0], acc[b][1], Areg[((u - b * SH) % WA + WA) % WA], bf);
-                        }
-                    }
-                }
-            };
-            // ramp-down group with D = nk - q0 known at compile time (D + OFF = 1 .. WA - 1 + OFF; short A windows only)
-            constexpr int OFF = (MT - 1) * SH;
-            auto steps_tail = [&](const int q0, auto d_tag) {
-                constexpr int D = decltype(d_tag)::value - OFF;
-#pragma unroll
-                for (int u = 0; u < WA; ++u) {
-                    if (u < D + OFF) {
-                        Areg[u] = u < D ? aw[4 * (q0 + u)] : 0.0;
-                        const double bf = xw[4 * (q0 + u)];
-#pragma unroll
-                        for (int b = 0; b < MT; ++b)
-                            if (u - b * SH < D) dmma884(acc[b][0], acc[b][1], Areg[((u - b * SH) % WA + WA) % WA], bf);
-                    }
-                }
-            };
-            const int q_steady = min(g.nk, qb) - WA;  // last q0 of an all-valid group
-            for (int q0 = qa; q0 < qb; q0 += WA) {  // qa is a multiple of WA: the rotating A window carries over
-                if (q0 >= (MT - 1) * SH && q0 <= q_steady) steps(q0, std::integral_constant<int, 0>{});
-                else if (q0 == 0 && q_steady >= 0) steps(q0, std::integral_constant<int, 2>{});
-                else if (qb == nq && WA <= 25 && q0 >= OFF && g.nk - q0 + OFF >= 1 && g.nk - q0 < WA)
-                    dispatch_count<WA - 1 + OFF, 1>(g.nk - q0 + OFF, [&](auto t) {
-                        if constexpr (decltype(t)::value != 0) steps_tail(q0, t);
-                    });
-                else steps(q0, std::integral_constant<int, 1>{});
-            }
+            // WA steps per group: steady-state groups (all MT tiles inside the filter) are straight-line code, the first group and
+            // the ramp-down groups use compile-time tile masks (mma_cores.cuh, shared with the chain kernel K5)
+            fir_mma_warp_tiles<MT, SH>(acc, Areg, xw, aw, g.nk, nq, qa, qb);
             if (!KC || qb == nq) {
                 // ---- D[row = lane/4][cols 2*(lane%4), +1]: output (pos0 + jb)*NF + row of the columns' rows ----
                 const int r8 = lane >> 2;

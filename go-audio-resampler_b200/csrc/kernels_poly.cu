@@ -2,7 +2,7 @@
 // K3 (one thread per output), K3i (lanes = lock-step rows, coefficients interpolated once per batch), K3m (the same
 // contraction on the FP64 tensor cores), K3p (K3m as a TMA producer / MMA consumer pipeline with the coefficient matrix in
 // registers), and launch_poly.
-#include "device_common.cuh"
+#include "mma_cores.cuh"
 #include <type_traits>
 
 namespace gar {
@@ -530,25 +530,8 @@ __global__ void __launch_bounds__(288, 2) poly_rows_pipe_kernel(const PolyCall c
     const int o_i = (int)(dv - d_base) - base;
     const bool live = nf + i < n1;
     const int nks = g.kp >> 2;
-    double A[NK];
-    {
-        const double* __restrict__ ga = static_cast<const double*>(c.bank_a);
-        const double* __restrict__ gb = static_cast<const double*>(c.bank_b);
-        const double* __restrict__ gc = static_cast<const double*>(c.bank_c);
-        const double* __restrict__ gd = static_cast<const double*>(c.bank_d);
-        const double x = (double)(int)(at & 0xFFFF) * (1.0 / 65536.0);
-#pragma unroll
-        for (int kk = 0; kk < NK; ++kk) {
-            const int k = 4 * kk + (lane & 3) - o_i;
-            double v = 0.0;
-            if (kk < nks && live && k >= 0 && k < c.taps) {
-                const int co = ph * c.taps + k;
-                v = ga[co];
-                if (c.interp) v = fma(x, fma(x, fma(x, gd[co], gc[co]), gb[co]), v);
-            }
-            A[kk] = v;
-        }
-    }
+    double A[NK];  // (gather and MMA loop: mma_cores.cuh, shared with the chain kernel K5)
+    poly_gather_coeffs<NK>(A, c, ph, o_i, (double)(int)(at & 0xFFFF) * (1.0 / 65536.0), live, nks, lane);
     for (int j = 0; j < nj; ++j) {
         const int buf = j % NST;
         const int row0 = rows_base + j * RB;
@@ -566,13 +549,7 @@ __global__ void __launch_bounds__(288, 2) poly_rows_pipe_kernel(const PolyCall c
             // B fragment: X[w = 4*kk + l%4][row 8*t + l/4]
             const double* __restrict__ bp = xs + (lane >> 2) * g.pitch + base + apad + (lane & 3);
             // (a straight-line block per k-step count, without the uniform predicates, measured 4 % SLOWER here: 871 vs 835 us)
-#pragma unroll
-            for (int kk = 0; kk < NK; ++kk) {
-                if (kk < nks) {
-#pragma unroll
-                    for (int t = 0; t < NT8; ++t) dmma884(acc[t][0], acc[t][1], A[kk], bp[t * 8 * g.pitch + 4 * kk]);
-                }
-            }
+            poly_mma_stage<NK, NT8>(acc, A, bp, g.pitch, nks);
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty + buf)) : "memory");
             if (live) {
