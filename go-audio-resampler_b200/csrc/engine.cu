@@ -572,28 +572,52 @@ bool Engine::io32_foldable(int row0, int64_t n_in, bool flush) const {
 }
 
 bool Engine::pair32_foldable(int row0, int count, int64_t n_in, int64_t in_stride) const {
-    if (device_ < 0 || dtype_ != DT_F64 || !fuse_ || n_in <= 32768 || count < 32 || (in_stride & 3) != 0) return false;
+    if (device_ < 0 || dtype_ != DT_F64 || !fuse_ || n_in <= 32768 || count < 8 || (in_stride & 3) != 0) return false;
     if (slice_length(row0, rows_, n_in) > 0) return false;  // time-sliced calls keep the cast launches
     StreamState st = streams_[(size_t)row0];
     Plan P;
     plan(st, n_in, false, P);
-    // the op that reads the caller's input is an x2 stage (K1m), the op that writes the caller's output a polyphase stage (K3p);
-    // whatever lies between (the further x2 stages of an 8k -> 192k pipeline) runs on float64 inter-stage buffers as ever
-    if (P.ops.size() < 2) return false;
+    // the op that reads the caller's input must be an integer-factor FIR stage that the float64 tensor-core kernels take (K1m x2,
+    // K2m /2 /3 /4), the op that writes the caller's output such a stage or a polyphase stage that K3p takes; whatever lies
+    // between (the further x2 stages of an 8k -> 192k pipeline) runs on float64 inter-stage buffers as ever
+    if (P.ops.empty()) return false;
     const Op &a = P.ops.front(), &b = P.ops.back();
-    if (a.stage < 0 || b.stage < 0 || a.src_buf != BUF_EXT_IN || b.dst_buf != BUF_OUT || a.dst_buf < 0 || b.src_buf < 0 ||
-        a.n_out <= 0 || b.n_out <= 0 || b.dst_off != 0)
+    if (a.stage < 0 || b.stage < 0 || a.src_buf != BUF_EXT_IN || b.dst_buf != BUF_OUT || a.n_out <= 0 || b.n_out <= 0 || b.dst_off != 0)
         return false;
-    for (size_t k = 1; k + 1 < P.ops.size(); ++k)
-        if (P.ops[k].stage < 0 || P.ops[k].src_buf == BUF_EXT_IN || P.ops[k].dst_buf == BUF_OUT || P.ops[k].n_out <= 0) return false;
-    const StageDesign &su = chain_.stages[(size_t)a.stage], &sp = chain_.stages[(size_t)b.stage];
-    if (!(su.kind == STAGE_UP && su.factor == 2 && sp.kind == STAGE_POLY)) return false;
-    FirCall fc{};
-    fc.taps = su.taps; fc.stride = 1; fc.nf = 2; fc.n_pos = (int32_t)(a.n_out / 2); fc.n_streams = count; fc.in_stride = in_stride;
+    for (size_t k = 0; k < P.ops.size(); ++k) {
+        const Op& o = P.ops[k];
+        if (o.stage < 0 || o.n_out <= 0 || (k > 0 && o.src_buf == BUF_EXT_IN) || (k + 1 < P.ops.size() && o.dst_buf == BUF_OUT)) return false;
+    }
+    auto fir_call = [&](const Op& o, bool in32, bool out32) -> bool {
+        const StageDesign& sd = chain_.stages[(size_t)o.stage];
+        FirCall fc{};
+        fc.taps = sd.taps; fc.n_streams = count; fc.in_stride = in32 ? in_stride : 0; fc.in_f32 = in32; fc.out_f32 = out32;
+        if (sd.kind == STAGE_UP) { fc.stride = 1; fc.nf = sd.factor; fc.n_pos = (int32_t)(o.n_out / sd.factor); }
+        else if (sd.kind == STAGE_DECIM) { fc.stride = sd.factor; fc.nf = 1; fc.first = (int32_t)o.first; fc.n_pos = (int32_t)o.n_out; }
+        else return false;
+        return fir_mma_io32_takes(fc);
+    };
+    // an x2 -> polyphase pair that the ordinary dispatch would run as ONE fused launch (few rows: K4r / K4 / K4s are the faster
+    // kernels there) keeps it, casts included
+    for (size_t k = 0; k + 1 < P.ops.size(); ++k) {
+        const Op &u = P.ops[k], &q = P.ops[k + 1];
+        const StageDesign &su = chain_.stages[(size_t)u.stage], &sq = chain_.stages[(size_t)q.stage];
+        if (q.stage == u.stage + 1 && su.kind == STAGE_UP && su.factor == 2 && sq.kind == STAGE_POLY && q.src_buf == u.dst_buf &&
+            q.n_in == u.n_out && sq.engine_index == su.engine_index) {
+            FusedCall f{};
+            f.np = (int32_t)(u.n_out / 2); f.n_streams = count; f.at0 = q.first; f.step = sq.step; f.interp = q.interp ? 1 : 0;
+            if (!up2_poly_runs_as_tensor_pair(f)) return false;
+        }
+    }
+    const bool single = P.ops.size() == 1;
+    if (!fir_call(a, true, single)) return false;
+    if (single) return true;
+    const StageDesign& sp = chain_.stages[(size_t)b.stage];
+    if (sp.kind != STAGE_POLY) return fir_call(b, false, true);
     PolyCall pc{};
     pc.taps = sp.taps; pc.L = sp.factor; pc.at0 = b.first; pc.step = sp.step; pc.n_out = (int32_t)b.n_out;
     pc.interp = b.interp ? 1 : 0; pc.n_streams = count;
-    return fir_mma_up2_in32_takes(fc) && poly_rows_pipe_out32_takes(pc);
+    return poly_rows_pipe_out32_takes(pc);
 }
 
 int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_t n_in, void* d_out, int64_t out_stride,
@@ -822,9 +846,10 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                 }
                 c.n_streams = count;
                 c.in_f32 = io32 == 2 && op.src_buf == BUF_EXT_IN ? 1 : 0;
+                c.out_f32 = io32 == 2 && op.dst_buf == BUF_OUT ? 1 : 0;
                 const char* kn = launch_fir(c, dtype_, s);
                 if (!kn) {
-                    err = "internal: float32 input was folded into a call the x2 tensor-core kernel did not take";
+                    err = "internal: float32 I/O was folded into a call the tensor-core FIR kernels did not take";
                     return 5;
                 }
                 note_kernel(kn);

@@ -114,8 +114,9 @@ class Engine {
     // A Process call of n_in samples on rows in row0's state is ONE fused x2 -> polyphase launch of streaming size, which can
     // take float32 input / output directly (constant.go:161-199 ProcessFloat32Into without the two cast passes).
     bool io32_foldable(int row0, int64_t n_in, bool flush) const;
-    // io32 = 2: a large batched call that runs as the two tensor-core launches K1m (x2 stage) + K3p (polyphase stage) can take
-    // float32 input / output as well: K1m widens its sample windows in shared memory, K3p narrows on the store
+    // io32 = 2: a large batched call whose first and last stage calls run on the float64 tensor-core kernels (K1m x2 / K2m
+    // decimators / K3p polyphase) can take float32 input / output as well: K1m / K2m widen their sample windows in shared
+    // memory, the last kernel narrows on the store
     bool pair32_foldable(int row0, int count, int64_t n_in, int64_t in_stride) const;
     // Time slicing of multi-stage calls: a Process call whose inter-stage buffers would exceed `bytes` is run as a
     // sequence of shorter Process calls (identical samples and counts: every stage is greedy), so that the intermediate-rate

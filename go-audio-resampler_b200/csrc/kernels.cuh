@@ -30,7 +30,8 @@ struct FirCall {
     int32_t taps;         int32_t stride;       int32_t nf;
     int32_t first;        int32_t n_pos;
     int32_t n_streams;    // rows processed by this launch (row r of every pointer = base + r*stride)
-    int32_t in_f32;       // `in` holds float32 samples (in_stride in float32 elements); only the x2 tensor-core kernel (K1m) takes it
+    int32_t in_f32;       // `in` / `out` hold float32 samples (strides in float32 elements); only the float64 tensor-core FIR
+    int32_t out_f32;      // kernels (K1m / K2m) take them (fir_mma_io32_takes)
 };
 
 // out[n] = sum_k v[div_n + k] * (a + x(b + x(c + x d)))[phase_n][k]   (polyphase_stage.go:186-312)
@@ -46,7 +47,7 @@ struct PolyCall {
     int64_t at0;          int64_t step;
     int32_t n_out;        int32_t interp;       // interp: (step & 0xFFFF) != 0 || (at0 & 0xFFFF) != 0
     int32_t n_streams;
-    int32_t out_f32;      // `out` holds float32 samples (out_stride in float32 elements); only the pipelined tensor-core kernel (K3p) takes it
+    int32_t out_f32;      // `out` holds float32 samples (out_stride in float32 elements); only the tensor-core kernels (K3m / K3p) take it
 };
 
 // K4: x2 up-sampler fused with the polyphase stage that follows it inside one engine.Resampler
@@ -129,7 +130,8 @@ void set_chain_kernel(int mode);
 int chain_kernel_mode();
 // float32 I/O folded into the two tensor-core launches of a batched x2 -> polyphase chain: will launch_fir / launch_poly take the
 // call with in_f32 / out_f32 set? (the engine asks before it decides against the cast launches)
-bool fir_mma_up2_in32_takes(const FirCall& c);
+bool fir_mma_io32_takes(const FirCall& c);
+bool up2_poly_runs_as_tensor_pair(const FusedCall& c);  // launch_fused_up2_poly leaves the pair to K1m + K3m / K3p (geometry only)
 bool poly_rows_pipe_out32_takes(const PolyCall& c);
 // carry only (a call that produced no output but appended to the tail)
 void launch_carry(const void* hist, int64_t hist_stride, int32_t hist_len, const void* in, int64_t in_stride,

@@ -388,6 +388,15 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : (NW 
                     if (sbase + col >= g.nvs) continue;
                     const int64_t pos0 = col_pos0(col);
                     const int64_t plim = min((int64_t)c.n_pos, pos0 + g.ps);  // the column's segment ends here
+                    if (c.out_f32) {  // float32(v) on the way out (constant.go:195-197): no cast launch behind this one
+                        float* __restrict__ orow = static_cast<float*>(c.out) + col_row(col) * c.out_stride;
+#pragma unroll
+                        for (int b = 0; b < MT; ++b) {
+                            const int64_t jb = pos0 + jb0 + (warp * MT + b) * JT;
+                            if (jb + r8 / NF < plim) orow[jb * NF + r8] = (float)acc[b][e];
+                        }
+                        continue;
+                    }
                     double* __restrict__ orow = static_cast<double*>(c.out) + col_row(col) * c.out_stride;
 #pragma unroll
                     for (int b = 0; b < MT; ++b) {
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__(NW * 32, (NW == 8 && M == 1 && !KC) ? 4 : (NW 
 }
 
 template <int M, int NF>
-static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
+static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s, const bool dry = false) {
     constexpr int JT = 8 / NF, SH = JT * M / 4;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -452,8 +461,9 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
         tpb = std::max<int64_t>(1, std::min<int64_t>(tpb, 8));
         g.tiles_per_block = (int32_t)std::min<int64_t>(tpb, g.n_tiles);
         g.n_groups = (g.n_tiles + g.tiles_per_block - 1) / g.tiles_per_block;
-        static size_t configured[64][6] = {{0}};
-        size_t& conf = configured[dev & 63][slot];
+        if (dry) return true;
+        static size_t configured[64][8] = {{0}};
+        size_t& conf = configured[dev & 63][slot + (c.in_f32 ? 4 : 0)];
         if (smem > conf) {
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             conf = smem;
@@ -470,22 +480,21 @@ static bool launch_fir_mma_t(const FirCall& c, cudaStream_t s) {
     // GAR_MMA_CFG = 1 / 3 forces 16 / 8 warps with the whole window, GAR_MMA_NKC = n the chunk count.
     static const int forced = [] { const char* e = gar::tune_env("GAR_MMA_CFG"); return e ? std::atoi(e) : -1; }();
     static const int nkc_env = [] { const char* e = gar::tune_env("GAR_MMA_NKC"); return e ? std::atoi(e) : 0; }();
-    if constexpr (M == 1 && NF == 2) {
-        if (c.in_f32) return c.taps <= 600 && run(fir_mma_f64_kernel<M, NF, 8, 4, false, true>, 8, 4, 4, 1, 0);
-    } else {
-        if (c.in_f32) return false;
-    }
-    if (forced == 1) return run(fir_mma_f64_kernel<M, NF, 16, 4, false>, 16, 4, 1, 1, 0);
-    if (forced == 3) return run(fir_mma_f64_kernel<M, NF, 8, 4, false>, 8, 4, 3, 1, 0);
+    // float32 input (FirCall::in_f32): the IN32 instantiation of the same variant
+    auto k16 = c.in_f32 ? fir_mma_f64_kernel<M, NF, 16, 4, false, true> : fir_mma_f64_kernel<M, NF, 16, 4, false, false>;
+    auto k8 = c.in_f32 ? fir_mma_f64_kernel<M, NF, 8, 4, false, true> : fir_mma_f64_kernel<M, NF, 8, 4, false, false>;
+    auto k8c = c.in_f32 ? fir_mma_f64_kernel<M, NF, 8, 4, true, true> : fir_mma_f64_kernel<M, NF, 8, 4, true, false>;
+    if (forced == 1) return run(k16, 16, 4, 1, 1, 0);
+    if (forced == 3) return run(k8, 8, 4, 3, 1, 0);
     if (c.taps > 600) {
         constexpr size_t two_per_sm = 113 * 1024;
-        if (nkc_env > 1) return run(fir_mma_f64_kernel<M, NF, 8, 4, true>, 8, 4, 2, nkc_env, 0);
-        if (run(fir_mma_f64_kernel<M, NF, 8, 4, false>, 8, 4, 3, 1, two_per_sm)) return true;
+        if (nkc_env > 1) return run(k8c, 8, 4, 2, nkc_env, 0);
+        if (run(k8, 8, 4, 3, 1, two_per_sm)) return true;
         for (int nkc = 2; nkc <= 4; ++nkc)
-            if (run(fir_mma_f64_kernel<M, NF, 8, 4, true>, 8, 4, 2, nkc, two_per_sm)) return true;
-        return run(fir_mma_f64_kernel<M, NF, 16, 4, false>, 16, 4, 1, 1, 0) || run(fir_mma_f64_kernel<M, NF, 8, 4, false>, 8, 4, 3, 1, 0);
+            if (run(k8c, 8, 4, 2, nkc, two_per_sm)) return true;
+        return run(k16, 16, 4, 1, 1, 0) || run(k8, 8, 4, 3, 1, 0);
     }
-    return run(fir_mma_f64_kernel<M, NF, 8, 4, false>, 8, 4, 3, 1, 0);
+    return run(k8, 8, 4, 3, 1, 0);
 }
 
 static bool g_fir_mma = [] {
@@ -494,16 +503,16 @@ static bool g_fir_mma = [] {
 }();
 // float64 FIR on the FP64 tensor cores: x2 up-sampler and /2 /3 /4 decimators, any number of lock-step rows (fewer than 8:
 // time segments of the rows fill the MMA columns), calls of at least 32768 positions
-static const char* launch_fir_mma(const FirCall& c, cudaStream_t s) {
+static const char* launch_fir_mma(const FirCall& c, cudaStream_t s, const bool dry = false) {
     if (!g_fir_mma || c.n_streams < 1 || (int64_t)c.n_pos * c.n_streams < 32768 || c.taps < 16) return nullptr;
     // fewer than 8 rows (time-segment columns): only long calls — measured +5 % on 60 s of stereo 96k->48k, but a loss on the
     // sub-millisecond stages of a single 10 s stream (C5a), which are launch-latency-bound
     static const int64_t seg_min = [] { const char* e = gar::tune_env("GAR_MMA_SEG_MIN"); return e ? std::atoll(e) : 2000000ll; }();
     if (c.n_streams < 8 && (int64_t)c.n_pos * c.n_streams < seg_min) return nullptr;
-    if (c.stride == 1 && c.nf == 2) return launch_fir_mma_t<1, 2>(c, s) ? "fir_f64_mma_up2" : nullptr;
-    if (c.nf == 1 && c.stride == 2) return launch_fir_mma_t<2, 1>(c, s) ? "fir_f64_mma_s2" : nullptr;
-    if (c.nf == 1 && c.stride == 3) return launch_fir_mma_t<3, 1>(c, s) ? "fir_f64_mma_s3" : nullptr;
-    if (c.nf == 1 && c.stride == 4) return launch_fir_mma_t<4, 1>(c, s) ? "fir_f64_mma_s4" : nullptr;
+    if (c.stride == 1 && c.nf == 2) return launch_fir_mma_t<1, 2>(c, s, dry) ? "fir_f64_mma_up2" : nullptr;
+    if (c.nf == 1 && c.stride == 2) return launch_fir_mma_t<2, 1>(c, s, dry) ? "fir_f64_mma_s2" : nullptr;
+    if (c.nf == 1 && c.stride == 3) return launch_fir_mma_t<3, 1>(c, s, dry) ? "fir_f64_mma_s3" : nullptr;
+    if (c.nf == 1 && c.stride == 4) return launch_fir_mma_t<4, 1>(c, s, dry) ? "fir_f64_mma_s4" : nullptr;
     return nullptr;
 }
 
@@ -1182,10 +1191,15 @@ const char* fir_variant_name(int dtype, int stride, int nf, int taps, int64_t n_
     return dtype == DT_F32 ? "fir_f32_generic" : "fir_f64_generic";
 }
 
-// float32 input folded into the x2 tensor-core kernel: the conditions under which launch_fir takes it (those of launch_fir_mma)
-bool fir_mma_up2_in32_takes(const FirCall& c) {
-    return g_fir_mma && c.n_streams >= 8 && (int64_t)c.n_pos * c.n_streams >= 32768 && c.taps >= 16 && c.taps <= 600 &&
-           c.stride == 1 && c.nf == 2 && (c.in_stride & 3) == 0;
+// float32 input / output folded into the float64 tensor-core FIR kernels (K1m / K2m): will launch_fir take the call with
+// in_f32 / out_f32 set? (a dry run of the same dispatch)
+bool fir_mma_io32_takes(const FirCall& c) {
+    // Long filters stage every input sample 4-5 times (the window of a tile is mostly taps, and it is staged per tap chunk), so
+    // widening in shared memory costs more than the one-pass cast launch once the call is large: measured on the 913-tap /2
+    // stage of 48k -> 16k x 256 rows x 10 s, 3.5 against 2.8 + 0.25 ms. Small calls (launch-latency-bound) still gain:
+    // 8 channels x 10 s of 96k -> 48k VeryHigh, 0.316 against 0.344 ms.
+    if (c.in_f32 && c.taps > 600 && (int64_t)c.n_pos * c.n_streams > (4 << 20)) return false;
+    return c.n_pos > 0 && (!c.in_f32 || (c.in_stride & 3) == 0) && launch_fir_mma(c, nullptr, true) != nullptr;
 }
 
 const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s) {
@@ -1197,7 +1211,7 @@ const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s) {
     }
     if (dtype == DT_F64)
         if (const char* nm = launch_fir_mma(c, s)) return nm;
-    if (c.in_f32) return nullptr;  // only the x2 tensor-core kernel widens float32 input (the engine asked fir_mma_up2_in32_takes first)
+    if (c.in_f32 || c.out_f32) return nullptr;  // only the tensor-core kernels take float32 I/O (the engine asked fir_mma_io32_takes first)
 #define X(M, NF, R, NAME)                                       \
     if (dtype == DT_F32 && c.stride == M && c.nf == NF) {       \
         launch_fir_f32x2<M, NF, R>(c, s);                       \

@@ -1234,6 +1234,14 @@ static bool launch_rat(const FusedCall& c, cudaStream_t s, RatCache* cache) {
 
 bool launch_rat_poly_only_f64(const FusedCall& c, cudaStream_t s, RatCache* cache) { return launch_rat<double, false>(c, s, cache); }
 
+// float64 x2 -> polyphase pairs that run as the two tensor-core launches (K1m + K3m / K3p) rather than as one fused launch
+bool up2_poly_runs_as_tensor_pair(const FusedCall& c) {
+    const bool rational = !c.interp && ((c.step | c.at0) & 0xFFFF) == 0;
+    static const int rational_min_rows = [] { const char* e = gar::tune_env("GAR_TENSOR_MIN_ROWS"); return e ? std::atoi(e) : 32; }();
+    return tensor_fir_enabled() && g_fused_rat && (int64_t)c.np * c.n_streams >= 32768 &&
+           c.n_streams >= (rational ? rational_min_rows : 8);
+}
+
 const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s, RatCache* cache) {
     if (c.n_streams <= 0) return "none";
     if (dtype == DT_F64 && (c.in_f32 || c.out_f32)) {  // float32 I/O folded into the kernel: the generic K4 only
@@ -1251,13 +1259,7 @@ const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s,
     //    is the better kernel for a few long rows (GAR_TENSOR_MIN_ROWS overrides the threshold);
     //  * irrational ratios: batches of >= 8 rows (K3m / K3i evaluate the interpolated coefficients once per batch; the fused
     //    one-thread-per-output kernel is 10x slower there).
-    {
-        const bool rational = !c.interp && ((c.step | c.at0) & 0xFFFF) == 0;
-        static const int rational_min_rows = [] { const char* e = gar::tune_env("GAR_TENSOR_MIN_ROWS"); return e ? std::atoi(e) : 32; }();
-        if (tensor_fir_enabled() && g_fused_rat && (int64_t)c.np * c.n_streams >= 32768 &&
-            c.n_streams >= (rational ? rational_min_rows : 8))
-            return nullptr;
-    }
+    if (up2_poly_runs_as_tensor_pair(c)) return nullptr;
     if (!c.interp && launch_rat<double, true>(c, s, cache)) return "fused_up2_rat_f64";
     // a large lock-step batch that the rational kernel does not cover runs as two launches: the stand-alone x2 kernel and
     // K3i (lanes = rows, interpolated coefficients evaluated once per batch) beat the one-thread-per-output fused kernel

@@ -397,11 +397,20 @@ __global__ void __launch_bounds__(NTASK * 32, NTASK == 8 ? 2 : 3) poly_rows_mma_
             }
             const int i = lane >> 2;
             if (nf + i < n1) {
+                if (c.out_f32) {  // float32(v) on the way out (constant.go:195-197)
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int64_t s0 = (int64_t)row0 + t * 8 + 2 * (lane & 3);
-                    if (s0 < c.n_streams) (static_cast<double*>(c.out) + s0 * c.out_stride)[nf + i] = acc[t][0];
-                    if (s0 + 1 < c.n_streams) (static_cast<double*>(c.out) + (s0 + 1) * c.out_stride)[nf + i] = acc[t][1];
+                    for (int t = 0; t < 4; ++t) {
+                        const int64_t s0 = (int64_t)row0 + t * 8 + 2 * (lane & 3);
+                        if (s0 < c.n_streams) (static_cast<float*>(c.out) + s0 * c.out_stride)[nf + i] = (float)acc[t][0];
+                        if (s0 + 1 < c.n_streams) (static_cast<float*>(c.out) + (s0 + 1) * c.out_stride)[nf + i] = (float)acc[t][1];
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int64_t s0 = (int64_t)row0 + t * 8 + 2 * (lane & 3);
+                        if (s0 < c.n_streams) (static_cast<double*>(c.out) + s0 * c.out_stride)[nf + i] = acc[t][0];
+                        if (s0 + 1 < c.n_streams) (static_cast<double*>(c.out) + (s0 + 1) * c.out_stride)[nf + i] = acc[t][1];
+                    }
                 }
             }
         }
@@ -618,7 +627,7 @@ static bool launch_poly_rows_pipe(const PolyCall& c, cudaStream_t s, const bool 
 }
 
 template <int NTASK>
-static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s) {
+static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s, const bool dry = false) {
     constexpr int TO = 8 * NTASK;
     const double r = (double)c.step / ((double)c.L * 65536.0);
     RowsMmaGeom g{};
@@ -640,6 +649,7 @@ static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s) {
     g.nbuf = force_nbuf ? force_nbuf : 1;
     const size_t smem = fixed + g.nbuf * xbytes;
     if (smem > (g.nbuf == 2 ? 227 : 113) * 1024) return false;
+    if (dry) return true;
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -653,7 +663,7 @@ static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s) {
     return true;
 }
 
-// 0: not taken, 1: K3m, 2: K3p. dry: eligibility only (no launch); K3m is then reported as not taken.
+// 0: not taken, 1: K3m, 2: K3p. dry: eligibility only (no launch).
 static int launch_poly_rows_mma(const PolyCall& c, cudaStream_t s, const bool dry = false) {
     if (!tensor_fir_enabled() || c.n_streams < 8 || (int64_t)c.n_out * c.n_streams < 16384 || c.L > 4096 || c.taps > 1024) return 0;
     const double r = (double)c.step / ((double)c.L * 65536.0);
@@ -663,9 +673,8 @@ static int launch_poly_rows_mma(const PolyCall& c, cudaStream_t s, const bool dr
     static const int pipe_rows = [] { const char* e = gar::tune_env("GAR_K3M_PIPE_ROWS"); return e ? std::atoi(e) : 32; }();
     // measured (44.1k->48k, 21 M samples): K3p against K3m 32 rows 20.9 / 19.9, 48 rows 21.8 / 20.4 TFLOP/s, equal below
     if (pipe && c.n_streams >= pipe_rows && launch_poly_rows_pipe(c, s, dry)) return 2;
-    if (dry || c.out_f32) return 0;  // only K3p narrows to float32 on the way out
-    if (ntask == 4) return (launch_poly_rows_mma_t<4>(c, s) || launch_poly_rows_mma_t<8>(c, s)) ? 1 : 0;
-    return (launch_poly_rows_mma_t<8>(c, s) || launch_poly_rows_mma_t<4>(c, s)) ? 1 : 0;
+    if (ntask == 4) return (launch_poly_rows_mma_t<4>(c, s, dry) || launch_poly_rows_mma_t<8>(c, s, dry)) ? 1 : 0;
+    return (launch_poly_rows_mma_t<8>(c, s, dry) || launch_poly_rows_mma_t<4>(c, s, dry)) ? 1 : 0;
 }
 
 // K3i dispatch: batches of at least 8 lock-step rows with enough outputs; S = ceil(samples per output)
@@ -781,7 +790,7 @@ __global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_
 }  // namespace
 
 bool poly_rows_pipe_out32_takes(const PolyCall& c) {
-    return c.n_out > 0 && tiled_polyphase_enabled() && launch_poly_rows_mma(c, nullptr, true) == 2;
+    return c.n_out > 0 && tiled_polyphase_enabled() && launch_poly_rows_mma(c, nullptr, true) != 0;  // K3m and K3p narrow on the store
 }
 
 const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* cache) {

@@ -98,6 +98,10 @@ def test_chain_kernel_replaces_time_slices_above_the_memory_budget():
     (44100, 48000, 40, 120001, "engine32"),   # NewEngineFloat32 at a non-integer ratio (float64 tensor-core arithmetic inside)
     (44100, 47999, 33, 100000, "pipeline"),   # interpolated coefficients, ragged row groups
     (8000, 192000, 32, 70000, "pipeline"),    # five x2 stages + polyphase: only the first and the last launch touch float32
+    (96000, 48000, 16, 140000, "pipeline"),   # one /2 decimator (K2m): float32 in and float32 out in the same launch
+    (48000, 16000, 40, 100001, "pipeline"),   # /2 -> x2 -> polyphase: float32 in on the decimator (K2m), float32 out of K3p
+    (48000, 8000, 33, 120000, "pipeline"),    # two engines going down
+    (192000, 48000, 9, 150001, "pipeline"),   # /4 decimator, ragged column group (9 rows)
 ])
 def test_float32_io_folded_into_the_tensor_core_pair_equals_the_cast_launches(ir, orr, rows, n, make):
     """Large float32-I/O batches on float64 arithmetic: K1m widens its float32 sample windows in shared memory and K3p narrows on
@@ -133,7 +137,7 @@ def test_float32_io_folded_into_the_tensor_core_pair_equals_the_cast_launches(ir
 
     ya, la, ka = run(True)
     yb, lb, kb = run(False)
-    assert la == lb - 2 and la >= 2, (la, lb, ka, kb)  # x2 + polyphase against cast + x2 + polyphase + cast
+    assert la <= lb - 2 and la >= 1, (la, lb, ka, kb)  # no cast launch in front, none behind
     assert ya.dtype == np.float32 and ya.shape == yb.shape
     assert np.array_equal(ya, yb), float(np.max(np.abs(ya.astype(np.float64) - yb)))
     if make == "pipeline":
