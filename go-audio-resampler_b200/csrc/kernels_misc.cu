@@ -59,6 +59,10 @@ __global__ void carry_kernel(const T* hist, int64_t hist_stride, int hist_len, c
 
 template <typename S, typename D>
 __global__ void cast_kernel(const S* src, int64_t src_stride, D* dst, int64_t dst_stride, int n, int n_rows) {
+    // launched as a programmatic dependent: its blocks may be resident before the launch in front has drained (and it lets the
+    // launch behind it in early) — the cast launches around a streaming-size call are pure launch latency otherwise
+    pdl_wait();
+    if (gridDim.x * gridDim.y <= 296) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // rows are strided over gridDim.y (limited to 65535) so any row count is covered
     for (int64_t row = blockIdx.y; row < n_rows; row += gridDim.y)
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -175,14 +179,23 @@ void launch_cast(const void* src, int64_t src_stride, int src_dtype, void* dst, 
     if (n <= 0 || n_rows <= 0) return;
     dim3 grid((unsigned)((n + 1023) / 1024 < 4096 ? (n + 1023) / 1024 : 4096), (unsigned)(n_rows < 65535 ? n_rows : 65535));
     count_launch();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
     if (src_dtype == DT_F32 && dst_dtype == DT_F64)
-        cast_kernel<float, double><<<grid, 256, 0, s>>>((const float*)src, src_stride, (double*)dst, dst_stride, n, n_rows);
+        cudaLaunchKernelEx(&cfg, cast_kernel<float, double>, (const float*)src, src_stride, (double*)dst, dst_stride, (int)n, (int)n_rows);
     else if (src_dtype == DT_F64 && dst_dtype == DT_F32)
-        cast_kernel<double, float><<<grid, 256, 0, s>>>((const double*)src, src_stride, (float*)dst, dst_stride, n, n_rows);
+        cudaLaunchKernelEx(&cfg, cast_kernel<double, float>, (const double*)src, src_stride, (float*)dst, dst_stride, (int)n, (int)n_rows);
     else if (src_dtype == DT_F32)
-        cast_kernel<float, float><<<grid, 256, 0, s>>>((const float*)src, src_stride, (float*)dst, dst_stride, n, n_rows);
+        cudaLaunchKernelEx(&cfg, cast_kernel<float, float>, (const float*)src, src_stride, (float*)dst, dst_stride, (int)n, (int)n_rows);
     else
-        cast_kernel<double, double><<<grid, 256, 0, s>>>((const double*)src, src_stride, (double*)dst, dst_stride, n, n_rows);
+        cudaLaunchKernelEx(&cfg, cast_kernel<double, double>, (const double*)src, src_stride, (double*)dst, dst_stride, (int)n, (int)n_rows);
 }
 
 namespace {
