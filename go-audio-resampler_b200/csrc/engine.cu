@@ -863,6 +863,7 @@ int Engine::run_once(int row0, int count, const void* d_in, int64_t in_stride, i
                 c.hist_out = hout; c.hist_out_stride = dv.hist_cap;
                 c.drop = (int32_t)op.drop; c.new_hist_len = (int32_t)op.new_hist_len;
                 c.bank_a = dv.bank[0]; c.bank_b = dv.bank[1]; c.bank_c = dv.bank[2]; c.bank_d = dv.bank[3];
+                c.bank_il = dv.bank_il;
                 c.taps = sd.taps; c.L = sd.factor; c.at0 = op.first; c.step = sd.step;
                 c.n_out = (int32_t)op.n_out; c.interp = op.interp ? 1 : 0;
                 c.n_streams = count;

@@ -43,6 +43,7 @@ struct PolyCall {
     void* hist_out;       int64_t hist_out_stride;
     int32_t drop;         int32_t new_hist_len;
     const void* bank_a;   const void* bank_b;   const void* bank_c;   const void* bank_d;  // [L][taps]
+    const void* bank_il;  // optional: the four banks interleaved per tap, [L][taps][4] = a,b,c,d (flush-size launches gather rows of it)
     int32_t taps;         int32_t L;
     int64_t at0;          int64_t step;
     int32_t n_out;        int32_t interp;       // interp: (step & 0xFFFF) != 0 || (at0 & 0xFFFF) != 0

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
     };
     const int64_t n_lo = min((int64_t)c.n_out, first_n(lo));
     const int64_t n_hi = tile == n_tiles - 1 ? (int64_t)c.n_out : min((int64_t)c.n_out, first_n(hi));
-    const bool gather = !INTERP && rowcap > 0 && n_hi - n_lo <= rowcap;
+    const bool gather = rowcap > 0 && n_hi - n_lo <= rowcap;  // (INTERP: rows of the interleaved bank, [tap]{a,b,c,d}, always aligned)
     auto row_pad = [&](const T* rowp) -> int {  // elements between the 16-byte aligned address below the row and the row
         return (int)((reinterpret_cast<uintptr_t>(rowp) & 15u) / sizeof(T));
     };
@@ -155,9 +155,10 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
         uint32_t bytes = 0;
         for (int64_t n = n_lo + tid; n < n_hi; n += NT) {
             const int64_t full = (c.at0 + n * c.step) >> 16;
-            const T* rowp = static_cast<const T*>(c.bank_a) + (full % c.L) * c.t2;
-            const int pad = row_pad(rowp);
-            const uint32_t nb = (uint32_t)(((c.t2 + pad) * sizeof(T) + 15) & ~(size_t)15);
+            const T* rowp = INTERP ? static_cast<const T*>(c.bank_il) + (full % c.L) * c.t2 * 4
+                                   : static_cast<const T*>(c.bank_a) + (full % c.L) * c.t2;
+            const int pad = INTERP ? 0 : row_pad(rowp);
+            const uint32_t nb = INTERP ? (uint32_t)(c.t2 * 4 * sizeof(T)) : (uint32_t)(((c.t2 + pad) * sizeof(T) + 15) & ~(size_t)15);
             bulk_g2s(crow + (size_t)(n - n_lo) * cpitch, rowp - pad, nb, bar + 1);
             bytes += nb;
         }
@@ -265,10 +266,19 @@ __global__ void __launch_bounds__(NT) fused_up2_poly_kernel(const FusedCall c, c
         if (INTERP) {
             const T x = (T)(int)(at & 0xFFFF) * (T)(1.0 / 65536.0);
             const int64_t co = (int64_t)phase * c.t2;
-            for (int k = 0; k < c.t2; ++k) {
-                const T coef = fma(x, fma(x, fma(x, gd[co + k], gc[co + k]), gb[co + k]), ga[co + k]);
-                if ((k & 1) && sizeof(T) == 4) acc1 = fma((double)h[k], (double)coef, acc1);
-                else acc0 = fma((double)h[k], (double)coef, acc0);
+            if (gather) {  // the gathered row of the interleaved bank: same operation order
+                const T* __restrict__ sl = crow + (size_t)(n - n_lo) * cpitch;
+                for (int k = 0; k < c.t2; ++k) {
+                    const T coef = fma(x, fma(x, fma(x, sl[4 * k + 3], sl[4 * k + 2]), sl[4 * k + 1]), sl[4 * k]);
+                    if ((k & 1) && sizeof(T) == 4) acc1 = fma((double)h[k], (double)coef, acc1);
+                    else acc0 = fma((double)h[k], (double)coef, acc0);
+                }
+            } else {
+                for (int k = 0; k < c.t2; ++k) {
+                    const T coef = fma(x, fma(x, fma(x, gd[co + k], gc[co + k]), gb[co + k]), ga[co + k]);
+                    if ((k & 1) && sizeof(T) == 4) acc1 = fma((double)h[k], (double)coef, acc1);
+                    else acc0 = fma((double)h[k], (double)coef, acc0);
+                }
             }
         } else {
             const T* __restrict__ ca = bank_pitch > 0 ? pbank + phase * bank_pitch : ga + (int64_t)phase * c.t2;
@@ -969,6 +979,18 @@ static bool launch_fused_r(const FusedCall& c, cudaStream_t s) {
         int pitch = ((c.t2 + VEC + VEC - 1) / VEC) * VEC;  // room for the alignment pad
         while ((pitch * (int)sizeof(T)) % 128 != 16) pitch += VEC;
         if ((words + (size_t)cap * pitch) * sizeof(T) + 16 <= 200 * 1024) {
+            rowcap = cap;
+            cpitch = pitch;
+            words += (size_t)cap * pitch;
+        }
+    }
+    if (INTERP && sizeof(T) == 8 && c.bank_il && (int64_t)n_tiles * c.n_streams <= 4) {
+        // interpolated coefficients: rows of the interleaved bank (32 bytes per tap); as many outputs as 128 KB of rows hold —
+        // a Flush has a few dozen to a few hundred (a tile with more reads its coefficients through L1 as before)
+        int pitch = 4 * c.t2;
+        while ((pitch * 8) % 128 != 16) pitch += 2;
+        const int cap = (int)((128 * 1024) / ((size_t)pitch * 8));
+        if (cap >= 16 && (words + (size_t)cap * pitch) * sizeof(T) + 16 <= 200 * 1024) {
             rowcap = cap;
             cpitch = pitch;
             words += (size_t)cap * pitch;

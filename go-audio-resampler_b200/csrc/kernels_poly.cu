@@ -734,13 +734,16 @@ __global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_
     const T* __restrict__ cd = static_cast<const T*>(c.bank_d) + co;
     // streaming-size launches: one TMA bulk copy per output fetches its coefficient row (all in flight at once) while the
     // samples are staged; larger launches prefetch the rows into L1
-    const bool gather = !INTERP && cpitch > 0;
-    const int cpad = (int)((reinterpret_cast<uintptr_t>(ca) & 15u) / sizeof(T));
+    // (interpolated coefficients, float64: the row of the INTERLEAVED bank, [tap]{a,b,c,d}, 32 bytes per tap, always aligned)
+    const bool gather = cpitch > 0;
+    const bool gather_il = INTERP && gather;
+    const int cpad = gather_il ? 0 : (int)((reinterpret_cast<uintptr_t>(ca) & 15u) / sizeof(T));
     if (gather) {
         if (threadIdx.x == 0) mbar_init(bar, 1);
         __syncthreads();
-        const uint32_t nb = live ? (uint32_t)(((c.taps + cpad) * sizeof(T) + 15) & ~(size_t)15) : 0u;
-        if (live) bulk_g2s(crow + (size_t)threadIdx.x * cpitch, ca - cpad, nb, bar);
+        const uint32_t nb = !live ? 0u : gather_il ? (uint32_t)(c.taps * 4 * sizeof(T)) : (uint32_t)(((c.taps + cpad) * sizeof(T) + 15) & ~(size_t)15);
+        if (live)
+            bulk_g2s(crow + (size_t)threadIdx.x * cpitch, gather_il ? static_cast<const T*>(c.bank_il) + co * 4 : ca - cpad, nb, bar);
         uint32_t bytes = nb;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
@@ -778,8 +781,12 @@ __global__ void __launch_bounds__(TO) poly_kernel(const PolyCall c, const int n_
     double acc0 = 0, acc1 = 0;
     const int base = div - div0;
     for (int k = 0; k < c.taps; ++k) {
-        T coef = cg[k];
-        if (INTERP) coef = fma(x, fma(x, fma(x, cd[k], cc[k]), cb[k]), coef);
+        T coef;
+        if (gather_il) coef = fma(x, fma(x, fma(x, cg[4 * k + 3], cg[4 * k + 2]), cg[4 * k + 1]), cg[4 * k]);  // same operation order
+        else {
+            coef = cg[k];
+            if (INTERP) coef = fma(x, fma(x, fma(x, cd[k], cc[k]), cb[k]), coef);
+        }
         const T h = staged ? xs[base + k] : vload(hist, c.hist_len, in, c.n_in, div + k);
         if ((k & 1) && sizeof(T) == 4) acc1 = fma((double)h, (double)coef, acc1);
         else acc0 = fma((double)h, (double)coef, acc0);
@@ -838,12 +845,18 @@ const char* launch_poly(const PolyCall& c, int dtype, cudaStream_t s, RatCache* 
         int pitch = ((c.taps + vec + vec - 1) / vec) * vec;
         while ((pitch * (int)esz) % 128 != 16) pitch += vec;
         if ((size_t)(xcap + 4 + TO * pitch) * esz + 16 <= 160 * 1024) cpitch = pitch;
+    } else if (c.interp && dtype == DT_F64 && c.bank_il && blocks <= 8) {
+        // interpolated coefficients, Flush-size launches: each output's row of the interleaved bank (32 bytes per tap) by TMA —
+        // the thread-per-output loop otherwise waits for four scattered loads per tap
+        int pitch = 4 * c.taps;
+        while ((pitch * 8) % 128 != 16) pitch += 2;
+        if ((size_t)(xcap + 4 + TO * pitch) * 8 + 16 <= 200 * 1024) cpitch = pitch;
     }
     size_t smem = 16 + (size_t)((xcap + 3) & ~3) * esz + (size_t)TO * cpitch * esz;
 #define LAUNCH(T, I)                                                                                          \
     {                                                                                                         \
         auto k = poly_kernel<T, I, TO>;                                                                       \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024); \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024); \
         launch_pdl(k, (unsigned)blocks, (unsigned)TO, smem, s, c, n_tiles, xcap, cpitch);                     \
         count_launch();                                                                                       \
     }
