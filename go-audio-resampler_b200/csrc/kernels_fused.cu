@@ -1295,6 +1295,13 @@ const char* launch_fused_up2_poly(const FusedCall& c, int dtype, cudaStream_t s,
     if (c.interp && g_fused_rat && c.bank_il && (int64_t)c.n_out >= 16 * (int64_t)c.L &&
         launch_fused_sorted(c, c.bank_il, s))
         return "fused_up2_poly_sorted_f64";
+    if (c.interp && c.bank_il && c.n_streams <= 4 && (int64_t)c.np * 2 <= 512 && c.n_out > 88) {
+        // A Flush-size call with interpolated coefficients and more outputs than the fused kernel can gather coefficient rows for
+        // (its shared memory holds ~90 rows of the interleaved bank beside the tile): two launches — the x2 kernel, then the
+        // stand-alone polyphase kernel, which gathers the rows of 128 outputs per block — are faster than one launch that reads
+        // four scattered coefficients per tap (config 5b's Flush: 6.6 + 5.7 against 21.4 us)
+        return nullptr;
+    }
     if (c.interp) return launch_fused_t<double, true>(c, s) ? "fused_up2_poly_f64_interp" : nullptr;
     return launch_fused_t<double, false>(c, s) ? "fused_up2_poly_f64" : nullptr;
 }
