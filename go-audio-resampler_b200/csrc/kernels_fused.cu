@@ -431,11 +431,43 @@ __global__ void __launch_bounds__(NT, 1) fused_up2_poly_sorted_kernel(const Fuse
     __syncthreads();  // tile complete, histogram complete
 
     // ---- 4. counting sort by phase: sorted position -> (phase, output, window start, fraction) ----
-    for (int p = tid; p <= c.L; p += NT) {
-        int sum = 0;
-        for (int j = 0; j < p; ++j) sum += hist[j];
-        start[p] = sum;
-        if (p < c.L) cursor[p] = sum;
+    {   // exclusive prefix sum of the histogram: warp scans + a scan of the warp totals (the serial form — thread p adding up
+        // hist[0 .. p) — was ~200 dependent shared-memory loads long for the last phases)
+        __shared__ int wtot[NT / 32 + 1];
+        const int lane = tid & 31, wid = tid >> 5;
+        int carry = 0;
+        for (int b0 = 0; b0 < c.L; b0 += NT) {
+            const int p = b0 + tid;
+            const int v = p < c.L ? hist[p] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) wtot[wid] = incl;
+            __syncthreads();
+            if (wid == 0) {
+                const int w = lane < NT / 32 ? wtot[lane] : 0;
+                int wi = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                    if (lane >= o) wi += t;
+                }
+                if (lane < NT / 32) wtot[lane] = wi - w;  // exclusive offset of warp `lane`
+                if (lane == 31) wtot[NT / 32] = wi;       // total of this round
+            }
+            __syncthreads();
+            const int excl = carry + wtot[wid] + incl - v;
+            if (p < c.L) {
+                start[p] = excl;
+                cursor[p] = excl;
+            }
+            carry += wtot[NT / 32];
+            __syncthreads();
+        }
+        if (tid == 0) start[c.L] = carry;
     }
     __syncthreads();
     for (int i = tid; i < cnt; i += NT) {
