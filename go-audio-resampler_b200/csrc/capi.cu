@@ -541,6 +541,10 @@ int32_t gar_set_slice_budget(gar_handle* h, int64_t bytes) {
 void gar_set_tiled_polyphase(int32_t enabled) { gar::set_tiled_polyphase(enabled != 0); }
 void gar_set_tensor_fir(int32_t enabled) { gar::set_tensor_fir(enabled != 0); }
 void gar_set_chain_kernel(int32_t mode) { gar::set_chain_kernel(mode); }
+int32_t gar_debug_chain_tile_hi(int32_t chunk_len, int32_t kp, int32_t n_chunks, int32_t n_tiles, int32_t chunk, int32_t hist_len,
+                                int64_t L, int64_t at0, int64_t step, int32_t n_out) {
+    return gar::chain_debug_tile_hi(chunk_len, kp, n_chunks, n_tiles, chunk, hist_len, L, at0, step, n_out);
+}
 
 int64_t gar_kernel_launches(const gar_handle* h, int32_t reset) {
     (void)h;  // process-wide counter: every <<<>>> of this library

@@ -129,6 +129,7 @@ bool launch_chain_up2_poly(const FusedCall& c, cudaStream_t s, ChainWs* ws, bool
 // would exceed the engine's inter-stage memory budget
 void set_chain_kernel(int mode);
 int chain_kernel_mode();
+int chain_debug_tile_hi(int S, int kp, int NC, int n_tiles_p, int c, int hp, int64_t L, int64_t at0, int64_t step, int n_out);
 // float32 I/O folded into the two tensor-core launches of a batched x2 -> polyphase chain: will launch_fir / launch_poly take the
 // call with in_f32 / out_f32 set? (the engine asks before it decides against the cast launches)
 bool fir_mma_io32_takes(const FirCall& c);

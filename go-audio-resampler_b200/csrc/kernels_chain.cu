@@ -701,6 +701,13 @@ bool launch_chain_t(const FusedCall& c, cudaStream_t s, ChainWs* wsp, const int 
 
 }  // namespace
 
+// test hook (gar_debug_chain_tile_hi): the chunk -> tile assignment of the polyphase items, for the CPU tests of its invariants
+int chain_debug_tile_hi(int S, int kp, int NC, int n_tiles_p, int c, int hp, int64_t L, int64_t at0, int64_t step, int n_out) {
+    ChainGeom g{};
+    g.S = S; g.kp = kp; g.NC = NC; g.n_tiles_p = n_tiles_p;
+    return chain_p_tile_hi(g, c, hp, L, at0, step, n_out);
+}
+
 // 0: never, 1: every eligible call, 2 (default): eligible calls whose full-size intermediate buffer would exceed the engine's
 // inter-stage memory budget (the engine decides; see Engine::run)
 static int g_chain_mode = [] {

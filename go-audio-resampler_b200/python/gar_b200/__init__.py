@@ -136,6 +136,7 @@ SYMBOLS = {
     "gar_set_slice_budget": (_i32, [_vp, _i64]),
     "gar_set_tensor_fir": (None, [_i32]),
     "gar_set_chain_kernel": (None, [_i32]),
+    "gar_debug_chain_tile_hi": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i32]),
     "gar_measure_fma_peak": (_i32, [_i32, _i32, C.POINTER(C.c_double)]),
     "gar_version": (C.c_char_p, []),
 }

@@ -261,6 +261,11 @@ void gar_set_tensor_fir(int32_t enabled);
  * 0: never; 1: every eligible call; 2 (default): eligible calls whose intermediate buffer would exceed the inter-stage
  * memory budget (gar_set_slice_budget) — they run as one launch instead of a sequence of time slices. */
 void gar_set_chain_kernel(int32_t mode);
+/* Test hook (no device needed): K5 assigns the 64-output tiles of the polyphase stage to chunks of `chunk_len` intermediate
+ * samples — a tile belongs to the first chunk that contains the END of everything its staging reads. Returns the number of
+ * tiles assigned to chunks 0 .. chunk. tests/test_chain_geometry.py checks the invariants the kernel's dependency counters rely on. */
+int32_t gar_debug_chain_tile_hi(int32_t chunk_len, int32_t kp, int32_t n_chunks, int32_t n_tiles, int32_t chunk, int32_t hist_len,
+                                int64_t L, int64_t at0, int64_t step, int32_t n_out);
 /* Number of this library's kernels launched through the handle since creation / last reset of the counter. */
 int64_t gar_kernel_launches(const gar_handle* h, int32_t reset);
 /* Name of the dominant kernel variant chosen for stage `stage` (for bench/ncu filters). */
