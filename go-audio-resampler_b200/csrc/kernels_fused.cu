@@ -993,7 +993,7 @@ static bool launch_fused_r(const FusedCall& c, cudaStream_t s) {
     int bank_pitch = 0;
     // a-bank copy in shared memory: pays only when a block's set-up is amortised over many outputs. A streaming-size call
     // (a few small tiles) reads its coefficients through L1 instead: ncu showed 55 % of such a launch inside the copy.
-    if (!INTERP && (int64_t)n_tiles * c.n_streams >= 2 * 148) {
+    if (!INTERP && (int64_t)n_tiles * c.n_streams >= 64) {  // (64: a single 10 s stream has 288 tiles — it ran 4x slower through L1)
         const int pitch = c.t2 | 1;
         if (((size_t)c.L * pitch + words) * sizeof(T) + 16 <= 100 * 1024) {
             bank_pitch = pitch;
