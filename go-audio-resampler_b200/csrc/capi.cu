@@ -227,13 +227,15 @@ int32_t gar_create(const gar_config* cfg, gar_handle** out) {
         compute = cfg->dtype == GAR_F32 ? DT_F32 : DT_F64;
     }
     chain.ratio = ratio;
-    // wide mode: a float32 batch at a non-integer ratio (x2 stage + polyphase stage) large enough for the FP64 tensor-core
-    // kernels (K1m + K3m/K3p: irrational ratios from 8 rows, rational ones from 32 — below that the fused kernels win)
+    // wide mode: a float32 engine at a non-integer ratio (x2 stage + polyphase stage) computes in float64 where those kernels are
+    // the faster ones: rational ratios from 32 rows (K1m + K3p on the FP64 tensor cores; below that the float32 fused kernel is
+    // on a par), ratios with a fractional phase step at ANY row count — the float32 thread-per-output kernel with interpolated
+    // coefficients runs a 10 s stream in 199 us, the phase-sorted float64 kernel K4s in 72 us (tools/bench_few_rows.py)
     bool wide = false;
     if (path == GAR_PATH_ENGINE && compute == DT_F32) {
         const int rows_total = channels * (cfg->n_streams > 1 ? cfg->n_streams : 1);
         for (const StageDesign& sd : chain.stages)
-            if (sd.kind == STAGE_POLY && rows_total >= (sd.interp ? 8 : 32)) wide = true;
+            if (sd.kind == STAGE_POLY && rows_total >= (sd.interp ? 1 : 32)) wide = true;
         if (const char* e = gar::tune_env("GAR_NO_WIDE_F32")) wide = wide && !(e[0] && e[0] != '0');
         if (wide) compute = DT_F64;
     }

@@ -523,3 +523,23 @@ def test_float32_engine_batches_run_wide_on_the_tensor_cores_within_1e6_of_the_f
         h._process(0, x[0].astype(np.float64), np.float64)
     bank = h.bank(0)
     assert np.array_equal(bank, bank.astype(np.float32).astype(np.float64))  # coefficients are float32 values
+
+
+@pytest.mark.parametrize("ir,orr,rows,n", [(44100, 47999, 1, 120000), (48000, 44101, 2, 90000), (22050, 47999, 5, 60000)])
+def test_float32_engines_with_a_fractional_phase_step_run_wide_at_any_row_count(ir, orr, rows, n):
+    """A float32 engine whose polyphase stage interpolates its coefficients (fractional phase step) computes in float64 at every row
+    count: the phase-sorted kernel K4s serves 1-7 rows (a 10 s stream: 77 us against 199 us for the float32 thread-per-output
+    kernel). Counts exact, <= 1e-6 against the oracle's float32 path, 4096-frame streaming chunks == one shot to 1e-6."""
+    rng = np.random.default_rng(100 + rows)
+    x = (0.5 * rng.standard_normal((rows, n))).astype(np.float32)
+    h = G.NewBatch(ir, orr, G.QualityHigh, rows, np.float32)
+    y = np.concatenate([h.ProcessBatch(x)[0], h.FlushBatch()[0]], axis=1)
+    assert y.dtype == np.float32
+    assert "fused_up2_poly_sorted_f64" in h.last_kernels(), h.last_kernels()
+    want, counts = O.batch_resample(x, ir, orr, O.Q_HIGH, n_threads=2)
+    assert np.all(counts == y.shape[1])
+    assert np.max(np.abs(y.astype(np.float64) - want[:, :y.shape[1]].astype(np.float64))) <= 1e-6
+    h.Reset()
+    parts = [h.ProcessBatch(np.ascontiguousarray(x[:, i:i + 4096]))[0].copy() for i in range(0, n, 4096)]
+    y2 = np.concatenate(parts + [h.FlushBatch()[0]], axis=1)
+    assert y2.shape == y.shape and np.max(np.abs(y2.astype(np.float64) - y)) <= 1e-6
