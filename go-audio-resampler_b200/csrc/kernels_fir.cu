@@ -1022,6 +1022,86 @@ __global__ void __launch_bounds__(256) fir_generic_kernel(const FirCall c, const
     (static_cast<T*>(c.out) + row * c.out_stride)[o] = (T)(tot + (double)acc);
 }
 
+// Integer factors without a register-tiled variant (x5, x6, x8 ... x24 up-samplers, /5 ... decimators: path-B engines such as
+// 8k -> 48k or 8k -> 192k, dft_stage.go:156-338 / :488-554 with any factor): filter bank and sample window in SHARED memory,
+// one thread per output, strictly sequential taps (the arithmetic of fir_generic_kernel, bit-identical), blocks persistent over
+// `tiles_per_block` tiles so that the bank is staged once. Not FMA-bound (two LDS per FMA), but 5-10x the generic kernel, which
+// reads every operand through guarded global loads.
+template <typename T>
+__global__ void __launch_bounds__(256) fir_smem_kernel(const FirCall c, const int tj /*positions per tile*/, const int n_tiles,
+                                                       const int tiles_per_block, const int n_groups, const int bpitch,
+                                                       const int xcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* bs = reinterpret_cast<T*>(smem_raw);  // [nf][bpitch] filter bank (odd pitch: the lanes' phases sit in different banks)
+    T* xs = bs + (size_t)c.nf * bpitch;      // [xcap] sample window of the tile
+    const int grp = blockIdx.x % (n_groups + 1);
+    const int64_t row = blockIdx.x / (n_groups + 1);
+    const T* __restrict__ hist = static_cast<const T*>(c.hist) + row * c.hist_stride;
+    const T* __restrict__ in = static_cast<const T*>(c.in) + row * c.in_stride;
+    if (grp == n_groups) {
+        carry_row(hist, c.hist_len, in, c.n_in, static_cast<T*>(c.hist_out) + row * c.hist_out_stride, c.drop, c.new_hist_len);
+        return;
+    }
+    const T* __restrict__ bank = static_cast<const T*>(c.bank);
+    for (int i = threadIdx.x; i < c.nf * c.taps; i += 256) bs[(i / c.taps) * bpitch + (i % c.taps)] = bank[i];
+    T* __restrict__ out = static_cast<T*>(c.out) + row * c.out_stride;
+    const int kc = (c.taps - 1) / 2;
+    for (int t = grp * tiles_per_block; t < min(n_tiles, (grp + 1) * tiles_per_block); ++t) {
+        const int j0 = t * tj;
+        const int npos = min(tj, c.n_pos - j0);
+        const int span = (npos - 1) * c.stride + c.taps;
+        __syncthreads();  // the previous tile's window is no longer read (first tile: nothing pending)
+        block_copy4(span, [&](int i) { return vload(hist, c.hist_len, in, c.n_in, c.first + j0 * c.stride + i); },
+                    [&](int i, T v) { xs[i] = v; });
+        __syncthreads();
+        for (int o = threadIdx.x; o < npos * c.nf; o += 256) {
+            const int j = o / c.nf, p = o - j * c.nf;
+            const T* __restrict__ w = xs + j * c.stride;
+            const T* __restrict__ cf = bs + p * bpitch;
+            double tot = 0;
+            T acc = 0;
+            for (int k = 0; k < c.taps; ++k) {
+                acc = fma(w[k], cf[k], acc);
+                if (sizeof(T) == 4 && ((k & 255) == 255 || (k >= kc && k < kc + 12 && ((k - kc) & 3) == 3))) {
+                    tot += (double)acc;
+                    acc = 0;
+                }
+            }
+            out[(int64_t)(j0 + j) * c.nf + p] = (T)(tot + (double)acc);
+        }
+    }
+}
+
+template <typename T>
+static bool launch_fir_smem(const FirCall& c, cudaStream_t s) {
+    if ((int64_t)c.n_pos * c.nf < 4096 || c.nf > 64 || c.stride > 64) return false;
+    const int bpitch = c.taps | 1;
+    // outputs per tile: up to 2048 (eight per thread) for large calls, down to 256 (one per thread) so that a single row of a
+    // long-filter decimator (48k -> 8k: 80 000 outputs of ~3000 taps each) still spreads over four blocks per SM
+    const int64_t n_el_total = (int64_t)c.n_pos * c.nf * c.n_streams;
+    const int per_tile = (int)std::max<int64_t>(256, std::min<int64_t>(2048, n_el_total / (4 * 148)));
+    const int tj = std::max(8, per_tile / c.nf);
+    const int xcap = (tj - 1) * c.stride + c.taps;
+    const size_t smem = ((size_t)c.nf * bpitch + xcap + 4) * sizeof(T);
+    if (smem > 160 * 1024) return false;
+    const int n_tiles = (c.n_pos + tj - 1) / tj;
+    // persistent over a few tiles (the bank is staged once per block) while the grid still fills the GPU
+    int tpb = (int)std::max<int64_t>(1, std::min<int64_t>(16, (int64_t)n_tiles * c.n_streams / (4 * 148)));
+    const int n_groups = (n_tiles + tpb - 1) / tpb;
+    auto k = fir_smem_kernel<T>;
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > configured[dev & 63]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured[dev & 63] = smem;
+    }
+    const int64_t blocks = (int64_t)(n_groups + 1) * c.n_streams;
+    k<<<(unsigned)blocks, 256, smem, s>>>(c, tj, n_tiles, tpb, n_groups, bpitch, xcap);
+    count_launch();
+    return true;
+}
+
 template <typename T, int M, int NF, int R>
 void launch_fir_tiled(const FirCall& c, cudaStream_t s) {
     constexpr int NT = 128;
@@ -1166,7 +1246,20 @@ bool tensor_fir_enabled() { return g_fir_mma; }
     X(double, DT_F64, 4, 1, 5, "fir_f64_s4_r5")   \
     X(double, DT_F64, 1, 2, 6, "fir_f64_up2_r6")  \
     X(double, DT_F64, 1, 3, 2, "fir_f64_up3_r2")  \
-    X(double, DT_F64, 1, 4, 2, "fir_f64_up4_r2")
+    X(double, DT_F64, 1, 4, 2, "fir_f64_up4_r2")  \
+    /* path-B engines at /5 /6 /8 and x5 x6 x8 (8k <-> 48k, 44.1k -> 8.82k ...). A thread's window starts M*R samples after its \
+       neighbour's and is read with 16-byte loads: M*R must be even (float64) / a multiple of 4 (float32) */ \
+    X(double, DT_F64, 5, 1, 2, "fir_f64_s5_r2")   \
+    X(double, DT_F64, 6, 1, 3, "fir_f64_s6_r3")   \
+    X(double, DT_F64, 8, 1, 2, "fir_f64_s8_r2")   \
+    X(double, DT_F64, 1, 5, 2, "fir_f64_up5_r2")  \
+    X(double, DT_F64, 1, 6, 2, "fir_f64_up6_r2")  \
+    X(double, DT_F64, 1, 8, 2, "fir_f64_up8_r2")  \
+    X(float, DT_F32, 5, 1, 4, "fir_f32_s5_r4")    \
+    X(float, DT_F32, 6, 1, 6, "fir_f32_s6_r6")    \
+    X(float, DT_F32, 8, 1, 3, "fir_f32_s8_r3")    \
+    X(float, DT_F32, 1, 5, 4, "fir_f32_up5_r4")   \
+    X(float, DT_F32, 1, 6, 4, "fir_f32_up6_r4")
 
 // float64 streaming-size / flush calls (a handful of tiles at most): 2-3 positions per thread instead of 6-7, so the one
 // tile that is the whole critical path is three times shorter and the positions spread over more threads; same tap order
@@ -1177,6 +1270,16 @@ bool tensor_fir_enabled() { return g_fir_mma; }
     X(double, DT_F64, 3, 1, 2, "fir_f64_s3_r2")
 
 void set_tensor_fir(bool on) { g_fir_mma = on; }
+
+// shared memory a register-tiled variant needs for this call (filter + two window buffers): long filters of large factors
+// (/8 VeryHigh: ~10 000 taps) do not fit and take the shared-memory / generic kernels
+template <typename T, int M, int NF, int R>
+static bool fir_tiled_fits(const FirCall& c) {
+    constexpr int NT = 128, VEC = VecOf<T>::N, NCH = (M * (R - 1) + VEC - 1) / VEC + 1;
+    const int cp = ((c.taps + VEC - 1 + VEC - 1) / VEC) * VEC;
+    const int xlen = M * R * (NT - 1) + (cp / VEC + NCH + 1) * VEC;
+    return 16 + (size_t)(NF * cp + 2 * xlen) * sizeof(T) <= 227 * 1024;
+}
 
 const char* fir_variant_name(int dtype, int stride, int nf, int taps, int64_t n_pos, int n_streams) {
     (void)taps; (void)n_pos; (void)n_streams;
@@ -1229,13 +1332,18 @@ const char* launch_fir(const FirCall& c, int dtype, cudaStream_t s) {
         GAR_FIR_SMALL_VARIANTS(X)
 #undef X
     }
-#define X(T, DT, M, NF, R, NAME)                           \
-    if (dtype == DT && c.stride == M && c.nf == NF) {      \
-        launch_fir_tiled<T, M, NF, R>(c, s);               \
-        return NAME;                                       \
+#define X(T, DT, M, NF, R, NAME)                                                          \
+    if (dtype == DT && c.stride == M && c.nf == NF && fir_tiled_fits<T, M, NF, R>(c)) {   \
+        launch_fir_tiled<T, M, NF, R>(c, s);                                              \
+        return NAME;                                                                      \
     }
     GAR_FIR_VARIANTS(X)
 #undef X
+    static const bool smem_on = [] { const char* e = gar::tune_env("GAR_NO_FIR_SMEM"); return !(e && e[0] && e[0] != '0'); }();
+    if (smem_on && g_fir_mma) {  // (gar_set_tensor_fir(0) = the "simple kernels" A/B switch also restores the generic kernel here)
+        if (dtype == DT_F32 ? launch_fir_smem<float>(c, s) : launch_fir_smem<double>(c, s))
+            return dtype == DT_F32 ? "fir_f32_smem" : "fir_f64_smem";
+    }
     const int64_t n_el = (int64_t)c.n_pos * c.nf;
     const int n_tiles = (int)((n_el + 255) / 256);
     const int64_t blocks = (int64_t)(n_tiles + 1) * c.n_streams;

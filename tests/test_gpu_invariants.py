@@ -543,3 +543,72 @@ def test_float32_engines_with_a_fractional_phase_step_run_wide_at_any_row_count(
     parts = [h.ProcessBatch(np.ascontiguousarray(x[:, i:i + 4096]))[0].copy() for i in range(0, n, 4096)]
     y2 = np.concatenate(parts + [h.FlushBatch()[0]], axis=1)
     assert y2.shape == y.shape and np.max(np.abs(y2.astype(np.float64) - y)) <= 1e-6
+
+
+@pytest.mark.parametrize("ir,orr,rows,n,dt", [
+    (8000, 192000, 1, 12000, np.float64),    # x24 (BASELINE config 5a's rates as ONE engine: path B)
+    (8000, 56000, 2, 20000, np.float64),     # x7
+    (48000, 4000, 3, 120000, np.float64),    # /12 decimator
+    (44100, 6300, 1, 120000, np.float64),    # /7
+    (8000, 96000, 2, 20000, np.float32),     # x12, float32 engine
+    (48000, 4800, 2, 90000, np.float32),     # /10, float32 engine
+])
+def test_integer_factors_without_a_tiled_variant_shared_memory_kernel_vs_generic_and_oracle(ir, orr, rows, n, dt):
+    """Path-B engines at integer ratios without a register-tiled variant (dft_stage.go with any factor): the shared-memory kernel
+    (bank + window staged, one thread per output, sequential taps) against the generic one-thread-per-output kernel — bit-identical
+    in float64, identical fold points in float32 — and the oracle."""
+    rng = np.random.default_rng(77)
+    x = (0.5 * rng.standard_normal((rows, n))).astype(dt)
+    cuts = [0, n // 3 + 1, n]
+
+    def run(fast):
+        G.set_tensor_fir(fast)
+        try:
+            h = G.NewBatch(ir, orr, G.QualityHigh, rows, dt)
+            ys = [h.ProcessBatch(np.ascontiguousarray(x[:, lo:hi]))[0].copy() for lo, hi in zip(cuts[:-1], cuts[1:])]
+            ys.append(h.FlushBatch()[0].copy())
+            return np.concatenate(ys, axis=1), h.last_kernels()
+        finally:
+            G.set_tensor_fir(True)
+
+    ya, ka = run(True)
+    yb, kb = run(False)
+    assert any(k.endswith("_smem") for k in ka), ka
+    assert not any(k.endswith("_smem") for k in kb) and any(k.endswith("_generic") for k in kb), kb
+    assert np.array_equal(ya, yb), float(np.max(np.abs(ya.astype(np.float64) - yb)))
+    want, counts = O.batch_resample(x[:1], ir, orr, O.Q_HIGH, n_threads=1)
+    assert counts[0] == ya.shape[1]
+    assert np.max(np.abs(ya[0].astype(np.float64) - want[0, :ya.shape[1]].astype(np.float64))) <= (1e-12 if dt == np.float64 else 1e-6)
+
+
+@pytest.mark.parametrize("ir,orr,rows,n,dt,kernel", [
+    (8000, 48000, 2, 30000, np.float64, "fir_f64_up6_r2"),
+    (8000, 40000, 1, 30000, np.float64, "fir_f64_up5_r2"),
+    (8000, 64000, 3, 20000, np.float64, "fir_f64_up8_r2"),
+    (48000, 8000, 3, 90000, np.float64, "fir_f64_s6_r3"),
+    (44100, 8820, 1, 120000, np.float64, "fir_f64_s5_r2"),
+    (64000, 8000, 2, 120000, np.float64, "fir_f64_s8_r2"),
+    (8000, 40000, 2, 20000, np.float32, "fir_f32_up5_r4"),
+    (8000, 48000, 2, 20000, np.float32, "fir_f32_up6_r4"),
+    (48000, 8000, 2, 60000, np.float32, "fir_f32_s6_r6"),
+    (44100, 8820, 2, 60000, np.float32, "fir_f32_s5_r4"),
+])
+def test_register_tiled_fir_variants_for_factors_5_6_8(ir, orr, rows, n, dt, kernel):
+    """x5 x6 x8 and /5 /6 /8 (8k <-> 48k, 44.1k -> 8.82k ...): the register-tiled kernel's variants for these factors against the
+    oracle; float64 chunked == one shot bit for bit (same tap order whatever the chunking), counts exact."""
+    rng = np.random.default_rng(78)
+    x = (0.5 * rng.standard_normal((rows, n))).astype(dt)
+    h = G.NewBatch(ir, orr, G.QualityHigh, rows, dt)
+    y = np.concatenate([h.ProcessBatch(x)[0], h.FlushBatch()[0]], axis=1)
+    assert kernel in h.last_kernels(), h.last_kernels()
+    want, counts = O.batch_resample(x[:1], ir, orr, O.Q_HIGH, n_threads=1)
+    assert counts[0] == y.shape[1]
+    assert np.max(np.abs(y[0].astype(np.float64) - want[0, :y.shape[1]].astype(np.float64))) <= (1e-12 if dt == np.float64 else 1e-6)
+    h.Reset()
+    parts = [h.ProcessBatch(np.ascontiguousarray(c))[0].copy() for c in np.array_split(x, 3, axis=1)]
+    y2 = np.concatenate(parts + [h.FlushBatch()[0]], axis=1)
+    assert y2.shape == y.shape
+    if dt == np.float64:
+        assert np.array_equal(y2, y)
+    else:
+        assert np.max(np.abs(y2.astype(np.float64) - y)) <= 1e-6
