@@ -657,7 +657,8 @@ static int process_rows_host(gar_handle* h, int row0, int count, int io_dtype, c
     // Streaming-size calls skip the copy engines: the chunk is placed in pinned, device-mapped staging that the kernels read
     // and write directly over PCIe (two cudaMemcpyAsync calls and their DMA start-up cost more than the 16 KB they move).
     const size_t in_bytes = (size_t)count * (size_t)in_stride * iosz, out_bytes = (size_t)count * (size_t)out_stride * iosz;
-    const bool zero_copy = in_bytes + out_bytes <= (512u << 10);
+    static const size_t zc_max = [] { const char* e = gar::tune_env("GAR_ZC_MAX_KB"); return (size_t)(e ? std::atoi(e) : 2048) << 10; }();  // (8k -> 192k chunks: 786 KB out, 182 -> 106 us)
+    const bool zero_copy = in_bytes + out_bytes <= zc_max;
     if (zero_copy && in_bytes + out_bytes > h->pin_cap) {
         if (h->pin) {
             cudaStreamSynchronize(s);

@@ -1079,7 +1079,9 @@ static bool launch_fir_smem(const FirCall& c, cudaStream_t s) {
     // outputs per tile: up to 2048 (eight per thread) for large calls, down to 256 (one per thread) so that a single row of a
     // long-filter decimator (48k -> 8k: 80 000 outputs of ~3000 taps each) still spreads over four blocks per SM
     const int64_t n_el_total = (int64_t)c.n_pos * c.nf * c.n_streams;
-    const int per_tile = (int)std::max<int64_t>(256, std::min<int64_t>(2048, n_el_total / (4 * 148)));
+    // (up-samplers stage nf filters per block: at least 1024 outputs per tile there, or a streaming-size x24 call spends its
+    //  time copying the bank — 173 us per 4096-frame chunk with 256-output tiles)
+    const int per_tile = (int)std::max<int64_t>(c.nf > 1 ? 1024 : 256, std::min<int64_t>(2048, n_el_total / (4 * 148)));
     const int tj = std::max(8, per_tile / c.nf);
     const int xcap = (tj - 1) * c.stride + c.taps;
     const size_t smem = ((size_t)c.nf * bpitch + xcap + 4) * sizeof(T);
