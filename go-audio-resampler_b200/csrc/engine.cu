@@ -422,16 +422,34 @@ void Engine::plan(StreamState& st, int64_t n_in, bool flush, Plan& P) const {
                 op.table_off = (int64_t)P.cubic_idx.size();
                 double ph = ss.cubic_phase;
                 const double inc = 1.0 / sd.ratio;
+                // one sequential float64 addition per output (this loop IS the cost of the preset): raw stores into tables sized
+                // once — ceil(n * ratio) + 2 bounds the count — instead of two push_backs per output
+                const size_t base = P.cubic_idx.size();
+                const size_t cap = base + (size_t)std::ceil((double)n * sd.ratio) + 8;
+                P.cubic_idx.resize(cap);
+                P.cubic_phase.resize(cap);
+                int32_t* __restrict__ pi = P.cubic_idx.data();
+                double* __restrict__ pp = P.cubic_phase.data();
+                size_t w = base;
                 for (int64_t i = 0; i < n; ++i) {
                     while (ph < 1.0) {
-                        P.cubic_idx.push_back((int32_t)i);
-                        P.cubic_phase.push_back(ph);
+                        if (w == P.cubic_idx.size()) {  // (cannot happen by the bound; keeps the loop safe against rounding)
+                            P.cubic_idx.resize(w + w / 4 + 1024);
+                            P.cubic_phase.resize(P.cubic_idx.size());
+                            pi = P.cubic_idx.data();
+                            pp = P.cubic_phase.data();
+                        }
+                        pi[w] = (int32_t)i;
+                        pp[w] = ph;
+                        ++w;
                         ph += inc;
                     }
                     ph -= 1.0;
                 }
+                P.cubic_idx.resize(w);
+                P.cubic_phase.resize(w);
                 ss.cubic_phase = ph;
-                op.n_out = (int64_t)P.cubic_idx.size() - op.table_off;
+                op.n_out = (int64_t)w - op.table_off;
                 op.hist_len = 3;
                 op.drop = n;
                 op.new_hist_len = 3;
