@@ -627,13 +627,15 @@ static bool launch_poly_rows_pipe(const PolyCall& c, cudaStream_t s, const bool 
 }
 
 template <int NTASK>
-static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s, const bool dry = false) {
+static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s, const bool dry = false, const bool one_per_sm = false) {
     constexpr int TO = 8 * NTASK;
     const double r = (double)c.step / ((double)c.L * 65536.0);
     RowsMmaGeom g{};
     const int omax = (int)std::ceil(7 * r) + 1;
     g.kp = ((omax + c.taps + 3) / 4) * 4;
-    if (g.kp > 2 * c.taps + 8) return false;  // too many structural zeros: K3i
+    // too many structural zeros: K3i — which stops at 8 samples per output; beyond that the alternative is the one-thread-per-output
+    // kernel, and a coefficient matrix that is two thirds zeros still beats it several times over
+    if (g.kp > (r > 8.0 ? 3 : 2) * c.taps + 8) return false;
     g.span = (int)std::ceil((TO - 1) * r) + 1 + g.kp + 8;
     g.pitch = ((g.span + 2 + 15) / 16) * 16 + 4;  // rows 32 bytes apart modulo 128 (B fragment reads: two wavefronts)
     g.n_tiles = (c.n_out + TO - 1) / TO;
@@ -648,7 +650,8 @@ static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s, const bool
     const size_t xbytes = (size_t)32 * g.pitch * sizeof(double);
     g.nbuf = force_nbuf ? force_nbuf : 1;
     const size_t smem = fixed + g.nbuf * xbytes;
-    if (smem > (g.nbuf == 2 ? 227 : 113) * 1024) return false;
+    // two blocks per SM normally; one (up to 227 KB) for steep ratios, whose tiles span several hundred samples per row
+    if (smem > ((g.nbuf == 2 || one_per_sm) ? 227 : 113) * 1024) return false;
     if (dry) return true;
     static size_t configured[64] = {0};
     int dev = 0;
@@ -667,14 +670,17 @@ static bool launch_poly_rows_mma_t(const PolyCall& c, cudaStream_t s, const bool
 static int launch_poly_rows_mma(const PolyCall& c, cudaStream_t s, const bool dry = false) {
     if (!tensor_fir_enabled() || c.n_streams < 8 || (int64_t)c.n_out * c.n_streams < 16384 || c.L > 4096 || c.taps > 1024) return 0;
     const double r = (double)c.step / ((double)c.L * 65536.0);
-    if (!(r > 0.0) || r > 8.0) return 0;
+    if (!(r > 0.0) || r > 16.0) return 0;
     static const int ntask = [] { const char* e = gar::tune_env("GAR_K3M_NTASK"); return e ? std::atoi(e) : 8; }();
     static const bool pipe = [] { const char* e = gar::tune_env("GAR_K3M_PIPE"); return !e || e[0] != '0'; }();
     static const int pipe_rows = [] { const char* e = gar::tune_env("GAR_K3M_PIPE_ROWS"); return e ? std::atoi(e) : 32; }();
     // measured (44.1k->48k, 21 M samples): K3p against K3m 32 rows 20.9 / 19.9, 48 rows 21.8 / 20.4 TFLOP/s, equal below
     if (pipe && c.n_streams >= pipe_rows && launch_poly_rows_pipe(c, s, dry)) return 2;
     if (ntask == 4) return (launch_poly_rows_mma_t<4>(c, s, dry) || launch_poly_rows_mma_t<8>(c, s, dry)) ? 1 : 0;
-    return (launch_poly_rows_mma_t<8>(c, s, dry) || launch_poly_rows_mma_t<4>(c, s, dry)) ? 1 : 0;
+    if (launch_poly_rows_mma_t<8>(c, s, dry) || launch_poly_rows_mma_t<4>(c, s, dry)) return 1;
+    // steep decimation (more than ~5 samples per output, e.g. the 384k -> 44.1k polyphase stage of a 192k -> 44.1k engine): the
+    // tile does not fit half an SM; one block per SM still beats the one-thread-per-output kernel several times over
+    return (launch_poly_rows_mma_t<4>(c, s, dry, true) || launch_poly_rows_mma_t<8>(c, s, dry, true)) ? 1 : 0;
 }
 
 // K3i dispatch: batches of at least 8 lock-step rows with enough outputs; S = ceil(samples per output)

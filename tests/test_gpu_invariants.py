@@ -378,6 +378,7 @@ def test_tensor_core_fir_matches_vector_kernels_and_oracle(ir, orr, preset, rows
     (48000, 44100, 70, 60000),    # rational 320/147, ragged last group of rows
     (44100, 48000, 64, 30000),    # rational 147/80
     (8000, 22051, 19, 30000),     # fewer than one intermediate sample per output
+    (192000, 44100, 33, 120000),  # steep: 8.7 intermediate samples per output (one block per SM)
 ])
 def test_tensor_core_polyphase_rows_kernel_vs_thread_per_output_kernels_and_oracle(ir, orr, rows, n):
     """K3m (polyphase stage as 8-output x K coefficient matrices times the rows' windows, DMMA): same samples as the
