@@ -648,7 +648,9 @@ int Engine::run(int row0, int count, const void* d_in, int64_t in_stride, int64_
     // The call exceeds the inter-stage memory budget. A call over ALL rows of the handle whose x2 -> polyphase pair the
     // persistent chain kernel (K5) takes needs no full-size intermediate buffer at all: one launch instead of time slices.
     // (Row groups of a batch must make the same number of stage calls to stay in lock step, hence all rows or none.)
-    if (chain_kernel_mode() != 0 && fuse_ && count == rows_ && dtype_ == DT_F64) {
+    // Time slices of 64 K samples or more cost little (a launch ramp and tail per slice) and the two tensor-core launches are
+    // the faster kernels, so the default policy turns to K5 only when the budget forces shorter slices.
+    if ((chain_kernel_mode() == 1 || (chain_kernel_mode() == 2 && slice < 65536)) && fuse_ && count == rows_ && dtype_ == DT_F64) {
         const int rc = run_once(row0, count, d_in, in_stride, n_in, d_out, out_stride, out_cap, false, s, n_out, err, false, true);
         if (rc != -1) return rc;  // -1: K5 does not take it, nothing was touched
     }

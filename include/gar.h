@@ -259,7 +259,8 @@ void gar_set_tensor_fir(int32_t enabled);
  * full-size device buffer (resampler.go:182-227). Bit-identical to the two stand-alone tensor-core launches; measured on
  * B200 it moves 2.2 GB instead of 5.5 GB through HBM for 256 rows x 10 s of 44.1k->48k but takes 4.0 instead of 3.1 ms.
  * 0: never; 1: every eligible call; 2 (default): eligible calls whose intermediate buffer would exceed the inter-stage
- * memory budget (gar_set_slice_budget) — they run as one launch instead of a sequence of time slices. */
+ * memory budget (gar_set_slice_budget) by so much that time slices would be shorter than 64 K samples — they run as one
+ * launch instead of a sequence of short slices. */
 void gar_set_chain_kernel(int32_t mode);
 /* Test hook (no device needed): K5 assigns the 64-output tiles of the polyphase stage to chunks of `chunk_len` intermediate
  * samples — a tile belongs to the first chunk that contains the END of everything its staging reads. Returns the number of

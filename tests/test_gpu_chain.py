@@ -74,13 +74,13 @@ def test_chain_kernel_keeps_streaming_state():
 
 
 def test_chain_kernel_replaces_time_slices_above_the_memory_budget():
-    """Default policy (mode 2): a call over all rows whose intermediate buffer would exceed the inter-stage budget runs as ONE
-    chain launch without that buffer instead of a sequence of time slices; below the budget the two stand-alone launches
-    stay. Identical samples either way."""
+    """Default policy (mode 2): a call over all rows whose intermediate buffer exceeds the inter-stage budget by so much that time
+    slices would be shorter than 64 K samples runs as ONE chain launch without that buffer instead; below the budget (and with
+    longer slices) the two stand-alone launches stay. Identical samples either way."""
     rng = np.random.default_rng(7)
     rows, n = 64, 200000
     x = 0.5 * rng.standard_normal((rows, n))
-    budget = 64 << 20                                  # the intermediate buffer would be 64 x 400k x 8 = 205 MB
+    budget = 32 << 20                                  # the intermediate buffer would be 64 x 400k x 8 = 205 MB: 32 K-sample slices
     ya, ka, la, ha = _run(44100, 48000, x, [0, n], 2, budget)
     yb, kb, lb, hb = _run(44100, 48000, x, [0, n], 0, budget)   # time slices
     yc, kc, _, hc = _run(44100, 48000, x, [0, n], 2)            # default budget (2 GiB): not exceeded
